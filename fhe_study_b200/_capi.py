@@ -1,0 +1,72 @@
+"""ctypes binding of libfhe_b200.so (the C ABI in include/fhe_b200.h).
+
+There is NO fallback: if the CUDA library cannot be loaded, importing this module raises.  Nothing in
+this package imports ``oracle`` (the CPU restatement is test infrastructure only)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfhe_b200.so")
+
+U64 = C.c_uint64
+SZ = C.c_size_t
+P = C.c_void_p
+I = C.c_int
+
+
+class FheError(RuntimeError):
+    """Raised where the reference panics / returns Err (the C call returned non-zero)."""
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m fhe_study_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+# name -> (restype, argtypes); mirrors include/fhe_b200.h one to one (tests/test_capi_symbols.py checks
+# that the header, this table and the .so agree).
+SIGNATURES = {
+    "fhe_last_error": (C.c_char_p, []),
+    "fhe_device_count": (I, [C.POINTER(I)]),
+    "fhe_set_device": (I, [I]),
+    "fhe_set_stream": (I, [P]),
+    "fhe_synchronize": (I, []),
+    "fhe_launch_count": (U64, []),
+    "fhe_ntt_plan_create": (I, [U64, U64, C.POINTER(P)]),
+    "fhe_ntt_plan_destroy": (None, [P]),
+    "fhe_ntt_plan_info": (I, [P, C.POINTER(U64), C.POINTER(U64), P, P]),
+    "fhe_ntt_fwd": (I, [P, P, P, SZ]),
+    "fhe_ntt_inv": (I, [P, P, P, SZ]),
+    "fhe_rq_mul": (I, [P, P, P, P, SZ, I, P]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise FheError(lib.fhe_last_error().decode("utf-8", "replace") + f" (code {rc})")
+
+
+def ptr(x):
+    """Address of a numpy array (host) or a torch tensor (host or CUDA); None -> NULL."""
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):  # torch tensor
+        return C.c_void_p(x.data_ptr())
+    if hasattr(x, "ctypes"):  # numpy array
+        return x.ctypes.data_as(C.c_void_p)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    raise TypeError(f"cannot take the address of {type(x)!r}")

@@ -1,0 +1,194 @@
+// lib_core.cu -- runtime state (errors, stream, launch counter) and the NTT-plan / Rq entry points of the
+// C ABI declared in include/fhe_b200.h.
+#include <atomic>
+#include <map>
+#include <memory>
+#include <tuple>
+
+#include "../../include/fhe_b200.h"
+#include "ntt_kernels.cuh"
+#include "plan_host.hpp"
+#include "runtime.cuh"
+
+namespace fhe {
+
+static thread_local std::string t_error;
+static thread_local cudaStream_t t_stream = nullptr;
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const std::string &msg) { t_error = msg; }
+cudaStream_t current_stream() { return t_stream; }
+void count_launch(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int num_sms() {
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (sms[dev & 63] == 0) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+        sms[dev & 63] = p.multiProcessorCount;
+    }
+    return sms[dev & 63];
+}
+
+int ntt_launch_lazy32(int, int, const NttParams<Lazy32> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int,
+                      cudaStream_t);
+int ntt_launch_lazy64(int, int, const NttParams<Lazy64> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int,
+                      cudaStream_t);
+int ntt_launch_strict64(int, int, const NttParams<Strict64> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int,
+                        cudaStream_t);
+
+}  // namespace fhe
+
+using namespace fhe;
+
+// One plan per (device, q, n); owned by the cache, reference-counted by create/destroy.
+struct fhe_ntt_plan {
+    int device = 0;
+    int kind = 0;  // modulus_kind(q)
+    int logn = 0;
+    int refs = 0;
+    HostTables host;
+    void *d_fwd = nullptr, *d_inv = nullptr;
+    NttParams<Lazy32> p32;
+    NttParams<Lazy64> p64;
+    NttParams<Strict64> ps64;
+};
+
+namespace {
+std::mutex g_plan_mu;
+std::map<std::tuple<int, u64, u64>, fhe_ntt_plan *> g_plans;
+
+template <class M> int upload_tables(fhe_ntt_plan *p, NttParams<M> &dst) {
+    ExpandedTables<M> x;
+    expand_tables(p->host, x);
+    const size_t bytes = sizeof(typename M::T) * p->host.n;
+    FHE_CUDA_OK(cudaMalloc(&p->d_fwd, bytes));
+    FHE_CUDA_OK(cudaMalloc(&p->d_inv, bytes));
+    FHE_CUDA_OK(cudaMemcpy(p->d_fwd, x.fwd.data(), bytes, cudaMemcpyHostToDevice));
+    FHE_CUDA_OK(cudaMemcpy(p->d_inv, x.inv.data(), bytes, cudaMemcpyHostToDevice));
+    dst.mod = x.mod;
+    dst.fwd = reinterpret_cast<const typename M::T *>(p->d_fwd);
+    dst.inv = reinterpret_cast<const typename M::T *>(p->d_inv);
+    dst.ninv = x.ninv;
+    dst.s_ninv = x.s_ninv;
+    for (u64 i = 0; i < 64; i++) {
+        dst.c_fwd[i] = x.fwd[i < p->host.n ? i : 0];
+        dst.c_inv[i] = x.inv[i < p->host.n ? i : 0];
+    }
+    return 0;
+}
+
+int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
+            int flags) {
+    FHE_REQUIRE(plan != nullptr, "null plan");
+    if (batch == 0) return 0;
+    FHE_REQUIRE(a != nullptr && c != nullptr && (mode != MODE_MUL || b != nullptr), "null polynomial pointer");
+    cudaStream_t st = current_stream();
+    const size_t bytes = batch * plan->host.n * sizeof(u64);
+    IoBuf ba, bb, bc, be;
+    int rc;
+    if ((rc = ba.init(a, bytes, true, false, st))) return rc;
+    if ((rc = bb.init(mode == MODE_MUL ? b : nullptr, bytes, true, false, st))) return rc;
+    if ((rc = bc.init(c, bytes, false, true, st))) return rc;
+    if ((rc = be.init(c_evals, bytes, false, true, st))) return rc;
+    switch (plan->kind) {
+        case 0:
+            rc = ntt_launch_lazy32(plan->logn, mode, plan->p32, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
+                                   be.ptr<u64>(), batch, flags, st);
+            break;
+        case 1:
+            rc = ntt_launch_lazy64(plan->logn, mode, plan->p64, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
+                                   be.ptr<u64>(), batch, flags, st);
+            break;
+        default:
+            rc = ntt_launch_strict64(plan->logn, mode, plan->ps64, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
+                                     be.ptr<u64>(), batch, flags, st);
+    }
+    if (rc) return rc;
+    count_launch(1);
+    return finish_all({&ba, &bb, &bc, &be}, st);
+}
+}  // namespace
+
+extern "C" {
+
+const char *fhe_last_error(void) { return t_error.c_str(); }
+int fhe_device_count(int *count) {
+    FHE_REQUIRE(count != nullptr, "null count");
+    FHE_CUDA_OK(cudaGetDeviceCount(count));
+    return 0;
+}
+int fhe_set_device(int device) {
+    FHE_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+int fhe_set_stream(void *cuda_stream) {
+    t_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return 0;
+}
+int fhe_synchronize(void) {
+    FHE_CUDA_OK(cudaStreamSynchronize(t_stream));
+    return 0;
+}
+uint64_t fhe_launch_count(void) { return g_launches.load(); }
+
+int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
+    FHE_REQUIRE(out != nullptr, "null plan out-pointer");
+    *out = nullptr;
+    int dev = 0;
+    FHE_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto key = std::make_tuple(dev, (u64)q, (u64)n);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) {
+        it->second->refs++;
+        *out = it->second;
+        return 0;
+    }
+    std::unique_ptr<fhe_ntt_plan> p(new fhe_ntt_plan());
+    std::string why = build_host_tables(q, n, p->host);
+    FHE_REQUIRE(why.empty(), "fhe_ntt_plan_create: " + why);
+    p->device = dev;
+    p->kind = modulus_kind(q);
+    p->logn = hp_ilog2(n);
+    FHE_REQUIRE(p->logn <= (p->kind == 0 ? 15 : 14),
+                "fhe_ntt_plan_create: n too large (max 2^15 for q < 2^30, 2^14 for larger q)");
+    int rc = p->kind == 0 ? upload_tables(p.get(), p->p32)
+             : p->kind == 1 ? upload_tables(p.get(), p->p64)
+                            : upload_tables(p.get(), p->ps64);
+    if (rc) return rc;
+    p->refs = 1;
+    *out = p.get();
+    g_plans[key] = p.release();
+    return 0;
+}
+void fhe_ntt_plan_destroy(fhe_ntt_plan *plan) {
+    if (plan == nullptr) return;
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (--plan->refs > 0) return;
+    g_plans.erase(std::make_tuple(plan->device, plan->host.q, plan->host.n));
+    cudaFree(plan->d_fwd);
+    cudaFree(plan->d_inv);
+    delete plan;
+}
+int fhe_ntt_plan_info(const fhe_ntt_plan *plan, uint64_t *psi, uint64_t *n_inv, uint64_t *roots, uint64_t *roots_inv) {
+    FHE_REQUIRE(plan != nullptr, "null plan");
+    if (psi) *psi = plan->host.psi;
+    if (n_inv) *n_inv = plan->host.n_inv;
+    if (roots) memcpy(roots, plan->host.roots.data(), plan->host.n * sizeof(u64));
+    if (roots_inv) memcpy(roots_inv, plan->host.roots_inv.data(), plan->host.n * sizeof(u64));
+    return 0;
+}
+int fhe_ntt_fwd(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *out, size_t batch) {
+    return run_ntt(plan, MODE_FWD, in, nullptr, out, nullptr, batch, 0);
+}
+int fhe_ntt_inv(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *out, size_t batch) {
+    return run_ntt(plan, MODE_INV, in, nullptr, out, nullptr, batch, 0);
+}
+int fhe_rq_mul(const fhe_ntt_plan *plan, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, int flags,
+               uint64_t *c_evals) {
+    return run_ntt(plan, MODE_MUL, a, b, c, c_evals, batch, flags);
+}
+
+}  // extern "C"

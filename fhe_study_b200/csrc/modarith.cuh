@@ -1,0 +1,189 @@
+// modarith.cuh -- modular-arithmetic policies shared by every NTT kernel (host+device so that the
+// per-thread logic can be replayed on the CPU by tests/emu, which is test infrastructure only).
+//
+// The reference's scalar is Zq{q,v} with mul = (u128)a*b % q, add = cond-subtract, sub = cond-add
+// (arith/src/zq.rs:219-328).  All of those are exact operations in Z_q, so any exact evaluation
+// strategy gives bit-identical canonical results; what must match is the *sequence of ring
+// operations* (which twiddle multiplies which element), not the reduction technique.  Here:
+//   * Lazy32  : q < 2^30, values kept in [0,4q) (forward) / [0,2q) (inverse), Shoup twiddles
+//   * Lazy64  : q < 2^62, same scheme on 64-bit words (64x64->128 via __umul64hi)
+//   * Strict64: 2^62 <= q < 2^63 (the reference's limit: Zq::add is an un-widened u64 add)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FHE_HD __host__ __device__ __forceinline__
+#else
+#define FHE_HD inline
+#endif
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef int64_t i64;
+
+namespace fhe {
+
+FHE_HD u32 mulhi_u32(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (u32)(((u64)a * b) >> 32);
+#endif
+}
+FHE_HD u64 mulhi_u64(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+FHE_HD u32 umin(u32 a, u32 b) { return a < b ? a : b; }
+FHE_HD u64 umin(u64 a, u64 b) { return a < b ? a : b; }
+
+// A twiddle w with its Shoup companion wp = floor(w * 2^wordbits / q).
+template <typename W> struct Tw { W w, wp; };
+typedef Tw<u32> Tw32;
+typedef Tw<u64> Tw64;
+
+// ---------------------------------------------------------------------------------------------------
+// Lazy32: q < 2^30.
+// ---------------------------------------------------------------------------------------------------
+struct Lazy32 {
+    typedef u32 W;
+    typedef Tw32 T;
+    u32 q, q2;       // q, 2q
+    u32 bk_shift;    // k-1, with 2^(k-1) <= q < 2^k
+    u32 bk_mu;       // floor(2^(2k) / q)  (< 2^(k+1))
+
+    // w*y mod q in [0,2q) for ANY 32-bit y (Harvey / Shoup).
+    FHE_HD u32 mul_tw(u32 y, T t) const { return y * t.w - mulhi_u32(y, t.wp) * q; }
+    FHE_HD u32 csub(u32 x, u32 m) const { return umin(x, x - m); }  // [0,2m) -> [0,m)
+    // forward (Cooley-Tukey) butterfly, arith/src/ntt.rs:56-60: U=x, V=y*S, x=U+V, y=U-V.
+    // x in [0,4q), y any 32-bit word congruent to its value; outputs in [0,4q).
+    FHE_HD void fwd(u32 &x, u32 &y, T t) const {
+        u32 X = csub(x, q2);
+        u32 V = mul_tw(y, t);
+        x = X + V;
+        y = X - V + q2;
+    }
+    // inverse (Gentleman-Sande) butterfly, arith/src/ntt.rs:92-97: x=U+V, y=(U-V)*S.  in/out [0,2q).
+    FHE_HD void inv(u32 &x, u32 &y, T t) const {
+        u32 s = csub(x + y, q2);
+        u32 d = x - y + q2;
+        x = s;
+        y = mul_tw(d, t);
+    }
+    // last inverse stage with the n^-1 scaling (arith/src/ntt.rs:100-102) folded into both outputs:
+    // x = (U+V)*ninv, y = (U-V)*(S*ninv).  in [0,2q), out [0,2q).
+    FHE_HD void inv_last(u32 &x, u32 &y, T ninv, T s_ninv) const {
+        u32 s = x + y;
+        u32 d = x - y + q2;
+        x = mul_tw(s, ninv);
+        y = mul_tw(d, s_ninv);
+    }
+    FHE_HD u32 canon4(u32 x) const { return csub(csub(x, q2), q); }  // [0,4q) -> [0,q)
+    FHE_HD u32 canon2(u32 x) const { return csub(x, q); }            // [0,2q) -> [0,q)
+    // a*b mod q for canonical a,b (Barrett on the 2k-bit product), result in [0,q).
+    FHE_HD u32 mul(u32 a, u32 b) const {
+        u64 x = (u64)a * b;
+        u64 qh = ((x >> bk_shift) * bk_mu) >> (bk_shift + 2);
+        u32 r = (u32)x - (u32)qh * q;  // in [0,3q)
+        r = csub(r, q2);
+        return csub(r, q);
+    }
+    FHE_HD static u32 load(u64 v) { return (u32)v; }
+    FHE_HD static u64 store(u32 v) { return (u64)v; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Lazy64: q < 2^62.
+// ---------------------------------------------------------------------------------------------------
+struct Lazy64 {
+    typedef u64 W;
+    typedef Tw64 T;
+    u64 q, q2;
+    u64 qinv_neg;  // -q^-1 mod 2^64
+    u64 r2;        // 2^128 mod q
+
+    FHE_HD u64 mul_tw(u64 y, T t) const { return y * t.w - mulhi_u64(y, t.wp) * q; }
+    FHE_HD u64 csub(u64 x, u64 m) const { return umin(x, x - m); }
+    FHE_HD void fwd(u64 &x, u64 &y, T t) const {
+        u64 X = csub(x, q2);
+        u64 V = mul_tw(y, t);
+        x = X + V;
+        y = X - V + q2;
+    }
+    FHE_HD void inv(u64 &x, u64 &y, T t) const {
+        u64 s = csub(x + y, q2);
+        u64 d = x - y + q2;
+        x = s;
+        y = mul_tw(d, t);
+    }
+    FHE_HD void inv_last(u64 &x, u64 &y, T ninv, T s_ninv) const {
+        u64 s = x + y;
+        u64 d = x - y + q2;
+        x = mul_tw(s, ninv);
+        y = mul_tw(d, s_ninv);
+    }
+    FHE_HD u64 canon4(u64 x) const { return csub(csub(x, q2), q); }
+    FHE_HD u64 canon2(u64 x) const { return csub(x, q); }
+    // Montgomery product a*b*2^-64 mod q in [0,q) (a*b < q*2^64).
+    FHE_HD u64 mont(u64 a, u64 b) const {
+        u64 lo = a * b, hi = mulhi_u64(a, b);
+        u64 m = lo * qinv_neg;
+        u64 t = hi + mulhi_u64(m, q) + (lo != 0ull ? 1ull : 0ull);
+        return csub(t, q);
+    }
+    FHE_HD u64 mul(u64 a, u64 b) const { return mont(mont(a, b), r2); }
+    FHE_HD static u64 load(u64 v) { return v; }
+    FHE_HD static u64 store(u64 v) { return v; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Strict64: 2^62 <= q < 2^63; everything canonical after every operation.
+// ---------------------------------------------------------------------------------------------------
+struct Strict64 {
+    typedef u64 W;
+    typedef Tw64 T;
+    u64 q, q2;  // q2 unused
+    u64 qinv_neg;
+    u64 r2;
+
+    FHE_HD u64 mul_tw(u64 y, T t) const {  // canonical result
+        u64 r = y * t.w - mulhi_u64(y, t.wp) * q;  // [0,2q), 2q < 2^64
+        return r >= q ? r - q : r;
+    }
+    FHE_HD u64 add(u64 a, u64 b) const { u64 s = a + b; return s >= q ? s - q : s; }
+    FHE_HD u64 sub(u64 a, u64 b) const { return a >= b ? a - b : a + q - b; }
+    FHE_HD void fwd(u64 &x, u64 &y, T t) const {
+        u64 V = mul_tw(y, t);
+        u64 X = x;
+        x = add(X, V);
+        y = sub(X, V);
+    }
+    FHE_HD void inv(u64 &x, u64 &y, T t) const {
+        u64 s = add(x, y);
+        u64 d = sub(x, y);
+        x = s;
+        y = mul_tw(d, t);
+    }
+    FHE_HD void inv_last(u64 &x, u64 &y, T ninv, T s_ninv) const {
+        u64 s = add(x, y);
+        u64 d = sub(x, y);
+        x = mul_tw(s, ninv);
+        y = mul_tw(d, s_ninv);
+    }
+    FHE_HD u64 canon4(u64 x) const { return x; }
+    FHE_HD u64 canon2(u64 x) const { return x; }
+    FHE_HD u64 mont(u64 a, u64 b) const {
+        u64 lo = a * b, hi = mulhi_u64(a, b);
+        u64 m = lo * qinv_neg;
+        u64 t = hi + mulhi_u64(m, q) + (lo != 0ull ? 1ull : 0ull);  // < 2q < 2^64
+        return t >= q ? t - q : t;
+    }
+    FHE_HD u64 mul(u64 a, u64 b) const { return mont(mont(a, b), r2); }
+    FHE_HD static u64 load(u64 v) { return v; }
+    FHE_HD static u64 store(u64 v) { return v; }
+};
+
+}  // namespace fhe

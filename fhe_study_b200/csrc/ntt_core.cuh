@@ -1,0 +1,112 @@
+// ntt_core.cuh -- register-blocked negacyclic NTT passes (host+device per-thread logic).
+//
+// Reference semantics (arith/src/ntt.rs:44-110): in-place Cooley-Tukey forward (natural in,
+// bit-reversed out, twiddle roots[m+i] at stage m=2^s for block i) and Gentleman-Sande inverse
+// (twiddle roots_inv[m+i]) followed by a multiplication by n^-1.  The array index of an element
+// never changes, so "position p" below is the reference's `r[p]`.
+//
+// Decomposition used here.  A polynomial of N=2^LOGN coefficients is owned by T=N/E threads with
+// E=2^LOGE coefficients in registers each.  The LOGN stages are cut into P=ceil(LOGN/LOGE) passes of
+// g_p stages (sum g_p = LOGN).  In pass p (stages s0..s0+g-1, s0 = g_0+..+g_{p-1}) a butterfly group
+// is the 2^g positions   (H << (LOGN-s0)) | (r << nL) | L ,  r = 0..2^g-1,  nL = LOGN-s0-g,
+// i.e. H = the s0 high bits (selects the twiddle block), L = the nL low bits.  A thread owns the
+// E>>g groups  u = tid + qi*T  (H = u >> nL, L = u & (2^nL-1)), so all g stages of the pass are
+// register-local, and the twiddle of local stage ls for the pair (ru, ru|half) is
+//   roots[(1 << s) + (H << ls) + (ru >> (g-ls))] ,  s = s0+ls, half = 2^(g-1-ls).
+// Between passes the E registers go through shared memory once (tools/ntt_model.py is the executable
+// model of this index algebra, checked against the reference loop).
+#pragma once
+#include "modarith.cuh"
+
+namespace fhe {
+
+template <int LOGN, int LOGE> struct NttShape {
+    static_assert(LOGE >= 1 && LOGE <= LOGN, "need 1 <= LOGE <= LOGN");
+    static constexpr int N = 1 << LOGN;
+    static constexpr int E = 1 << LOGE;
+    static constexpr int T = N / E;                         // threads per polynomial
+    static constexpr int P = (LOGN + LOGE - 1) / LOGE;      // passes
+    static constexpr int BASE = LOGN / P, REM = LOGN % P;
+    FHE_HD static constexpr int g(int p) { return BASE + (p < REM ? 1 : 0); }
+    FHE_HD static constexpr int s0(int p) { return p * BASE + (p < REM ? p : REM); }
+    FHE_HD static constexpr int nL(int p) { return LOGN - s0(p) - g(p); }
+    // position of register slot e of thread tid in the layout of pass p
+    FHE_HD static constexpr int pos(int p, int tid, int e) {
+        return (((tid + (e >> g(p)) * T) >> nL(p)) << (LOGN - s0(p))) | ((e & ((1 << g(p)) - 1)) << nL(p)) |
+               ((tid + (e >> g(p)) * T) & ((1 << nL(p)) - 1));
+    }
+};
+
+// Twiddle source: pass 0 twiddles are identical for every thread (H = 0), so they are taken from a
+// small by-value table living in the kernel-parameter constant bank; later passes index the global
+// table (L1/L2 resident, n entries).
+template <class M> struct TwSrc {
+    const typename M::T *c0;    // first 2^g(0) entries (constant bank / host array)
+    const typename M::T *tab;   // full table, n entries, reference order roots[m+i]
+};
+
+// One butterfly stage (local stage LS of pass PASS) over the thread's registers.  All trip counts are
+// compile-time constants so the register array never gets dynamically indexed.
+template <class M, int LOGN, int LOGE, int PASS, int LS>
+FHE_HD void fwd_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw) {
+    typedef NttShape<LOGN, LOGE> S;
+    constexpr int g = S::g(PASS), s0 = S::s0(PASS), nL = S::nL(PASS), G = 1 << g;
+    constexpr int half = 1 << (g - 1 - LS);
+#pragma unroll
+    for (int qi = 0; qi < (S::E >> g); qi++) {
+        const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);  // pass 0: u < 2^nL
+#pragma unroll
+        for (int hi = 0; hi < (1 << LS); hi++) {
+            const int twi = (1 << (s0 + LS)) + (H << LS) + hi;
+            const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
+#pragma unroll
+            for (int lo = 0; lo < half; lo++) {
+                const int ru = (hi << (g - LS)) | lo;
+                m.fwd(x[qi * G + ru], x[qi * G + ru + half], t);
+            }
+        }
+    }
+}
+template <class M, int LOGN, int LOGE, int PASS, int LS = 0>
+FHE_HD void fwd_pass(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw) {
+    fwd_stage<M, LOGN, LOGE, PASS, LS>(x, tid, m, tw);
+    if constexpr (LS + 1 < NttShape<LOGN, LOGE>::g(PASS)) fwd_pass<M, LOGN, LOGE, PASS, LS + 1>(x, tid, m, tw);
+}
+
+// Inverse: the same groups, local stages in descending order.  When PASS == 0 the final stage
+// (s = 0, the single twiddle roots_inv[1]) also applies n^-1 (M::inv_last).
+template <class M, int LOGN, int LOGE, int PASS, int LS>
+FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw,
+                      typename M::T ninv, typename M::T s_ninv) {
+    typedef NttShape<LOGN, LOGE> S;
+    constexpr int g = S::g(PASS), s0 = S::s0(PASS), nL = S::nL(PASS), G = 1 << g;
+    constexpr int half = 1 << (g - 1 - LS);
+#pragma unroll
+    for (int qi = 0; qi < (S::E >> g); qi++) {
+        const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
+#pragma unroll
+        for (int hi = 0; hi < (1 << LS); hi++) {
+            if constexpr (PASS == 0 && LS == 0) {
+#pragma unroll
+                for (int lo = 0; lo < half; lo++) m.inv_last(x[qi * G + lo], x[qi * G + lo + half], ninv, s_ninv);
+            } else {
+                const int twi = (1 << (s0 + LS)) + (H << LS) + hi;
+                const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
+#pragma unroll
+                for (int lo = 0; lo < half; lo++) {
+                    const int ru = (hi << (g - LS)) | lo;
+                    m.inv(x[qi * G + ru], x[qi * G + ru + half], t);
+                }
+            }
+        }
+    }
+}
+template <class M, int LOGN, int LOGE, int PASS, int LS = -1>
+FHE_HD void inv_pass(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw,
+                     typename M::T ninv, typename M::T s_ninv) {
+    constexpr int ls = LS < 0 ? NttShape<LOGN, LOGE>::g(PASS) - 1 : LS;
+    inv_stage<M, LOGN, LOGE, PASS, ls>(x, tid, m, tw, ninv, s_ninv);
+    if constexpr (ls > 0) inv_pass<M, LOGN, LOGE, PASS, ls - 1>(x, tid, m, tw, ninv, s_ninv);
+}
+
+}  // namespace fhe

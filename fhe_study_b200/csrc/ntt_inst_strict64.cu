@@ -1,0 +1,9 @@
+// ntt_inst_strict64.cu -- instantiates the NTT / INTT / polymul kernels for the Strict64 modular policy.
+#include "ntt_kernels.cuh"
+
+namespace fhe {
+int ntt_launch_strict64(int logn, int mode, const NttParams<Strict64> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals,
+                  size_t batch, int flags, cudaStream_t st) {
+    return launch_ntt<Strict64>(logn, mode, P, a, b, c, c_evals, batch, flags, st);
+}
+}  // namespace fhe

@@ -1,0 +1,217 @@
+// ntt_kernels.cuh -- batched negacyclic NTT / INTT / R_q polymul kernels (one polynomial per group of
+// T = N/E threads, E coefficients per thread in registers, one shared-memory exchange between
+// register-local passes).  Included by one translation unit per modular policy (ntt_inst_*.cu).
+//
+// Follows arith/src/ntt.rs:44-110 (NTT::ntt / NTT::intt) and arith/src/ring_nq.rs:564-607
+// (mul / mul_mut: A = evals or ntt(a), B = evals or ntt(b), C = A.B pointwise, c = intt(C), the
+// result keeps C as its cached evals).
+#pragma once
+#include "common.cuh"
+#include "ntt_core.cuh"
+
+namespace fhe {
+
+// Device-visible plan for one (q, n).  Passed BY VALUE (__grid_constant__): c_fwd / c_inv (the first
+// 2^g0 <= 64 table entries, all that pass 0 needs) are then read straight from the constant bank.
+template <class M> struct NttParams {
+    M mod;
+    const typename M::T *fwd;   // n entries: roots[i]     = psi^bitrev(i)      (arith/src/ntt.rs:133-147)
+    const typename M::T *inv;   // n entries: roots_inv[i] = roots[i]^-1        (arith/src/ntt.rs:149-161)
+    typename M::T ninv;         // n^-1                                        (arith/src/ntt.rs:27-30)
+    typename M::T s_ninv;       // roots_inv[1] * n^-1
+    typename M::T c_fwd[64], c_inv[64];
+};
+
+enum NttMode { MODE_FWD = 0, MODE_INV = 1, MODE_MUL = 2 };
+enum MulFlags { A_IS_EVALS = 1, B_IS_EVALS = 2 };
+
+template <int LOGN, int LOGE> struct KernelGeom {
+    typedef NttShape<LOGN, LOGE> S;
+    static constexpr int CT = S::T > 128 ? S::T : 128;   // threads per CTA
+    static constexpr int PPC = CT / S::T;                // polynomials per CTA
+    static constexpr int PADN = S::N + (S::N >> 5);      // padded words per polynomial in smem
+};
+__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
+
+template <int T> __device__ __forceinline__ void group_sync() {
+    if (T <= 32) __syncwarp(); else __syncthreads();
+}
+
+// registers (layout of pass FROM) -> shared -> registers (layout of pass TO)
+template <class M, int LOGN, int LOGE, int FROM, int TO>
+__device__ __forceinline__ void exchange(typename M::W (&x)[1 << LOGE], typename M::W *sm, int tid) {
+    typedef NttShape<LOGN, LOGE> S;
+    group_sync<S::T>();  // earlier readers of sm are done
+#pragma unroll
+    for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(FROM, tid, e))] = x[e];
+    group_sync<S::T>();
+#pragma unroll
+    for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(TO, tid, e))];
+}
+
+template <class M, int LOGN, int LOGE, int PASS = 0>
+__device__ __forceinline__ void fwd_chain(typename M::W (&x)[1 << LOGE], typename M::W *sm, int tid, const M &m,
+                                          const TwSrc<M> &tw) {
+    typedef NttShape<LOGN, LOGE> S;
+    if constexpr (PASS > 0) exchange<M, LOGN, LOGE, PASS - 1, PASS>(x, sm, tid);
+    fwd_pass<M, LOGN, LOGE, PASS>(x, tid, m, tw);
+    if constexpr (PASS + 1 < S::P) fwd_chain<M, LOGN, LOGE, PASS + 1>(x, sm, tid, m, tw);
+}
+template <class M, int LOGN, int LOGE, int PASS>
+__device__ __forceinline__ void inv_chain(typename M::W (&x)[1 << LOGE], typename M::W *sm, int tid, const M &m,
+                                          const TwSrc<M> &tw, typename M::T ninv, typename M::T s_ninv) {
+    inv_pass<M, LOGN, LOGE, PASS>(x, tid, m, tw, ninv, s_ninv);
+    if constexpr (PASS > 0) {
+        exchange<M, LOGN, LOGE, PASS, PASS - 1>(x, sm, tid);
+        inv_chain<M, LOGN, LOGE, PASS - 1>(x, sm, tid, m, tw, ninv, s_ninv);
+    }
+}
+
+// global (coalesced, layout of pass 0) -> registers in the layout of pass TO
+template <class M, int LOGN, int LOGE, int TO>
+__device__ __forceinline__ void load_poly(typename M::W (&x)[1 << LOGE], const u64 *__restrict__ g, bool valid,
+                                          typename M::W *sm, int tid) {
+    typedef NttShape<LOGN, LOGE> S;
+#pragma unroll
+    for (int e = 0; e < S::E; e++) x[e] = valid ? M::load(__ldg(g + S::pos(0, tid, e))) : (typename M::W)0;
+    if constexpr (TO != 0) exchange<M, LOGN, LOGE, 0, TO>(x, sm, tid);
+}
+// registers in the layout of pass FROM -> global (coalesced)
+template <class M, int LOGN, int LOGE, int FROM>
+__device__ __forceinline__ void store_poly(typename M::W (&x)[1 << LOGE], u64 *__restrict__ g, bool valid,
+                                           typename M::W *sm, int tid) {
+    typedef NttShape<LOGN, LOGE> S;
+    if constexpr (FROM != 0) exchange<M, LOGN, LOGE, FROM, 0>(x, sm, tid);
+    if (valid) {
+#pragma unroll
+        for (int e = 0; e < S::E; e++) g[S::pos(0, tid, e)] = M::store(x[e]);
+    }
+}
+
+template <class M, int LOGN, int LOGE, int MODE>
+__global__ void __launch_bounds__(KernelGeom<LOGN, LOGE>::CT)
+ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, const u64 *__restrict__ b,
+           u64 *__restrict__ c, u64 *__restrict__ c_evals, size_t batch, int flags) {
+    typedef NttShape<LOGN, LOGE> S;
+    typedef KernelGeom<LOGN, LOGE> G;
+    typedef typename M::W W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int slot = threadIdx.x / S::T, tid = threadIdx.x % S::T;
+    W *sm = reinterpret_cast<W *>(smem_raw) + (size_t)slot * G::PADN;
+    const size_t poly = (size_t)blockIdx.x * G::PPC + slot;
+    const bool valid = poly < batch;
+    const size_t off = poly * S::N;
+    const M &m = P.mod;
+    constexpr int LAST = S::P - 1;
+    W x[S::E];
+
+    if constexpr (MODE == MODE_FWD) {
+        const TwSrc<M> tw = {P.c_fwd, P.fwd};
+        load_poly<M, LOGN, LOGE, 0>(x, a + off, valid, sm, tid);
+        fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, tw);
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = m.canon4(x[e]);
+        store_poly<M, LOGN, LOGE, LAST>(x, c + off, valid, sm, tid);
+    } else if constexpr (MODE == MODE_INV) {
+        const TwSrc<M> tw = {P.c_inv, P.inv};
+        load_poly<M, LOGN, LOGE, LAST>(x, a + off, valid, sm, tid);
+        inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, tw, P.ninv, P.s_ninv);
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
+        store_poly<M, LOGN, LOGE, 0>(x, c + off, valid, sm, tid);
+    } else {
+        const TwSrc<M> twf = {P.c_fwd, P.fwd};
+        const TwSrc<M> twi = {P.c_inv, P.inv};
+        W A[S::E];
+        if (flags & A_IS_EVALS) {
+            load_poly<M, LOGN, LOGE, LAST>(A, a + off, valid, sm, tid);
+        } else {
+            load_poly<M, LOGN, LOGE, 0>(A, a + off, valid, sm, tid);
+            fwd_chain<M, LOGN, LOGE>(A, sm, tid, m, twf);
+#pragma unroll
+            for (int e = 0; e < S::E; e++) A[e] = m.canon4(A[e]);
+        }
+        if (flags & B_IS_EVALS) {
+            load_poly<M, LOGN, LOGE, LAST>(x, b + off, valid, sm, tid);
+        } else {
+            load_poly<M, LOGN, LOGE, 0>(x, b + off, valid, sm, tid);
+            fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
+#pragma unroll
+            for (int e = 0; e < S::E; e++) x[e] = m.canon4(x[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = m.mul(A[e], x[e]);
+        if (c_evals != nullptr) {  // ring_nq.rs:606 -- the product keeps its evals
+#pragma unroll
+            for (int e = 0; e < S::E; e++) A[e] = x[e];
+            store_poly<M, LOGN, LOGE, LAST>(A, c_evals + off, valid, sm, tid);
+        }
+        inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, twi, P.ninv, P.s_ninv);
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
+        store_poly<M, LOGN, LOGE, 0>(x, c + off, valid, sm, tid);
+    }
+}
+
+template <class M, int LOGN, int LOGE, int MODE>
+int launch_one(const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch, int flags,
+               cudaStream_t st) {
+    typedef KernelGeom<LOGN, LOGE> G;
+    auto kern = ntt_kernel<M, LOGN, LOGE, MODE>;
+    const size_t smem = (size_t)G::PPC * G::PADN * sizeof(typename M::W);
+    if (smem > 48 * 1024) {  // opt in once per device (and per instantiation)
+        static unsigned long long done_mask = 0;
+        int dev = 0;
+        FHE_CUDA_OK(cudaGetDevice(&dev));
+        if (!((done_mask >> (dev & 63)) & 1ull)) {
+            FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            done_mask |= 1ull << (dev & 63);
+        }
+    }
+    const size_t grid = (batch + G::PPC - 1) / G::PPC;
+    FHE_REQUIRE(grid <= 0x7fffffffull, "batch too large for one launch");
+    kern<<<(unsigned)grid, G::CT, smem, st>>>(P, a, b, c, c_evals, batch, flags);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// LOGE policy: 32 coefficients per thread for 32-bit words, 16 for 64-bit words (register budget of
+// the polymul kernel, which keeps NTT(a) in registers while transforming b).
+template <class M> struct LogE {
+    static constexpr int MAXE = sizeof(typename M::W) == 4 ? 5 : 4;
+    static constexpr int of(int logn) { return logn < MAXE ? logn : MAXE; }
+};
+
+template <class M, int LOGN>
+int launch_logn(int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
+                int flags, cudaStream_t st) {
+    constexpr int LE = LogE<M>::of(LOGN);
+    switch (mode) {
+        case MODE_FWD: return launch_one<M, LOGN, LE, MODE_FWD>(P, a, b, c, c_evals, batch, flags, st);
+        case MODE_INV: return launch_one<M, LOGN, LE, MODE_INV>(P, a, b, c, c_evals, batch, flags, st);
+        default: return launch_one<M, LOGN, LE, MODE_MUL>(P, a, b, c, c_evals, batch, flags, st);
+    }
+}
+
+template <class M>
+int launch_ntt(int logn, int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals,
+               size_t batch, int flags, cudaStream_t st) {
+    constexpr int MAXLOGN = sizeof(typename M::W) == 4 ? 15 : 14;  // one CTA's shared memory holds the polynomial
+    if (logn < 1 || logn > MAXLOGN) {
+        set_error("unsupported ring degree for this modulus width (n must be 2..2^15 for q<2^30, 2..2^14 otherwise)");
+        return -1;
+    }
+    switch (logn) {
+#define FHE_CASE(L) case L: return launch_logn<M, L>(mode, P, a, b, c, c_evals, batch, flags, st);
+        FHE_CASE(1) FHE_CASE(2) FHE_CASE(3) FHE_CASE(4) FHE_CASE(5) FHE_CASE(6) FHE_CASE(7) FHE_CASE(8)
+        FHE_CASE(9) FHE_CASE(10) FHE_CASE(11) FHE_CASE(12) FHE_CASE(13) FHE_CASE(14)
+#undef FHE_CASE
+        case 15:
+            if constexpr (sizeof(typename M::W) == 4)
+                return launch_logn<M, 15>(mode, P, a, b, c, c_evals, batch, flags, st);
+    }
+    set_error("unsupported ring degree");
+    return -1;
+}
+
+}  // namespace fhe

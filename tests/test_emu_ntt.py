@@ -1,0 +1,75 @@
+"""CPU replay of the CUDA NTT kernels' per-thread code (tests/emu) against the oracle.  No GPU needed:
+this is what keeps the index / twiddle / lazy-reduction algebra of csrc/ntt_core.cuh honest between
+GPU runs.  The real kernels are checked in test_gpu_ntt.py."""
+import numpy as np
+import pytest
+
+from primes import Q17, Q30, Q62, Q63
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emu import lib
+
+    return lib()
+
+
+def _check(emu, orc, kind, q, n, loge):
+    a = orc.uniform(n + 1, (n,), q)
+    b = orc.uniform(n + 2, (n,), q)
+    fa = orc.ntt(q, n, a)
+    out = np.zeros(n, dtype=np.uint64)
+    assert emu.emu_ntt(kind, q, n, loge, 0, orc.ptr(a), None, orc.ptr(out), None, 0) == 0
+    assert (out == fa).all()
+    assert emu.emu_ntt(kind, q, n, loge, 1, orc.ptr(fa), None, orc.ptr(out), None, 0) == 0
+    assert (out == a).all()
+    c, ev = orc.rq_mul(q, n, a, b, want_evals=True)
+    ce = np.zeros(n, dtype=np.uint64)
+    assert emu.emu_ntt(kind, q, n, loge, 2, orc.ptr(a), orc.ptr(b), orc.ptr(out), orc.ptr(ce), 0) == 0
+    assert (out == c).all() and (ce == ev).all()
+    fb = orc.ntt(q, n, b)
+    for fl, (aa, bb) in {1: (fa, b), 2: (a, fb), 3: (fa, fb)}.items():
+        assert emu.emu_ntt(kind, q, n, loge, 2, orc.ptr(aa), orc.ptr(bb), orc.ptr(out), None, fl) == 0
+        assert (out == c).all()
+
+
+@pytest.mark.parametrize("logn", range(1, 16))
+def test_lazy32_all_sizes(emu, orc, logn):
+    n = 1 << logn
+    for loge in (0, 2, 3, 6):
+        _check(emu, orc, 0, Q17, n, loge)
+    _check(emu, orc, 0, Q30, n, 0)
+
+
+@pytest.mark.parametrize("logn", range(1, 15))
+def test_64bit_policies_all_sizes(emu, orc, logn):
+    n = 1 << logn
+    _check(emu, orc, 1, Q62, n, 0)
+    _check(emu, orc, 1, Q17, n, 5)
+    _check(emu, orc, 2, Q63, n, 0)
+    _check(emu, orc, 2, Q62, n, 3)
+
+
+def test_plan_matches_oracle_tables(emu, orc):
+    for q, n in [(Q17, 4), (Q17, 1024), (Q62, 512), (Q63, 64), (Q30, 2048)]:
+        psi, ninv = np.zeros(1, np.uint64), np.zeros(1, np.uint64)
+        r, ri = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        assert emu.emu_plan(q, n, orc.ptr(psi), orc.ptr(ninv), orc.ptr(r), orc.ptr(ri)) == 0
+        ro, rio, ninvo = orc.ntt_tables(q, n)
+        assert (r == ro).all() and (ri == rio).all() and int(ninv[0]) == ninvo
+        assert int(psi[0]) == orc.lib().orc_primitive_root_of_unity(q, 2 * n)
+    # psi for the reference's modulus
+    for n, want in [(4, 4096), (512, 19139), (1024, 61869), (4096, 6561), (16384, 9)]:
+        psi = np.zeros(1, np.uint64)
+        r = np.zeros(n, np.uint64)
+        assert emu.emu_plan(Q17, n, orc.ptr(psi), orc.ptr(psi.copy()), orc.ptr(r), orc.ptr(r.copy())) == 0
+        assert int(psi[0]) == want
+
+
+def test_modmul_policies(emu):
+    rng = np.random.default_rng(5)
+    for kind, q in [(0, Q17), (0, Q30), (0, 7), (0, 17), (1, Q62), (1, Q17), (2, Q63), (2, Q62)]:
+        cases = [(q - 1, q - 1), (0, q - 1), (1, q - 1), (q - 1, 1), (0, 0)]
+        cases += [(int(x), int(y)) for x, y in zip(rng.integers(0, q, 5000, dtype=np.uint64), rng.integers(0, q, 5000, dtype=np.uint64))]
+        for a, b in cases:
+            assert emu.emu_modmul(kind, q, a, b) == a * b % q
