@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 ring-arithmetic hot path (BASELINE.json configs[1]).
+
+A "step" is one pass of the hot path over one batch of synthetic input: `batch` independent negacyclic
+R_q polymuls c = intt(ntt(a) . ntt(b)) at N=1024, q=65537 (the reference's NTT prime; ring_nq::mul,
+arith/src/ring_nq.rs:586-607).  `value` is whole-job polymul/s with inputs resident in HBM; `e2e` is the
+same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region); `roofline`
+is the polymul kernel against the measured HBM peak; `cpu_baseline` is the oracle port timed on this
+box's host cores; `extras` carries the rest of the sweep and the TFHE / BFV paths.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Under torchrun (N>1) every rank runs the same per-GPU batch (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q = 65537
+N = 1024
+BATCH = 65536  # 3 * 65536 * 8 KiB = 1.5 GiB per step: far larger than the 126 MB L2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.005):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    NAMES = {
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+        0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting",
+    }
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {
+            "sm_mhz": statistics.median(self.samples),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def cpu_polymul_baseline(target_s: float = 12.0):
+    """Oracle port (oracle/fhe_oracle.c: u128 % q butterflies, arith/src/ntt.rs + ring_nq.rs) on all host cores."""
+    import numpy as np
+
+    import oracle
+
+    cores = os.cpu_count() or 1
+    a = oracle.uniform(1, (cores * 8, N), Q)
+    b = oracle.uniform(2, (cores * 8, N), Q)
+    t0 = time.perf_counter()
+    oracle.rq_mul_batch(Q, N, a, b, threads=cores)
+    dt = time.perf_counter() - t0
+    rate = a.shape[0] / dt
+    sample = int(max(cores * 8, min(rate * target_s, 4_000_000)))
+    a = oracle.uniform(3, (sample, N), Q)
+    b = oracle.uniform(4, (sample, N), Q)
+    t0 = time.perf_counter()
+    c = oracle.rq_mul_batch(Q, N, a, b, threads=cores)
+    dt = time.perf_counter() - t0
+    return {
+        "value": sample / dt, "unit": "polymul/s", "cores": cores, "kind": "port",
+        "sample": f"{sample} polymuls N={N} q={Q} (oracle C port, OpenMP over the batch), {dt:.2f} s",
+    }, (a, b, c)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; no Rust toolchain exists here) on all host
+    cores, same metric/config.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 64, 2048)
+    a = oracle.uniform(3, (per_step, N), Q)
+    b = oracle.uniform(4, (per_step, N), Q)
+    for _ in range(args.warmup):
+        oracle.rq_mul_batch(Q, N, a, b, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.rq_mul_batch(Q, N, a, b, threads=cores)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "NTT polymul/s", "value": v, "unit": "polymul/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"Rq negacyclic NTT polymul N={N} q={Q}", "batch_per_step": per_step},
+        "cpu_baseline": {"value": v, "unit": "polymul/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} polymuls per step, oracle C port of arith/src/ntt.rs + ring_nq.rs"},
+        "e2e": {"value": v, "unit": "polymul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import fhe_study_b200 as fhe
+
+    fhe.use_torch_stream()
+    dev = torch.device("cuda", local)
+    batch = args.batch
+    plan = fhe.NttPlan(Q, N)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    a = torch.randint(0, Q, (batch, N), dtype=torch.int64, device=dev, generator=g)
+    b = torch.randint(0, Q, (batch, N), dtype=torch.int64, device=dev, generator=g)
+    c = torch.empty_like(a)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") + per-launch kernel time ("roofline") ------------------
+    for _ in range(args.warmup):
+        plan.mul(a, b, out=c)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = fhe.launch_count()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s, e in ev:
+        s.record()
+        plan.mul(a, b, out=c)
+        e.record()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = fhe.launch_count() - l0
+    total_ms = t_start.elapsed_time(t_end)
+    kern_ms = statistics.mean(s.elapsed_time(e) for s, e in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * batch * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers ---------------------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+    ha = torch.empty((batch, N), dtype=torch.int64).pin_memory()
+    hb = torch.empty((batch, N), dtype=torch.int64).pin_memory()
+    hc = torch.empty((batch, N), dtype=torch.int64).pin_memory()
+    ha.copy_(a)
+    hb.copy_(b)
+    plan.mul(ha, hb, out=hc)  # warm the staging pool
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        plan.mul(ha, hb, out=hc)  # H2D(a,b) -> kernel -> D2H(c); returns when c is on the host
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch * e2e_steps / (float(t.item()) * 1e-3)
+    same = bool(torch.equal(hc.to(dev), c))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_kind = peaks()
+    alg_bytes = 3 * N * 8 * batch
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": "NTT polymul/s", "value": value, "unit": "polymul/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 (32-bit lazy Shoup/Barrett arithmetic for q<2^30)",
+        "data": "synthetic",
+        "config": {
+            "workload": f"BASELINE configs[1]: batched Rq negacyclic NTT polymul, N={N}, q={Q}, batch {batch} per GPU",
+            "batch_per_gpu": batch, "n": N, "q": Q,
+            "l2_policy": f"inputs+outputs {alg_bytes / 2**20:.0f} MiB per step, larger than the 126 MB L2",
+            "parallelism": f"independent polynomials sharded over {world} GPU(s), no collective",
+        },
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": None, "peak_source": peak_kind, "kernel": "ntt_kernel<Lazy32,10,5,MUL>",
+            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+        },
+        "e2e": {
+            "value": e2e_value, "unit": "polymul/s", "h2d_bytes_per_step": 2 * N * 8 * batch,
+            "d2h_bytes_per_step": N * 8 * batch, "steps": e2e_steps, "matches_device_result": same,
+        },
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu:
+        base, (xa, xb, xc) = cpu_polymul_baseline()
+        # the timed kernel is also checked against the CPU port on the baseline's sample
+        k = min(xa.shape[0], 4096)
+        got = plan.mul(np.ascontiguousarray(xa[:k]), np.ascontiguousarray(xb[:k]))
+        base["gpu_matches_on_sample"] = bool((got == xc[:k]).all())
+        line["cpu_baseline"] = base
+    if not args.no_extras:
+        try:
+            import bench_extras
+
+            line["extras"] = bench_extras.run(fhe, dev, quick=args.steps < 20)
+        except Exception as ex:  # extras never invalidate the headline line
+            line["extras"] = {"error": repr(ex)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
