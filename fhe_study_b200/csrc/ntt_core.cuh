@@ -37,6 +37,35 @@ template <int LOGN, int LOGE> struct NttShape {
     }
 };
 
+// Device twiddle-table order.  The reference stores stage s (m = 2^s) at roots[2^s + j], j = (H << ls) + hi
+// for the butterfly block H of pass p (ls = s - s0(p)).  Threads of a warp differ in H, so reading that
+// order would touch a different cache line per lane.  The device tables therefore keep stage s at
+//   2^s + (hi << s0(p)) + H
+// (a rotation of the index bits inside each stage block, identity for pass 0), which makes every warp
+// load lane-contiguous.  tw_slot() is the host-side map reference index -> device slot.
+inline int ntt_num_passes(int logn, int loge) { return (logn + loge - 1) / loge; }
+inline int ntt_pass_s0(int logn, int loge, int p) {
+    const int P = ntt_num_passes(logn, loge), base = logn / P, rem = logn % P;
+    return p * base + (p < rem ? p : rem);
+}
+inline u64 tw_slot(int logn, int loge, u64 ref_index) {
+    if (ref_index == 0) return 0;
+    int s = 0;
+    while ((2ull << s) <= ref_index) s++;  // 2^s <= ref_index < 2^(s+1)
+    const int P = ntt_num_passes(logn, loge);
+    int p = 0;
+    while (p + 1 < P && ntt_pass_s0(logn, loge, p + 1) <= s) p++;
+    const int s0 = ntt_pass_s0(logn, loge, p), ls = s - s0;
+    const u64 j = ref_index - (1ull << s), H = j >> ls, hi = j & ((1ull << ls) - 1);
+    return (1ull << s) + (hi << s0) + H;
+}
+// coefficients per thread (log2): 32 for 32-bit words, 16 for 64-bit words (register budget of the
+// polymul kernel, which keeps NTT(a) in registers while transforming b)
+template <class M> struct LogE {
+    static constexpr int MAXE = sizeof(typename M::W) == 4 ? 5 : 4;
+    static constexpr int of(int logn) { return logn < MAXE ? logn : MAXE; }
+};
+
 // Twiddle source: pass 0 twiddles are identical for every thread (H = 0), so they are taken from a
 // small by-value table living in the kernel-parameter constant bank; later passes index the global
 // table (L1/L2 resident, n entries).
@@ -57,7 +86,8 @@ FHE_HD void fwd_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);  // pass 0: u < 2^nL
 #pragma unroll
         for (int hi = 0; hi < (1 << LS); hi++) {
-            const int twi = (1 << (s0 + LS)) + (H << LS) + hi;
+            // reference index (1<<s) + (H<<LS) + hi, stored at the lane-contiguous slot (see tw_slot)
+            const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
             const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
 #pragma unroll
             for (int lo = 0; lo < half; lo++) {
@@ -90,7 +120,7 @@ FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
 #pragma unroll
                 for (int lo = 0; lo < half; lo++) m.inv_last(x[qi * G + lo], x[qi * G + lo + half], ninv, s_ninv);
             } else {
-                const int twi = (1 << (s0 + LS)) + (H << LS) + hi;
+                const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
                 const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
 #pragma unroll
                 for (int lo = 0; lo < half; lo++) {

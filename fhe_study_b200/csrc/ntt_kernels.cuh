@@ -175,13 +175,6 @@ int launch_one(const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c
     return 0;
 }
 
-// LOGE policy: 32 coefficients per thread for 32-bit words, 16 for 64-bit words (register budget of
-// the polymul kernel, which keeps NTT(a) in registers while transforming b).
-template <class M> struct LogE {
-    static constexpr int MAXE = sizeof(typename M::W) == 4 ? 5 : 4;
-    static constexpr int of(int logn) { return logn < MAXE ? logn : MAXE; }
-};
-
 template <class M, int LOGN>
 int launch_logn(int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
                 int flags, cudaStream_t st) {

@@ -7,7 +7,7 @@
 #include <string>
 #include <vector>
 
-#include "modarith.cuh"
+#include "ntt_core.cuh"
 
 namespace fhe {
 
@@ -132,15 +132,20 @@ template <class M> struct ExpandedTables {
     typename M::T ninv, s_ninv;
     M mod;
 };
-template <class M> void expand_tables(const HostTables &t, ExpandedTables<M> &x) {
+// loge <= 0 selects the library's policy LogE<M>; tables are stored in device order (ntt_core.cuh: tw_slot).
+template <class M> void expand_tables(const HostTables &t, ExpandedTables<M> &x, int loge = 0) {
     typedef typename M::W W;
     typedef typename M::T T;
     init_mod(x.mod, t.q);
     x.fwd.resize(t.n);
     x.inv.resize(t.n);
+    const int logn = hp_ilog2(t.n);
+    if (loge <= 0) loge = LogE<M>::of(logn);
+    if (loge > logn) loge = logn;
     for (u64 i = 0; i < t.n; i++) {
-        x.fwd[i] = make_tw((W)t.roots[i], (W)t.q, (T *)nullptr);
-        x.inv[i] = make_tw((W)t.roots_inv[i], (W)t.q, (T *)nullptr);
+        const u64 slot = tw_slot(logn, loge, i);
+        x.fwd[slot] = make_tw((W)t.roots[i], (W)t.q, (T *)nullptr);
+        x.inv[slot] = make_tw((W)t.roots_inv[i], (W)t.q, (T *)nullptr);
     }
     x.ninv = make_tw((W)t.n_inv, (W)t.q, (T *)nullptr);
     x.s_ninv = make_tw((W)hp_mulmod(t.roots_inv[1], t.n_inv, t.q), (W)t.q, (T *)nullptr);

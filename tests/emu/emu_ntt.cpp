@@ -99,11 +99,11 @@ template <class M>
 static int emu_any(u64 q, u64 n, int loge, int mode, const u64 *a, const u64 *b, u64 *c, u64 *ce, int fl) {
     HostTables t;
     if (!build_host_tables(q, n, t).empty()) return -1;
-    ExpandedTables<M> x;
-    expand_tables(t, x);
     int logn = hp_ilog2(n);
-    if (loge <= 0) loge = (sizeof(typename M::W) == 4 ? 5 : 4);
+    if (loge <= 0) loge = LogE<M>::of(logn);
     if (loge > logn) loge = logn;
+    ExpandedTables<M> x;
+    expand_tables(t, x, loge);
     switch (logn) {
 #define C(L) case L: Disp<M, L>::go(loge, mode, x, a, b, c, ce, fl); return 0;
         C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15)

@@ -1,0 +1,31 @@
+"""Tiny driver for ncu captures: runs one hot-path op a few times on cuda:0 (device-resident buffers).
+  python tools/prof.py polymul|ntt|intt [logn] [q] [batch] [reps]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import fhe_study_b200 as fhe
+
+op = sys.argv[1] if len(sys.argv) > 1 else "polymul"
+logn = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+q = int(sys.argv[3], 0) if len(sys.argv) > 3 else 65537
+n = 1 << logn
+batch = int(sys.argv[4]) if len(sys.argv) > 4 else (1 << 26) // n
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+torch.cuda.set_device(0)
+fhe.use_torch_stream()
+plan = fhe.NttPlan(q, n)
+a = torch.randint(0, min(q, 2**62), (batch, n), dtype=torch.int64, device="cuda")
+b = torch.randint(0, min(q, 2**62), (batch, n), dtype=torch.int64, device="cuda")
+c = torch.empty_like(a)
+for _ in range(reps):
+    if op == "polymul":
+        plan.mul(a, b, out=c)
+    elif op == "ntt":
+        plan.ntt(a, out=c)
+    else:
+        plan.intt(a, out=c)
+torch.cuda.synchronize()
+print("done", op, n, q, batch, reps)
