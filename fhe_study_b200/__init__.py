@@ -122,3 +122,261 @@ class NttPlan:
             raise ValueError("operand sizes differ")
         check(lib.fhe_rq_mul(self._h, ptr(a), ptr(b), ptr(out), self._batch(a), int(flags), ptr(evals_out)))
         return out
+
+
+# -------------------------------------------------------------------------------------------------------
+# torus / TFHE / BFV / coefficient-wise entry points (thin wrappers; names follow the reference)
+# -------------------------------------------------------------------------------------------------------
+def _new(like, shape):
+    if _is_torch(like):
+        import torch
+
+        return torch.empty(shape, dtype=like.dtype, device=like.device)
+    return np.empty(shape, dtype=np.uint64)
+
+
+def tn_mul(n, a, b, out=None):
+    """impl Mul<Tn> for Tn (arith/src/ring_torus.rs:251-298): exact negacyclic product mod 2^64."""
+    out = _empty_like(a) if out is None else out
+    _check_u64(a, b, out)
+    check(lib.fhe_tn_mul(int(n), ptr(a), ptr(b), ptr(out), _numel(a) // int(n)))
+    return out
+
+
+def tn_add(a, b, out=None):
+    out = _empty_like(a) if out is None else out
+    _check_u64(a, b, out)
+    check(lib.fhe_tn_add(ptr(a), ptr(b), ptr(out), _numel(a)))
+    return out
+
+
+def tn_sub(a, b, out=None):
+    out = _empty_like(a) if out is None else out
+    _check_u64(a, b, out)
+    check(lib.fhe_tn_sub(ptr(a), ptr(b), ptr(out), _numel(a)))
+    return out
+
+
+def tn_neg(a, out=None):
+    out = _empty_like(a) if out is None else out
+    _check_u64(a, out)
+    check(lib.fhe_tn_neg(ptr(a), ptr(out), _numel(a)))
+    return out
+
+
+def tn_left_rotate(n, a, h, group=1, out=None):
+    """Tn::left_rotate / TGLWE::left_rotate; `h` holds one amount per group of `group` polynomials."""
+    out = _empty_like(a) if out is None else out
+    _check_u64(a, h, out)
+    check(lib.fhe_tn_left_rotate(int(n), ptr(a), ptr(h), int(group), ptr(out), _numel(a) // int(n)))
+    return out
+
+
+class Tggsw:
+    """Device-resident TGGSW (tfhe/src/tggsw.rs:14), transformed once at load."""
+
+    def __init__(self, n, k, rows):
+        self.n, self.k = int(n), int(k)
+        _check_u64(rows)
+        if _numel(rows) != (self.k + 1) * 64 * (self.k + 1) * self.n:
+            raise ValueError("TGGSW must hold (k+1)*64*(k+1)*n words")
+        h = C.c_void_p()
+        check(lib.fhe_tggsw_load(self.n, self.k, ptr(rows), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.fhe_tggsw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _batch(self, ct):
+        return _numel(ct) // ((self.k + 1) * self.n)
+
+    def extprod(self, ct, out=None):
+        """impl Mul<TGLWE> for TGGSW (tggsw.rs:45-62)."""
+        out = _empty_like(ct) if out is None else out
+        _check_u64(ct, out)
+        check(lib.fhe_extprod(self._h, ptr(ct), ptr(out), self._batch(ct)))
+        return out
+
+    def cmux(self, ct1, ct2, out=None):
+        """TGGSW::cmux (tggsw.rs:39-41)."""
+        out = _empty_like(ct1) if out is None else out
+        _check_u64(ct1, ct2, out)
+        check(lib.fhe_cmux(self._h, ptr(ct1), ptr(ct2), ptr(out), self._batch(ct1)))
+        return out
+
+
+class Ksk:
+    """Device-resident key-switching key (tfhe/src/tlwe.rs:84-100)."""
+
+    def __init__(self, kn_in, kn_out, l, rows):
+        self.kn_in, self.kn_out, self.l = int(kn_in), int(kn_out), int(l)
+        _check_u64(rows)
+        if _numel(rows) != self.kn_in * self.l * (self.kn_out + 1):
+            raise ValueError("KSK must hold kn_in*l*(kn_out+1) words")
+        h = C.c_void_p()
+        check(lib.fhe_ksk_load(self.kn_in, self.kn_out, self.l, ptr(rows), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.fhe_ksk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def key_switch(self, ct, out=None):
+        """TLWE::key_switch (tlwe.rs:101-112)."""
+        batch = _numel(ct) // (self.kn_in + 1)
+        out = _new(ct, (batch, self.kn_out + 1)) if out is None else out
+        _check_u64(ct, out)
+        check(lib.fhe_key_switch(self._h, ptr(ct), ptr(out), batch))
+        return out
+
+
+def bootstrap(n, k, ksk: Ksk, table, ct, c_kn, out=None):
+    """bootstrapping (tfhe/src/tlwe.rs:150-161) as the reference executes it."""
+    batch = _numel(ct) // (int(c_kn) + 1)
+    out = _new(ct, (batch, ksk.kn_out + 1)) if out is None else out
+    _check_u64(table, ct, out)
+    check(lib.fhe_bootstrap(int(n), int(k), ksk._h, ptr(table), ptr(ct), int(c_kn), ptr(out), batch))
+    return out
+
+
+def blind_rotate(n, k, table, ct, c_kn, bsk=None, as_written=False, out=None):
+    """blind_rotation (tfhe/src/tlwe.rs:121-148); bsk = list of k Tggsw (needed for as_written and k > 1)."""
+    batch = _numel(ct) // (int(c_kn) + 1)
+    out = _new(ct, (batch, (int(k) + 1) * int(n))) if out is None else out
+    _check_u64(table, ct, out)
+    arr = None
+    if bsk is not None:
+        arr = (C.c_void_p * len(bsk))(*[b._h for b in bsk])
+    check(lib.fhe_blind_rotate(int(n), int(k), arr, int(bool(as_written)), ptr(table), ptr(ct), int(c_kn), ptr(out), batch))
+    return out
+
+
+def sample_extract(n, k, ct, h, out=None):
+    batch = _numel(ct) // ((int(k) + 1) * int(n))
+    out = _new(ct, (batch, int(k) * int(n) + 1)) if out is None else out
+    _check_u64(ct, out)
+    check(lib.fhe_sample_extract(int(n), int(k), ptr(ct), int(h), ptr(out), batch))
+    return out
+
+
+def tlwe_mod_switch(ct, q2, out=None):
+    out = _empty_like(ct) if out is None else out
+    _check_u64(ct, out)
+    check(lib.fhe_tlwe_mod_switch(ptr(ct), int(q2), ptr(out), _numel(ct)))
+    return out
+
+
+def bfv_tensor(q, n, t, a, b, out=None):
+    batch = _numel(a) // (2 * int(n))
+    out = _new(a, (batch, 3 * int(n))) if out is None else out
+    _check_u64(a, b, out)
+    check(lib.fhe_bfv_tensor(int(q), int(n), int(t), ptr(a), ptr(b), ptr(out), batch))
+    return out
+
+
+def bfv_relinearize(q, n, pq, rlk, c012, out=None):
+    batch = _numel(c012) // (3 * int(n))
+    out = _new(c012, (batch, 2 * int(n))) if out is None else out
+    _check_u64(rlk, c012, out)
+    check(lib.fhe_bfv_relinearize(int(q), int(n), int(pq), ptr(rlk), ptr(c012), ptr(out), batch))
+    return out
+
+
+def bfv_mul_relin(q, n, t, pq, rlk, a, b, out=None):
+    """RLWE::mul (bfv/src/lib.rs:87-90): tensor + relinearize_204."""
+    out = _empty_like(a) if out is None else out
+    _check_u64(rlk, a, b, out)
+    check(lib.fhe_bfv_mul_relin(int(q), int(n), int(t), int(pq), ptr(rlk), ptr(a), ptr(b), ptr(out), _numel(a) // (2 * int(n))))
+    return out
+
+
+def _map1(fn, a, *scalars, pre=()):
+    out = _empty_like(a)
+    _check_u64(a, out)
+    check(fn(*pre, ptr(a), *scalars, ptr(out), _numel(a)))
+    return out
+
+
+def rq_add(q, a, b):
+    out = _empty_like(a)
+    _check_u64(a, b, out)
+    check(lib.fhe_rq_add(int(q), ptr(a), ptr(b), ptr(out), _numel(a)))
+    return out
+
+
+def rq_sub(q, a, b):
+    out = _empty_like(a)
+    _check_u64(a, b, out)
+    check(lib.fhe_rq_sub(int(q), ptr(a), ptr(b), ptr(out), _numel(a)))
+    return out
+
+
+def rq_neg(q, a):
+    return _map1(lib.fhe_rq_neg, a, pre=(int(q),))
+
+
+def rq_mul_u64(q, a, s):
+    return _map1(lib.fhe_rq_mul_u64, a, int(s), pre=(int(q),))
+
+
+def rq_remodule(a, p):
+    return _map1(lib.fhe_rq_remodule, a, int(p))
+
+
+def rq_mod_switch(q, a, p):
+    return _map1(lib.fhe_rq_mod_switch, a, int(p), pre=(int(q),))
+
+
+def rq_mul_div_round(q, a, num, den):
+    return _map1(lib.fhe_rq_mul_div_round, a, int(num), int(den), pre=(int(q),))
+
+
+def rq_from_vec(q, n, v, in_len):
+    batch = _numel(v) // int(in_len)
+    out = _new(v, (batch, int(n)))
+    _check_u64(v, out)
+    check(lib.fhe_rq_from_vec(int(q), int(n), ptr(v), int(in_len), ptr(out), batch))
+    return out
+
+
+def rq_decompose(q, n, a, beta, l):
+    polys = _numel(a) // int(n)
+    out = _new(a, (polys, int(l), int(n)))
+    _check_u64(a, out)
+    check(lib.fhe_rq_decompose(int(q), int(n), ptr(a), int(beta), int(l), ptr(out), polys))
+    return out
+
+
+def tn_decompose(n, a, l=64):
+    polys = _numel(a) // int(n)
+    out = _new(a, (polys, int(l), int(n)))
+    _check_u64(a, out)
+    check(lib.fhe_tn_decompose(int(n), ptr(a), int(l), ptr(out), polys))
+    return out
+
+
+def tn_mod_switch(a, p):
+    return _map1(lib.fhe_tn_mod_switch, a, int(p))
+
+
+def tn_mul_u64(a, s):
+    return _map1(lib.fhe_tn_mul_u64, a, int(s))
+
+
+def tn_mul_div_round(a, num, den):
+    return _map1(lib.fhe_tn_mul_div_round, a, int(num), int(den))

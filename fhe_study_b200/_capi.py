@@ -46,6 +46,38 @@ SIGNATURES = {
     "fhe_ntt_fwd": (I, [P, P, P, SZ]),
     "fhe_ntt_inv": (I, [P, P, P, SZ]),
     "fhe_rq_mul": (I, [P, P, P, P, SZ, I, P]),
+    "fhe_tn_mul": (I, [U64, P, P, P, SZ]),
+    "fhe_tn_add": (I, [P, P, P, SZ]),
+    "fhe_tn_sub": (I, [P, P, P, SZ]),
+    "fhe_tn_neg": (I, [P, P, SZ]),
+    "fhe_tn_left_rotate": (I, [U64, P, P, U64, P, SZ]),
+    "fhe_tggsw_load": (I, [U64, U64, P, C.POINTER(P)]),
+    "fhe_tggsw_destroy": (None, [P]),
+    "fhe_extprod": (I, [P, P, P, SZ]),
+    "fhe_cmux": (I, [P, P, P, P, SZ]),
+    "fhe_ksk_load": (I, [U64, U64, U64, P, C.POINTER(P)]),
+    "fhe_ksk_destroy": (None, [P]),
+    "fhe_key_switch": (I, [P, P, P, SZ]),
+    "fhe_tlwe_mod_switch": (I, [P, U64, P, SZ]),
+    "fhe_sample_extract": (I, [U64, U64, P, U64, P, SZ]),
+    "fhe_blind_rotate": (I, [U64, U64, P, I, P, P, U64, P, SZ]),
+    "fhe_bootstrap": (I, [U64, U64, P, P, P, U64, P, SZ]),
+    "fhe_bfv_tensor": (I, [U64, U64, U64, P, P, P, SZ]),
+    "fhe_bfv_relinearize": (I, [U64, U64, U64, P, P, P, SZ]),
+    "fhe_bfv_mul_relin": (I, [U64, U64, U64, U64, P, P, P, P, SZ]),
+    "fhe_rq_add": (I, [U64, P, P, P, SZ]),
+    "fhe_rq_sub": (I, [U64, P, P, P, SZ]),
+    "fhe_rq_neg": (I, [U64, P, P, SZ]),
+    "fhe_rq_mul_u64": (I, [U64, P, U64, P, SZ]),
+    "fhe_rq_remodule": (I, [P, U64, P, SZ]),
+    "fhe_rq_mod_switch": (I, [U64, P, U64, P, SZ]),
+    "fhe_rq_mul_div_round": (I, [U64, P, U64, U64, P, SZ]),
+    "fhe_rq_from_vec": (I, [U64, U64, P, U64, P, SZ]),
+    "fhe_rq_decompose": (I, [U64, U64, P, C.c_uint32, C.c_uint32, P, SZ]),
+    "fhe_tn_decompose": (I, [U64, P, C.c_uint32, P, SZ]),
+    "fhe_tn_mod_switch": (I, [P, U64, P, SZ]),
+    "fhe_tn_mul_u64": (I, [P, U64, P, SZ]),
+    "fhe_tn_mul_div_round": (I, [P, U64, U64, P, SZ]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

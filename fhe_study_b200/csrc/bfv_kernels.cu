@@ -1,0 +1,146 @@
+// bfv_kernels.cu -- BFV ciphertext x ciphertext multiplication with relinearisation, exactly as the reference
+// computes it (bfv/src/lib.rs:59-90,251-271): NOT an NTT.  Each product is ring_n::naive_mul, the
+// exact LINEAR convolution (2n-1 outputs) in i128 truncated to i64 (arith/src/ring_n.rs:307-320) -- i.e. the
+// low 64 bits of the sum, which 64-bit wrapping multiply-adds reproduce bit for bit -- followed, per UNFOLDED
+// coefficient, by f64 round((num*v)/den) (ring_n.rs:130-138), Zq::from_f64 (zq.rs:32-40), and only then the
+// X^n+1 fold as a Zq subtraction (ring_nq.rs:132-141).  The f64 steps use explicit IEEE round-to-nearest
+// intrinsics (no FMA contraction) so they match the CPU's arithmetic.
+#include "../../include/fhe_b200.h"
+#include "runtime.cuh"
+
+namespace fhe {
+
+// Rust `f64 as i64`: saturating, NaN -> 0 (cvt.rzi.s64.f64 has exactly these semantics)
+__device__ __forceinline__ i64 f64_as_i64(double x) { return __double2ll_rz(x); }
+// Zq::from_f64 (zq.rs:32-40)
+__device__ __forceinline__ u64 zq_from_f64(u64 q, double e) {
+    const i64 ei = f64_as_i64(round(e));
+    const i64 qi = (i64)q;
+    if (ei < 0 || ei >= qi) {
+        const u64 v = (u64)(((ei % qi) + qi) % qi);
+        return v >= q ? v % q : v;  // Zq::from_u64 (zq.rs:21-31)
+    }
+    return (u64)ei;
+}
+// one coefficient of ring_n::mul_div_round (ring_n.rs:130-138): round((num as f64 * v as f64) / den as f64) -> Zq
+__device__ __forceinline__ u64 scale_round(u64 q, i64 v, double num, double den) {
+    return zq_from_f64(q, __ddiv_rn(__dmul_rn(num, __ll2double_rn(v)), den));
+}
+__device__ __forceinline__ u64 zq_sub(u64 q, u64 a, u64 b) { return a >= b ? a - b : (q + a) - b; }  // zq.rs:259-277
+__device__ __forceinline__ u64 zq_add(u64 q, u64 a, u64 b) { u64 v = a + b; return v >= q ? v - q : v; }  // zq.rs:219-231
+
+// coefficients idx and idx+n of the linear product a*b (wrapping 64-bit == `i128 as i64`)
+__device__ __forceinline__ void conv_pair(const u64 *__restrict__ a, const u64 *__restrict__ b, u32 n, u32 c, u64 &lo,
+                                          u64 &hi) {
+    u64 s0 = 0, s1 = 0;
+    for (u32 i = 0; i <= c; i++) s0 += a[i] * b[c - i];              // i + j = c
+    for (u32 i = c + 1; i < n; i++) s1 += a[i] * b[c + n - i];        // i + j = c + n  (j = c+n-i <= n-1)
+    lo = s0;
+    hi = s1;
+}
+// fold of the scaled pair (ring_nq.rs:132-141): res[c] = f(conv[c]) - f(conv[c+n]); index c+n exists for c <= n-2
+__device__ __forceinline__ u64 scale_fold(u64 q, u32 n, u32 c, u64 lo, u64 hi, double num, double den) {
+    const u64 x = scale_round(q, (i64)lo, num, den);
+    if (c + 1 >= n) return x;
+    return zq_sub(q, x, scale_round(q, (i64)hi, num, den));
+}
+
+// mode 0: RLWE::tensor only (out = c0|c1|c2, 3n words) ; 1: RLWE::mul (tensor + relinearize_204, out 2n words) ;
+// 2: relinearize_204 only (a = c0|c1|c2, out 2n words).  One CTA row of n threads per ciphertext product.
+__global__ void bfv_mul_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, const u64 *__restrict__ rlk,
+                               u64 *__restrict__ out, size_t batch, u32 n, u64 q, u64 t, u64 pq, int mode, u32 per_cta) {
+    extern __shared__ u64 sm[];
+    const u32 slot = threadIdx.x / n, c = threadIdx.x % n;
+    const size_t ct = (size_t)blockIdx.x * per_cta + slot;
+    const bool valid = ct < batch && slot < per_cta;
+    u64 *s = sm + (size_t)slot * 7 * n;  // a0 a1 b0 b1 c2 rlk0 rlk1
+    u64 *a0 = s, *a1 = s + n, *b0 = s + 2 * n, *b1 = s + 3 * n, *c2s = s + 4 * n, *k0 = s + 5 * n, *k1 = s + 6 * n;
+    const double dq = __ull2double_rn(q), dt = __ull2double_rn(t);
+    u64 c0 = 0, c1 = 0, c2 = 0;
+    if (valid) {
+        if (mode != 2) {
+            const u64 *pa = a + ct * 2 * n, *pb = b + ct * 2 * n;
+            a0[c] = pa[c]; a1[c] = pa[n + c]; b0[c] = pb[c]; b1[c] = pb[n + c];
+        } else {
+            const u64 *pa = a + ct * 3 * n;
+            c0 = pa[c]; c1 = pa[n + c]; c2 = pa[2 * n + c];
+        }
+        if (mode != 0) { k0[c] = rlk[c]; k1[c] = rlk[n + c]; }
+    }
+    __syncthreads();
+    if (valid && mode != 2) {  // RLWE::tensor (lib.rs:59-85)
+        u64 lo, hi, lo2, hi2;
+        conv_pair(a0, b0, n, c, lo, hi);
+        c0 = scale_fold(q, n, c, lo, hi, dt, dq);
+        conv_pair(a0, b1, n, c, lo, hi);
+        conv_pair(a1, b0, n, c, lo2, hi2);
+        c1 = scale_fold(q, n, c, lo + lo2, hi + hi2, dt, dq);  // i64 `+` of the two cross terms (lib.rs:76)
+        conv_pair(a1, b1, n, c, lo, hi);
+        c2 = scale_fold(q, n, c, lo, hi, dt, dq);
+    }
+    if (mode == 0) {
+        if (valid) {
+            u64 *po = out + ct * 3 * n;
+            po[c] = c0; po[n + c] = c1; po[2 * n + c] = c2;
+        }
+        return;
+    }
+    if (valid) c2s[c] = c2;
+    __syncthreads();
+    if (valid) {  // relinearize_204 (lib.rs:251-271)
+        const double dp = __ull2double_rn(pq / q);
+        u64 lo, hi;
+        conv_pair(c2s, k0, n, c, lo, hi);
+        const u64 r0 = scale_fold(q, n, c, lo, hi, 1.0, dp);
+        conv_pair(c2s, k1, n, c, lo, hi);
+        const u64 r1 = scale_fold(q, n, c, lo, hi, 1.0, dp);
+        u64 *po = out + ct * 2 * n;
+        po[c] = zq_add(q, c0, r0);
+        po[n + c] = zq_add(q, c1, r1);
+    }
+}
+
+static int bfv_launch(int mode, u64 q, u64 n, u64 t, u64 pq, const u64 *rlk, const u64 *a, const u64 *b, u64 *out,
+                      size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(n >= 1 && n <= 1024, "bfv: n must be in 1..1024 (one thread per coefficient)");
+    FHE_REQUIRE(q >= 2 && q < (1ull << 63), "bfv: q must be < 2^63");
+    FHE_REQUIRE(a && out && (mode == 2 || b) && (mode == 0 || rlk), "bfv: null pointer");
+    FHE_REQUIRE(mode == 0 || pq / q >= 1, "bfv: rlk modulus must be a multiple p*q with p >= 1");
+    cudaStream_t st = current_stream();
+    const size_t in_words = (mode == 2 ? 3 : 2) * n, out_words = (mode == 0 ? 3 : 2) * n;
+    IoBuf ba, bb, bk, bo;
+    int rc;
+    if ((rc = ba.init(a, batch * in_words * 8, true, false, st))) return rc;
+    if ((rc = bb.init(mode == 2 ? nullptr : b, batch * in_words * 8, true, false, st))) return rc;
+    if ((rc = bk.init(mode == 0 ? nullptr : rlk, 2 * n * 8, true, false, st))) return rc;
+    if ((rc = bo.init(out, batch * out_words * 8, false, true, st))) return rc;
+    const u32 per_cta = n >= 128 ? 1 : (u32)(128 / n);
+    const u32 threads = per_cta * (u32)n;
+    const size_t smem = (size_t)per_cta * 7 * n * sizeof(u64);
+    const size_t grid = (batch + per_cta - 1) / per_cta;
+    FHE_REQUIRE(grid <= 0x7fffffffull, "bfv: batch too large");
+    if (smem > 48 * 1024) FHE_CUDA_OK(cudaFuncSetAttribute(bfv_mul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bfv_mul_kernel<<<(unsigned)grid, threads, smem, st>>>(ba.ptr<u64>(), bb.ptr<u64>(), bk.ptr<u64>(), bo.ptr<u64>(), batch,
+                                                         (u32)n, q, t, pq, mode, per_cta);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return finish_all({&ba, &bb, &bk, &bo}, st);
+}
+
+}  // namespace fhe
+
+using namespace fhe;
+extern "C" {
+int fhe_bfv_tensor(uint64_t q, uint64_t n, uint64_t t, const uint64_t *a, const uint64_t *b, uint64_t *c012, size_t batch) {
+    return bfv_launch(0, q, n, t, 0, nullptr, a, b, c012, batch);
+}
+int fhe_bfv_relinearize(uint64_t q, uint64_t n, uint64_t pq, const uint64_t *rlk, const uint64_t *c012, uint64_t *out,
+                        size_t batch) {
+    return bfv_launch(2, q, n, 0, pq, rlk, c012, nullptr, out, batch);
+}
+int fhe_bfv_mul_relin(uint64_t q, uint64_t n, uint64_t t, uint64_t pq, const uint64_t *rlk, const uint64_t *a,
+                      const uint64_t *b, uint64_t *out, size_t batch) {
+    return bfv_launch(1, q, n, t, pq, rlk, a, b, out, batch);
+}
+}

@@ -6,8 +6,7 @@
 #include <tuple>
 
 #include "../../include/fhe_b200.h"
-#include "ntt_kernels.cuh"
-#include "plan_host.hpp"
+#include "plan.cuh"
 #include "runtime.cuh"
 
 namespace fhe {
@@ -41,19 +40,6 @@ int ntt_launch_strict64(int, int, const NttParams<Strict64> &, const u64 *, cons
 }  // namespace fhe
 
 using namespace fhe;
-
-// One plan per (device, q, n); owned by the cache, reference-counted by create/destroy.
-struct fhe_ntt_plan {
-    int device = 0;
-    int kind = 0;  // modulus_kind(q)
-    int logn = 0;
-    int refs = 0;
-    HostTables host;
-    void *d_fwd = nullptr, *d_inv = nullptr;
-    NttParams<Lazy32> p32;
-    NttParams<Lazy64> p64;
-    NttParams<Strict64> ps64;
-};
 
 namespace {
 std::mutex g_plan_mu;

@@ -1,0 +1,157 @@
+// lib_tlwe.cu -- C-ABI entry points of the TLWE path: key switch, sample extraction, mod switch, blind rotation
+// and bootstrapping (tfhe/src/tlwe.rs:101-161, tfhe/src/tglwe.rs:89-119).
+#include <memory>
+#include <vector>
+
+#include "../../include/fhe_b200.h"
+#include "runtime.cuh"
+#include "tlwe.cuh"
+#include "torus.cuh"
+
+using namespace fhe;
+
+struct fhe_ksk {
+    Ksk k;
+};
+
+extern "C" {
+
+int fhe_ksk_load(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *rows, fhe_ksk **out) {
+    FHE_REQUIRE(out && rows, "null pointer");
+    *out = nullptr;
+    FHE_REQUIRE(kn_in >= 1 && kn_out >= 1 && l >= 1 && l <= 64, "fhe_ksk_load: need kn_in, kn_out >= 1 and 1 <= l <= 64");
+    std::unique_ptr<fhe_ksk> h(new fhe_ksk());
+    h->k.kn_in = kn_in;
+    h->k.kn_out = kn_out;
+    h->k.l = l;
+    const size_t bytes = kn_in * l * (kn_out + 1) * sizeof(u64);
+    FHE_CUDA_OK(cudaMalloc((void **)&h->k.rows, bytes));
+    cudaStream_t st = current_stream();
+    // host or device source; the handle owns its own resident copy
+    cudaError_t e = cudaMemcpyAsync(h->k.rows, rows, bytes, cudaMemcpyDefault, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaFree(h->k.rows);
+        set_error(std::string("fhe_ksk_load: ") + cudaGetErrorString(e));
+        return -2;
+    }
+    *out = h.release();
+    return 0;
+}
+void fhe_ksk_destroy(fhe_ksk *h) {
+    if (!h) return;
+    cudaFree(h->k.rows);
+    delete h;
+}
+
+int fhe_key_switch(const fhe_ksk *h, const uint64_t *ct, uint64_t *out, size_t batch) {
+    FHE_REQUIRE(h != nullptr, "null KSK handle");
+    if (batch == 0) return 0;
+    FHE_REQUIRE(ct && out, "null ciphertext pointer");
+    cudaStream_t st = current_stream();
+    IoBuf bi, bo;
+    int rc;
+    if ((rc = bi.init(ct, batch * (h->k.kn_in + 1) * 8, true, false, st))) return rc;
+    if ((rc = bo.init(out, batch * (h->k.kn_out + 1) * 8, false, true, st))) return rc;
+    if ((rc = key_switch_device(h->k, bi.ptr<u64>(), bo.ptr<u64>(), batch, st))) return rc;
+    return finish_all({&bi, &bo}, st);
+}
+
+int fhe_tlwe_mod_switch(const uint64_t *ct, uint64_t q2, uint64_t *out, size_t len) {
+    if (len == 0) return 0;
+    FHE_REQUIRE(ct && out, "null pointer");
+    FHE_REQUIRE(q2 >= 1 && (q2 & (q2 - 1)) == 0, "fhe_tlwe_mod_switch: q2 must be a power of two (torus.rs:58-66)");
+    cudaStream_t st = current_stream();
+    IoBuf bi, bo;
+    int rc;
+    if ((rc = bi.init(ct, len * 8, true, false, st))) return rc;
+    if ((rc = bo.init(out, len * 8, false, true, st))) return rc;
+    const u32 shift = 64 - (63 - __builtin_clzll(q2));
+    if ((rc = shift_right_device(bi.ptr<u64>(), bo.ptr<u64>(), len, shift, st))) return rc;
+    return finish_all({&bi, &bo}, st);
+}
+
+int fhe_sample_extract(uint64_t n, uint64_t k, const uint64_t *ct, uint64_t h, uint64_t *out, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(ct && out, "null pointer");
+    FHE_REQUIRE(n >= 1 && k >= 1 && h < n, "fhe_sample_extract: need h < n");
+    cudaStream_t st = current_stream();
+    IoBuf bi, bo;
+    int rc;
+    if ((rc = bi.init(ct, batch * (k + 1) * n * 8, true, false, st))) return rc;
+    if ((rc = bo.init(out, batch * (k * n + 1) * 8, false, true, st))) return rc;
+    if ((rc = sample_extract_device(bi.ptr<u64>(), bo.ptr<u64>(), batch, (u32)n, (u32)k, (u32)h, st))) return rc;
+    return finish_all({&bi, &bo}, st);
+}
+
+// blind_rotation (tlwe.rs:121-148).  bsk == NULL or as_written == 0: AS EXECUTED by the reference (the CMux
+// closure is a lazy iterator that is dropped): acc = table.left_rotate(mod_switch(c).b).
+// as_written != 0: additionally runs the loop the source spells out, for j in 1..k:
+//   acc = cmux(bsk[j], acc, acc.left_rotate(mod_switch(c).a[j]))   (extension; no reference execution runs it).
+int fhe_blind_rotate(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, int as_written, const uint64_t *table,
+                     const uint64_t *ct, uint64_t c_kn, uint64_t *acc_out, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(table && ct && acc_out, "null pointer");
+    FHE_REQUIRE(n >= 1 && k >= 1 && (n & (n - 1)) == 0, "fhe_blind_rotate: n must be a power of two");
+    FHE_REQUIRE(!as_written || k == 1 || bsk != nullptr, "fhe_blind_rotate: as_written needs the k TGGSW handles");
+    cudaStream_t st = current_stream();
+    const size_t glwe = (k + 1) * n;
+    IoBuf bt, bc, bo;
+    int rc;
+    if ((rc = bt.init(table, glwe * 8, true, false, st))) return rc;
+    if ((rc = bc.init(ct, batch * (c_kn + 1) * 8, true, false, st))) return rc;
+    if ((rc = bo.init(acc_out, batch * glwe * 8, false, true, st))) return rc;
+    u64 *ext = nullptr;
+    FHE_CUDA_OK(cudaMallocAsync((void **)&ext, batch * (k * n + 1) * 8, st));
+    rc = rotate_extract_device(bt.ptr<u64>(), bc.ptr<u64>(), ext, bo.ptr<u64>(), batch, (u32)n, (u32)k, (u32)c_kn, st);
+    cudaFreeAsync(ext, st);
+    if (rc) return rc;
+    if (as_written && k > 1) {
+        FHE_REQUIRE(c_kn >= k, "fhe_blind_rotate: ciphertext has fewer than k mask elements");
+        u64 *rot = nullptr, *hs = nullptr, *nxt = nullptr;
+        FHE_CUDA_OK(cudaMallocAsync((void **)&rot, batch * glwe * 8, st));
+        FHE_CUDA_OK(cudaMallocAsync((void **)&nxt, batch * glwe * 8, st));
+        FHE_CUDA_OK(cudaMallocAsync((void **)&hs, batch * 8, st));
+        const u32 shift = 64 - (63 - __builtin_clzll(k * n));
+        for (u64 j = 1; j < k && !rc; j++) {
+            FHE_REQUIRE(bsk[j] != nullptr && bsk[j]->n == n && bsk[j]->g.k == k, "fhe_blind_rotate: bad TGGSW handle");
+            // hs[b] = mod_switch(c_b.a[j]) : strided gather + shift
+            FHE_CUDA_OK(cudaMemcpy2DAsync(hs, 8, bc.ptr<u64>() + j, (c_kn + 1) * 8, 8, batch, cudaMemcpyDeviceToDevice, st));
+            if ((rc = shift_right_device(hs, hs, batch, shift, st))) break;
+            if ((rc = tn_left_rotate_device(bo.ptr<u64>(), rot, batch * (k + 1), (u32)n, hs, 0, (u32)(k + 1), st))) break;
+            if ((rc = tn_addsub_device(rot, bo.ptr<u64>(), rot, batch * glwe, 1, st))) break;  // ct2 - ct1
+            if ((rc = extprod_device(bsk[j]->g, rot, bo.ptr<u64>(), nxt, batch, st))) break;   // ct1 + bit (x) diff
+            FHE_CUDA_OK(cudaMemcpyAsync(bo.ptr<u64>(), nxt, batch * glwe * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        cudaFreeAsync(rot, st);
+        cudaFreeAsync(nxt, st);
+        cudaFreeAsync(hs, st);
+        if (rc) return rc;
+    }
+    return finish_all({&bt, &bc, &bo}, st);
+}
+
+// bootstrapping (tlwe.rs:150-161) as executed: blind_rotation -> sample_extraction(0) -> key_switch(2, l, ksk).
+int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *table, const uint64_t *ct, uint64_t c_kn,
+                  uint64_t *out, size_t batch) {
+    FHE_REQUIRE(ksk != nullptr, "null KSK handle");
+    if (batch == 0) return 0;
+    FHE_REQUIRE(table && ct && out, "null pointer");
+    FHE_REQUIRE(n >= 1 && k >= 1 && (n & (n - 1)) == 0, "fhe_bootstrap: n must be a power of two");
+    FHE_REQUIRE(ksk->k.kn_in == k * n, "fhe_bootstrap: KSK input dimension must be k*n");
+    cudaStream_t st = current_stream();
+    IoBuf bt, bc, bo;
+    int rc;
+    if ((rc = bt.init(table, (k + 1) * n * 8, true, false, st))) return rc;
+    if ((rc = bc.init(ct, batch * (c_kn + 1) * 8, true, false, st))) return rc;
+    if ((rc = bo.init(out, batch * (ksk->k.kn_out + 1) * 8, false, true, st))) return rc;
+    u64 *ext = nullptr;
+    FHE_CUDA_OK(cudaMallocAsync((void **)&ext, batch * (k * n + 1) * 8, st));
+    rc = rotate_extract_device(bt.ptr<u64>(), bc.ptr<u64>(), ext, nullptr, batch, (u32)n, (u32)k, (u32)c_kn, st);
+    if (!rc) rc = key_switch_device(ksk->k, ext, bo.ptr<u64>(), batch, st);
+    cudaFreeAsync(ext, st);
+    if (rc) return rc;
+    return finish_all({&bt, &bc, &bo}, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+// lib_torus.cu -- C-ABI entry points of the torus (q = 2^64) path: Tn arithmetic, TGGSW external product, CMux.
+#include <map>
+#include <memory>
+
+#include "../../include/fhe_b200.h"
+#include "runtime.cuh"
+#include "torus.cuh"
+
+using namespace fhe;
+
+namespace fhe {
+static std::mutex g_tc_mu;
+static std::map<std::pair<int, u64>, std::unique_ptr<TorusCtx>> g_tcs;
+
+// per-(device, n) torus context, created on first use and kept for the life of the process
+int get_torus_ctx(u64 n, TorusCtx **out) {
+    int dev = 0;
+    FHE_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tc_mu);
+    auto key = std::make_pair(dev, n);
+    auto it = g_tcs.find(key);
+    if (it == g_tcs.end()) {
+        std::unique_ptr<TorusCtx> tc(new TorusCtx());
+        int rc = tc->init(n);
+        if (rc) return rc;
+        it = g_tcs.emplace(key, std::move(tc)).first;
+    }
+    *out = it->second.get();
+    return 0;
+}
+}  // namespace fhe
+
+extern "C" {
+
+int fhe_tn_mul(uint64_t n, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch) {
+    TorusCtx *tc;
+    int rc = get_torus_ctx(n, &tc);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    FHE_REQUIRE(a && b && c, "null polynomial pointer");
+    cudaStream_t st = current_stream();
+    const size_t bytes = batch * n * sizeof(u64);
+    IoBuf ba, bb, bc;
+    if ((rc = ba.init(a, bytes, true, false, st))) return rc;
+    if ((rc = bb.init(b, bytes, true, false, st))) return rc;
+    if ((rc = bc.init(c, bytes, false, true, st))) return rc;
+    if ((rc = tn_mul_device(*tc, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(), batch, st))) return rc;
+    return finish_all({&ba, &bb, &bc}, st);
+}
+
+static int tn_elementwise(const uint64_t *a, const uint64_t *b, uint64_t *c, size_t len, int op) {
+    if (len == 0) return 0;
+    FHE_REQUIRE(a && c && (op == 2 || b), "null pointer");
+    cudaStream_t st = current_stream();
+    IoBuf ba, bb, bc;
+    int rc;
+    if ((rc = ba.init(a, len * 8, true, false, st))) return rc;
+    if ((rc = bb.init(op == 2 ? nullptr : b, len * 8, true, false, st))) return rc;
+    if ((rc = bc.init(c, len * 8, false, true, st))) return rc;
+    if ((rc = tn_addsub_device(ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(), len, op, st))) return rc;
+    return finish_all({&ba, &bb, &bc}, st);
+}
+int fhe_tn_add(const uint64_t *a, const uint64_t *b, uint64_t *c, size_t len) { return tn_elementwise(a, b, c, len, 0); }
+int fhe_tn_sub(const uint64_t *a, const uint64_t *b, uint64_t *c, size_t len) { return tn_elementwise(a, b, c, len, 1); }
+int fhe_tn_neg(const uint64_t *a, uint64_t *c, size_t len) { return tn_elementwise(a, nullptr, c, len, 2); }
+
+int fhe_tn_left_rotate(uint64_t n, const uint64_t *a, const uint64_t *h, uint64_t group, uint64_t *out, size_t polys) {
+    if (polys == 0) return 0;
+    FHE_REQUIRE(a && h && out && a != out, "fhe_tn_left_rotate: null pointer or in-place call");
+    FHE_REQUIRE(n >= 1 && group >= 1 && polys % group == 0, "fhe_tn_left_rotate: polys must be a multiple of group");
+    cudaStream_t st = current_stream();
+    IoBuf ba, bh, bo;
+    int rc;
+    if ((rc = ba.init(a, polys * n * 8, true, false, st))) return rc;
+    if ((rc = bh.init(h, (polys / group) * 8, true, false, st))) return rc;
+    if ((rc = bo.init(out, polys * n * 8, false, true, st))) return rc;
+    if ((rc = tn_left_rotate_device(ba.ptr<u64>(), bo.ptr<u64>(), polys, (u32)n, bh.ptr<u64>(), 0, (u32)group, st)))
+        return rc;
+    return finish_all({&ba, &bh, &bo}, st);
+}
+
+int fhe_tggsw_load(uint64_t n, uint64_t k, const uint64_t *rows, fhe_tggsw **out) {
+    FHE_REQUIRE(out != nullptr && rows != nullptr, "null pointer");
+    *out = nullptr;
+    FHE_REQUIRE(k >= 1 && k <= 64, "fhe_tggsw_load: k must be in 1..64");
+    TorusCtx *tc;
+    int rc = get_torus_ctx(n, &tc);
+    if (rc) return rc;
+    // exactness bound of the CRT lift: (k+1)*64*n*2^32 < P/2
+    FHE_REQUIRE((unsigned __int128)(k + 1) * 64 * n * ((u64)1 << 32) < tc->cp.halfP,
+                "fhe_tggsw_load: (k+1)*64*n too large for the exact two-prime lift");
+    std::unique_ptr<fhe_tggsw> h(new fhe_tggsw());
+    h->g.tc = tc;
+    h->g.k = k;
+    h->n = n;
+    cudaStream_t st = current_stream();
+    const size_t bytes = (k + 1) * 64 * (k + 1) * n * sizeof(u64);
+    IoBuf br;
+    if ((rc = br.init(rows, bytes, true, false, st))) return rc;
+    if ((rc = tggsw_precompute(h->g, br.ptr<u64>(), st))) return rc;
+    *out = h.release();
+    return 0;
+}
+void fhe_tggsw_destroy(fhe_tggsw *h) {
+    if (!h) return;
+    cudaFree(h->g.R1);
+    cudaFree(h->g.R2);
+    delete h;
+}
+
+static int extprod_entry(const fhe_tggsw *h, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out, size_t batch,
+                         bool cmux) {
+    FHE_REQUIRE(h != nullptr, "null TGGSW handle");
+    if (batch == 0) return 0;
+    FHE_REQUIRE(ct1 && out && (!cmux || ct2), "null ciphertext pointer");
+    cudaStream_t st = current_stream();
+    const size_t words = batch * (h->g.k + 1) * h->n, bytes = words * sizeof(u64);
+    IoBuf b1, b2, bo;
+    int rc;
+    if ((rc = b1.init(ct1, bytes, true, false, st))) return rc;
+    if ((rc = b2.init(cmux ? ct2 : nullptr, bytes, true, false, st))) return rc;
+    if ((rc = bo.init(out, bytes, false, true, st))) return rc;
+    if (!cmux) {
+        rc = extprod_device(h->g, b1.ptr<u64>(), nullptr, bo.ptr<u64>(), batch, st);
+    } else {
+        // TGGSW::cmux (tggsw.rs:39-41): ct1 + bit (x) (ct2 - ct1)
+        u64 *diff = nullptr;
+        FHE_CUDA_OK(cudaMallocAsync((void **)&diff, bytes, st));
+        rc = tn_addsub_device(b2.ptr<u64>(), b1.ptr<u64>(), diff, words, 1, st);
+        if (!rc) rc = extprod_device(h->g, diff, b1.ptr<u64>(), bo.ptr<u64>(), batch, st);
+        cudaFreeAsync(diff, st);
+    }
+    if (rc) return rc;
+    return finish_all({&b1, &b2, &bo}, st);
+}
+int fhe_extprod(const fhe_tggsw *h, const uint64_t *ct, uint64_t *out, size_t batch) {
+    return extprod_entry(h, ct, nullptr, out, batch, false);
+}
+int fhe_cmux(const fhe_tggsw *h, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out, size_t batch) {
+    return extprod_entry(h, ct1, ct2, out, batch, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,19 @@
+// tlwe.cuh -- declarations of the TLWE key-switch / bootstrapping path.
+#pragma once
+#include "common.cuh"
+
+namespace fhe {
+
+// device-resident key-switching key (tfhe/src/tlwe.rs:84-100): rows[(i*l + j)*(kn_out+1) + x]
+struct Ksk {
+    u64 kn_in = 0, kn_out = 0, l = 0;
+    u64 *rows = nullptr;
+};
+
+int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
+int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_out, size_t batch, u32 n, u32 k, u32 c_kn,
+                          cudaStream_t st);
+int sample_extract_device(const u64 *ct, u64 *out, size_t batch, u32 n, u32 k, u32 h, cudaStream_t st);
+int shift_right_device(const u64 *a, u64 *out, size_t len, u32 shift, cudaStream_t st);
+
+}  // namespace fhe

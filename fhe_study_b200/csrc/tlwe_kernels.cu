@@ -1,0 +1,172 @@
+// tlwe_kernels.cu -- TLWE key switch and the bootstrapping pipeline as the reference EXECUTES it
+// (tfhe/src/tlwe.rs:101-161): mod_switch -> one public left_rotate of the table TGLWE ->
+// sample_extraction(0) -> key_switch(beta=2, l).  The key switch is a {0,1} x u64 matrix product mod 2^64:
+//   out = (0,..,0, b) - sum_{i<kn_in} sum_{j<l} bit_{l-1-j}(a_i) * KSK[i][j][:]      (tlwe.rs:101-112,
+//   tlev.rs:95-105, tlwe.rs:269-279, torus.rs:43-52)
+// with a kn_in*l*(kn_out+1)*8-byte key resident in HBM (537 MB for n=1024, k=1, l=64).
+#include "../../include/fhe_b200.h"
+#include "runtime.cuh"
+#include "tlwe.cuh"
+
+namespace fhe {
+
+// ---------------------------------------------------------------------------------------------------
+// CUDA-core key switch.  CTA = KS_TX threads = KS_TX output columns; each thread keeps KS_BT accumulators
+// (one per ciphertext of the CTA's batch tile) in registers and streams the KSK column slab once.
+// ---------------------------------------------------------------------------------------------------
+constexpr int KS_TX = 128;
+constexpr int KS_BT = 16;
+constexpr int KS_IC = 32;  // mask words staged per shared-memory refill
+
+__global__ void __launch_bounds__(KS_TX)
+key_switch_kernel(const u64 *__restrict__ ksk, const u64 *__restrict__ ct, u64 *__restrict__ out, size_t batch,
+                  u32 kn_in, u32 kn_out, u32 l) {
+    __shared__ u64 s_a[KS_IC][KS_BT];
+    const u32 w = kn_out + 1;
+    const u32 x = blockIdx.x * KS_TX + threadIdx.x;
+    const size_t b0 = (size_t)blockIdx.y * KS_BT;
+    const bool col_ok = x < w;
+    u64 acc[KS_BT];
+#pragma unroll
+    for (int b = 0; b < KS_BT; b++) acc[b] = 0;
+    for (u32 i0 = 0; i0 < kn_in; i0 += KS_IC) {
+        __syncthreads();
+        for (u32 t = threadIdx.x; t < KS_IC * KS_BT; t += KS_TX) {
+            const u32 ii = t / KS_BT, b = t % KS_BT;
+            const bool ok = (i0 + ii) < kn_in && (b0 + b) < batch;
+            s_a[ii][b] = ok ? ct[(b0 + b) * (size_t)(kn_in + 1) + i0 + ii] : 0;
+        }
+        __syncthreads();
+        const u32 ni = min((u32)KS_IC, kn_in - i0);
+        for (u32 ii = 0; ii < ni; ii++) {
+            u64 a[KS_BT];
+#pragma unroll
+            for (int b = 0; b < KS_BT; b++) a[b] = s_a[ii][b] << (64 - l);  // digit j is now bit (63-j)
+            const u64 *row = ksk + ((size_t)(i0 + ii) * l) * w + x;
+            for (u32 j = 0; j < l; j++) {
+                const u64 v = col_ok ? __ldg(row + (size_t)j * w) : 0;
+#pragma unroll
+                for (int b = 0; b < KS_BT; b++) {
+                    if ((i64)a[b] < 0) acc[b] += v;  // TLWE * T64(bit) summed (tlev.rs:95-105)
+                    a[b] <<= 1;
+                }
+            }
+        }
+    }
+    if (col_ok) {
+#pragma unroll
+        for (int b = 0; b < KS_BT; b++) {
+            if (b0 + b < batch) {
+                const u64 lhs = x == kn_out ? ct[(b0 + b) * (size_t)(kn_in + 1) + kn_in] : 0;  // (0,..,0,b)
+                out[(b0 + b) * (size_t)w + x] = lhs - acc[b];                                    // tlwe.rs:111
+            }
+        }
+    }
+}
+
+int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
+    const u32 w = (u32)k.kn_out + 1;
+    dim3 grid((w + KS_TX - 1) / KS_TX, (unsigned)((batch + KS_BT - 1) / KS_BT));
+    FHE_REQUIRE(grid.y <= 65535, "key switch: batch too large for one launch (max 65535*16)");
+    key_switch_kernel<<<grid, KS_TX, 0, st>>>(k.rows, ct, out, batch, (u32)k.kn_in, (u32)k.kn_out, (u32)k.l);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// blind_rotation as executed + sample_extraction(0), fused (tlwe.rs:121-148, tglwe.rs:89-119):
+//   h   = mod_switch(c.b, k*n) = c.b >> (64 - log2(k*n))                      (torus.rs:58-66)
+//   acc = table.left_rotate(h)   : acc_i[c] = c+h' < n ? t_i[c+h'] : -t_i[c+h'-n], h' = h mod n
+//   ext[n*i + j] = j <= 0 ? acc_i[0-j] : -acc_i[n-j] ;  ext[k*n] = acc_k[0]
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 rotated_coeff(const u64 *__restrict__ poly, u32 n, u32 h, u32 c) {
+    const u32 s = c + h;
+    return s < n ? poly[s] : (u64)0 - poly[s - n];
+}
+__global__ void rotate_extract_kernel(const u64 *__restrict__ table, const u64 *__restrict__ ct, u64 *__restrict__ ext,
+                                      u64 *__restrict__ acc_out, size_t batch, u32 n, u32 k, u32 c_kn, u32 shift) {
+    const u32 kn = k * n;
+    const size_t total = batch * (size_t)(kn + 1);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / (kn + 1);
+        const u32 e = (u32)(idx % (kn + 1));
+        const u64 body = ct[b * (size_t)(c_kn + 1) + c_kn];
+        const u32 h = (u32)((shift >= 64 ? body : body >> shift) % n);
+        u64 v;
+        if (e == kn) {
+            v = rotated_coeff(table + (size_t)k * n, n, h, 0);
+        } else {
+            const u32 i = e / n, j = e % n;
+            v = j == 0 ? rotated_coeff(table + (size_t)i * n, n, h, 0)
+                       : (u64)0 - rotated_coeff(table + (size_t)i * n, n, h, n - j);
+        }
+        ext[idx] = v;
+    }
+    if (acc_out != nullptr) {  // optional: the rotated accumulator itself (blind_rotation's return value)
+        const size_t tot2 = batch * (size_t)(k + 1) * n;
+        for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < tot2;
+             idx += (size_t)gridDim.x * blockDim.x) {
+            const size_t b = idx / ((size_t)(k + 1) * n);
+            const u32 r = (u32)(idx % ((size_t)(k + 1) * n)), i = r / n, c = r % n;
+            const u64 body = ct[b * (size_t)(c_kn + 1) + c_kn];
+            const u32 h = (u32)((shift >= 64 ? body : body >> shift) % n);
+            acc_out[idx] = rotated_coeff(table + (size_t)i * n, n, h, c);
+        }
+    }
+}
+
+// TGLWE::sample_extraction(h) (tglwe.rs:89-115) for `batch` TGLWEs, one common h
+__global__ void sample_extract_kernel(const u64 *__restrict__ ct, u64 *__restrict__ out, size_t batch, u32 n, u32 k,
+                                      u32 h) {
+    const u32 kn = k * n;
+    const size_t total = batch * (size_t)(kn + 1);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / (kn + 1);
+        const u32 e = (u32)(idx % (kn + 1));
+        const u64 *g = ct + b * (size_t)(k + 1) * n;
+        u64 v;
+        if (e == kn) v = g[(size_t)k * n + h];
+        else {
+            const u32 i = e / n, j = e % n;
+            v = j <= h ? g[(size_t)i * n + (h - j)] : (u64)0 - g[(size_t)i * n + (n + h - j)];
+        }
+        out[idx] = v;
+    }
+}
+// TLWE::mod_switch (tlwe.rs:114-118): every element >> shift
+__global__ void shift_right_kernel(const u64 *__restrict__ a, u64 *__restrict__ out, size_t len, u32 shift) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = shift >= 64 ? a[i] : a[i] >> shift;
+}
+
+static inline unsigned grid_for(size_t work, int threads = 256) {
+    size_t g = (work + threads - 1) / threads;
+    const size_t cap = (size_t)num_sms() * 16;
+    return (unsigned)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_out, size_t batch, u32 n, u32 k, u32 c_kn,
+                          cudaStream_t st) {
+    const u32 log2kn = 63 - __builtin_clzll((u64)k * n);
+    const u32 shift = 64 - log2kn;  // torus.rs:58-66 (release-mode shift; kn >= 2 in every caller)
+    rotate_extract_kernel<<<grid_for(batch * (size_t)((k + 1) * n)), 256, 0, st>>>(table, ct, ext, acc_out, batch, n, k,
+                                                                                  c_kn, shift);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int sample_extract_device(const u64 *ct, u64 *out, size_t batch, u32 n, u32 k, u32 h, cudaStream_t st) {
+    sample_extract_kernel<<<grid_for(batch * (size_t)(k * n + 1)), 256, 0, st>>>(ct, out, batch, n, k, h);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int shift_right_device(const u64 *a, u64 *out, size_t len, u32 shift, cudaStream_t st) {
+    shift_right_kernel<<<grid_for(len), 256, 0, st>>>(a, out, len, shift);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fhe

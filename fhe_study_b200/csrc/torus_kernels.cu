@@ -1,0 +1,294 @@
+// torus_kernels.cu -- exact arithmetic in T_q[X]/(X^N+1), q = 2^64 (the reference's Tn, arith/src/ring_torus.rs)
+// and the TFHE external product / CMux built on it (tfhe/src/tggsw.rs:39-62).
+//
+// The reference multiplies torus polynomials with an O(N^2) u128 schoolbook, negacyclic fold by
+// wrapping_sub and truncation to u64 (ring_torus.rs:266-298): that IS the exact negacyclic convolution
+// in Z_{2^64}[X]/(X^N+1), so any exact algorithm is bit-identical.  Here the convolution is
+// computed over the integers with two 30-bit NTT primes (P = p1*p2 ~ 2^60) on small limbs, lifted to the
+// centred representative by CRT, and recombined mod 2^64:
+//   * Tn*Tn     : both operands in four 16-bit limbs; plane products are bounded by N*2^32, the four
+//                 weight classes 2^(16w), w = 0..3, by 4*N*2^32 < P/2 (N <= 2^15);
+//   * ext. prod.: the TGLWE input is decomposed into its 64 bit-planes (Tn::decompose, beta=2,l=64:
+//                 torus.rs:43-52), the TGGSW rows into two 32-bit limbs transformed ONCE at load time;
+//                 sum over the (k+1)*64 rows is bounded by (k+1)*64*N*2^32 < P/2 (checked at load).
+// This file holds the unfused building blocks (split / MAC / CRT kernels) around the batched NTT kernels.
+#include "../../include/fhe_b200.h"
+#include "ntt_kernels.cuh"
+#include "plan_host.hpp"
+#include "runtime.cuh"
+#include "torus.cuh"
+
+namespace fhe {
+
+int ntt_launch_lazy32(int, int, const NttParams<Lazy32> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int,
+                      cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------
+// elementwise torus kernels
+// ---------------------------------------------------------------------------------------------------
+// planes[(poly*4 + w)*n + c] = 16-bit limb w of a[poly*n + c]
+__global__ void split16_kernel(const u64 *__restrict__ a, u64 *__restrict__ planes, size_t polys, u32 n) {
+    const size_t total = polys * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = i / n, c = i % n;
+        const u64 v = a[i];
+#pragma unroll
+        for (int w = 0; w < 4; w++) planes[(poly * 4 + w) * n + c] = (v >> (16 * w)) & 0xffffull;
+    }
+}
+// Tn::decompose(2,64) (ring_torus.rs:67-77 + torus.rs:43-52): plane j holds bit (63-j) of every coefficient.
+// planes[(poly*64 + j)*n + c]
+__global__ void bitplanes_kernel(const u64 *__restrict__ a, u64 *__restrict__ planes, size_t polys, u32 n) {
+    const size_t total = polys * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = i / n, c = i % n;
+        const u64 v = a[i];
+#pragma unroll 8
+        for (int j = 0; j < 64; j++) planes[(poly * 64 + j) * n + c] = (v >> (63 - j)) & 1ull;
+    }
+}
+// rows: u64 values -> limb planes reduced mod p: out[(row*2 + limb)*n + c] = ((v >> 32*limb) & 0xffffffff) % p
+__global__ void split32_mod_kernel(const u64 *__restrict__ rows, u64 *__restrict__ out, size_t polys, u32 n, u32 p) {
+    const size_t total = polys * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = i / n, c = i % n;
+        const u64 v = rows[i];
+        out[(poly * 2 + 0) * n + c] = (u32)v % p;
+        out[(poly * 2 + 1) * n + c] = (u32)(v >> 32) % p;
+    }
+}
+
+// weight-class products of the limb planes in the NTT domain (Tn*Tn):
+//   C[(poly*4 + w)*n + x] = sum_{u+v=w} A[(poly*4+u)*n + x] * B[(poly*4+v)*n + x]  mod p
+__global__ void limb_conv_kernel(const u64 *__restrict__ A, const u64 *__restrict__ B, u64 *__restrict__ C,
+                                 size_t polys, u32 n, Lazy32 m) {
+    const size_t total = polys * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = i / n, x = i % n;
+        u32 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            a[u] = (u32)A[(poly * 4 + u) * n + x];
+            b[u] = (u32)B[(poly * 4 + u) * n + x];
+        }
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            u32 acc = 0;
+#pragma unroll
+            for (int u = 0; u <= w; u++) acc = m.csub(acc + m.mul(a[u], b[w - u]), m.q);
+            C[(poly * 4 + w) * n + x] = acc;
+        }
+    }
+}
+
+// External-product MAC in the NTT domain (tggsw.rs:45-62 with tggsw.rs:139-149):
+//   out[((b*(k+1) + c)*2 + limb)*n + x] = sum_{d < (k+1)*64} D[(b*(k+1)*64 + d)*n + x] * R[((d*(k+1) + c)*2 + limb)*n + x]
+// D = NTT of the bit-planes of accumulator b, R = NTT of the limb planes of the TGGSW rows.
+__global__ void extprod_mac_kernel(const u64 *__restrict__ D, const u64 *__restrict__ R, u64 *__restrict__ out,
+                                   size_t batch, u32 n, u32 k1, Lazy32 m) {
+    const u32 items = k1 * 2 * n;  // (c, limb, x)
+    const size_t total = batch * items;
+    const u32 nd = k1 * 64;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / items;
+        const u32 item = (u32)(i % items), x = item % n;
+        const u64 *Db = D + b * nd * (size_t)n + x;
+        const u64 *Rp = R + item;
+        u64 acc = 0;  // products < 2^60: fold every 8 terms
+        for (u32 d = 0; d < nd; d += 8) {
+#pragma unroll
+            for (u32 dd = 0; dd < 8; dd++) {
+                const u32 dv = (u32)Db[(size_t)(d + dd) * n];
+                const u32 rv = (u32)Rp[(size_t)(d + dd) * items];
+                acc += (u64)m.mul(dv, rv);
+            }
+        }
+        out[i] = acc % m.q;
+    }
+}
+
+// CRT lift + recombination: res1/res2 hold residues mod p1/p2 of W integer polynomials per output
+// polynomial ([poly][w][n]); out[poly*n + c] = sum_w centre(CRT(r1, r2)) << shift[w]   (mod 2^64),
+// optionally + addend[poly*n + c] (the CMux's ct1, tggsw.rs:39-41).
+__global__ void crt_recombine_kernel(const u64 *__restrict__ res1, const u64 *__restrict__ res2,
+                                     const u64 *__restrict__ addend, u64 *__restrict__ out, size_t polys, u32 n,
+                                     CrtParams cp) {
+    const size_t total = polys * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = i / n, c = i % n;
+        u64 acc = addend ? addend[i] : 0;
+        for (int w = 0; w < cp.W; w++) {
+            const u32 r1 = (u32)res1[(poly * cp.W + w) * n + c];
+            const u32 r2 = (u32)res2[(poly * cp.W + w) * n + c];
+            acc += crt_centered(r1, r2, cp.p1, cp.p2, cp.p1_inv_mod_p2, cp.P, cp.halfP, cp.m2) << cp.shift[w];
+        }
+        out[i] = acc;
+    }
+}
+
+// wrapping elementwise ops on Tn / T64 vectors (ring_torus.rs:153-249, torus.rs:80-153): op 0 add, 1 sub, 2 neg
+__global__ void tn_addsub_kernel(const u64 *a, const u64 *b, u64 *c, size_t len,
+                                 int op) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x)
+        c[i] = op == 0 ? a[i] + b[i] : op == 1 ? a[i] - b[i] : (u64)0 - a[i];
+}
+// Tn::left_rotate(h) (ring_torus.rs:118-132): out = [c_h..c_{n-1}, -c_0..-c_{h-1}], h reduced mod n.
+// One rotation amount per polynomial group: h = hs[poly / group] (hs == nullptr: h_const).
+__global__ void tn_left_rotate_kernel(const u64 *__restrict__ a, u64 *__restrict__ out, size_t polys, u32 n,
+                                      const u64 *__restrict__ hs, u64 h_const, u32 group) {
+    const size_t total = polys * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = i / n;
+        const u32 c = (u32)(i % n);
+        const u32 h = (u32)((hs ? hs[poly / group] : h_const) % n);
+        const u32 src = c + h;
+        out[i] = src < n ? a[poly * n + src] : (u64)0 - a[poly * n + (src - n)];
+    }
+}
+
+static inline unsigned grid_for(size_t work, int threads = 256) {
+    size_t g = (work + threads - 1) / threads;
+    const size_t cap = (size_t)num_sms() * 16;
+    return (unsigned)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------
+int TorusCtx::init(u64 n) {
+    this->n = n;
+    FHE_REQUIRE(n >= 2 && (n & (n - 1)) == 0 && n <= (1u << 15), "torus ring degree must be a power of two in 2..2^15");
+    int rc;
+    if ((rc = fhe_ntt_plan_create(TORUS_P1, n, &plan1))) return rc;
+    if ((rc = fhe_ntt_plan_create(TORUS_P2, n, &plan2))) return rc;
+    logn = hp_ilog2(n);
+    init_mod(m1, TORUS_P1);
+    init_mod(m2, TORUS_P2);
+    cp.p1 = (u32)TORUS_P1;
+    cp.p2 = (u32)TORUS_P2;
+    cp.p1_inv_mod_p2 = (u32)hp_powmod(TORUS_P1 % TORUS_P2, TORUS_P2 - 2, TORUS_P2);
+    cp.P = TORUS_P1 * TORUS_P2;
+    cp.halfP = cp.P / 2;
+    cp.m2 = m2;
+    return 0;
+}
+TorusCtx::~TorusCtx() {
+    fhe_ntt_plan_destroy(plan1);
+    fhe_ntt_plan_destroy(plan2);
+}
+
+// forward / inverse NTT of `polys` device polynomials under prime index r (0: p1, 1: p2)
+int TorusCtx::ntt(int r, int mode, const u64 *in, u64 *out, size_t polys, cudaStream_t st) const {
+    const NttParams<Lazy32> &P = *reinterpret_cast<const NttParams<Lazy32> *>(plan_params32(r == 0 ? plan1 : plan2));
+    int rc = ntt_launch_lazy32(logn, mode, P, in, nullptr, out, nullptr, polys, 0, st);
+    if (!rc) count_launch(1);
+    return rc;
+}
+
+// c = a * b in Tn, `batch` independent products; device pointers.
+int tn_mul_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t batch, cudaStream_t st) {
+    const u32 n = (u32)tc.n;
+    const size_t plane_words = batch * 4 * (size_t)n;
+    u64 *buf = nullptr;
+    // A planes, B planes, C residues for p1 and p2
+    FHE_CUDA_OK(cudaMallocAsync((void **)&buf, plane_words * 4 * sizeof(u64), st));
+    u64 *A = buf, *B = buf + plane_words, *C1 = B + plane_words, *C2 = C1 + plane_words;
+    int rc = 0;
+    for (int r = 0; r < 2 && !rc; r++) {
+        split16_kernel<<<grid_for(batch * n), 256, 0, st>>>(a, A, batch, n);
+        split16_kernel<<<grid_for(batch * n), 256, 0, st>>>(b, B, batch, n);
+        count_launch(2);
+        if ((rc = tc.ntt(r, MODE_FWD, A, A, batch * 4, st))) break;
+        if ((rc = tc.ntt(r, MODE_FWD, B, B, batch * 4, st))) break;
+        u64 *C = r == 0 ? C1 : C2;
+        limb_conv_kernel<<<grid_for(batch * n), 256, 0, st>>>(A, B, C, batch, n, r == 0 ? tc.m1 : tc.m2);
+        count_launch(1);
+        rc = tc.ntt(r, MODE_INV, C, C, batch * 4, st);
+    }
+    if (!rc) {
+        CrtParams cp = tc.cp;
+        cp.W = 4;
+        for (int w = 0; w < 4; w++) cp.shift[w] = 16 * w;
+        crt_recombine_kernel<<<grid_for(batch * n), 256, 0, st>>>(C1, C2, nullptr, c, batch, n, cp);
+        count_launch(1);
+        if (cudaGetLastError() != cudaSuccess) { set_error("tn_mul kernel launch failed"); rc = -2; }
+    }
+    cudaFreeAsync(buf, st);
+    return rc;
+}
+
+// out = tggsw (x) ct  [+ addend]; `batch` TGLWE accumulators sharing one TGGSW; device pointers.
+int extprod_device(const Tggsw &g, const u64 *ct, const u64 *addend, u64 *out, size_t batch, cudaStream_t st) {
+    const TorusCtx &tc = *g.tc;
+    const u32 n = (u32)tc.n, k1 = (u32)g.k + 1;
+    const size_t nd = (size_t)k1 * 64;                 // digit polynomials per accumulator
+    const size_t chunk_max = std::max<size_t>(1, (512ull << 20) / (nd * n * sizeof(u64)));  // <= 512 MiB of planes
+    const size_t chunk = std::min(batch, chunk_max);
+    u64 *planes = nullptr, *D = nullptr, *res = nullptr;
+    FHE_CUDA_OK(cudaMallocAsync((void **)&planes, chunk * nd * n * sizeof(u64), st));
+    FHE_CUDA_OK(cudaMallocAsync((void **)&D, chunk * nd * n * sizeof(u64), st));
+    FHE_CUDA_OK(cudaMallocAsync((void **)&res, 2 * chunk * k1 * 2 * n * sizeof(u64), st));
+    int rc = 0;
+    for (size_t b0 = 0; b0 < batch && !rc; b0 += chunk) {
+        const size_t nb = std::min(chunk, batch - b0);
+        const size_t res_words = nb * k1 * 2 * n;
+        bitplanes_kernel<<<grid_for(nb * k1 * n), 256, 0, st>>>(ct + b0 * k1 * n, planes, nb * k1, n);
+        count_launch(1);
+        for (int r = 0; r < 2 && !rc; r++) {
+            if ((rc = tc.ntt(r, MODE_FWD, planes, D, nb * nd, st))) break;
+            u64 *R = res + (size_t)r * chunk * k1 * 2 * n;
+            extprod_mac_kernel<<<grid_for(res_words), 256, 0, st>>>(D, r == 0 ? g.R1 : g.R2, R, nb, n, k1,
+                                                                  r == 0 ? tc.m1 : tc.m2);
+            count_launch(1);
+            rc = tc.ntt(r, MODE_INV, R, R, nb * k1 * 2, st);
+        }
+        if (rc) break;
+        CrtParams cp = tc.cp;
+        cp.W = 2;
+        cp.shift[0] = 0;
+        cp.shift[1] = 32;
+        crt_recombine_kernel<<<grid_for(nb * k1 * n), 256, 0, st>>>(res, res + chunk * k1 * 2 * n,
+                                                                   addend ? addend + b0 * k1 * n : nullptr,
+                                                                   out + b0 * k1 * n, nb * k1, n, cp);
+        count_launch(1);
+        if (cudaGetLastError() != cudaSuccess) { set_error("extprod kernel launch failed"); rc = -2; }
+    }
+    cudaFreeAsync(planes, st);
+    cudaFreeAsync(D, st);
+    cudaFreeAsync(res, st);
+    return rc;
+}
+
+// Transforms the TGGSW rows once: R_r[((d*(k+1) + c)*2 + limb)*n + x] = NTT_{p_r}(limb plane of row d, component c)
+int tggsw_precompute(Tggsw &g, const u64 *rows_dev, cudaStream_t st) {
+    const TorusCtx &tc = *g.tc;
+    const u32 n = (u32)tc.n, k1 = (u32)g.k + 1;
+    const size_t polys = (size_t)k1 * 64 * k1;  // row polynomials
+    FHE_CUDA_OK(cudaMalloc((void **)&g.R1, polys * 2 * n * sizeof(u64)));
+    FHE_CUDA_OK(cudaMalloc((void **)&g.R2, polys * 2 * n * sizeof(u64)));
+    for (int r = 0; r < 2; r++) {
+        u64 *R = r == 0 ? g.R1 : g.R2;
+        split32_mod_kernel<<<grid_for(polys * n), 256, 0, st>>>(rows_dev, R, polys, n, r == 0 ? tc.cp.p1 : tc.cp.p2);
+        count_launch(1);
+        int rc = tc.ntt(r, MODE_FWD, R, R, polys * 2, st);
+        if (rc) return rc;
+    }
+    FHE_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int tn_addsub_device(const u64 *a, const u64 *b, u64 *c, size_t len, int op, cudaStream_t st) {
+    tn_addsub_kernel<<<grid_for(len), 256, 0, st>>>(a, b, c, len, op);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int tn_left_rotate_device(const u64 *a, u64 *out, size_t polys, u32 n, const u64 *hs, u64 h_const, u32 group,
+                          cudaStream_t st) {
+    tn_left_rotate_kernel<<<grid_for(polys * n), 256, 0, st>>>(a, out, polys, n, hs, h_const, group);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fhe

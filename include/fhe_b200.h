@@ -72,6 +72,82 @@ FHE_API int fhe_ntt_inv(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *
 FHE_API int fhe_rq_mul(const fhe_ntt_plan *plan, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, int flags,
                uint64_t *c_evals);
 
+/* ---- Tn = T_q[X]/(X^n+1), q = 2^64 (arith/src/ring_torus.rs) ------------------------------------------- */
+/* impl Mul<Tn> for Tn -> naive_poly_mul (ring_torus.rs:251-298): exact negacyclic product mod 2^64. */
+FHE_API int fhe_tn_mul(uint64_t n, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch);
+/* Add / Sub / Neg (ring_torus.rs:153-249; also T64 vectors, torus.rs:80-153): wrapping, `len` words. */
+FHE_API int fhe_tn_add(const uint64_t *a, const uint64_t *b, uint64_t *c, size_t len);
+FHE_API int fhe_tn_sub(const uint64_t *a, const uint64_t *b, uint64_t *c, size_t len);
+FHE_API int fhe_tn_neg(const uint64_t *a, uint64_t *c, size_t len);
+/* Tn::left_rotate / TGLWE::left_rotate (ring_torus.rs:118-132, tfhe/src/tglwe.rs:116-119): multiply by
+ * X^-h.  `polys` polynomials in groups of `group` consecutive polynomials (group = k+1 rotates whole TGLWEs);
+ * group g uses h[g] (reduced mod n).  out must not alias a. */
+FHE_API int fhe_tn_left_rotate(uint64_t n, const uint64_t *a, const uint64_t *h, uint64_t group, uint64_t *out, size_t polys);
+
+/* ---- TGGSW external product / CMux (tfhe/src/tggsw.rs) ---------------------------------------------------- */
+typedef struct fhe_tggsw fhe_tggsw;
+/* Uploads one TGGSW ((k+1)*64 TGLWE rows, beta=2 / l=64 as hard-coded at tggsw.rs:49-50) and transforms it
+ * once; the handle keeps it resident in HBM.  rows: (k+1) * 64 * (k+1) * n words. */
+FHE_API int fhe_tggsw_load(uint64_t n, uint64_t k, const uint64_t *rows, fhe_tggsw **handle);
+FHE_API void fhe_tggsw_destroy(fhe_tggsw *handle);
+/* impl Mul<TGLWE> for TGGSW (tggsw.rs:45-62): out_b = tggsw (x) ct_b for `batch` TGLWEs of (k+1)*n words. */
+FHE_API int fhe_extprod(const fhe_tggsw *handle, const uint64_t *ct, uint64_t *out, size_t batch);
+/* TGGSW::cmux (tggsw.rs:39-41): out_b = ct1_b + tggsw (x) (ct2_b - ct1_b). */
+FHE_API int fhe_cmux(const fhe_tggsw *handle, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out, size_t batch);
+
+/* ---- TLWE key switch / bootstrapping (tfhe/src/tlwe.rs, tfhe/src/tglwe.rs) ------------------------------ */
+typedef struct fhe_ksk fhe_ksk;
+/* KSK(Vec<TLev>) (tlwe.rs:84-100, tlev.rs:53-77): kn_in * l TLWE rows of kn_out+1 words, resident in HBM. */
+FHE_API int fhe_ksk_load(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *rows, fhe_ksk **handle);
+FHE_API void fhe_ksk_destroy(fhe_ksk *handle);
+/* TLWE::key_switch(param, 2, l, ksk) (tlwe.rs:101-112): `batch` TLWEs of kn_in+1 words -> kn_out+1 words. */
+FHE_API int fhe_key_switch(const fhe_ksk *handle, const uint64_t *ct, uint64_t *out, size_t batch);
+/* TLWE::mod_switch(q2) (tlwe.rs:114-118, torus.rs:58-66): every word >> (64 - log2 q2); q2 a power of two. */
+FHE_API int fhe_tlwe_mod_switch(const uint64_t *ct, uint64_t q2, uint64_t *out, size_t len);
+/* TGLWE::sample_extraction(h) (tglwe.rs:89-115): `batch` TGLWEs ((k+1)*n) -> TLWEs (k*n+1). */
+FHE_API int fhe_sample_extract(uint64_t n, uint64_t k, const uint64_t *ct, uint64_t h, uint64_t *out, size_t batch);
+/* blind_rotation (tlwe.rs:121-148).  as_written == 0: AS THE REFERENCE EXECUTES IT (its CMux loop is a lazy
+ * iterator that is dropped): acc = table.left_rotate(mod_switch(c, k*n).b).  as_written != 0 additionally runs
+ * the loop the source spells out, for j in 1..k: acc = cmux(bsk[j], acc, acc.left_rotate(mod_switch(c).a[j]))
+ * (an extension: no reference execution runs it).  bsk: k TGGSW handles (may be NULL when as_written == 0). */
+FHE_API int fhe_blind_rotate(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, int as_written, const uint64_t *table,
+                             const uint64_t *ct, uint64_t c_kn, uint64_t *acc_out, size_t batch);
+/* bootstrapping (tlwe.rs:150-161) as executed: blind_rotation -> sample_extraction(0) -> key_switch.
+ * table: one TGLWE ((k+1)*n words, e.g. compute_lookup_table's); ct: `batch` TLWEs of c_kn+1 words. */
+FHE_API int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *table, const uint64_t *ct, uint64_t c_kn,
+                          uint64_t *out, size_t batch);
+
+/* ---- BFV ciphertext multiplication (bfv/src/lib.rs) ----------------------------------------------------------- */
+/* RLWE::tensor (lib.rs:59-85): a, b = `batch` RLWEs (2n words) -> c0|c1|c2 (3n words each). */
+FHE_API int fhe_bfv_tensor(uint64_t q, uint64_t n, uint64_t t, const uint64_t *a, const uint64_t *b, uint64_t *c012, size_t batch);
+/* BFV::relinearize_204 (lib.rs:251-271): c0|c1|c2 and the RLK (2n words, coefficients mod pq) -> RLWE. */
+FHE_API int fhe_bfv_relinearize(uint64_t q, uint64_t n, uint64_t pq, const uint64_t *rlk, const uint64_t *c012, uint64_t *out,
+                                size_t batch);
+/* RLWE::mul (lib.rs:87-90) = tensor + relinearize_204, fused. */
+FHE_API int fhe_bfv_mul_relin(uint64_t q, uint64_t n, uint64_t t, uint64_t pq, const uint64_t *rlk, const uint64_t *a,
+                              const uint64_t *b, uint64_t *out, size_t batch);
+
+/* ---- coefficient-wise Rq / Tn operations (arith/src/ring_nq.rs, ring_torus.rs, zq.rs, torus.rs) ------------- */
+/* Add / Sub / Neg / mul_by_u64 (ring_nq.rs:267-281,406-561) on `len` coefficients mod q (any q < 2^63). */
+FHE_API int fhe_rq_add(uint64_t q, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t len);
+FHE_API int fhe_rq_sub(uint64_t q, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t len);
+FHE_API int fhe_rq_neg(uint64_t q, const uint64_t *a, uint64_t *c, size_t len);
+FHE_API int fhe_rq_mul_u64(uint64_t q, const uint64_t *a, uint64_t s, uint64_t *c, size_t len);
+/* Rq::remodule / mod_switch / mul_div_round (ring_nq.rs:82-113; f64 semantics of zq.rs:32-40,133-138). */
+FHE_API int fhe_rq_remodule(const uint64_t *a, uint64_t p, uint64_t *c, size_t len);
+FHE_API int fhe_rq_mod_switch(uint64_t q, const uint64_t *a, uint64_t p, uint64_t *c, size_t len);
+FHE_API int fhe_rq_mul_div_round(uint64_t q, const uint64_t *a, uint64_t num, uint64_t den, uint64_t *c, size_t len);
+/* Rq::from_vec_u64 (ring_nq.rs:55-63,132-141,156-159): reduce mod q and fold X^n = -1; in: `batch` x in_len. */
+FHE_API int fhe_rq_from_vec(uint64_t q, uint64_t n, const uint64_t *in, uint64_t in_len, uint64_t *out, size_t batch);
+/* Rq::decompose(beta, l) (ring_nq.rs:67-77, zq.rs:140-186): out = `polys` x l x n digit polynomials. */
+FHE_API int fhe_rq_decompose(uint64_t q, uint64_t n, const uint64_t *a, uint32_t beta, uint32_t l, uint64_t *out, size_t polys);
+/* Tn::decompose(2, l) (ring_torus.rs:67-77, torus.rs:43-52): out = `polys` x l x n bit polynomials. */
+FHE_API int fhe_tn_decompose(uint64_t n, const uint64_t *a, uint32_t l, uint64_t *out, size_t polys);
+/* Tn::mod_switch(p) -> Rq_p (ring_torus.rs:85-101), Mul<u64>/Mul<T64> (ring_torus.rs:300-327), mul_div_round. */
+FHE_API int fhe_tn_mod_switch(const uint64_t *a, uint64_t p, uint64_t *c, size_t len);
+FHE_API int fhe_tn_mul_u64(const uint64_t *a, uint64_t s, uint64_t *c, size_t len);
+FHE_API int fhe_tn_mul_div_round(const uint64_t *a, uint64_t num, uint64_t den, uint64_t *c, size_t len);
+
 #ifdef __cplusplus
 }
 #endif

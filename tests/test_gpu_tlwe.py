@@ -1,0 +1,134 @@
+"""GPU parity (bit-exact) of the TLWE path against the oracle: key switch (tfhe/src/tlwe.rs:101-112), sample
+extraction (tglwe.rs:89-115), mod switch, blind rotation as executed and as written, and bootstrapping
+(tlwe.rs:150-161) at the reference's own parameters (n=1024, k=1, t=128, l=64; tlwe.rs:467-475), plus
+the reference's functional property that bootstrapping preserves the message."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fhe():
+    import fhe_study_b200 as f
+
+    f.set_device(0)
+    return f
+
+
+@pytest.fixture(scope="module")
+def p5(orc):
+    """keys of the reference's bootstrapping test: n=1024, k=1, KSK beta=2, l=64 (537 MB)."""
+    L = orc.lib()
+    n, k, t = 1024, 1, 128
+    kn = n * k
+    sk = np.empty(kn, dtype=np.uint64)
+    sk2 = np.empty(kn, dtype=np.uint64)
+    L.orc_tlwe_keygen(1, kn, orc.ptr(sk))
+    L.orc_tlwe_keygen(2, kn, orc.ptr(sk2))
+    ksk = np.empty(kn * 64 * (kn + 1), dtype=np.uint64)
+    L.orc_tlwe_new_ksk(3, kn, kn, 64, 3.2, orc.ptr(sk), orc.ptr(sk2), 1, orc.ptr(ksk))
+    return dict(n=n, k=k, t=t, kn=kn, sk=sk, sk2=sk2, ksk=ksk)
+
+
+@pytest.mark.parametrize("kn_in,kn_out,l,batch", [(16, 16, 64, 5), (16, 8, 16, 19), (100, 130, 64, 17), (1, 1, 1, 3)])
+def test_key_switch_small(fhe, orc, kn_in, kn_out, l, batch):
+    ksk = orc.uniform(kn_in * 1000 + l, kn_in * l * (kn_out + 1))
+    ct = orc.uniform(kn_in + 7, (batch, kn_in + 1))
+    ct[0, :] = 2**64 - 1
+    k = fhe.Ksk(kn_in, kn_out, l, ksk)
+    got = k.key_switch(ct)
+    want = orc.key_switch(kn_in, kn_out, l, ksk, ct.reshape(-1)).reshape(batch, kn_out + 1)
+    assert (got == want).all()
+
+
+def test_key_switch_functional(fhe, orc):
+    # tfhe/src/tlwe.rs:423-463: k=16, n=1, t=128
+    L = orc.lib()
+    kn, t, l = 16, 128, 64
+    sk = np.empty(kn, dtype=np.uint64)
+    sk2 = np.empty(kn, dtype=np.uint64)
+    L.orc_tlwe_keygen(1, kn, orc.ptr(sk))
+    L.orc_tlwe_keygen(2, kn, orc.ptr(sk2))
+    ksk = np.empty(kn * l * (kn + 1), dtype=np.uint64)
+    L.orc_tlwe_new_ksk(3, kn, kn, l, 3.2, orc.ptr(sk), orc.ptr(sk2), 0, orc.ptr(ksk))
+    delta = (2**64 - 1) // t
+    K = fhe.Ksk(kn, kn, l, ksk)
+    for m in (0, 1, 77, 127):
+        ct = np.empty(kn + 1, dtype=np.uint64)
+        L.orc_tlwe_encrypt_s(10 + m, kn, 3.2, orc.ptr(sk), (m * delta) % 2**64, 1, orc.ptr(ct))
+        out = K.key_switch(ct).reshape(-1)
+        assert (out == orc.key_switch(kn, kn, l, ksk, ct)).all()
+        p = L.orc_tlwe_decrypt(kn, orc.ptr(sk2), orc.ptr(out))
+        assert L.orc_t64_mul_div_round(p, t, 2**64 - 1) % t == m
+
+
+def test_sample_extract_and_mod_switch(fhe, orc):
+    L = orc.lib()
+    n, k = 64, 4
+    ct = orc.uniform(3, (5, (k + 1) * n))
+    for h in (0, 1, 17, 63):
+        got = fhe.sample_extract(n, k, ct, h)
+        for b in range(5):
+            want = np.empty(k * n + 1, dtype=np.uint64)
+            L.orc_tglwe_sample_extraction(n, k, orc.ptr(np.ascontiguousarray(ct[b])), h, orc.ptr(want))
+            assert (got[b] == want).all()
+    x = orc.uniform(9, 1025)
+    for q2 in (2, 1024, 2**20):
+        want = np.empty_like(x)
+        L.orc_tlwe_mod_switch(1024, orc.ptr(x), q2, orc.ptr(want))
+        assert (fhe.tlwe_mod_switch(x, q2) == want).all()
+
+
+def test_bootstrapping_reference_params(fhe, orc, p5):
+    # tfhe/src/tlwe.rs:465-504 with the trivial lookup table (compute_lookup_table) ...
+    L = orc.lib()
+    n, k, t, kn = p5["n"], p5["k"], p5["t"], p5["kn"]
+    table = orc.lookup_table(n, k, t)
+    delta = (2**64 - 1) // t
+    K = fhe.Ksk(kn, kn, 64, p5["ksk"])
+    msgs = [0, 5, 100, 127, 64, 1]
+    cts = np.empty((len(msgs), kn + 1), dtype=np.uint64)
+    for i, m in enumerate(msgs):
+        L.orc_tlwe_encrypt_s(10 + m, kn, 3.2, orc.ptr(p5["sk"]), (m * delta) % 2**64, 0, orc.ptr(cts[i]))
+    got = fhe.bootstrap(n, k, K, table, cts, kn)
+    want = orc.bootstrapping(n, k, p5["ksk"], table, cts.reshape(-1), kn, threads=8).reshape(len(msgs), kn + 1)
+    assert (got == want).all()
+    for i, m in enumerate(msgs):  # the reference's functional assertion: the message survives
+        p = L.orc_tlwe_decrypt(kn, orc.ptr(p5["sk2"]), orc.ptr(np.ascontiguousarray(got[i])))
+        assert L.orc_t64_mul_div_round(p, t, 2**64 - 1) % t == m
+    # ... and with a dense (non-trivial) table so that the extracted mask has dense digits
+    dense = orc.uniform(77, (k + 1) * n)
+    rnd = orc.uniform(78, (9, kn + 1))
+    got = fhe.bootstrap(n, k, K, dense, rnd, kn)
+    want = orc.bootstrapping(n, k, p5["ksk"], dense, rnd.reshape(-1), kn, threads=8).reshape(9, kn + 1)
+    assert (got == want).all()
+    # key switch alone at full size, ragged batch
+    ks = K.key_switch(rnd)
+    assert (ks.reshape(-1) == orc.key_switch(kn, kn, 64, p5["ksk"], rnd.reshape(-1), threads=8)).all()
+
+
+def test_blind_rotation_as_executed_and_as_written(fhe, orc):
+    L = orc.lib()
+    # as executed (the CMux loop never runs): one public rotation of the table
+    n, k, batch = 1024, 1, 4
+    table = orc.uniform(5, (k + 1) * n)
+    cts = orc.uniform(6, (batch, n * k + 1))
+    got = fhe.blind_rotate(n, k, table, cts, n * k)
+    for b in range(batch):
+        want = np.empty((k + 1) * n, dtype=np.uint64)
+        L.orc_blind_rotation_as_executed(n, k, orc.ptr(np.ascontiguousarray(cts[b])), n * k, orc.ptr(table), orc.ptr(want))
+        assert (got[b] == want).all()
+    # as written (extension): k=3 so the loop body runs for j=1,2
+    n, k, batch = 64, 3, 3
+    glwe = (k + 1) * n
+    bsk = orc.uniform(8, (k, (k + 1) * 64 * glwe))
+    table = orc.uniform(9, glwe)
+    cts = orc.uniform(10, (batch, n * k + 1))
+    handles = [fhe.Tggsw(n, k, bsk[j]) for j in range(k)]
+    got = fhe.blind_rotate(n, k, table, cts, n * k, bsk=handles, as_written=True)
+    for b in range(batch):
+        want = np.empty(glwe, dtype=np.uint64)
+        L.orc_blind_rotation_as_written(n, k, orc.ptr(np.ascontiguousarray(cts[b])), n * k, orc.ptr(bsk.reshape(-1)),
+                                        orc.ptr(table), orc.ptr(want))
+        assert (got[b] == want).all()

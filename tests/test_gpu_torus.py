@@ -1,0 +1,179 @@
+"""GPU parity (bit-exact) of the torus path against the oracle through the C ABI: Tn arithmetic
+(arith/src/ring_torus.rs), TGGSW external product and CMux (tfhe/src/tggsw.rs:39-62) at the reference's
+own parameter sets (n=64,k=4,t=16 -- tggsw.rs:159-167; n=1024,k=1 -- tlwe.rs:467-475), plus the
+reference's functional property decrypt(tggsw(m1) (x) tglwe(m2)) == m1*m2."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+M64 = 2**64
+
+
+def neg64(v):
+    return [(x + M64) % M64 for x in v]
+
+
+@pytest.fixture(scope="module")
+def fhe():
+    import fhe_study_b200 as f
+
+    f.set_device(0)
+    return f
+
+
+def test_left_rotate_known_answers(fhe):
+    # arith/src/ring_torus.rs:334-366
+    f = np.array(neg64([2, 3, -4, -1]), dtype=np.uint64)
+    assert list(fhe.tn_left_rotate(4, f, np.array([3], dtype=np.uint64))) == neg64([-1, -2, -3, 4])
+    assert list(fhe.tn_left_rotate(4, f, np.array([1], dtype=np.uint64))) == neg64([3, -4, -1, -2])
+    assert list(fhe.tn_left_rotate(4, f, np.array([4 + 1], dtype=np.uint64))) == neg64([3, -4, -1, -2])  # h % n
+
+
+@pytest.mark.parametrize("n", [2, 4, 64, 128, 1024, 4096])
+def test_tn_mul_matches_schoolbook(fhe, orc, n):
+    batch = 3 if n >= 1024 else 9
+    a = orc.uniform(n + 1, (batch, n))
+    b = orc.uniform(n + 2, (batch, n))
+    a[0, :] = M64 - 1  # worst case for the exactness bound of the CRT lift
+    b[0, :] = M64 - 1
+    a[1, :] = 0
+    b[2, :] = 1
+    want = orc.tn_mul(n, a, b, threads=8)
+    assert (fhe.tn_mul(n, a, b) == want).all()
+
+
+def test_tn_elementwise(fhe, orc):
+    a, b = orc.uniform(1, 1000), orc.uniform(2, 1000)
+    assert (fhe.tn_add(a, b) == a + b).all()
+    assert (fhe.tn_sub(a, b) == a - b).all()
+    assert (fhe.tn_neg(a) == (np.uint64(0) - a)).all()
+    assert (fhe.tn_mul_u64(a, 12345678901234567) == a * np.uint64(12345678901234567)).all()
+    # Tn::decompose: recomposition identity of arith/src/torus.rs:163-190
+    d = fhe.tn_decompose(8, a[:64], 64)
+    want = np.zeros((8, 64, 8), dtype=np.uint64)
+    orcl = orc.lib()
+    for p in range(8):
+        orcl.orc_tn_decompose(8, orc.ptr(a[8 * p:]), 64, orc.ptr(want[p]))
+    assert (d == want).all()
+    for p, q in [(2**10, None), (2**32, None)]:
+        got = fhe.tn_mod_switch(a, p)
+        w = np.zeros_like(a)
+        orcl.orc_tn_mod_switch(a.size, orc.ptr(a), p, orc.ptr(w))
+        assert (got == w).all()
+    got = fhe.tn_mul_div_round(a, 128, 2**64 - 1)
+    w = np.zeros_like(a)
+    orcl.orc_tn_mul_div_round(a.size, orc.ptr(a), 128, 2**64 - 1, orc.ptr(w))
+    assert (got == w).all()
+
+
+def _keys_and_cts(orc, n, k, t, seed, batch, uniform_mask):
+    L = orc.lib()
+    sk = np.empty(k * n, dtype=np.uint64)
+    L.orc_tglwe_keygen(seed, n, k, orc.ptr(sk))
+    m1 = orc.uniform(seed + 1, n, t)
+    tggsw = np.empty((k + 1) * 64 * (k + 1) * n, dtype=np.uint64)
+    L.orc_tggsw_encrypt_s(seed + 2, n, k, 3.2, orc.ptr(sk), orc.ptr(m1), uniform_mask, orc.ptr(tggsw))
+    ms, cts = [], []
+    for i in range(batch):
+        m2 = orc.uniform(seed + 10 + i, n, t)
+        p2 = np.empty(n, dtype=np.uint64)
+        L.orc_tglwe_encode(n, t, orc.ptr(m2), orc.ptr(p2))
+        ct = np.empty((k + 1) * n, dtype=np.uint64)
+        L.orc_tglwe_encrypt_s(seed + 100 + i, n, k, 3.2, orc.ptr(sk), orc.ptr(p2), uniform_mask, orc.ptr(ct))
+        ms.append(m2)
+        cts.append(ct)
+    return sk, m1, tggsw, ms, np.stack(cts)
+
+
+def test_external_product_reference_params(fhe, orc):
+    # tfhe/src/tggsw.rs:157-196: n=64, k=4, t=16, the reference's sampling (mask from Xi_key)
+    L = orc.lib()
+    n, k, t = 64, 4, 16
+    sk, m1, tggsw, ms, cts = _keys_and_cts(orc, n, k, t, 1000, 6, 0)
+    g = fhe.Tggsw(n, k, tggsw)
+    got = g.extprod(cts)
+    want = orc.extprod(n, k, tggsw, cts.reshape(-1), fast=False).reshape(cts.shape)
+    assert (got == want).all()
+    for i in range(cts.shape[0]):  # decrypt(extprod) == m1 * m2 in Z_t[X]/(X^n+1)
+        p = np.empty(n, dtype=np.uint64)
+        L.orc_tglwe_decrypt(n, k, orc.ptr(sk), orc.ptr(np.ascontiguousarray(got[i])), orc.ptr(p))
+        rec = np.empty(n, dtype=np.uint64)
+        L.orc_tglwe_decode(n, t, orc.ptr(p), orc.ptr(rec))
+        expect = np.empty(n, dtype=np.uint64)
+        L.orc_r_mul_to_rq(n, orc.ptr(orc.i64(m1)), orc.ptr(orc.i64(ms[i])), t, orc.ptr(expect))
+        assert (rec == expect).all()
+
+
+@pytest.mark.parametrize("n,k,batch", [(64, 4, 33), (1024, 1, 5), (256, 2, 7), (2048, 1, 2)])
+def test_external_product_and_cmux_dense_inputs(fhe, orc, n, k, batch):
+    # uniformly random TGGSW rows and accumulators: every digit and limb is exercised
+    glwe = (k + 1) * n
+    tggsw = orc.uniform(7 * n + k, (k + 1) * 64 * glwe)
+    ct1 = orc.uniform(11 * n + k, (batch, glwe))
+    ct2 = orc.uniform(13 * n + k, (batch, glwe))
+    ct1[0, :] = M64 - 1
+    g = fhe.Tggsw(n, k, tggsw)
+    assert (g.extprod(ct1).reshape(-1) == orc.extprod(n, k, tggsw, ct1.reshape(-1))).all()
+    assert (g.cmux(ct1, ct2).reshape(-1) == orc.cmux(n, k, tggsw, ct1.reshape(-1), ct2.reshape(-1))).all()
+
+
+def test_extprod_worst_case_bound(fhe, orc):
+    # all-ones rows and accumulators maximise the integer magnitude the two-prime lift has to carry
+    n, k = 1024, 1
+    glwe = (k + 1) * n
+    tggsw = np.full((k + 1) * 64 * glwe, M64 - 1, dtype=np.uint64)
+    ct = np.full((1, glwe), M64 - 1, dtype=np.uint64)
+    g = fhe.Tggsw(n, k, tggsw)
+    assert (g.extprod(ct).reshape(-1) == orc.extprod(n, k, tggsw, ct.reshape(-1))).all()
+
+
+def test_cmux_selects(fhe, orc):
+    # no TGGSW cmux test exists in the reference: check the defining property with TGGSW(0)/TGGSW(1)
+    L = orc.lib()
+    n, k, t = 64, 2, 16
+    sk = np.empty(k * n, dtype=np.uint64)
+    L.orc_tglwe_keygen(1, n, k, orc.ptr(sk))
+    cts, msgs = [], []
+    for s in (10, 20):
+        m = orc.uniform(s, n, t)
+        p = np.empty(n, dtype=np.uint64)
+        L.orc_tglwe_encode(n, t, orc.ptr(m), orc.ptr(p))
+        ct = np.empty((k + 1) * n, dtype=np.uint64)
+        L.orc_tglwe_encrypt_s(s + 1, n, k, 3.2, orc.ptr(sk), orc.ptr(p), 0, orc.ptr(ct))
+        cts.append(ct)
+        msgs.append(m)
+    for bit in (0, 1):
+        mb = np.zeros(n, dtype=np.uint64)
+        mb[0] = bit
+        tggsw = np.empty((k + 1) * 64 * (k + 1) * n, dtype=np.uint64)
+        L.orc_tggsw_encrypt_s(30 + bit, n, k, 3.2, orc.ptr(sk), orc.ptr(mb), 0, orc.ptr(tggsw))
+        res = fhe.Tggsw(n, k, tggsw).cmux(cts[0], cts[1])
+        assert (res == orc.cmux(n, k, tggsw, cts[0], cts[1])).all()
+        p = np.empty(n, dtype=np.uint64)
+        L.orc_tglwe_decrypt(n, k, orc.ptr(sk), orc.ptr(res), orc.ptr(p))
+        rec = np.empty(n, dtype=np.uint64)
+        L.orc_tglwe_decode(n, t, orc.ptr(p), orc.ptr(rec))
+        assert (rec == msgs[bit]).all()
+
+
+def test_extprod_device_buffers_and_linearity(fhe, orc):
+    # size-independent property at a larger batch: the external product is additive in the accumulator
+    # when the two accumulators have disjoint bit supports (decompose(a+b) = decompose(a)+decompose(b))
+    import torch
+
+    n, k, batch = 1024, 1, 256
+    glwe = (k + 1) * n
+    tggsw = orc.uniform(99, (k + 1) * 64 * glwe)
+    g = fhe.Tggsw(n, k, tggsw)
+    x = orc.uniform(5, (batch, glwe))
+    lo = x & np.uint64(0x00000000FFFFFFFF)
+    hi = x & np.uint64(0xFFFFFFFF00000000)
+    fhe.use_torch_stream()
+    dx, dlo, dhi = (torch.from_numpy(v.view(np.int64)).cuda() for v in (x, lo, hi))
+    full = g.extprod(dx)
+    parts = g.extprod(dlo) + g.extprod(dhi)  # int64 add wraps mod 2^64
+    torch.cuda.synchronize()
+    assert torch.equal(full, parts)
+    got = full[:3].cpu().numpy().view(np.uint64)
+    assert (got.reshape(-1) == orc.extprod(n, k, tggsw, x[:3].reshape(-1))).all()
