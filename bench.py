@@ -276,7 +276,7 @@ def main():
         try:
             import bench_extras
 
-            line["extras"] = bench_extras.run(fhe, dev, quick=args.steps < 20)
+            line["extras"] = bench_extras.run(fhe, dev, quick=args.steps < 20, cpu=not args.no_cpu)
         except Exception as ex:  # extras never invalidate the headline line
             line["extras"] = {"error": repr(ex)}
     print(json.dumps(line), flush=True)

@@ -64,6 +64,137 @@ def ntt_sweep(fhe, dev, quick):
     return {"sweep": out, "polymul_n1024_batch1_us": lat * 1e3}
 
 
-def run(fhe, dev, quick=False):
-    res = {"ntt": ntt_sweep(fhe, dev, quick)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# TFHE / BFV paths (BASELINE configs[2..4]); device-resident buffers, CUDA events, each with a bounded CPU
+# sample of the oracle port on all host cores beside it.
+# ---------------------------------------------------------------------------------------------------------
+def _u64_rand(torch, shape, dev, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    return torch.randint(-(2**63), 2**63 - 1, shape, dtype=torch.int64, device=dev, generator=g)
+
+
+def tfhe_paths(fhe, dev, quick, cpu=True):
+    import time
+
+    import numpy as np
+    import torch
+
+    import oracle
+
+    cores = os.cpu_count() or 1
+    res = {}
+    reps = 2 if quick else 5
+    # --- config 3/4: TGGSW x TGLWE external product and CMux, reference parameter sets -----------------
+    for name, n, k, batch in (("P4a_n64_k4", 64, 4, 4096), ("P4b_n1024_k1", 1024, 1, 1024)):
+        glwe = (k + 1) * n
+        tggsw = _u64_rand(torch, ((k + 1) * 64 * glwe,), dev, 1)
+        g = fhe.Tggsw(n, k, tggsw)
+        ct1 = _u64_rand(torch, (batch, glwe), dev, 2)
+        ct2 = _u64_rand(torch, (batch, glwe), dev, 3)
+        out = torch.empty_like(ct1)
+        ms_e = _time(lambda: g.extprod(ct1, out=out), reps, warm=1)
+        ms_c = _time(lambda: g.cmux(ct1, ct2, out=out), reps, warm=1)
+        row = {"n": n, "k": k, "batch": batch, "extprod_per_s": batch / (ms_e * 1e-3), "cmux_per_s": batch / (ms_c * 1e-3),
+               "extprod_ms": ms_e, "cmux_ms": ms_c}
+        if cpu:
+            sample = max(1, min(batch, cores * (4 if n <= 64 else 1)))
+            hg = tggsw.cpu().numpy().view(np.uint64)
+            hc = ct1[:sample].cpu().numpy().view(np.uint64).reshape(-1).copy()
+            ho = np.empty_like(hc)
+            t0 = time.perf_counter()
+            oracle.lib().orc_extprod_batch(n, k, oracle.ptr(hg), oracle.ptr(hc), oracle.ptr(ho), sample, cores)
+            dt = time.perf_counter() - t0
+            same = bool((g.extprod(ct1[:sample].contiguous()).cpu().numpy().view(np.uint64).reshape(-1) == ho).all())
+            row["cpu_extprod_per_s"] = sample / dt
+            row["cpu_sample"] = f"{sample} external products, O(N^2) u128 schoolbook port, {cores} threads, {dt:.2f} s"
+            row["gpu_matches_cpu_sample"] = same
+        res[name] = row
+        del g, tggsw, ct1, ct2, out
+    # --- config 5: bootstrapping as executed (n=1024, k=1, l=64; 537 MB KSK resident) ---------------------
+    n, k, kn, l = 1024, 1, 1024, 64
+    batch = 2048 if quick else 8192
+    ksk = _u64_rand(torch, (kn * l * (kn + 1),), dev, 4)
+    K = fhe.Ksk(kn, kn, l, ksk)
+    table = _u64_rand(torch, ((k + 1) * n,), dev, 5)  # dense (non-trivial) table: dense digits in the key switch
+    cts = _u64_rand(torch, (batch, kn + 1), dev, 6)
+    out = torch.empty_like(cts)
+    ms_b = _time(lambda: fhe.bootstrap(n, k, K, table, cts, kn, out=out), reps, warm=1)
+    ms_k = _time(lambda: K.key_switch(cts, out=out), reps, warm=1)
+    row = {"n": n, "k": k, "l": l, "batch": batch, "bootstraps_per_s": batch / (ms_b * 1e-3), "bootstrap_ms": ms_b,
+           "key_switch_per_s": batch / (ms_k * 1e-3), "ksk_bytes": int(ksk.numel() * 8),
+           "u64_mac_per_s": batch * kn * l * (kn + 1) / (ms_b * 1e-3)}
+    if cpu:
+        sample = cores * 2
+        hk = ksk.cpu().numpy().view(np.uint64)
+        ht = table.cpu().numpy().view(np.uint64)
+        hc = cts[:sample].cpu().numpy().view(np.uint64).reshape(-1).copy()
+        t0 = time.perf_counter()
+        ho = oracle.bootstrapping(n, k, hk, ht, hc, kn, threads=cores)
+        dt = time.perf_counter() - t0
+        got = fhe.bootstrap(n, k, K, table, cts[:sample].contiguous(), kn).cpu().numpy().view(np.uint64).reshape(-1)
+        row["cpu_bootstraps_per_s"] = sample / dt
+        row["cpu_sample"] = f"{sample} bootstraps (as executed), oracle port, {cores} threads, {dt:.2f} s"
+        row["gpu_matches_cpu_sample"] = bool((got == ho).all())
+    res["P5_bootstrap_as_executed"] = row
+    del K, ksk, cts, out
+    return res
+
+
+def bfv_path(fhe, dev, quick, cpu=True):
+    import time
+
+    import numpy as np
+    import torch
+
+    import oracle
+
+    cores = os.cpu_count() or 1
+    q, n, t = Q17, 16, 2
+    pq = q * q * q
+    res = {}
+    for batch in (4096, 1 << 20):
+        a = torch.randint(0, q, (batch, 2 * n), dtype=torch.int64, device=dev)
+        b = torch.randint(0, q, (batch, 2 * n), dtype=torch.int64, device=dev)
+        rlk = torch.randint(0, pq, (2 * n,), dtype=torch.int64, device=dev)
+        out = torch.empty_like(a)
+        ms = _time(lambda: fhe.bfv_mul_relin(q, n, t, pq, rlk, a, b, out=out), 5 if quick else 20)
+        row = {"q": q, "n": n, "t": t, "batch": batch, "mul_relin_per_s": batch / (ms * 1e-3), "ms": ms,
+               "hbm_gbs": 48 * n * batch / (ms * 1e-3) / 1e9}
+        if cpu and batch == 4096:
+            ha, hb, hr = (x.cpu().numpy().view(np.uint64) for x in (a, b, rlk))
+            reps = 50
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ho = oracle.bfv_mul(q, n, t, pq, hr, ha.reshape(-1), hb.reshape(-1), threads=cores)
+            dt = time.perf_counter() - t0
+            row["cpu_mul_relin_per_s"] = reps * batch / dt
+            row["cpu_sample"] = f"{reps} x {batch} ct muls, oracle port, {cores} threads, {dt:.2f} s"
+            row["gpu_matches_cpu_sample"] = bool((out.cpu().numpy().view(np.uint64).reshape(-1) == ho).all())
+        res[f"batch_{batch}"] = row
+    return res
+
+
+def tn_mul_path(fhe, dev, quick):
+    import torch
+
+    res = {}
+    for n, batch in ((1024, 8192), (64, 65536)):
+        a = _u64_rand(torch, (batch, n), dev, 7)
+        b = _u64_rand(torch, (batch, n), dev, 8)
+        c = torch.empty_like(a)
+        ms = _time(lambda: fhe.tn_mul(n, a, b, out=c), 3 if quick else 10)
+        res[f"n{n}"] = {"batch": batch, "tn_mul_per_s": batch / (ms * 1e-3), "ms": ms}
+    return res
+
+
+def run(fhe, dev, quick=False, cpu=True):
+    res = {}
+    for name, fn in (("ntt", lambda: ntt_sweep(fhe, dev, quick)), ("tfhe", lambda: tfhe_paths(fhe, dev, quick, cpu)),
+                     ("bfv", lambda: bfv_path(fhe, dev, quick, cpu)), ("tn_mul", lambda: tn_mul_path(fhe, dev, quick))):
+        try:
+            res[name] = fn()
+        except Exception as ex:  # one failing extra must not hide the others
+            res[name] = {"error": repr(ex)}
     return res
