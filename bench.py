@@ -146,6 +146,62 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def measure_bootstrap(fhe, torch, dist, dev, rank, world, quick):
+    """Second headline metric (BASELINE metric: "TFHE bootstraps/s"): bootstrapping as the reference executes
+    it (tfhe/src/tlwe.rs:150-161; n=1024, k=1, l=64), TLWE inputs sharded over the ranks, the 537 MB
+    key-switching key and the table broadcast ONCE from rank 0 over NCCL, no per-op collective."""
+    from fhe_study_b200.dist import broadcast_key
+
+    n, k, kn, l = 1024, 1, 1024, 64
+    batch = 2048 if quick else 8192
+    steps = 2 if quick else 5
+    g = torch.Generator(device=dev).manual_seed(99)
+    if rank == 0:
+        ksk = torch.randint(-(2**63), 2**63 - 1, (kn * l * (kn + 1),), dtype=torch.int64, device=dev, generator=g)
+        table = torch.randint(-(2**63), 2**63 - 1, ((k + 1) * n,), dtype=torch.int64, device=dev, generator=g)
+    else:
+        ksk = torch.empty((kn * l * (kn + 1),), dtype=torch.int64, device=dev)
+        table = torch.empty(((k + 1) * n,), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    broadcast_key(ksk)
+    broadcast_key(table)
+    b1.record()
+    torch.cuda.synchronize()
+    bcast_ms = b0.elapsed_time(b1)
+    K = fhe.Ksk(kn, kn, l, ksk)
+    del ksk
+    cts = torch.randint(-(2**63), 2**63 - 1, (batch, kn + 1), dtype=torch.int64, device=dev,
+                        generator=torch.Generator(device=dev).manual_seed(7 + rank))
+    out = torch.empty_like(cts)
+    for _ in range(2):
+        fhe.bootstrap(n, k, K, table, cts, kn, out=out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fhe.bootstrap(n, k, K, table, cts, kn, out=out)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {
+        "metric": "TFHE bootstraps/s (as executed: mod_switch + rotate + sample_extract + key_switch)",
+        "value": world * batch * steps / (ms * 1e-3), "unit": "bootstraps/s", "n_gpus": world,
+        "batch_per_gpu": batch, "steps": steps, "ms_per_step": ms / steps, "scaling": "weak",
+        "params": {"n": n, "k": k, "l": l, "ksk_bytes": kn * l * (kn + 1) * 8},
+        "key_broadcast_ms": bcast_ms,
+        "u64_mac_per_s": world * batch * steps * kn * l * (kn + 1) / (ms * 1e-3),
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,6 +290,8 @@ def main():
     e2e_value = world * batch * e2e_steps / (float(t.item()) * 1e-3)
     same = bool(torch.equal(hc.to(dev), c))
 
+    boot = measure_bootstrap(fhe, torch, dist, dev, rank, world, quick=args.steps < 20)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -264,6 +322,7 @@ def main():
         },
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "bootstrap": boot,
     }
     if not args.no_cpu:
         base, (xa, xb, xc) = cpu_polymul_baseline()
@@ -272,7 +331,7 @@ def main():
         got = plan.mul(np.ascontiguousarray(xa[:k]), np.ascontiguousarray(xb[:k]))
         base["gpu_matches_on_sample"] = bool((got == xc[:k]).all())
         line["cpu_baseline"] = base
-    if not args.no_extras:
+    if not args.no_extras and world == 1:
         try:
             import bench_extras
 
