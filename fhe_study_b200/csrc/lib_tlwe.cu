@@ -35,12 +35,20 @@ int fhe_ksk_load(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *ro
         set_error(std::string("fhe_ksk_load: ") + cudaGetErrorString(e));
         return -2;
     }
+    if (l == 64 && kn_in % 2 == 0 && kn_in <= 131072) {
+        int rc = ksk_build_mma_layout(h->k, st);
+        if (rc) {
+            cudaFree(h->k.rows);
+            return rc;
+        }
+    }
     *out = h.release();
     return 0;
 }
 void fhe_ksk_destroy(fhe_ksk *h) {
     if (!h) return;
     cudaFree(h->k.rows);
+    cudaFree(h->k.mma_blocks);
     delete h;
 }
 

@@ -8,8 +8,14 @@ namespace fhe {
 struct Ksk {
     u64 kn_in = 0, kn_out = 0, l = 0;
     u64 *rows = nullptr;
+    // tensor-core layout (ks_mma.cu), built when l == 64 and kn_in is even: byte planes of the key in
+    // swizzled 32 KB blocks [n_tile][k_tile]
+    unsigned char *mma_blocks = nullptr;
+    u32 mma_n_tiles = 0;
 };
 
+int ksk_build_mma_layout(Ksk &k, cudaStream_t st);
+int key_switch_mma_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_out, size_t batch, u32 n, u32 k, u32 c_kn,
                           cudaStream_t st);

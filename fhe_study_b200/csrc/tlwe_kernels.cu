@@ -8,6 +8,8 @@
 #include "runtime.cuh"
 #include "tlwe.cuh"
 
+#include <stdlib.h>
+
 namespace fhe {
 
 // ---------------------------------------------------------------------------------------------------
@@ -65,6 +67,16 @@ key_switch_kernel(const u64 *__restrict__ ksk, const u64 *__restrict__ ct, u64 *
 }
 
 int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
+    // path selection: the tensor-core GEMM when its layout exists (l == 64) and the batch fills a few MMA rows;
+    // FHE_KS_PATH=cuda|mma forces one (used by the tests to cover both)
+    const char *force = getenv("FHE_KS_PATH");
+    const bool want_mma = k.mma_blocks != nullptr &&
+                          (force ? strcmp(force, "mma") == 0 : batch >= 16);
+    if (force && strcmp(force, "mma") == 0 && k.mma_blocks == nullptr) {
+        set_error("FHE_KS_PATH=mma but this key has no tensor-core layout (needs l == 64 and even kn_in)");
+        return -1;
+    }
+    if (want_mma) return key_switch_mma_device(k, ct, out, batch, st);
     const u32 w = (u32)k.kn_out + 1;
     dim3 grid((w + KS_TX - 1) / KS_TX, (unsigned)((batch + KS_BT - 1) / KS_BT));
     FHE_REQUIRE(grid.y <= 65535, "key switch: batch too large for one launch (max 65535*16)");

@@ -132,3 +132,31 @@ def test_blind_rotation_as_executed_and_as_written(fhe, orc):
         L.orc_blind_rotation_as_written(n, k, orc.ptr(np.ascontiguousarray(cts[b])), n * k, orc.ptr(bsk.reshape(-1)),
                                         orc.ptr(table), orc.ptr(want))
         assert (got[b] == want).all()
+
+
+@pytest.mark.parametrize("kn_in,kn_out,batch", [(100, 130, 150), (2, 1, 1), (64, 31, 129), (16, 16, 16)])
+def test_key_switch_tensor_core_and_cuda_core_paths(fhe, orc, kn_in, kn_out, batch, monkeypatch):
+    # l = 64: the byte-plane IMMA GEMM (ks_mma.cu) and the CUDA-core kernel must both equal the oracle
+    l = 64
+    ksk = orc.uniform(kn_in * 31 + kn_out, kn_in * l * (kn_out + 1))
+    ksk[: kn_out + 1] = 2**64 - 1
+    ct = orc.uniform(kn_in + 3, (batch, kn_in + 1))
+    ct[0, :] = 2**64 - 1  # every digit set: the largest plane sums
+    want = orc.key_switch(kn_in, kn_out, l, ksk, ct.reshape(-1), threads=8).reshape(batch, kn_out + 1)
+    K = fhe.Ksk(kn_in, kn_out, l, ksk)
+    for path in ("mma", "cuda"):
+        monkeypatch.setenv("FHE_KS_PATH", path)
+        assert (K.key_switch(ct) == want).all(), path
+    monkeypatch.delenv("FHE_KS_PATH")
+
+
+def test_key_switch_full_size_both_paths(fhe, orc, p5, monkeypatch):
+    kn = p5["kn"]
+    K = fhe.Ksk(kn, kn, 64, p5["ksk"])
+    ct = orc.uniform(4242, (200, kn + 1))
+    ct[7, :] = 2**64 - 1
+    want = orc.key_switch(kn, kn, 64, p5["ksk"], ct.reshape(-1), threads=8).reshape(200, kn + 1)
+    for path in ("mma", "cuda"):
+        monkeypatch.setenv("FHE_KS_PATH", path)
+        assert (K.key_switch(ct) == want).all(), path
+    monkeypatch.delenv("FHE_KS_PATH")

@@ -16,6 +16,29 @@ batch = int(sys.argv[4]) if len(sys.argv) > 4 else (1 << 26) // n
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 torch.cuda.set_device(0)
 fhe.use_torch_stream()
+if op in ("bootstrap", "extprod"):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    r = lambda *shape: torch.randint(-(2**63), 2**63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+    if op == "bootstrap":
+        kn = 1024
+        batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+        K = fhe.Ksk(kn, kn, 64, r(kn * 64 * (kn + 1)))
+        table, cts = r(2 * 1024), r(batch, kn + 1)
+        out = torch.empty_like(cts)
+        for _ in range(3):
+            fhe.bootstrap(1024, 1, K, table, cts, kn, out=out)
+    else:
+        n, k = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1024, 1)
+        batch = int(sys.argv[4]) if len(sys.argv) > 4 else 512
+        glwe = (k + 1) * n
+        G = fhe.Tggsw(n, k, r((k + 1) * 64 * glwe))
+        ct = r(batch, glwe)
+        out = torch.empty_like(ct)
+        for _ in range(3):
+            G.extprod(ct, out=out)
+    torch.cuda.synchronize()
+    print("done", op)
+    sys.exit(0)
 plan = fhe.NttPlan(q, n)
 a = torch.randint(0, min(q, 2**62), (batch, n), dtype=torch.int64, device="cuda")
 b = torch.randint(0, min(q, 2**62), (batch, n), dtype=torch.int64, device="cuda")
