@@ -1,5 +1,7 @@
 // lib_core.cu -- runtime state (errors, stream, launch counter) and the NTT-plan / Rq entry points of the
 // C ABI declared in include/fhe_b200.h.
+#include <stdlib.h>
+
 #include <atomic>
 #include <map>
 #include <memory>
@@ -30,13 +32,6 @@ int num_sms() {
     return sms[dev & 63];
 }
 
-int ntt_launch_lazy32(int, int, const NttParams<Lazy32> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int,
-                      cudaStream_t);
-int ntt_launch_lazy64(int, int, const NttParams<Lazy64> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int,
-                      cudaStream_t);
-int ntt_launch_strict64(int, int, const NttParams<Strict64> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int,
-                        cudaStream_t);
-
 }  // namespace fhe
 
 using namespace fhe;
@@ -47,7 +42,7 @@ std::map<std::tuple<int, u64, u64>, fhe_ntt_plan *> g_plans;
 
 template <class M> int upload_tables(fhe_ntt_plan *p, NttParams<M> &dst) {
     ExpandedTables<M> x;
-    expand_tables(p->host, x);
+    expand_tables(p->host, x, p->loge);
     const size_t bytes = sizeof(typename M::T) * p->host.n;
     FHE_CUDA_OK(cudaMalloc(&p->d_fwd, bytes));
     FHE_CUDA_OK(cudaMalloc(&p->d_inv, bytes));
@@ -58,6 +53,8 @@ template <class M> int upload_tables(fhe_ntt_plan *p, NttParams<M> &dst) {
     dst.inv = reinterpret_cast<const typename M::T *>(p->d_inv);
     dst.ninv = x.ninv;
     dst.s_ninv = x.s_ninv;
+    dst.ninv_pw = x.ninv_pw;
+    dst.s_ninv_pw = x.s_ninv_pw;
     for (u64 i = 0; i < 64; i++) {
         dst.c_fwd[i] = x.fwd[i < p->host.n ? i : 0];
         dst.c_inv[i] = x.inv[i < p->host.n ? i : 0];
@@ -79,16 +76,20 @@ int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 
     if ((rc = bc.init(c, bytes, false, true, st))) return rc;
     if ((rc = be.init(c_evals, bytes, false, true, st))) return rc;
     switch (plan->kind) {
+        case 3:
+            rc = ntt_launch_small32(plan->logn, plan->loge, mode, plan->psm, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
+                                    be.ptr<u64>(), batch, flags, st);
+            break;
         case 0:
-            rc = ntt_launch_lazy32(plan->logn, mode, plan->p32, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
+            rc = ntt_launch_lazy32(plan->logn, plan->loge, mode, plan->p32, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
                                    be.ptr<u64>(), batch, flags, st);
             break;
         case 1:
-            rc = ntt_launch_lazy64(plan->logn, mode, plan->p64, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
+            rc = ntt_launch_lazy64(plan->logn, plan->loge, mode, plan->p64, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
                                    be.ptr<u64>(), batch, flags, st);
             break;
         default:
-            rc = ntt_launch_strict64(plan->logn, mode, plan->ps64, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
+            rc = ntt_launch_strict64(plan->logn, plan->loge, mode, plan->ps64, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
                                      be.ptr<u64>(), batch, flags, st);
     }
     if (rc) return rc;
@@ -138,9 +139,20 @@ int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
     p->device = dev;
     p->kind = modulus_kind(q);
     p->logn = hp_ilog2(n);
-    FHE_REQUIRE(p->logn <= (p->kind == 0 ? 15 : 14),
+    FHE_REQUIRE(p->logn <= ((p->kind == 0 || p->kind == 3) ? 15 : 14),
                 "fhe_ntt_plan_create: n too large (max 2^15 for q < 2^30, 2^14 for larger q)");
+    // coefficients per thread: the library default, or FHE_NTT_LOGE (a tuning knob; only values that were
+    // instantiated are accepted)
+    p->loge = p->kind == 0 ? LogE<Lazy32>::of(p->logn) : p->kind == 3 ? LogE<Small32>::of(p->logn)
+              : p->kind == 1 ? LogE<Lazy64>::of(p->logn) : LogE<Strict64>::of(p->logn);
+    if (const char *e = getenv("FHE_NTT_LOGE")) {
+        const int v = atoi(e);
+        const bool ok = p->kind == 0 ? ntt_loge_ok_lazy32(p->logn, v) : p->kind == 3 ? ntt_loge_ok_small32(p->logn, v)
+                        : p->kind == 1 ? ntt_loge_ok_lazy64(p->logn, v) : ntt_loge_ok_strict64(p->logn, v);
+        if (ok) p->loge = v;
+    }
     int rc = p->kind == 0 ? upload_tables(p.get(), p->p32)
+             : p->kind == 3 ? upload_tables(p.get(), p->psm)
              : p->kind == 1 ? upload_tables(p.get(), p->p64)
                             : upload_tables(p.get(), p->ps64);
     if (rc) return rc;

@@ -91,6 +91,12 @@ struct Lazy32 {
         r = csub(r, q2);
         return csub(r, q);
     }
+    // interface used by the polymul kernel (see Small32 for the non-trivial case)
+    static constexpr bool PW_SCALED = false;           // pw_mul returns the true product
+    FHE_HD u32 fwd_out(u32 x) const { return canon4(x); }   // forward output -> pointwise operand
+    FHE_HD u32 fwd_canon(u32 x) const { return canon4(x); } // forward output -> canonical NTT value
+    FHE_HD u32 pw_mul(u32 a, u32 b) const { return mul(a, b); }
+    FHE_HD u32 pw_evals(u32 t) const { return t; }
     FHE_HD static u32 load(u64 v) { return (u32)v; }
     FHE_HD static u64 store(u32 v) { return (u64)v; }
 };
@@ -135,6 +141,11 @@ struct Lazy64 {
         return csub(t, q);
     }
     FHE_HD u64 mul(u64 a, u64 b) const { return mont(mont(a, b), r2); }
+    static constexpr bool PW_SCALED = false;
+    FHE_HD u64 fwd_out(u64 x) const { return canon4(x); }
+    FHE_HD u64 fwd_canon(u64 x) const { return canon4(x); }
+    FHE_HD u64 pw_mul(u64 a, u64 b) const { return mul(a, b); }
+    FHE_HD u64 pw_evals(u64 t) const { return t; }
     FHE_HD static u64 load(u64 v) { return v; }
     FHE_HD static u64 store(u64 v) { return v; }
 };
@@ -182,8 +193,64 @@ struct Strict64 {
         return t >= q ? t - q : t;
     }
     FHE_HD u64 mul(u64 a, u64 b) const { return mont(mont(a, b), r2); }
+    static constexpr bool PW_SCALED = false;
+    FHE_HD u64 fwd_out(u64 x) const { return canon4(x); }
+    FHE_HD u64 fwd_canon(u64 x) const { return canon4(x); }
+    FHE_HD u64 pw_mul(u64 a, u64 b) const { return mul(a, b); }
+    FHE_HD u64 pw_evals(u64 t) const { return t; }
     FHE_HD static u64 load(u64 v) { return v; }
     FHE_HD static u64 store(u64 v) { return v; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Small32: q < 2^22 (the reference's only NTT modulus, 65537, lives here).  With so much headroom in a
+// 32-bit word the forward butterfly needs no conditional subtraction at all: x' = x + V, y' = x - V + 2q
+// grows by at most 2q per stage, so after LOGN <= 15 stages values stay below 31q < 2^27.  The pointwise
+// product of two such lazy values (a*b < 961 q^2 < q*2^32) is one Montgomery reduction, whose 2^-32 factor
+// is folded into the n^-1 constants of the inverse transform (ninv_pw / s_ninv_pw in the plan).
+// ---------------------------------------------------------------------------------------------------
+struct Small32 {
+    typedef u32 W;
+    typedef Tw32 T;
+    u32 q, q2;
+    u32 qinv_neg;  // -q^-1 mod 2^32
+    Tw32 one;      // w = 1           : mul_tw(x, one) = x mod q in [0,2q) for any 32-bit x
+    Tw32 r;        // w = 2^32 mod q  : undoes the Montgomery factor
+    static constexpr bool PW_SCALED = true;
+
+    FHE_HD u32 mul_tw(u32 y, T t) const { return y * t.w - mulhi_u32(y, t.wp) * q; }
+    FHE_HD u32 csub(u32 x, u32 m) const { return umin(x, x - m); }
+    FHE_HD void fwd(u32 &x, u32 &y, T t) const {
+        u32 V = mul_tw(y, t);
+        y = x - V + q2;
+        x = x + V;
+    }
+    FHE_HD void inv(u32 &x, u32 &y, T t) const {
+        u32 s = csub(x + y, q2);
+        u32 d = x - y + q2;
+        x = s;
+        y = mul_tw(d, t);
+    }
+    FHE_HD void inv_last(u32 &x, u32 &y, T ninv, T s_ninv) const {
+        u32 s = x + y;
+        u32 d = x - y + q2;
+        x = mul_tw(s, ninv);
+        y = mul_tw(d, s_ninv);
+    }
+    FHE_HD u32 canon2(u32 x) const { return csub(x, q); }
+    FHE_HD u32 fwd_out(u32 x) const { return x; }
+    FHE_HD u32 fwd_canon(u32 x) const { return csub(mul_tw(x, one), q); }
+    // a*b*2^-32 mod q in [0,2q); needs a*b < q*2^32
+    FHE_HD u32 pw_mul(u32 a, u32 b) const {
+        u64 p = (u64)a * b;
+        u32 lo = (u32)p, hi = (u32)(p >> 32);
+        u32 m = lo * qinv_neg;
+        return hi + mulhi_u32(m, q) + (lo != 0u ? 1u : 0u);
+    }
+    FHE_HD u32 pw_evals(u32 t) const { return csub(mul_tw(t, r), q); }
+    FHE_HD u32 mul(u32 a, u32 b) const { return pw_evals(pw_mul(a, b)); }  // canonical a*b (a*b < q*2^32)
+    FHE_HD static u32 load(u64 v) { return (u32)v; }
+    FHE_HD static u64 store(u32 v) { return (u64)v; }
 };
 
 }  // namespace fhe

@@ -19,6 +19,7 @@ template <class M> struct NttParams {
     const typename M::T *inv;   // n entries: roots_inv[i] = roots[i]^-1        (arith/src/ntt.rs:149-161)
     typename M::T ninv;         // n^-1                                        (arith/src/ntt.rs:27-30)
     typename M::T s_ninv;       // roots_inv[1] * n^-1
+    typename M::T ninv_pw, s_ninv_pw;  // same, times the scale factor M::pw_mul leaves behind (polymul only)
     typename M::T c_fwd[64], c_inv[64];
 };
 
@@ -110,7 +111,7 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
         load_poly<M, LOGN, LOGE, 0>(x, a + off, valid, sm, tid);
         fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, tw);
 #pragma unroll
-        for (int e = 0; e < S::E; e++) x[e] = m.canon4(x[e]);
+        for (int e = 0; e < S::E; e++) x[e] = m.fwd_canon(x[e]);
         store_poly<M, LOGN, LOGE, LAST>(x, c + off, valid, sm, tid);
     } else if constexpr (MODE == MODE_INV) {
         const TwSrc<M> tw = {P.c_inv, P.inv};
@@ -123,30 +124,32 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
         const TwSrc<M> twf = {P.c_fwd, P.fwd};
         const TwSrc<M> twi = {P.c_inv, P.inv};
         W A[S::E];
-        if (flags & A_IS_EVALS) {
-            load_poly<M, LOGN, LOGE, LAST>(A, a + off, valid, sm, tid);
-        } else {
-            load_poly<M, LOGN, LOGE, 0>(A, a + off, valid, sm, tid);
-            fwd_chain<M, LOGN, LOGE>(A, sm, tid, m, twf);
+        // both operands run through ONE copy of the forward-transform code (the fully unrolled transform is
+        // the bulk of the kernel's instruction footprint; see profiles/: no_instruction stalls)
+#pragma unroll 1
+        for (int op = 0; op < 2; op++) {
+            const u64 *src = (op == 0 ? a : b) + off;
+            if (flags & (op == 0 ? A_IS_EVALS : B_IS_EVALS)) {
+                load_poly<M, LOGN, LOGE, LAST>(x, src, valid, sm, tid);
+            } else {
+                load_poly<M, LOGN, LOGE, 0>(x, src, valid, sm, tid);
+                fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
 #pragma unroll
-            for (int e = 0; e < S::E; e++) A[e] = m.canon4(A[e]);
+                for (int e = 0; e < S::E; e++) x[e] = m.fwd_out(x[e]);
+            }
+            if (op == 0) {
+#pragma unroll
+                for (int e = 0; e < S::E; e++) A[e] = x[e];
+            }
         }
-        if (flags & B_IS_EVALS) {
-            load_poly<M, LOGN, LOGE, LAST>(x, b + off, valid, sm, tid);
-        } else {
-            load_poly<M, LOGN, LOGE, 0>(x, b + off, valid, sm, tid);
-            fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
 #pragma unroll
-            for (int e = 0; e < S::E; e++) x[e] = m.canon4(x[e]);
-        }
-#pragma unroll
-        for (int e = 0; e < S::E; e++) x[e] = m.mul(A[e], x[e]);
+        for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(A[e], x[e]);
         if (c_evals != nullptr) {  // ring_nq.rs:606 -- the product keeps its evals
 #pragma unroll
-            for (int e = 0; e < S::E; e++) A[e] = x[e];
+            for (int e = 0; e < S::E; e++) A[e] = m.pw_evals(x[e]);
             store_poly<M, LOGN, LOGE, LAST>(A, c_evals + off, valid, sm, tid);
         }
-        inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, twi, P.ninv, P.s_ninv);
+        inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, twi, P.ninv_pw, P.s_ninv_pw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
         store_poly<M, LOGN, LOGE, 0>(x, c + off, valid, sm, tid);
@@ -175,10 +178,9 @@ int launch_one(const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c
     return 0;
 }
 
-template <class M, int LOGN>
-int launch_logn(int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
-                int flags, cudaStream_t st) {
-    constexpr int LE = LogE<M>::of(LOGN);
+template <class M, int LOGN, int LE>
+int launch_modes(int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
+                 int flags, cudaStream_t st) {
     switch (mode) {
         case MODE_FWD: return launch_one<M, LOGN, LE, MODE_FWD>(P, a, b, c, c_evals, batch, flags, st);
         case MODE_INV: return launch_one<M, LOGN, LE, MODE_INV>(P, a, b, c, c_evals, batch, flags, st);
@@ -186,8 +188,29 @@ int launch_logn(int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64
     }
 }
 
+// `loge` must be a value ntt_loge_supported() accepts for (M, logn): the default LogE<M>::of(logn), or, for
+// the tunable degrees, one of the alternatives instantiated below.
+template <class M, int LOGN>
+int launch_logn(int loge, int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals,
+                size_t batch, int flags, cudaStream_t st) {
+    constexpr int DEF = LogE<M>::of(LOGN);
+    if constexpr (LOGN >= 10 && LOGN <= 12 && sizeof(typename M::W) == 4) {
+        if (loge == 3) return launch_modes<M, LOGN, 3>(mode, P, a, b, c, c_evals, batch, flags, st);
+        if (loge == 4) return launch_modes<M, LOGN, 4>(mode, P, a, b, c, c_evals, batch, flags, st);
+    }
+    if (loge != DEF) {
+        set_error("internal: unsupported coefficients-per-thread setting");
+        return -1;
+    }
+    return launch_modes<M, LOGN, DEF>(mode, P, a, b, c, c_evals, batch, flags, st);
+}
+template <class M> bool ntt_loge_supported(int logn, int loge) {
+    if (loge == LogE<M>::of(logn)) return true;
+    return sizeof(typename M::W) == 4 && logn >= 10 && logn <= 12 && (loge == 3 || loge == 4);
+}
+
 template <class M>
-int launch_ntt(int logn, int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals,
+int launch_ntt(int logn, int loge, int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals,
                size_t batch, int flags, cudaStream_t st) {
     constexpr int MAXLOGN = sizeof(typename M::W) == 4 ? 15 : 14;  // one CTA's shared memory holds the polynomial
     if (logn < 1 || logn > MAXLOGN) {
@@ -195,13 +218,13 @@ int launch_ntt(int logn, int mode, const NttParams<M> &P, const u64 *a, const u6
         return -1;
     }
     switch (logn) {
-#define FHE_CASE(L) case L: return launch_logn<M, L>(mode, P, a, b, c, c_evals, batch, flags, st);
+#define FHE_CASE(L) case L: return launch_logn<M, L>(loge, mode, P, a, b, c, c_evals, batch, flags, st);
         FHE_CASE(1) FHE_CASE(2) FHE_CASE(3) FHE_CASE(4) FHE_CASE(5) FHE_CASE(6) FHE_CASE(7) FHE_CASE(8)
         FHE_CASE(9) FHE_CASE(10) FHE_CASE(11) FHE_CASE(12) FHE_CASE(13) FHE_CASE(14)
 #undef FHE_CASE
         case 15:
             if constexpr (sizeof(typename M::W) == 4)
-                return launch_logn<M, 15>(mode, P, a, b, c, c_evals, batch, flags, st);
+                return launch_logn<M, 15>(loge, mode, P, a, b, c, c_evals, batch, flags, st);
     }
     set_error("unsupported ring degree");
     return -1;

@@ -123,13 +123,27 @@ inline void init_mod(Strict64 &m, u64 q) {
     m.r2 = hp_mulmod(r, r, q);
 }
 
-// 0: Lazy32 (q < 2^30), 1: Lazy64 (q < 2^62), 2: Strict64 (q < 2^63)
-inline int modulus_kind(u64 q) { return q < (1ull << 30) ? 0 : q < (1ull << 62) ? 1 : 2; }
+inline u32 neg_inv32(u32 q) {
+    u32 x = q;
+    for (int i = 0; i < 5; i++) x *= 2 - q * x;
+    return (u32)0 - x;
+}
+inline void init_mod(Small32 &m, u64 q) {
+    m.q = (u32)q;
+    m.q2 = (u32)(2 * q);
+    m.qinv_neg = neg_inv32((u32)q);
+    m.one = make_tw((u32)1, (u32)q, (Tw32 *)nullptr);
+    m.r = make_tw((u32)((1ull << 32) % q), (u32)q, (Tw32 *)nullptr);
+}
+
+// 3: Small32 (q < 2^22), 0: Lazy32 (q < 2^30), 1: Lazy64 (q < 2^62), 2: Strict64 (q < 2^63)
+inline int modulus_kind(u64 q) { return q < (1ull << 22) ? 3 : q < (1ull << 30) ? 0 : q < (1ull << 62) ? 1 : 2; }
 
 // Shoup-expanded tables for policy M.
 template <class M> struct ExpandedTables {
     std::vector<typename M::T> fwd, inv;
-    typename M::T ninv, s_ninv;
+    typename M::T ninv, s_ninv;        // standalone inverse transform
+    typename M::T ninv_pw, s_ninv_pw;  // inverse transform after M::pw_mul (absorbs its 2^-wordbits factor)
     M mod;
 };
 // loge <= 0 selects the library's policy LogE<M>; tables are stored in device order (ntt_core.cuh: tw_slot).
@@ -149,6 +163,11 @@ template <class M> void expand_tables(const HostTables &t, ExpandedTables<M> &x,
     }
     x.ninv = make_tw((W)t.n_inv, (W)t.q, (T *)nullptr);
     x.s_ninv = make_tw((W)hp_mulmod(t.roots_inv[1], t.n_inv, t.q), (W)t.q, (T *)nullptr);
+    u64 comp = 1;
+    if (M::PW_SCALED) comp = (u64)((((u128_t)1) << (8 * sizeof(W))) % t.q);
+    const u64 ninv_pw = hp_mulmod(t.n_inv, comp, t.q);
+    x.ninv_pw = make_tw((W)ninv_pw, (W)t.q, (T *)nullptr);
+    x.s_ninv_pw = make_tw((W)hp_mulmod(t.roots_inv[1], ninv_pw, t.q), (W)t.q, (T *)nullptr);
 }
 
 }  // namespace fhe

@@ -20,8 +20,6 @@
 
 namespace fhe {
 
-int ntt_launch_lazy32(int, int, const NttParams<Lazy32> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int,
-                      cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------------
 // elementwise torus kernels
@@ -180,7 +178,7 @@ TorusCtx::~TorusCtx() {
 // forward / inverse NTT of `polys` device polynomials under prime index r (0: p1, 1: p2)
 int TorusCtx::ntt(int r, int mode, const u64 *in, u64 *out, size_t polys, cudaStream_t st) const {
     const NttParams<Lazy32> &P = *reinterpret_cast<const NttParams<Lazy32> *>(plan_params32(r == 0 ? plan1 : plan2));
-    int rc = ntt_launch_lazy32(logn, mode, P, in, nullptr, out, nullptr, polys, 0, st);
+    int rc = ntt_launch_lazy32(logn, (r == 0 ? plan1 : plan2)->loge, mode, P, in, nullptr, out, nullptr, polys, 0, st);
     if (!rc) count_launch(1);
     return rc;
 }

@@ -171,7 +171,7 @@ API u64 orc_ntt_tables(u64 q, u64 n, u64 *roots, u64 *roots_inv) {
 
 /* plan cache (the reference's CACHE, arith/src/ntt.rs:18-38) -- single-threaded test infra, tiny */
 typedef struct { u64 q, n, n_inv; u64 *roots, *roots_inv; } orc_plan;
-static orc_plan g_plans[64];
+static orc_plan g_plans[4096];
 static int g_nplans = 0;
 static const orc_plan *get_plan(u64 q, u64 n) {
     const orc_plan *found = NULL;
@@ -179,7 +179,7 @@ static const orc_plan *get_plan(u64 q, u64 n) {
     {
         for (int i = 0; i < g_nplans; i++)
             if (g_plans[i].q == q && g_plans[i].n == n) found = &g_plans[i];
-        if (!found && g_nplans < 64) {
+        if (!found && g_nplans < 4096) {
             orc_plan *p = &g_plans[g_nplans];
             p->q = q; p->n = n;
             p->roots = (u64 *)malloc(sizeof(u64) * n);

@@ -50,7 +50,8 @@ template <class M, int LOGN, int LOGE> struct Emu {
             inv_from<PASS - 1>(m, tw, ninv, s_ninv);
         }
     }
-    void canon4(const M &m) { for (auto &v : regs) v = m.canon4(v); }
+    void fwd_canon(const M &m) { for (auto &v : regs) v = m.fwd_canon(v); }
+    void fwd_out(const M &m) { for (auto &v : regs) v = m.fwd_out(v); }
     void canon2(const M &m) { for (auto &v : regs) v = m.canon2(v); }
 };
 
@@ -64,7 +65,7 @@ static void run(int mode, const ExpandedTables<M> &x, const u64 *a, const u64 *b
     if (mode == 0) {
         A.load(a, 0);
         A.template fwd_from<0>(x.mod, twf);
-        A.canon4(x.mod);
+        A.fwd_canon(x.mod);
         A.store(c, LAST);
     } else if (mode == 1) {
         A.load(a, LAST);
@@ -74,12 +75,15 @@ static void run(int mode, const ExpandedTables<M> &x, const u64 *a, const u64 *b
     } else {
         Emu<M, LOGN, LOGE> B;
         if (flags & 1) A.load(a, LAST);
-        else { A.load(a, 0); A.template fwd_from<0>(x.mod, twf); A.canon4(x.mod); }
+        else { A.load(a, 0); A.template fwd_from<0>(x.mod, twf); A.fwd_out(x.mod); }
         if (flags & 2) B.load(b, LAST);
-        else { B.load(b, 0); B.template fwd_from<0>(x.mod, twf); B.canon4(x.mod); }
-        for (size_t i = 0; i < A.regs.size(); i++) B.regs[i] = x.mod.mul(A.regs[i], B.regs[i]);
-        if (c_evals) { A.regs = B.regs; A.store(c_evals, LAST); }
-        B.template inv_from<LAST>(x.mod, twi, x.ninv, x.s_ninv);
+        else { B.load(b, 0); B.template fwd_from<0>(x.mod, twf); B.fwd_out(x.mod); }
+        for (size_t i = 0; i < A.regs.size(); i++) B.regs[i] = x.mod.pw_mul(A.regs[i], B.regs[i]);
+        if (c_evals) {
+            for (size_t i = 0; i < A.regs.size(); i++) A.regs[i] = x.mod.pw_evals(B.regs[i]);
+            A.store(c_evals, LAST);
+        }
+        B.template inv_from<LAST>(x.mod, twi, x.ninv_pw, x.s_ninv_pw);
         B.canon2(x.mod);
         B.store(c, 0);
     }
@@ -113,12 +117,13 @@ static int emu_any(u64 q, u64 n, int loge, int mode, const u64 *a, const u64 *b,
 }
 
 extern "C" {
-// kind: -1 auto (as the library picks), 0 Lazy32, 1 Lazy64, 2 Strict64 ; mode 0 fwd, 1 inv, 2 mul
+// kind: -1 auto (as the library picks), 0 Lazy32, 1 Lazy64, 2 Strict64, 3 Small32 ; mode 0 fwd, 1 inv, 2 mul
 int emu_ntt(int kind, uint64_t q, uint64_t n, int loge, int mode, const uint64_t *a, const uint64_t *b, uint64_t *c,
             uint64_t *c_evals, int flags) {
     if (kind < 0) kind = modulus_kind(q);
     if (kind == 0) return q < (1ull << 30) ? emu_any<Lazy32>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
     if (kind == 1) return q < (1ull << 62) ? emu_any<Lazy64>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
+    if (kind == 3) return q < (1ull << 22) ? emu_any<Small32>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
     return emu_any<Strict64>(q, n, loge, mode, a, b, c, c_evals, flags);
 }
 int emu_plan(uint64_t q, uint64_t n, uint64_t *psi, uint64_t *n_inv, uint64_t *roots, uint64_t *roots_inv) {
@@ -134,6 +139,7 @@ int emu_plan(uint64_t q, uint64_t n, uint64_t *psi, uint64_t *n_inv, uint64_t *r
 uint64_t emu_modmul(int kind, uint64_t q, uint64_t a, uint64_t b) {
     if (kind == 0) { Lazy32 m; init_mod(m, q); return m.mul((u32)a, (u32)b); }
     if (kind == 1) { Lazy64 m; init_mod(m, q); return m.mul(a, b); }
+    if (kind == 3) { Small32 m; init_mod(m, q); return m.mul((u32)a, (u32)b); }
     Strict64 m; init_mod(m, q); return m.mul(a, b);
 }
 }

@@ -4,7 +4,7 @@ GPU runs.  The real kernels are checked in test_gpu_ntt.py."""
 import numpy as np
 import pytest
 
-from primes import Q17, Q30, Q62, Q63
+from primes import Q17, Q22, Q30, Q62, Q63
 
 
 @pytest.fixture(scope="module")
@@ -41,6 +41,16 @@ def test_lazy32_all_sizes(emu, orc, logn):
     _check(emu, orc, 0, Q30, n, 0)
 
 
+@pytest.mark.parametrize("logn", range(1, 16))
+def test_small32_all_sizes(emu, orc, logn):
+    # q < 2^22: csub-free forward butterflies, Montgomery pointwise with the factor folded into n^-1
+    n = 1 << logn
+    for loge in (0, 3, 4):
+        _check(emu, orc, 3, Q17, n, loge)
+    _check(emu, orc, 3, Q22, n, 0)
+    _check(emu, orc, -1, Q17, n, 0)  # the policy the library picks for the reference's modulus
+
+
 @pytest.mark.parametrize("logn", range(1, 15))
 def test_64bit_policies_all_sizes(emu, orc, logn):
     n = 1 << logn
@@ -68,7 +78,7 @@ def test_plan_matches_oracle_tables(emu, orc):
 
 def test_modmul_policies(emu):
     rng = np.random.default_rng(5)
-    for kind, q in [(0, Q17), (0, Q30), (0, 7), (0, 17), (1, Q62), (1, Q17), (2, Q63), (2, Q62)]:
+    for kind, q in [(0, Q17), (0, Q30), (0, 7), (0, 17), (1, Q62), (1, Q17), (2, Q63), (2, Q62), (3, Q17), (3, Q22), (3, 17)]:
         cases = [(q - 1, q - 1), (0, q - 1), (1, q - 1), (q - 1, 1), (0, 0)]
         cases += [(int(x), int(y)) for x, y in zip(rng.integers(0, q, 5000, dtype=np.uint64), rng.integers(0, q, 5000, dtype=np.uint64))]
         for a, b in cases:
