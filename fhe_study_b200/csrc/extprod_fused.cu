@@ -1,0 +1,233 @@
+// extprod_fused.cu -- fused TGGSW x TGLWE external product / CMux (tfhe/src/tggsw.rs:39-62): one CTA per
+// accumulator, ONE HBM round trip (read the TGLWE, write the TGLWE); decompose -> NTT -> MAC -> INTT -> CRT
+// all stay on chip.  Same exact arithmetic as the unfused path in torus_kernels.cu (two NTT primes, TGGSW
+// rows as two 32-bit limbs transformed once at load, centred CRT lift, recombination mod 2^64).
+//
+// Per CTA (256 threads), for each prime r in {p1, p2}:
+//   rounds of SLOTS = 256/T concurrent digit NTTs (T = N/32 threads, 32 coefficients per thread in registers):
+//     - slot s builds the bit polynomial of digit d = (i, j): bit 63-j of x_i (Tn::decompose, torus.rs:43-52),
+//       runs the register-blocked forward NTT (csub-free butterflies: primes < 2^27 leave the headroom) and
+//       leaves NTT(digit) in its shared-memory slot, reduced to [0, 2p);
+//     - all threads then MAC the round's digits against the resident TGGSW: thread t owns the items
+//       I = t + 256 m of the (component, limb, position) space; 64-bit accumulators in registers
+//       (products < 2^55, at most (k+1)*64 <= 512 of them), one IMAD.WIDE per MAC, 128-bit key loads;
+//   then 2(k+1) inverse NTTs and the residues go to shared memory; after both primes the CRT lift, the
+//   recombination lo + (hi << 32) and the CMux addend produce the output coefficients.
+#include "../../include/fhe_b200.h"
+#include "ntt_kernels.cuh"
+#include "runtime.cuh"
+#include "torus.cuh"
+
+namespace fhe {
+
+template <int LOGN, int K1> struct XpGeom {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int LOGE = LOGN < 5 ? LOGN : 5;
+    typedef NttShape<LOGN, LOGE> S;
+    static constexpr int CT = 256;
+    static constexpr int SLOTS = CT / S::T;             // concurrent NTTs
+    static constexpr int ND = K1 * 64;                  // digit polynomials per accumulator
+    static constexpr int ROUNDS = (ND + SLOTS - 1) / SLOTS;
+    static constexpr int PADN = N + (N >> 5);
+    static constexpr int UNITS = K1 * 2;                // (component, limb)
+    static constexpr int ITEMS = UNITS * N;
+    static constexpr int IPT = (ITEMS + CT - 1) / CT;   // MAC items per thread
+    static constexpr int IPT4 = (IPT + 3) / 4 * 4;      // padded to whole uint4 loads
+    static constexpr size_t SMEM = (size_t)K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)2 * UNITS * N * 4;
+    static_assert(UNITS <= SLOTS, "need a slot per inverse transform");
+    static_assert(S::T <= 32, "one digit NTT must fit a warp (N <= 1024) in this kernel");
+};
+
+struct XpParams {
+    NttParams<Lazy32> P[2];   // plans of p1, p2 (device-order tables, n^-1 constants)
+    Small32 ms[2];            // same moduli, csub-free forward butterflies
+    u64 mu[2];                // floor(2^64 / p_r): Barrett constant for the 64-bit accumulators
+    const u32 *R[2];          // fused key layout: R[r][d][t*IPT4 + m] = NTT value of item t + 256 m of digit d
+    CrtParams cp;
+};
+
+// acc mod p for acc < 2^63 (result canonical)
+__device__ __forceinline__ u32 reduce64(u64 acc, u32 p, u64 mu) {
+    const u64 qh = __umul64hi(acc, mu);
+    u64 r = acc - qh * p;  // in [0, 2p)
+    return (u32)(r >= p ? r - p : r);
+}
+
+template <int LOGN, int K1>
+__global__ void __launch_bounds__(256, 2)
+extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__ ct1, const u64 *__restrict__ ct2,
+                     u64 *__restrict__ out, int cmux) {
+    typedef XpGeom<LOGN, K1> G;
+    typedef typename G::S S;
+    constexpr int LOGE = G::LOGE, N = G::N, LAST = S::P - 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *xin = reinterpret_cast<u64 *>(smem_raw);                         // [K1][N] decomposed input
+    u32 *xch = reinterpret_cast<u32 *>(xin + (size_t)K1 * N);             // [SLOTS][PADN] exchange / NTT(digit)
+    u32 *res = xch + (size_t)G::SLOTS * G::PADN;                          // [2][UNITS][N] residues of the result
+    const int t = threadIdx.x;
+    const int slot = t / S::T, tid = t % S::T;
+    u32 *sm = xch + (size_t)slot * G::PADN;
+    const size_t base = (size_t)blockIdx.x * K1 * N;
+
+    // input of the external product: ct (extprod) or ct2 - ct1 (TGGSW::cmux, tggsw.rs:39-41)
+    for (int i = t; i < K1 * N; i += G::CT) xin[i] = cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
+    __syncthreads();
+
+#pragma unroll 1
+    for (int r = 0; r < 2; r++) {
+        const Small32 &ms = X.ms[r];
+        const Lazy32 &ml = X.P[r].mod;
+        const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
+        u64 acc[G::IPT];
+#pragma unroll
+        for (int m = 0; m < G::IPT; m++) acc[m] = 0;
+#pragma unroll 1
+        for (int round = 0; round < G::ROUNDS; round++) {
+            const int d = round * G::SLOTS + slot;
+            if (d < G::ND) {
+                const u64 *xi = xin + (size_t)(d >> 6) * N;
+                const int sh = 63 - (d & 63);
+                u32 x[S::E];
+#pragma unroll
+                for (int e = 0; e < S::E; e++) x[e] = (u32)(xi[S::pos(0, tid, e)] >> sh) & 1u;
+                fwd_chain<Small32, LOGN, LOGE>(x, sm, tid, ms, twf);
+#pragma unroll
+                for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = ms.mul_tw(x[e], ms.one);  // [0,2p)
+            }
+            __syncthreads();
+            const int nslots = min(G::SLOTS, G::ND - round * G::SLOTS);
+            const uint4 *Rt = reinterpret_cast<const uint4 *>(X.R[r] + ((size_t)round * G::SLOTS * G::CT + t) * G::IPT4);
+#pragma unroll 2
+            for (int s = 0; s < nslots; s++) {
+                const u32 *D = xch + (size_t)s * G::PADN;
+                u32 rv[G::IPT4];
+#pragma unroll
+                for (int v = 0; v < G::IPT4 / 4; v++) {
+                    const uint4 q4 = __ldg(Rt + (size_t)s * G::CT * (G::IPT4 / 4) + v);
+                    rv[4 * v] = q4.x; rv[4 * v + 1] = q4.y; rv[4 * v + 2] = q4.z; rv[4 * v + 3] = q4.w;
+                }
+#pragma unroll
+                for (int m = 0; m < G::IPT; m++) {
+                    const int item = t + G::CT * m;
+                    const u32 dv = D[pad_idx(item & (N - 1))];
+                    acc[m] += (u64)dv * rv[m];  // item >= ITEMS only when ITEMS % 256 != 0: key padding is zero
+                }
+            }
+            __syncthreads();
+        }
+        // accumulators -> inverse-transform inputs (slot u, padded position order)
+#pragma unroll
+        for (int m = 0; m < G::IPT; m++) {
+            const int item = t + G::CT * m;
+            if (item < G::ITEMS) xch[(size_t)(item >> LOGN) * G::PADN + pad_idx(item & (N - 1))] = reduce64(acc[m], ml.q, X.mu[r]);
+        }
+        __syncthreads();
+        // warp-uniform condition: every lane of a warp that owns at least one live slot runs the transform
+        // (the exchanges inside synchronise whole warps); lanes of dead slots compute on scratch and store nothing
+        if ((t & ~31) / S::T < G::UNITS) {
+            const TwSrc<Lazy32> twi = {X.P[r].c_inv, X.P[r].inv};
+            u32 x[S::E];
+#pragma unroll
+            for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(LAST, tid, e))];
+            inv_chain<Lazy32, LOGN, LOGE, LAST>(x, sm, tid, ml, twi, X.P[r].ninv, X.P[r].s_ninv);
+            if (slot < G::UNITS) {
+                u32 *R = res + ((size_t)r * G::UNITS + slot) * N;
+#pragma unroll
+                for (int e = 0; e < S::E; e++) R[S::pos(0, tid, e)] = ml.canon2(x[e]);
+            }
+        }
+        __syncthreads();
+    }
+    // CRT lift, recombination, addend
+    const u32 *res1 = res, *res2 = res + (size_t)G::UNITS * N;
+    for (int i = t; i < K1 * N; i += G::CT) {
+        const int c = i >> LOGN, p = i & (N - 1);
+        const u64 lo = crt_centered(res1[(c * 2) * N + p], res2[(c * 2) * N + p], X.cp.p1, X.cp.p2, X.cp.p1_inv_mod_p2, X.cp.P,
+                                    X.cp.halfP, X.cp.m2);
+        const u64 hi = crt_centered(res1[(c * 2 + 1) * N + p], res2[(c * 2 + 1) * N + p], X.cp.p1, X.cp.p2,
+                                    X.cp.p1_inv_mod_p2, X.cp.P, X.cp.halfP, X.cp.m2);
+        out[base + i] = (cmux ? ct1[base + i] : 0) + lo + (hi << 32);
+    }
+}
+
+// unfused key layout (u64, [d][u][x]) -> fused layout (u32, [d][t][IPT4], item = t + 256 m), zero padded
+__global__ void tggsw_fused_layout_kernel(const u64 *__restrict__ R, u32 *__restrict__ Rf, int nd, int items, int ipt4) {
+    const size_t total = (size_t)nd * 256 * ipt4;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(idx % ipt4), t = (int)((idx / ipt4) % 256), d = (int)(idx / ((size_t)ipt4 * 256));
+        const int item = t + 256 * m;
+        Rf[idx] = item < items ? (u32)R[(size_t)d * items + item] : 0u;
+    }
+}
+
+template <int LOGN, int K1>
+static int launch_fused(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, int cmux, cudaStream_t st) {
+    typedef XpGeom<LOGN, K1> G;
+    const TorusCtx &tc = *g.tc;
+    XpParams X;
+    X.P[0] = tc.plan1->p32;
+    X.P[1] = tc.plan2->p32;
+    init_mod(X.ms[0], TORUS_P1);
+    init_mod(X.ms[1], TORUS_P2);
+    X.mu[0] = ~0ull / TORUS_P1;
+    X.mu[1] = ~0ull / TORUS_P2;
+    X.R[0] = g.R1f;
+    X.R[1] = g.R2f;
+    X.cp = tc.cp;
+    auto kern = extprod_fused_kernel<LOGN, K1>;
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    FHE_CUDA_OK(cudaGetDevice(&dev));
+    if (!((done_mask >> (dev & 63)) & 1ull)) {
+        FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        done_mask |= 1ull << (dev & 63);
+    }
+    FHE_REQUIRE(batch <= 0x7fffffffull, "extprod: batch too large");
+    kern<<<(unsigned)batch, G::CT, G::SMEM, st>>>(X, ct1, ct2, out, cmux);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+#define FHE_XP_SHAPES(F) F(10, 2) F(9, 2) F(8, 2) F(6, 5) F(6, 2) F(7, 2) F(8, 3) F(9, 3)
+
+bool extprod_fused_supported(int logn, int k1) {
+#define F(L, K) if (logn == L && k1 == K) return true;
+    FHE_XP_SHAPES(F)
+#undef F
+    return false;
+}
+static int fused_ipt4(int logn, int k1) {
+    const int items = k1 * 2 * (1 << logn), ipt = (items + 255) / 256;
+    return (ipt + 3) / 4 * 4;
+}
+
+// builds the fused key layout from the unfused one (called once at load when the shape is supported)
+int tggsw_build_fused_layout(Tggsw &g, cudaStream_t st) {
+    const int logn = g.tc->logn, k1 = (int)g.k + 1;
+    if (!extprod_fused_supported(logn, k1)) return 0;
+    const int nd = k1 * 64, items = k1 * 2 * (1 << logn), ipt4 = fused_ipt4(logn, k1);
+    const size_t words = (size_t)nd * 256 * ipt4;
+    FHE_CUDA_OK(cudaMalloc((void **)&g.R1f, words * sizeof(u32)));
+    FHE_CUDA_OK(cudaMalloc((void **)&g.R2f, words * sizeof(u32)));
+    size_t grid = (words + 255) / 256;
+    if (grid > (size_t)num_sms() * 32) grid = (size_t)num_sms() * 32;
+    tggsw_fused_layout_kernel<<<(unsigned)grid, 256, 0, st>>>(g.R1, g.R1f, nd, items, ipt4);
+    tggsw_fused_layout_kernel<<<(unsigned)grid, 256, 0, st>>>(g.R2, g.R2f, nd, items, ipt4);
+    count_launch(2);
+    FHE_CUDA_OK(cudaGetLastError());
+    FHE_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int extprod_fused_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, int cmux,
+                         cudaStream_t st) {
+    const int logn = g.tc->logn, k1 = (int)g.k + 1;
+#define F(L, K) if (logn == L && k1 == K) return launch_fused<L, K>(g, ct1, ct2, out, batch, cmux, st);
+    FHE_XP_SHAPES(F)
+#undef F
+    set_error("internal: fused external product called for an unsupported shape");
+    return -1;
+}
+
+}  // namespace fhe

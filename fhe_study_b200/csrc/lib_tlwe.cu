@@ -127,8 +127,7 @@ int fhe_blind_rotate(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, int as
             FHE_CUDA_OK(cudaMemcpy2DAsync(hs, 8, bc.ptr<u64>() + j, (c_kn + 1) * 8, 8, batch, cudaMemcpyDeviceToDevice, st));
             if ((rc = shift_right_device(hs, hs, batch, shift, st))) break;
             if ((rc = tn_left_rotate_device(bo.ptr<u64>(), rot, batch * (k + 1), (u32)n, hs, 0, (u32)(k + 1), st))) break;
-            if ((rc = tn_addsub_device(rot, bo.ptr<u64>(), rot, batch * glwe, 1, st))) break;  // ct2 - ct1
-            if ((rc = extprod_device(bsk[j]->g, rot, bo.ptr<u64>(), nxt, batch, st))) break;   // ct1 + bit (x) diff
+            if ((rc = extprod_device(bsk[j]->g, bo.ptr<u64>(), rot, nxt, batch, st))) break;  // cmux(bsk[j], acc, rot)
             FHE_CUDA_OK(cudaMemcpyAsync(bo.ptr<u64>(), nxt, batch * glwe * 8, cudaMemcpyDeviceToDevice, st));
         }
         cudaFreeAsync(rot, st);

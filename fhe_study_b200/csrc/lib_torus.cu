@@ -105,6 +105,8 @@ void fhe_tggsw_destroy(fhe_tggsw *h) {
     if (!h) return;
     cudaFree(h->g.R1);
     cudaFree(h->g.R2);
+    cudaFree(h->g.R1f);
+    cudaFree(h->g.R2f);
     delete h;
 }
 
@@ -120,16 +122,7 @@ static int extprod_entry(const fhe_tggsw *h, const uint64_t *ct1, const uint64_t
     if ((rc = b1.init(ct1, bytes, true, false, st))) return rc;
     if ((rc = b2.init(cmux ? ct2 : nullptr, bytes, true, false, st))) return rc;
     if ((rc = bo.init(out, bytes, false, true, st))) return rc;
-    if (!cmux) {
-        rc = extprod_device(h->g, b1.ptr<u64>(), nullptr, bo.ptr<u64>(), batch, st);
-    } else {
-        // TGGSW::cmux (tggsw.rs:39-41): ct1 + bit (x) (ct2 - ct1)
-        u64 *diff = nullptr;
-        FHE_CUDA_OK(cudaMallocAsync((void **)&diff, bytes, st));
-        rc = tn_addsub_device(b2.ptr<u64>(), b1.ptr<u64>(), diff, words, 1, st);
-        if (!rc) rc = extprod_device(h->g, diff, b1.ptr<u64>(), bo.ptr<u64>(), batch, st);
-        cudaFreeAsync(diff, st);
-    }
+    rc = extprod_device(h->g, b1.ptr<u64>(), cmux ? b2.ptr<u64>() : nullptr, bo.ptr<u64>(), batch, st);
     if (rc) return rc;
     return finish_all({&b1, &b2, &bo}, st);
 }

@@ -7,9 +7,10 @@
 
 namespace fhe {
 
-// Largest two primes below 2^30 with 2^16 | p-1 (so every ring degree up to 2^15 has a 2N-th root).
-static constexpr u64 TORUS_P1 = 0x3FFC0001ull;
-static constexpr u64 TORUS_P2 = 0x3FED0001ull;
+// Largest two primes below 2^27 with 2^16 | p-1 (every ring degree up to 2^15 has a 2N-th root; P = p1*p2 ~ 2^53.96).
+// Below 2^27 a forward NTT of up to 15 stages needs no conditional subtraction in 32-bit words (extprod_fused.cu).
+static constexpr u64 TORUS_P1 = 0x7E90001ull;
+static constexpr u64 TORUS_P2 = 0x7E00001ull;
 
 // centred CRT lift of (r1 mod p1, r2 mod p2) to the representative in (-P/2, P/2], as a wrapping u64
 FHE_HD u64 crt_centered(u32 r1, u32 r2, u32 p1, u32 p2, u32 p1_inv_mod_p2, u64 P, u64 halfP, const Lazy32 &m2) {
@@ -49,6 +50,7 @@ struct Tggsw {
     TorusCtx *tc = nullptr;
     u64 k = 0;
     u64 *R1 = nullptr, *R2 = nullptr;  // [(k+1)*64 rows][k+1 comps][2 limbs][n]
+    u32 *R1f = nullptr, *R2f = nullptr;  // fused-kernel layout (extprod_fused.cu), when the shape is instantiated
 };
 
 }  // namespace fhe
@@ -62,7 +64,11 @@ struct fhe_tggsw {
 namespace fhe {
 
 int tn_mul_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t batch, cudaStream_t st);
-int extprod_device(const Tggsw &g, const u64 *ct, const u64 *addend, u64 *out, size_t batch, cudaStream_t st);
+// out = g (x) ct1 (ct2 == nullptr)  or  ct1 + g (x) (ct2 - ct1)  (CMux)
+int extprod_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, cudaStream_t st);
+bool extprod_fused_supported(int logn, int k1);
+int tggsw_build_fused_layout(Tggsw &g, cudaStream_t st);
+int extprod_fused_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, int cmux, cudaStream_t st);
 int tggsw_precompute(Tggsw &g, const u64 *rows_dev, cudaStream_t st);
 int tn_addsub_device(const u64 *a, const u64 *b, u64 *c, size_t len, int op, cudaStream_t st);
 int tn_left_rotate_device(const u64 *a, u64 *out, size_t polys, u32 n, const u64 *hs, u64 h_const, u32 group,

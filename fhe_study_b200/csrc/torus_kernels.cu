@@ -18,6 +18,8 @@
 #include "runtime.cuh"
 #include "torus.cuh"
 
+#include <stdlib.h>
+
 namespace fhe {
 
 
@@ -215,22 +217,38 @@ int tn_mul_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t
     return rc;
 }
 
-// out = tggsw (x) ct  [+ addend]; `batch` TGLWE accumulators sharing one TGGSW; device pointers.
-int extprod_device(const Tggsw &g, const u64 *ct, const u64 *addend, u64 *out, size_t batch, cudaStream_t st) {
+// out = tggsw (x) ct1, or ct1 + tggsw (x) (ct2 - ct1) when ct2 != nullptr (TGGSW::cmux, tggsw.rs:39-41);
+// `batch` TGLWE accumulators sharing one TGGSW; device pointers.  Dispatches to the fused kernel when the
+// shape is instantiated (FHE_EXTPROD_PATH=fused|unfused forces a path; the tests cover both).
+int extprod_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, cudaStream_t st) {
+    const char *force = getenv("FHE_EXTPROD_PATH");
+    if (force && strcmp(force, "fused") == 0 && g.R1f == nullptr) {
+        set_error("FHE_EXTPROD_PATH=fused but this (n, k) has no fused instantiation");
+        return -1;
+    }
+    if (g.R1f != nullptr && !(force && strcmp(force, "unfused") == 0))
+        return extprod_fused_device(g, ct1, ct2, out, batch, ct2 != nullptr, st);
+
     const TorusCtx &tc = *g.tc;
     const u32 n = (u32)tc.n, k1 = (u32)g.k + 1;
     const size_t nd = (size_t)k1 * 64;                 // digit polynomials per accumulator
     const size_t chunk_max = std::max<size_t>(1, (512ull << 20) / (nd * n * sizeof(u64)));  // <= 512 MiB of planes
     const size_t chunk = std::min(batch, chunk_max);
-    u64 *planes = nullptr, *D = nullptr, *res = nullptr;
+    u64 *planes = nullptr, *D = nullptr, *res = nullptr, *diff = nullptr;
     FHE_CUDA_OK(cudaMallocAsync((void **)&planes, chunk * nd * n * sizeof(u64), st));
     FHE_CUDA_OK(cudaMallocAsync((void **)&D, chunk * nd * n * sizeof(u64), st));
     FHE_CUDA_OK(cudaMallocAsync((void **)&res, 2 * chunk * k1 * 2 * n * sizeof(u64), st));
+    if (ct2) FHE_CUDA_OK(cudaMallocAsync((void **)&diff, chunk * k1 * n * sizeof(u64), st));
     int rc = 0;
     for (size_t b0 = 0; b0 < batch && !rc; b0 += chunk) {
         const size_t nb = std::min(chunk, batch - b0);
         const size_t res_words = nb * k1 * 2 * n;
-        bitplanes_kernel<<<grid_for(nb * k1 * n), 256, 0, st>>>(ct + b0 * k1 * n, planes, nb * k1, n);
+        const u64 *in = ct1 + b0 * k1 * n;
+        if (ct2) {
+            if ((rc = tn_addsub_device(ct2 + b0 * k1 * n, ct1 + b0 * k1 * n, diff, nb * k1 * n, 1, st))) break;
+            in = diff;
+        }
+        bitplanes_kernel<<<grid_for(nb * k1 * n), 256, 0, st>>>(in, planes, nb * k1, n);
         count_launch(1);
         for (int r = 0; r < 2 && !rc; r++) {
             if ((rc = tc.ntt(r, MODE_FWD, planes, D, nb * nd, st))) break;
@@ -246,7 +264,7 @@ int extprod_device(const Tggsw &g, const u64 *ct, const u64 *addend, u64 *out, s
         cp.shift[0] = 0;
         cp.shift[1] = 32;
         crt_recombine_kernel<<<grid_for(nb * k1 * n), 256, 0, st>>>(res, res + chunk * k1 * 2 * n,
-                                                                   addend ? addend + b0 * k1 * n : nullptr,
+                                                                   ct2 ? ct1 + b0 * k1 * n : nullptr,
                                                                    out + b0 * k1 * n, nb * k1, n, cp);
         count_launch(1);
         if (cudaGetLastError() != cudaSuccess) { set_error("extprod kernel launch failed"); rc = -2; }
@@ -254,6 +272,7 @@ int extprod_device(const Tggsw &g, const u64 *ct, const u64 *addend, u64 *out, s
     cudaFreeAsync(planes, st);
     cudaFreeAsync(D, st);
     cudaFreeAsync(res, st);
+    if (diff) cudaFreeAsync(diff, st);
     return rc;
 }
 
@@ -272,7 +291,7 @@ int tggsw_precompute(Tggsw &g, const u64 *rows_dev, cudaStream_t st) {
         if (rc) return rc;
     }
     FHE_CUDA_OK(cudaStreamSynchronize(st));
-    return 0;
+    return tggsw_build_fused_layout(g, st);
 }
 
 int tn_addsub_device(const u64 *a, const u64 *b, u64 *c, size_t len, int op, cudaStream_t st) {

@@ -105,27 +105,44 @@ def test_external_product_reference_params(fhe, orc):
         assert (rec == expect).all()
 
 
-@pytest.mark.parametrize("n,k,batch", [(64, 4, 33), (1024, 1, 5), (256, 2, 7), (2048, 1, 2)])
-def test_external_product_and_cmux_dense_inputs(fhe, orc, n, k, batch):
-    # uniformly random TGGSW rows and accumulators: every digit and limb is exercised
+FUSED_SHAPES = {(64, 4), (1024, 1), (512, 1), (256, 1), (64, 1), (128, 1), (256, 2), (512, 2)}
+
+
+@pytest.mark.parametrize("n,k,batch", [(64, 4, 33), (1024, 1, 5), (256, 2, 7), (2048, 1, 2), (512, 1, 3), (128, 1, 9),
+                                       (64, 1, 40), (512, 2, 2), (256, 1, 4)])
+def test_external_product_and_cmux_dense_inputs(fhe, orc, n, k, batch, monkeypatch):
+    # uniformly random TGGSW rows and accumulators: every digit and limb is exercised; both the fused kernel
+    # (extprod_fused.cu) and the unfused building blocks must equal the oracle
     glwe = (k + 1) * n
     tggsw = orc.uniform(7 * n + k, (k + 1) * 64 * glwe)
     ct1 = orc.uniform(11 * n + k, (batch, glwe))
     ct2 = orc.uniform(13 * n + k, (batch, glwe))
     ct1[0, :] = M64 - 1
     g = fhe.Tggsw(n, k, tggsw)
-    assert (g.extprod(ct1).reshape(-1) == orc.extprod(n, k, tggsw, ct1.reshape(-1))).all()
-    assert (g.cmux(ct1, ct2).reshape(-1) == orc.cmux(n, k, tggsw, ct1.reshape(-1), ct2.reshape(-1))).all()
+    want_e = orc.extprod(n, k, tggsw, ct1.reshape(-1))
+    want_c = orc.cmux(n, k, tggsw, ct1.reshape(-1), ct2.reshape(-1))
+    for path in (["fused"] if (n, k) in FUSED_SHAPES else []) + ["unfused"]:
+        monkeypatch.setenv("FHE_EXTPROD_PATH", path)
+        assert (g.extprod(ct1).reshape(-1) == want_e).all(), path
+        assert (g.cmux(ct1, ct2).reshape(-1) == want_c).all(), path
+    monkeypatch.delenv("FHE_EXTPROD_PATH")
 
 
-def test_extprod_worst_case_bound(fhe, orc):
+def test_extprod_worst_case_bound(fhe, orc, monkeypatch):
     # all-ones rows and accumulators maximise the integer magnitude the two-prime lift has to carry
-    n, k = 1024, 1
-    glwe = (k + 1) * n
-    tggsw = np.full((k + 1) * 64 * glwe, M64 - 1, dtype=np.uint64)
-    ct = np.full((1, glwe), M64 - 1, dtype=np.uint64)
-    g = fhe.Tggsw(n, k, tggsw)
-    assert (g.extprod(ct).reshape(-1) == orc.extprod(n, k, tggsw, ct.reshape(-1))).all()
+    for n, k in ((1024, 1), (64, 4), (2048, 1)):
+        glwe = (k + 1) * n
+        tggsw = np.full((k + 1) * 64 * glwe, M64 - 1, dtype=np.uint64)
+        ct = np.full((1, glwe), M64 - 1, dtype=np.uint64)
+        g = fhe.Tggsw(n, k, tggsw)
+        want = orc.extprod(n, k, tggsw, ct.reshape(-1))
+        for path in (["fused"] if (n, k) in FUSED_SHAPES else []) + ["unfused"]:
+            monkeypatch.setenv("FHE_EXTPROD_PATH", path)
+            assert (g.extprod(ct).reshape(-1) == want).all(), (n, k, path)
+        monkeypatch.delenv("FHE_EXTPROD_PATH")
+    # the exactness bound of the lift is enforced at load: (k+1)*64*n*2^32 < P/2
+    with pytest.raises(fhe.FheError):
+        fhe.Tggsw(8192, 3, np.zeros(4 * 64 * 4 * 8192, dtype=np.uint64))
 
 
 def test_cmux_selects(fhe, orc):
