@@ -34,6 +34,7 @@ void set_error(const std::string &msg);
 
 cudaStream_t current_stream();
 int num_sms();
+void device_init_once();  // per-device runtime configuration (memory pool)
 void count_launch(unsigned long long n);  // feeds fhe_launch_count()
 
 // ---- host modular helpers (plan construction) ---------------------------------------------------

@@ -2,6 +2,7 @@
 // C ABI declared in include/fhe_b200.h.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <memory>
@@ -20,6 +21,20 @@ static std::atomic<unsigned long long> g_launches{0};
 void set_error(const std::string &msg) { t_error = msg; }
 cudaStream_t current_stream() { return t_stream; }
 void count_launch(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// keep stream-ordered scratch cached in the pool instead of returning it to the OS at every synchronisation
+void device_init_once() {
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if ((done_mask >> (dev & 63)) & 1ull) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    done_mask |= 1ull << (dev & 63);
+}
 int num_sms() {
     static int sms[64] = {0};
     int dev = 0;
@@ -62,6 +77,94 @@ template <class M> int upload_tables(fhe_ntt_plan *p, NttParams<M> &dst) {
     return 0;
 }
 
+int launch_plan(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
+                int flags, cudaStream_t st) {
+    int rc;
+    switch (plan->kind) {
+        case 3: rc = ntt_launch_small32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
+        case 0: rc = ntt_launch_lazy32(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
+        case 1: rc = ntt_launch_lazy64(plan->logn, plan->loge, mode, plan->p64, a, b, c, c_evals, batch, flags, st); break;
+        default: rc = ntt_launch_strict64(plan->logn, plan->loge, mode, plan->ps64, a, b, c, c_evals, batch, flags, st);
+    }
+    if (!rc) count_launch(1);
+    return rc;
+}
+
+bool is_host_ptr(const void *p) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return !(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+}
+
+// Host-buffer path for large batches: the batch is cut into chunks and H2D copies, kernels and D2H copies of
+// consecutive chunks overlap on three streams (PCIe is full duplex), double-buffered on the device.
+struct PipeStreams {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+    int device = -1;
+    int init() {
+        int dev = 0;
+        FHE_CUDA_OK(cudaGetDevice(&dev));
+        if (device == dev) return 0;
+        FHE_CUDA_OK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        FHE_CUDA_OK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            FHE_CUDA_OK(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
+            FHE_CUDA_OK(cudaEventCreateWithFlags(&comp_done[i], cudaEventDisableTiming));
+            FHE_CUDA_OK(cudaEventCreateWithFlags(&d2h_done[i], cudaEventDisableTiming));
+        }
+        device = dev;
+        return 0;
+    }
+};
+thread_local PipeStreams t_pipe;
+
+int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
+                      int flags, cudaStream_t st, size_t chunk) {
+    int rc = t_pipe.init();
+    if (rc) return rc;
+    PipeStreams &ps = t_pipe;
+    const size_t n = plan->host.n, cbytes = chunk * n * sizeof(u64);
+    const int nbuf = 1 + (b ? 1 : 0) + 1 + (c_evals ? 1 : 0);
+    u64 *dev = nullptr;
+    FHE_CUDA_OK(cudaMallocAsync((void **)&dev, 2 * nbuf * cbytes, st));
+    FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch is used from the side streams as well
+    auto buf = [&](int which, int parity) { return dev + ((size_t)parity * nbuf + which) * chunk * n; };
+    const int ib = 1, ic = b ? 2 : 1, ie = ic + 1;
+    size_t i = 0;
+    for (size_t off = 0; off < batch; off += chunk, i++) {
+        const size_t nb = std::min(chunk, batch - off), bytes = nb * n * sizeof(u64);
+        const int par = (int)(i & 1);
+        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // inputs of chunk i-2 consumed
+        FHE_CUDA_OK(cudaMemcpyAsync(buf(0, par), a + off * n, bytes, cudaMemcpyHostToDevice, ps.h2d));
+        if (b) FHE_CUDA_OK(cudaMemcpyAsync(buf(ib, par), b + off * n, bytes, cudaMemcpyHostToDevice, ps.h2d));
+        FHE_CUDA_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
+        FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.h2d_done[par], 0));
+        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
+        if ((rc = launch_plan(plan, mode, buf(0, par), b ? buf(ib, par) : nullptr, buf(ic, par),
+                              c_evals ? buf(ie, par) : nullptr, nb, flags, st)))
+            break;
+        FHE_CUDA_OK(cudaEventRecord(ps.comp_done[par], st));
+        FHE_CUDA_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
+        FHE_CUDA_OK(cudaMemcpyAsync(c + off * n, buf(ic, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
+        if (c_evals) FHE_CUDA_OK(cudaMemcpyAsync(c_evals + off * n, buf(ie, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
+        FHE_CUDA_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st);
+    cudaFreeAsync(dev, st);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        set_error(std::string("pipelined transfer failed: ") +
+                  cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+        return -2;
+    }
+    return 0;
+}
+
 int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
             int flags) {
     FHE_REQUIRE(plan != nullptr, "null plan");
@@ -69,31 +172,21 @@ int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 
     FHE_REQUIRE(a != nullptr && c != nullptr && (mode != MODE_MUL || b != nullptr), "null polynomial pointer");
     cudaStream_t st = current_stream();
     const size_t bytes = batch * plan->host.n * sizeof(u64);
+    if (mode != MODE_MUL) b = nullptr;
+    {   // all-host call on a batch worth pipelining (>= 4 chunks of ~32 MiB per operand)
+        const size_t chunk = std::max<size_t>(1, (32ull << 20) / (plan->host.n * sizeof(u64)));
+        if (batch >= 4 * chunk && is_host_ptr(a) && (!b || is_host_ptr(b)) && is_host_ptr(c) &&
+            (!c_evals || is_host_ptr(c_evals)) && a != c && b != c)
+            return run_ntt_pipelined(plan, mode, a, b, c, c_evals, batch, flags, st, chunk);
+    }
     IoBuf ba, bb, bc, be;
     int rc;
     if ((rc = ba.init(a, bytes, true, false, st))) return rc;
     if ((rc = bb.init(mode == MODE_MUL ? b : nullptr, bytes, true, false, st))) return rc;
     if ((rc = bc.init(c, bytes, false, true, st))) return rc;
     if ((rc = be.init(c_evals, bytes, false, true, st))) return rc;
-    switch (plan->kind) {
-        case 3:
-            rc = ntt_launch_small32(plan->logn, plan->loge, mode, plan->psm, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
-                                    be.ptr<u64>(), batch, flags, st);
-            break;
-        case 0:
-            rc = ntt_launch_lazy32(plan->logn, plan->loge, mode, plan->p32, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
-                                   be.ptr<u64>(), batch, flags, st);
-            break;
-        case 1:
-            rc = ntt_launch_lazy64(plan->logn, plan->loge, mode, plan->p64, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
-                                   be.ptr<u64>(), batch, flags, st);
-            break;
-        default:
-            rc = ntt_launch_strict64(plan->logn, plan->loge, mode, plan->ps64, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(),
-                                     be.ptr<u64>(), batch, flags, st);
-    }
+    rc = launch_plan(plan, mode, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(), be.ptr<u64>(), batch, flags, st);
     if (rc) return rc;
-    count_launch(1);
     return finish_all({&ba, &bb, &bc, &be}, st);
 }
 }  // namespace
@@ -125,6 +218,7 @@ int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
     *out = nullptr;
     int dev = 0;
     FHE_CUDA_OK(cudaGetDevice(&dev));
+    device_init_once();
     std::lock_guard<std::mutex> lk(g_plan_mu);
     auto key = std::make_tuple(dev, (u64)q, (u64)n);
     auto it = g_plans.find(key);

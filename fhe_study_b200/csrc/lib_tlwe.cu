@@ -20,6 +20,7 @@ int fhe_ksk_load(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *ro
     FHE_REQUIRE(out && rows, "null pointer");
     *out = nullptr;
     FHE_REQUIRE(kn_in >= 1 && kn_out >= 1 && l >= 1 && l <= 64, "fhe_ksk_load: need kn_in, kn_out >= 1 and 1 <= l <= 64");
+    device_init_once();
     std::unique_ptr<fhe_ksk> h(new fhe_ksk());
     h->k.kn_in = kn_in;
     h->k.kn_out = kn_out;
