@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 Q = 65537
 N = 1024
 BATCH = 65536  # 3 * 65536 * 8 KiB = 1.5 GiB per step: far larger than the 126 MB L2
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of this exact workload (ncu --set full capture)
+NCU_TRAFFIC_BYTES = 1073811000 + 502642176
+NCU_TRAFFIC_SOURCE = "profiles/r1_polymul_n1024_q65537_ncu_full_b.csv"
 
 
 def peaks():
@@ -40,7 +43,7 @@ def peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.005):
+    def __init__(self, index: int, period_s: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons = [], set()
@@ -115,7 +118,7 @@ def cpu_polymul_baseline(target_s: float = 12.0):
     }, (a, b, c)
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's CPU algorithm (oracle port; no Rust toolchain exists here) on all host
     cores, same metric/config.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -124,7 +127,7 @@ def run_reference(args):
     import oracle
 
     cores = os.cpu_count() or 1
-    per_step = max(cores * 64, 2048)
+    per_step = cores * 1024  # ~0.1 s of CPU work per step
     a = oracle.uniform(3, (per_step, N), Q)
     b = oracle.uniform(4, (per_step, N), Q)
     for _ in range(args.warmup):
@@ -143,7 +146,7 @@ def run_reference(args):
                          "sample": f"{per_step} polymuls per step, oracle C port of arith/src/ntt.rs + ring_nq.rs"},
         "e2e": {"value": v, "unit": "polymul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def measure_bootstrap(fhe, torch, dist, dev, rank, world, quick):
@@ -213,8 +216,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # the contract is ONE JSON line on stdout: anything libraries print (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import numpy as np
     import torch
@@ -259,7 +269,6 @@ def main():
         e.record()
     t_end.record()
     barrier()
-    clocks = sampler.stop()
     launches = fhe.launch_count() - l0
     total_ms = t_start.elapsed_time(t_end)
     kern_ms = statistics.mean(s.elapsed_time(e) for s, e in ev)
@@ -287,6 +296,7 @@ def main():
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()  # sampled across both timed regions (device-resident steps and end-to-end steps)
     e2e_value = world * batch * e2e_steps / (float(t.item()) * 1e-3)
     same = bool(torch.equal(hc.to(dev), c))
 
@@ -303,7 +313,7 @@ def main():
     line = {
         "metric": "NTT polymul/s", "value": value, "unit": "polymul/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64 (32-bit lazy Shoup/Barrett arithmetic for q<2^30)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 words; 32-bit lazy Shoup/Montgomery arithmetic for q<2^22",
         "data": "synthetic",
         "config": {
             "workload": f"BASELINE configs[1]: batched Rq negacyclic NTT polymul, N={N}, q={Q}, batch {batch} per GPU",
@@ -313,7 +323,8 @@ def main():
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "peak_source": peak_kind, "kernel": "ntt_kernel<Lazy32,10,5,MUL>",
+            "traffic": NCU_TRAFFIC_BYTES if batch == BATCH else None, "traffic_source": NCU_TRAFFIC_SOURCE,
+            "peak_source": peak_kind, "kernel": "ntt_kernel<Small32,10,5,MUL>",
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
         },
         "e2e": {
@@ -338,7 +349,7 @@ def main():
             line["extras"] = bench_extras.run(fhe, dev, quick=args.steps < 20, cpu=not args.no_cpu)
         except Exception as ex:  # extras never invalidate the headline line
             line["extras"] = {"error": repr(ex)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
