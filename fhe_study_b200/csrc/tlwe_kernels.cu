@@ -67,16 +67,20 @@ key_switch_kernel(const u64 *__restrict__ ksk, const u64 *__restrict__ ct, u64 *
 }
 
 int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
-    // path selection: the tensor-core GEMM when its layout exists (l == 64) and the batch fills a few MMA rows;
-    // FHE_KS_PATH=cuda|mma forces one (used by the tests to cover both)
+    // path selection (l == 64 keys carry the byte-plane tensor-core layout): tcgen05 GEMM for batches that fill
+    // an MMA tile, the mma.sync GEMM for small batches, CUDA cores otherwise.  FHE_KS_PATH=tc|mma|cuda forces
+    // one (the tests cover all three).
     const char *force = getenv("FHE_KS_PATH");
-    const bool want_mma = k.mma_blocks != nullptr &&
-                          (force ? strcmp(force, "mma") == 0 : batch >= 16);
-    if (force && strcmp(force, "mma") == 0 && k.mma_blocks == nullptr) {
-        set_error("FHE_KS_PATH=mma but this key has no tensor-core layout (needs l == 64 and even kn_in)");
-        return -1;
+    int path = k.mma_blocks == nullptr ? 0 : batch >= 64 ? 2 : batch >= 16 ? 1 : 0;
+    if (force) {
+        path = strcmp(force, "tc") == 0 ? 2 : strcmp(force, "mma") == 0 ? 1 : 0;
+        if (path != 0 && k.mma_blocks == nullptr) {
+            set_error("FHE_KS_PATH asks for a tensor-core path but this key has no byte-plane layout (needs l == 64, even kn_in)");
+            return -1;
+        }
     }
-    if (want_mma) return key_switch_mma_device(k, ct, out, batch, st);
+    if (path == 2) return key_switch_tc_device(k, ct, out, batch, st);
+    if (path == 1) return key_switch_mma_device(k, ct, out, batch, st);
     const u32 w = (u32)k.kn_out + 1;
     dim3 grid((w + KS_TX - 1) / KS_TX, (unsigned)((batch + KS_BT - 1) / KS_BT));
     FHE_REQUIRE(grid.y <= 65535, "key switch: batch too large for one launch (max 65535*16)");

@@ -144,7 +144,7 @@ def test_key_switch_tensor_core_and_cuda_core_paths(fhe, orc, kn_in, kn_out, bat
     ct[0, :] = 2**64 - 1  # every digit set: the largest plane sums
     want = orc.key_switch(kn_in, kn_out, l, ksk, ct.reshape(-1), threads=8).reshape(batch, kn_out + 1)
     K = fhe.Ksk(kn_in, kn_out, l, ksk)
-    for path in ("mma", "cuda"):
+    for path in ("tc", "mma", "cuda"):
         monkeypatch.setenv("FHE_KS_PATH", path)
         assert (K.key_switch(ct) == want).all(), path
     monkeypatch.delenv("FHE_KS_PATH")
@@ -153,10 +153,10 @@ def test_key_switch_tensor_core_and_cuda_core_paths(fhe, orc, kn_in, kn_out, bat
 def test_key_switch_full_size_both_paths(fhe, orc, p5, monkeypatch):
     kn = p5["kn"]
     K = fhe.Ksk(kn, kn, 64, p5["ksk"])
-    ct = orc.uniform(4242, (200, kn + 1))
+    ct = orc.uniform(4242, (300, kn + 1))
     ct[7, :] = 2**64 - 1
-    want = orc.key_switch(kn, kn, 64, p5["ksk"], ct.reshape(-1), threads=8).reshape(200, kn + 1)
-    for path in ("mma", "cuda"):
+    want = orc.key_switch(kn, kn, 64, p5["ksk"], ct.reshape(-1), threads=8).reshape(300, kn + 1)
+    for path in ("tc", "mma", "cuda"):
         monkeypatch.setenv("FHE_KS_PATH", path)
         assert (K.key_switch(ct) == want).all(), path
     monkeypatch.delenv("FHE_KS_PATH")
