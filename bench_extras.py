@@ -61,7 +61,16 @@ def ntt_sweep(fhe, dev, quick):
     a = torch.randint(0, Q17, (1, 1024), dtype=torch.int64, device=dev)
     c = torch.empty_like(a)
     lat = _time(lambda: plan.mul(a, a, out=c), 200, warm=20)
-    return {"sweep": out, "polymul_n1024_batch1_us": lat * 1e3}
+    # integer rooflines: modmuls per second of each sweep point against the register-only Shoup-modmul peak
+    peaks = {"imad32_per_s": fhe.int_peak(0), "shoup32_modmul_per_s": fhe.int_peak(1), "shoup64_modmul_per_s": fhe.int_peak(2)}
+    for row in out:
+        n, logn = row["n"], row["n"].bit_length() - 1
+        pk = peaks["shoup32_modmul_per_s"] if row["q"] < 2**30 else peaks["shoup64_modmul_per_s"]
+        work = {"ntt": n // 2 * logn, "intt": n // 2 * logn + n, "polymul": 3 * (n // 2) * logn + 2 * n}
+        for name in ("ntt", "intt", "polymul"):
+            row[name]["modmul_frac"] = row[name]["per_s"] * work[name] / pk
+            row[name]["roofline_frac"] = max(row[name]["hbm_frac"], row[name]["modmul_frac"])
+    return {"sweep": out, "polymul_n1024_batch1_us": lat * 1e3, "int_peaks": peaks}
 
 
 

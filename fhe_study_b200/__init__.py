@@ -62,6 +62,13 @@ def synchronize() -> None:
     check(lib.fhe_synchronize())
 
 
+def int_peak(kind: int) -> float:
+    """Measured integer-pipe peak (ops/s): 0 = IMAD32, 1 = Shoup modmul 32-bit, 2 = Shoup modmul 64-bit."""
+    v = C.c_double()
+    check(lib.fhe_int_peak(int(kind), C.byref(v)))
+    return float(v.value)
+
+
 def launch_count() -> int:
     return int(lib.fhe_launch_count())
 

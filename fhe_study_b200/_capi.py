@@ -40,6 +40,7 @@ SIGNATURES = {
     "fhe_set_stream": (I, [P]),
     "fhe_synchronize": (I, []),
     "fhe_launch_count": (U64, []),
+    "fhe_int_peak": (I, [I, C.POINTER(C.c_double)]),
     "fhe_ntt_plan_create": (I, [U64, U64, C.POINTER(P)]),
     "fhe_ntt_plan_destroy": (None, [P]),
     "fhe_ntt_plan_info": (I, [P, C.POINTER(U64), C.POINTER(U64), P, P]),

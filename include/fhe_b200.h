@@ -48,6 +48,10 @@ FHE_API int fhe_synchronize(void);                   /* wait for this thread's s
 /* number of kernels this library has launched from this process (bench.py's gpu_launches) */
 FHE_API uint64_t fhe_launch_count(void);
 
+/* Register-only microbenchmarks of the integer pipes (the denominators of the integer rooflines):
+ * kind 0 = 32-bit IMAD lane-ops/s, 1 = 32-bit Shoup modmul/s, 2 = 64-bit Shoup modmul/s. */
+FHE_API int fhe_int_peak(int kind, double *ops_per_s);
+
 /* ---- NTT plans: arith/src/ntt.rs:18-38 (the (q,n) -> (roots, roots_inv, n_inv) cache) ------------- */
 typedef struct fhe_ntt_plan fhe_ntt_plan;
 /* Builds (or fetches from the per-device cache) the plan for Z_q[X]/(X^n+1).  Fails where the reference
