@@ -18,6 +18,8 @@
 #include "runtime.cuh"
 #include "torus.cuh"
 
+#include <stdlib.h>
+
 namespace fhe {
 
 template <int LOGN, int K1> struct XpGeom {
@@ -53,6 +55,24 @@ __device__ __forceinline__ u32 reduce64(u64 acc, u32 p, u64 mu) {
     return (u32)(r >= p ? r - p : r);
 }
 
+// NTT of digit polynomial d = (i, j) of the decomposed input under prime r, left in `sm` (padded position
+// order, values in [0, 2p)): bit 63-j of x_i (Tn::decompose, torus.rs:43-52) -> register-blocked forward NTT.
+template <int LOGN>
+__device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32> &twf, int d, const u64 *xin, u32 *sm,
+                                          int tid) {
+    constexpr int LOGE = LOGN < 5 ? LOGN : 5;
+    typedef NttShape<LOGN, LOGE> S;
+    constexpr int LAST = S::P - 1;
+    const u64 *xi = xin + (size_t)(d >> 6) * S::N;
+    const int sh = 63 - (d & 63);
+    u32 x[S::E];
+#pragma unroll
+    for (int e = 0; e < S::E; e++) x[e] = (u32)(xi[S::pos(0, tid, e)] >> sh) & 1u;
+    fwd_chain<Small32, LOGN, LOGE>(x, sm, tid, ms, twf);
+#pragma unroll
+    for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = ms.mul_tw(x[e], ms.one);
+}
+
 template <int LOGN, int K1>
 __global__ void __launch_bounds__(256, 2)
 extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__ ct1, const u64 *__restrict__ ct2,
@@ -75,9 +95,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
 
 #pragma unroll 1
     for (int r = 0; r < 2; r++) {
-        const Small32 &ms = X.ms[r];
         const Lazy32 &ml = X.P[r].mod;
-        const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
         u64 acc[G::IPT];
 #pragma unroll
         for (int m = 0; m < G::IPT; m++) acc[m] = 0;
@@ -85,14 +103,8 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
         for (int round = 0; round < G::ROUNDS; round++) {
             const int d = round * G::SLOTS + slot;
             if (d < G::ND) {
-                const u64 *xi = xin + (size_t)(d >> 6) * N;
-                const int sh = 63 - (d & 63);
-                u32 x[S::E];
-#pragma unroll
-                for (int e = 0; e < S::E; e++) x[e] = (u32)(xi[S::pos(0, tid, e)] >> sh) & 1u;
-                fwd_chain<Small32, LOGN, LOGE>(x, sm, tid, ms, twf);
-#pragma unroll
-                for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = ms.mul_tw(x[e], ms.one);  // [0,2p)
+                const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
+                digit_ntt<LOGN>(X.ms[r], twf, d, xin, sm, tid);
             }
             __syncthreads();
             const int nslots = min(G::SLOTS, G::ND - round * G::SLOTS);
@@ -174,16 +186,18 @@ static int launch_fused(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out
     X.R[0] = g.R1f;
     X.R[1] = g.R2f;
     X.cp = tc.cp;
-    auto kern = extprod_fused_kernel<LOGN, K1>;
+    FHE_REQUIRE(batch <= 0x7fffffffull, "extprod: batch too large");
     static unsigned long long done_mask = 0;
     int dev = 0;
     FHE_CUDA_OK(cudaGetDevice(&dev));
+    auto kern = extprod_fused_kernel<LOGN, K1>;
+    const int threads = G::CT;
+    const size_t smem = G::SMEM;
     if (!((done_mask >> (dev & 63)) & 1ull)) {
-        FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done_mask |= 1ull << (dev & 63);
     }
-    FHE_REQUIRE(batch <= 0x7fffffffull, "extprod: batch too large");
-    kern<<<(unsigned)batch, G::CT, G::SMEM, st>>>(X, ct1, ct2, out, cmux);
+    kern<<<(unsigned)batch, threads, smem, st>>>(X, ct1, ct2, out, cmux);
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -222,7 +222,7 @@ int tn_mul_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t
 // shape is instantiated (FHE_EXTPROD_PATH=fused|unfused forces a path; the tests cover both).
 int extprod_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, cudaStream_t st) {
     const char *force = getenv("FHE_EXTPROD_PATH");
-    if (force && strcmp(force, "fused") == 0 && g.R1f == nullptr) {
+    if (force && strncmp(force, "fused", 5) == 0 && g.R1f == nullptr) {
         set_error("FHE_EXTPROD_PATH=fused but this (n, k) has no fused instantiation");
         return -1;
     }
