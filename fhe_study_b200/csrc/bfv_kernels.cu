@@ -29,15 +29,6 @@ __device__ __forceinline__ u64 scale_round(u64 q, i64 v, double num, double den)
 __device__ __forceinline__ u64 zq_sub(u64 q, u64 a, u64 b) { return a >= b ? a - b : (q + a) - b; }  // zq.rs:259-277
 __device__ __forceinline__ u64 zq_add(u64 q, u64 a, u64 b) { u64 v = a + b; return v >= q ? v - q : v; }  // zq.rs:219-231
 
-// coefficients idx and idx+n of the linear product a*b (wrapping 64-bit == `i128 as i64`)
-__device__ __forceinline__ void conv_pair(const u64 *__restrict__ a, const u64 *__restrict__ b, u32 n, u32 c, u64 &lo,
-                                          u64 &hi) {
-    u64 s0 = 0, s1 = 0;
-    for (u32 i = 0; i <= c; i++) s0 += a[i] * b[c - i];              // i + j = c
-    for (u32 i = c + 1; i < n; i++) s1 += a[i] * b[c + n - i];        // i + j = c + n  (j = c+n-i <= n-1)
-    lo = s0;
-    hi = s1;
-}
 // fold of the scaled pair (ring_nq.rs:132-141): res[c] = f(conv[c]) - f(conv[c+n]); index c+n exists for c <= n-2
 __device__ __forceinline__ u64 scale_fold(u64 q, u32 n, u32 c, u64 lo, u64 hi, double num, double den) {
     const u64 x = scale_round(q, (i64)lo, num, den);
@@ -46,37 +37,52 @@ __device__ __forceinline__ u64 scale_fold(u64 q, u32 n, u32 c, u64 lo, u64 hi, d
 }
 
 // mode 0: RLWE::tensor only (out = c0|c1|c2, 3n words) ; 1: RLWE::mul (tensor + relinearize_204, out 2n words) ;
-// 2: relinearize_204 only (a = c0|c1|c2, out 2n words).  One CTA row of n threads per ciphertext product.
+// 2: relinearize_204 only (a = c0|c1|c2, out 2n words).  n threads per ciphertext product, thread c owns the
+// unfolded coefficients c and c+n of every product: one uniform loop over i with j = (c - i) mod n, the term
+// going to the low sum when i <= c and to the high sum otherwise (wrapping 64-bit == `i128 as i64`).
+// CT = u32 when q < 2^32 (ciphertext coefficients are < q): the products are then single IMAD.WIDE.U32.
+template <typename CT>
 __global__ void bfv_mul_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, const u64 *__restrict__ rlk,
                                u64 *__restrict__ out, size_t batch, u32 n, u64 q, u64 t, u64 pq, int mode, u32 per_cta) {
-    extern __shared__ u64 sm[];
+    extern __shared__ __align__(16) unsigned char sm_raw[];
     const u32 slot = threadIdx.x / n, c = threadIdx.x % n;
     const size_t ct = (size_t)blockIdx.x * per_cta + slot;
     const bool valid = ct < batch && slot < per_cta;
-    u64 *s = sm + (size_t)slot * 7 * n;  // a0 a1 b0 b1 c2 rlk0 rlk1
-    u64 *a0 = s, *a1 = s + n, *b0 = s + 2 * n, *b1 = s + 3 * n, *c2s = s + 4 * n, *k0 = s + 5 * n, *k1 = s + 6 * n;
+    // per CTA: rlk0 rlk1 (u64, shared by every slot) ; per slot: a0 a1 b0 b1 c2 (CT)
+    u64 *k0 = reinterpret_cast<u64 *>(sm_raw), *k1 = k0 + n;
+    CT *s = reinterpret_cast<CT *>(k1 + n) + (size_t)slot * 5 * n;
+    CT *a0 = s, *a1 = s + n, *b0 = s + 2 * n, *b1 = s + 3 * n, *c2s = s + 4 * n;
     const double dq = __ull2double_rn(q), dt = __ull2double_rn(t);
     u64 c0 = 0, c1 = 0, c2 = 0;
+    if (mode != 0) {
+        for (u32 i = threadIdx.x; i < 2 * n; i += blockDim.x) k0[i] = rlk[i];
+    }
     if (valid) {
         if (mode != 2) {
             const u64 *pa = a + ct * 2 * n, *pb = b + ct * 2 * n;
-            a0[c] = pa[c]; a1[c] = pa[n + c]; b0[c] = pb[c]; b1[c] = pb[n + c];
+            a0[c] = (CT)pa[c]; a1[c] = (CT)pa[n + c]; b0[c] = (CT)pb[c]; b1[c] = (CT)pb[n + c];
         } else {
             const u64 *pa = a + ct * 3 * n;
             c0 = pa[c]; c1 = pa[n + c]; c2 = pa[2 * n + c];
         }
-        if (mode != 0) { k0[c] = rlk[c]; k1[c] = rlk[n + c]; }
     }
     __syncthreads();
     if (valid && mode != 2) {  // RLWE::tensor (lib.rs:59-85)
-        u64 lo, hi, lo2, hi2;
-        conv_pair(a0, b0, n, c, lo, hi);
-        c0 = scale_fold(q, n, c, lo, hi, dt, dq);
-        conv_pair(a0, b1, n, c, lo, hi);
-        conv_pair(a1, b0, n, c, lo2, hi2);
-        c1 = scale_fold(q, n, c, lo + lo2, hi + hi2, dt, dq);  // i64 `+` of the two cross terms (lib.rs:76)
-        conv_pair(a1, b1, n, c, lo, hi);
-        c2 = scale_fold(q, n, c, lo, hi, dt, dq);
+        u64 l00 = 0, h00 = 0, l01 = 0, h01 = 0, l11 = 0, h11 = 0;
+        u32 j = c;  // j = (c - i) mod n
+#pragma unroll 4
+        for (u32 i = 0; i < n; i++) {
+            const u64 x0 = a0[i], x1 = a1[i], y0 = b0[j], y1 = b1[j];
+            if (i <= c) {
+                l00 += x0 * y0; l01 += x0 * y1 + x1 * y0; l11 += x1 * y1;  // i64 `+` of the cross terms (lib.rs:76)
+            } else {
+                h00 += x0 * y0; h01 += x0 * y1 + x1 * y0; h11 += x1 * y1;
+            }
+            j = j == 0 ? n - 1 : j - 1;
+        }
+        c0 = scale_fold(q, n, c, l00, h00, dt, dq);
+        c1 = scale_fold(q, n, c, l01, h01, dt, dq);
+        c2 = scale_fold(q, n, c, l11, h11, dt, dq);
     }
     if (mode == 0) {
         if (valid) {
@@ -85,15 +91,20 @@ __global__ void bfv_mul_kernel(const u64 *__restrict__ a, const u64 *__restrict_
         }
         return;
     }
-    if (valid) c2s[c] = c2;
+    if (valid) c2s[c] = (CT)c2;
     __syncthreads();
     if (valid) {  // relinearize_204 (lib.rs:251-271)
         const double dp = __ull2double_rn(pq / q);
-        u64 lo, hi;
-        conv_pair(c2s, k0, n, c, lo, hi);
-        const u64 r0 = scale_fold(q, n, c, lo, hi, 1.0, dp);
-        conv_pair(c2s, k1, n, c, lo, hi);
-        const u64 r1 = scale_fold(q, n, c, lo, hi, 1.0, dp);
+        u64 l0 = 0, h0 = 0, l1 = 0, h1 = 0;
+        u32 j = c;
+#pragma unroll 4
+        for (u32 i = 0; i < n; i++) {
+            const u64 x = c2s[i], y0 = k0[j], y1 = k1[j];
+            if (i <= c) { l0 += x * y0; l1 += x * y1; } else { h0 += x * y0; h1 += x * y1; }
+            j = j == 0 ? n - 1 : j - 1;
+        }
+        const u64 r0 = scale_fold(q, n, c, l0, h0, 1.0, dp);
+        const u64 r1 = scale_fold(q, n, c, l1, h1, 1.0, dp);
         u64 *po = out + ct * 2 * n;
         po[c] = zq_add(q, c0, r0);
         po[n + c] = zq_add(q, c1, r1);
@@ -117,12 +128,20 @@ static int bfv_launch(int mode, u64 q, u64 n, u64 t, u64 pq, const u64 *rlk, con
     if ((rc = bo.init(out, batch * out_words * 8, false, true, st))) return rc;
     const u32 per_cta = n >= 128 ? 1 : (u32)(128 / n);
     const u32 threads = per_cta * (u32)n;
-    const size_t smem = (size_t)per_cta * 7 * n * sizeof(u64);
+    const bool narrow = q <= 0xffffffffull;  // ciphertext coefficients (< q) fit 32 bits
+    const size_t smem = 2 * n * sizeof(u64) + (size_t)per_cta * 5 * n * (narrow ? sizeof(u32) : sizeof(u64));
     const size_t grid = (batch + per_cta - 1) / per_cta;
     FHE_REQUIRE(grid <= 0x7fffffffull, "bfv: batch too large");
-    if (smem > 48 * 1024) FHE_CUDA_OK(cudaFuncSetAttribute(bfv_mul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bfv_mul_kernel<<<(unsigned)grid, threads, smem, st>>>(ba.ptr<u64>(), bb.ptr<u64>(), bk.ptr<u64>(), bo.ptr<u64>(), batch,
-                                                         (u32)n, q, t, pq, mode, per_cta);
+    auto k32 = bfv_mul_kernel<u32>;
+    auto k64 = bfv_mul_kernel<u64>;
+    if (smem > 48 * 1024)
+        FHE_CUDA_OK(cudaFuncSetAttribute(narrow ? k32 : k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (narrow)
+        k32<<<(unsigned)grid, threads, smem, st>>>(ba.ptr<u64>(), bb.ptr<u64>(), bk.ptr<u64>(), bo.ptr<u64>(), batch, (u32)n, q, t,
+                                                 pq, mode, per_cta);
+    else
+        k64<<<(unsigned)grid, threads, smem, st>>>(ba.ptr<u64>(), bb.ptr<u64>(), bk.ptr<u64>(), bo.ptr<u64>(), batch, (u32)n, q, t,
+                                                 pq, mode, per_cta);
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return finish_all({&ba, &bb, &bk, &bo}, st);
