@@ -29,3 +29,11 @@ def test_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "fhe_oracle" not in txt, f
+
+
+def test_rust_bindings_cover_every_symbol():
+    # rust/fhe-b200-sys/src/lib.rs is generated from the header (tools/gen_rust_bindings.py); keep them in sync
+    names = _header_functions()
+    rs = open(os.path.join(ROOT, "rust", "fhe-b200-sys", "src", "lib.rs")).read()
+    bound = sorted(set(re.findall(r"pub fn (fhe_[a-z0-9_]+)\(", rs)))
+    assert bound == names
