@@ -130,8 +130,9 @@ int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const u64 *a, const u6
     PipeStreams &ps = t_pipe;
     const size_t n = plan->host.n, cbytes = chunk * n * sizeof(u64);
     const int nbuf = 1 + (b ? 1 : 0) + 1 + (c_evals ? 1 : 0);
-    u64 *dev = nullptr;
-    FHE_CUDA_OK(cudaMallocAsync((void **)&dev, 2 * nbuf * cbytes, st));
+    Scratch scratch;
+    if ((rc = scratch.alloc(2 * nbuf * cbytes, st))) return rc;
+    u64 *dev = scratch.ptr<u64>();
     FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch is used from the side streams as well
     auto buf = [&](int which, int parity) { return dev + ((size_t)parity * nbuf + which) * chunk * n; };
     const int ib = 1, ic = b ? 2 : 1, ie = ic + 1;
@@ -155,7 +156,6 @@ int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const u64 *a, const u6
         FHE_CUDA_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
     }
     cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st);
-    cudaFreeAsync(dev, st);
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
         set_error(std::string("pipelined transfer failed: ") +

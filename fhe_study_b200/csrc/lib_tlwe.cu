@@ -110,17 +110,20 @@ int fhe_blind_rotate(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, int as
     if ((rc = bt.init(table, glwe * 8, true, false, st))) return rc;
     if ((rc = bc.init(ct, batch * (c_kn + 1) * 8, true, false, st))) return rc;
     if ((rc = bo.init(acc_out, batch * glwe * 8, false, true, st))) return rc;
-    u64 *ext = nullptr;
-    FHE_CUDA_OK(cudaMallocAsync((void **)&ext, batch * (k * n + 1) * 8, st));
-    rc = rotate_extract_device(bt.ptr<u64>(), bc.ptr<u64>(), ext, bo.ptr<u64>(), batch, (u32)n, (u32)k, (u32)c_kn, st);
-    cudaFreeAsync(ext, st);
-    if (rc) return rc;
+    {
+        Scratch ext;
+        if ((rc = ext.alloc(batch * (k * n + 1) * 8, st))) return rc;
+        if ((rc = rotate_extract_device(bt.ptr<u64>(), bc.ptr<u64>(), ext.ptr<u64>(), bo.ptr<u64>(), batch, (u32)n, (u32)k,
+                                        (u32)c_kn, st)))
+            return rc;
+    }
     if (as_written && k > 1) {
         FHE_REQUIRE(c_kn >= k, "fhe_blind_rotate: ciphertext has fewer than k mask elements");
-        u64 *rot = nullptr, *hs = nullptr, *nxt = nullptr;
-        FHE_CUDA_OK(cudaMallocAsync((void **)&rot, batch * glwe * 8, st));
-        FHE_CUDA_OK(cudaMallocAsync((void **)&nxt, batch * glwe * 8, st));
-        FHE_CUDA_OK(cudaMallocAsync((void **)&hs, batch * 8, st));
+        Scratch s_rot, s_nxt, s_hs;
+        if ((rc = s_rot.alloc(batch * glwe * 8, st))) return rc;
+        if ((rc = s_nxt.alloc(batch * glwe * 8, st))) return rc;
+        if ((rc = s_hs.alloc(batch * 8, st))) return rc;
+        u64 *rot = s_rot.ptr<u64>(), *nxt = s_nxt.ptr<u64>(), *hs = s_hs.ptr<u64>();
         const u32 shift = 64 - (63 - __builtin_clzll(k * n));
         for (u64 j = 1; j < k && !rc; j++) {
             FHE_REQUIRE(bsk[j] != nullptr && bsk[j]->n == n && bsk[j]->g.k == k, "fhe_blind_rotate: bad TGGSW handle");
@@ -131,9 +134,6 @@ int fhe_blind_rotate(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, int as
             if ((rc = extprod_device(bsk[j]->g, bo.ptr<u64>(), rot, nxt, batch, st))) break;  // cmux(bsk[j], acc, rot)
             FHE_CUDA_OK(cudaMemcpyAsync(bo.ptr<u64>(), nxt, batch * glwe * 8, cudaMemcpyDeviceToDevice, st));
         }
-        cudaFreeAsync(rot, st);
-        cudaFreeAsync(nxt, st);
-        cudaFreeAsync(hs, st);
         if (rc) return rc;
     }
     return finish_all({&bt, &bc, &bo}, st);
@@ -153,11 +153,10 @@ int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *ta
     if ((rc = bt.init(table, (k + 1) * n * 8, true, false, st))) return rc;
     if ((rc = bc.init(ct, batch * (c_kn + 1) * 8, true, false, st))) return rc;
     if ((rc = bo.init(out, batch * (ksk->k.kn_out + 1) * 8, false, true, st))) return rc;
-    u64 *ext = nullptr;
-    FHE_CUDA_OK(cudaMallocAsync((void **)&ext, batch * (k * n + 1) * 8, st));
-    rc = rotate_extract_device(bt.ptr<u64>(), bc.ptr<u64>(), ext, nullptr, batch, (u32)n, (u32)k, (u32)c_kn, st);
-    if (!rc) rc = key_switch_device(ksk->k, ext, bo.ptr<u64>(), batch, st);
-    cudaFreeAsync(ext, st);
+    Scratch ext;
+    if ((rc = ext.alloc(batch * (k * n + 1) * 8, st))) return rc;
+    rc = rotate_extract_device(bt.ptr<u64>(), bc.ptr<u64>(), ext.ptr<u64>(), nullptr, batch, (u32)n, (u32)k, (u32)c_kn, st);
+    if (!rc) rc = key_switch_device(ksk->k, ext.ptr<u64>(), bo.ptr<u64>(), batch, st);
     if (rc) return rc;
     return finish_all({&bt, &bc, &bo}, st);
 }

@@ -51,8 +51,10 @@ using namespace fhe;
 extern "C" int fhe_int_peak(int kind, double *ops_per_s) {
     FHE_REQUIRE(ops_per_s != nullptr && kind >= 0 && kind <= 2, "fhe_int_peak: kind must be 0, 1 or 2");
     cudaStream_t st = current_stream();
-    u64 *sink = nullptr;
-    FHE_CUDA_OK(cudaMallocAsync((void **)&sink, 8, st));
+    Scratch s_sink;
+    int rc0 = s_sink.alloc(8, st);
+    if (rc0) return rc0;
+    u64 *sink = s_sink.ptr<u64>();
     const u32 iters = 4096;
     const unsigned grid = (unsigned)num_sms() * 16;
     const u64 q32 = 0x7E90001ull, q64 = 0x3FFFFFFFFFFF0001ull;
@@ -74,7 +76,6 @@ extern "C" int fhe_int_peak(int kind, double *ops_per_s) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFreeAsync(sink, st);
     *ops_per_s = (double)grid * 256.0 * 8.0 * iters / (best * 1e-3);
     return 0;
 }

@@ -58,6 +58,25 @@ class IoBuf {
     cudaStream_t st_ = nullptr;
 };
 
+// Stream-ordered device scratch with scope lifetime (freed on every exit path).
+class Scratch {
+  public:
+    Scratch() {}
+    ~Scratch() { if (p_ != nullptr) cudaFreeAsync(p_, st_); }
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+    int alloc(size_t bytes, cudaStream_t st) {
+        st_ = st;
+        FHE_CUDA_OK(cudaMallocAsync(&p_, bytes ? bytes : 1, st));
+        return 0;
+    }
+    template <typename T> T *ptr() const { return reinterpret_cast<T *>(p_); }
+
+  private:
+    void *p_ = nullptr;
+    cudaStream_t st_ = nullptr;
+};
+
 // Scope helper: finish() every buffer, and synchronise the stream iff any of them lives on the host
 // (the call then has the reference's blocking semantics; all-device calls stay asynchronous).
 inline int finish_all(std::initializer_list<IoBuf *> bufs, cudaStream_t st) {

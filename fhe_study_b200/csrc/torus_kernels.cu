@@ -189,11 +189,11 @@ int TorusCtx::ntt(int r, int mode, const u64 *in, u64 *out, size_t polys, cudaSt
 int tn_mul_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t batch, cudaStream_t st) {
     const u32 n = (u32)tc.n;
     const size_t plane_words = batch * 4 * (size_t)n;
-    u64 *buf = nullptr;
-    // A planes, B planes, C residues for p1 and p2
-    FHE_CUDA_OK(cudaMallocAsync((void **)&buf, plane_words * 4 * sizeof(u64), st));
+    Scratch scratch;  // A planes, B planes, C residues for p1 and p2
+    int rc = scratch.alloc(plane_words * 4 * sizeof(u64), st);
+    if (rc) return rc;
+    u64 *buf = scratch.ptr<u64>();
     u64 *A = buf, *B = buf + plane_words, *C1 = B + plane_words, *C2 = C1 + plane_words;
-    int rc = 0;
     for (int r = 0; r < 2 && !rc; r++) {
         split16_kernel<<<grid_for(batch * n), 256, 0, st>>>(a, A, batch, n);
         split16_kernel<<<grid_for(batch * n), 256, 0, st>>>(b, B, batch, n);
@@ -213,7 +213,6 @@ int tn_mul_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t
         count_launch(1);
         if (cudaGetLastError() != cudaSuccess) { set_error("tn_mul kernel launch failed"); rc = -2; }
     }
-    cudaFreeAsync(buf, st);
     return rc;
 }
 
@@ -234,12 +233,13 @@ int extprod_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, siz
     const size_t nd = (size_t)k1 * 64;                 // digit polynomials per accumulator
     const size_t chunk_max = std::max<size_t>(1, (512ull << 20) / (nd * n * sizeof(u64)));  // <= 512 MiB of planes
     const size_t chunk = std::min(batch, chunk_max);
-    u64 *planes = nullptr, *D = nullptr, *res = nullptr, *diff = nullptr;
-    FHE_CUDA_OK(cudaMallocAsync((void **)&planes, chunk * nd * n * sizeof(u64), st));
-    FHE_CUDA_OK(cudaMallocAsync((void **)&D, chunk * nd * n * sizeof(u64), st));
-    FHE_CUDA_OK(cudaMallocAsync((void **)&res, 2 * chunk * k1 * 2 * n * sizeof(u64), st));
-    if (ct2) FHE_CUDA_OK(cudaMallocAsync((void **)&diff, chunk * k1 * n * sizeof(u64), st));
-    int rc = 0;
+    Scratch s_planes, s_D, s_res, s_diff;
+    int rc;
+    if ((rc = s_planes.alloc(chunk * nd * n * sizeof(u64), st))) return rc;
+    if ((rc = s_D.alloc(chunk * nd * n * sizeof(u64), st))) return rc;
+    if ((rc = s_res.alloc(2 * chunk * k1 * 2 * n * sizeof(u64), st))) return rc;
+    if (ct2 && (rc = s_diff.alloc(chunk * k1 * n * sizeof(u64), st))) return rc;
+    u64 *planes = s_planes.ptr<u64>(), *D = s_D.ptr<u64>(), *res = s_res.ptr<u64>(), *diff = s_diff.ptr<u64>();
     for (size_t b0 = 0; b0 < batch && !rc; b0 += chunk) {
         const size_t nb = std::min(chunk, batch - b0);
         const size_t res_words = nb * k1 * 2 * n;
@@ -269,10 +269,6 @@ int extprod_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, siz
         count_launch(1);
         if (cudaGetLastError() != cudaSuccess) { set_error("extprod kernel launch failed"); rc = -2; }
     }
-    cudaFreeAsync(planes, st);
-    cudaFreeAsync(D, st);
-    cudaFreeAsync(res, st);
-    if (diff) cudaFreeAsync(diff, st);
     return rc;
 }
 
