@@ -147,7 +147,21 @@ def tfhe_paths(fhe, dev, quick, cpu=True):
         row["cpu_sample"] = f"{sample} bootstraps (as executed), oracle port, {cores} threads, {dt:.2f} s"
         row["gpu_matches_cpu_sample"] = bool((got == ho).all())
     res["P5_bootstrap_as_executed"] = row
-    del K, ksk, cts, out
+    # --- SURVEY 8f rank 1 (extension; no reference execution): blind rotation as a CMux chain with one TGGSW per
+    #     mask element, accumulator resident on chip for the whole chain, then sample extraction + key switch ----
+    steps = 32 if quick else 256
+    cb = 296 if quick else 592
+    rows = _u64_rand(torch, ((k + 1) * 64 * (k + 1) * n,), dev, 7)
+    bsk = [fhe.Tggsw(n, k, rows) for _ in range(steps)]  # distinct resident copies (12 MB each), as a real BSK
+    c2 = _u64_rand(torch, (cb, steps + 1), dev, 8)
+    o2 = torch.empty((cb, kn + 1), dtype=torch.int64, device=dev)
+    ms_p = _time(lambda: fhe.bootstrap_chain(n, k, bsk, table, c2, steps, mode=1, ksk=K, out=o2), 2, warm=1)
+    res["P6_bootstrap_cmux_chain_extension"] = {
+        "n": n, "k": k, "steps": steps, "batch": cb, "ms": ms_p, "cmux_per_s": cb * steps / (ms_p * 1e-3),
+        "bootstraps_per_s_at_these_steps": cb / (ms_p * 1e-3),
+        "note": "mod_switch(2n) + X^-b table + `steps` on-chip CMuxes (l=64, beta=2 as tggsw.rs:49-50) + sample_extract + "
+                "key_switch; the reference never executes such a chain (SURVEY F3)"}
+    del K, ksk, cts, out, bsk
     return res
 
 

@@ -273,6 +273,34 @@ def blind_rotate(n, k, table, ct, c_kn, bsk=None, as_written=False, out=None):
     return out
 
 
+def _handles(bsk):
+    return (C.c_void_p * max(len(bsk), 1))(*[b._h for b in bsk])
+
+
+def cmux_chain(n, k, bsk, acc, h, negacyclic=False, out=None):
+    """acc_b <- cmux(bsk[j], acc_b, X^{-h[b][j]} acc_b) for j < len(bsk): the loop of blind_rotation
+    (tfhe/src/tlwe.rs:138-147) for len(bsk) TGGSWs; the accumulator stays on chip for the whole chain.  Extension."""
+    batch = _numel(acc) // ((int(k) + 1) * int(n))
+    out = _empty_like(acc) if out is None else out
+    _check_u64(acc, out) if len(bsk) == 0 else _check_u64(acc, h, out)
+    if len(bsk) and _numel(h) != batch * len(bsk):
+        raise ValueError("h must hold batch * steps rotation amounts")
+    check(lib.fhe_cmux_chain(int(n), int(k), _handles(bsk), len(bsk), int(bool(negacyclic)), ptr(acc),
+                             ptr(h) if len(bsk) else None, ptr(out), batch))
+    return out
+
+
+def bootstrap_chain(n, k, bsk, table, ct, c_kn, mode=1, ksk: Ksk = None, out=None):
+    """Bootstrapping with one TGGSW per mask element (see fhe_bootstrap_chain in include/fhe_b200.h).  Extension."""
+    batch = _numel(ct) // (int(c_kn) + 1)
+    width = (ksk.kn_out if ksk is not None else int(k) * int(n)) + 1
+    out = _new(ct, (batch, width)) if out is None else out
+    _check_u64(table, ct, out)
+    check(lib.fhe_bootstrap_chain(int(n), int(k), _handles(bsk), len(bsk), int(mode), ksk._h if ksk is not None else None,
+                                  ptr(table), ptr(ct), int(c_kn), ptr(out), batch))
+    return out
+
+
 def sample_extract(n, k, ct, h, out=None):
     batch = _numel(ct) // ((int(k) + 1) * int(n))
     out = _new(ct, (batch, int(k) * int(n) + 1)) if out is None else out

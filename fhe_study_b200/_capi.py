@@ -63,6 +63,8 @@ SIGNATURES = {
     "fhe_sample_extract": (I, [U64, U64, P, U64, P, SZ]),
     "fhe_blind_rotate": (I, [U64, U64, P, I, P, P, U64, P, SZ]),
     "fhe_bootstrap": (I, [U64, U64, P, P, P, U64, P, SZ]),
+    "fhe_cmux_chain": (I, [U64, U64, P, U64, I, P, P, P, SZ]),
+    "fhe_bootstrap_chain": (I, [U64, U64, P, U64, I, P, P, P, U64, P, SZ]),
     "fhe_bfv_tensor": (I, [U64, U64, U64, P, P, P, SZ]),
     "fhe_bfv_relinearize": (I, [U64, U64, U64, P, P, P, SZ]),
     "fhe_bfv_mul_relin": (I, [U64, U64, U64, U64, P, P, P, P, SZ]),

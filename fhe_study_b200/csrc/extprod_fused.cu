@@ -36,6 +36,7 @@ template <int LOGN, int K1> struct XpGeom {
     static constexpr int IPT = (ITEMS + CT - 1) / CT;   // MAC items per thread
     static constexpr int IPT4 = (IPT + 3) / 4 * 4;      // padded to whole uint4 loads
     static constexpr size_t SMEM = (size_t)K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)2 * UNITS * N * 4;
+    static constexpr size_t SMEM_CHAIN = SMEM + (size_t)K1 * N * 8;  // + the accumulator, resident across steps
     static_assert(UNITS <= SLOTS, "need a slot per inverse transform");
     static_assert(S::T <= 32, "one digit NTT must fit a warp (N <= 1024) in this kernel");
 };
@@ -46,6 +47,15 @@ struct XpParams {
     u64 mu[2];                // floor(2^64 / p_r): Barrett constant for the 64-bit accumulators
     const u32 *R[2];          // fused key layout: R[r][d][t*IPT4 + m] = NTT value of item t + 256 m of digit d
     CrtParams cp;
+};
+
+// CMux chain (blind rotation): acc <- cmux(key[j], acc, X^{-h[j]} acc) for j < steps, the accumulator staying in
+// shared memory for the whole chain (ONE HBM round trip per chain instead of one per CMux).
+struct XpChain {
+    const u32 *const *R;   // [steps][2] fused key layouts of the TGGSW of every step (device array)
+    const u64 *h;          // [batch][steps] rotation amounts
+    int steps;
+    int negacyclic;        // 0: TGLWE::left_rotate (h mod n, ring_torus.rs:118-132); 1: true X^{-h}, h mod 2n
 };
 
 // acc mod p for acc < 2^63 (result canonical)
@@ -73,10 +83,10 @@ __device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32
     for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = ms.mul_tw(x[e], ms.one);
 }
 
-template <int LOGN, int K1>
+template <int LOGN, int K1, bool CHAIN>
 __global__ void __launch_bounds__(256, 2)
 extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__ ct1, const u64 *__restrict__ ct2,
-                     u64 *__restrict__ out, int cmux) {
+                     u64 *__restrict__ out, int cmux, const XpChain ch) {
     typedef XpGeom<LOGN, K1> G;
     typedef typename G::S S;
     constexpr int LOGE = G::LOGE, N = G::N, LAST = S::P - 1;
@@ -84,17 +94,40 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     u64 *xin = reinterpret_cast<u64 *>(smem_raw);                         // [K1][N] decomposed input
     u32 *xch = reinterpret_cast<u32 *>(xin + (size_t)K1 * N);             // [SLOTS][PADN] exchange / NTT(digit)
     u32 *res = xch + (size_t)G::SLOTS * G::PADN;                          // [2][UNITS][N] residues of the result
+    u64 *accs = reinterpret_cast<u64 *>(res + (size_t)2 * G::UNITS * N);  // [K1][N] chain accumulator (CHAIN only)
     const int t = threadIdx.x;
     const int slot = t / S::T, tid = t % S::T;
     u32 *sm = xch + (size_t)slot * G::PADN;
     const size_t base = (size_t)blockIdx.x * K1 * N;
 
-    // input of the external product: ct (extprod) or ct2 - ct1 (TGGSW::cmux, tggsw.rs:39-41)
-    for (int i = t; i < K1 * N; i += G::CT) xin[i] = cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
+    const int steps = CHAIN ? ch.steps : 1;
+    if (CHAIN) {
+        for (int i = t; i < K1 * N; i += G::CT) accs[i] = ct1[base + i];
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int step = 0; step < steps; step++) {
+    // input of the external product: ct (extprod), ct2 - ct1 (TGGSW::cmux, tggsw.rs:39-41), or for the chain
+    // X^{-h} acc - acc (the CMux of tlwe.rs:140-146 with ct2 = acc.left_rotate(h))
+    if (CHAIN) {
+        const u64 hraw = ch.h[(size_t)blockIdx.x * steps + step];
+        const u32 h = (u32)(hraw & (N - 1));
+        const bool flip = ch.negacyclic && ((hraw >> LOGN) & 1);
+        for (int i = t; i < K1 * N; i += G::CT) {
+            const int c = i >> LOGN, p = i & (N - 1);
+            const u32 src = (u32)p + h;
+            u64 v = src < (u32)N ? accs[(c << LOGN) + src] : (u64)0 - accs[(c << LOGN) + src - N];
+            if (flip) v = (u64)0 - v;
+            xin[i] = v - accs[i];
+        }
+    } else {
+        for (int i = t; i < K1 * N; i += G::CT) xin[i] = cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
+    }
     __syncthreads();
 
 #pragma unroll 1
     for (int r = 0; r < 2; r++) {
+        const u32 *Rr = CHAIN ? ch.R[2 * step + r] : X.R[r];
         const Lazy32 &ml = X.P[r].mod;
         u64 acc[G::IPT];
 #pragma unroll
@@ -108,7 +141,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
             }
             __syncthreads();
             const int nslots = min(G::SLOTS, G::ND - round * G::SLOTS);
-            const uint4 *Rt = reinterpret_cast<const uint4 *>(X.R[r] + ((size_t)round * G::SLOTS * G::CT + t) * G::IPT4);
+            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr + ((size_t)round * G::SLOTS * G::CT + t) * G::IPT4);
 #pragma unroll 2
             for (int s = 0; s < nslots; s++) {
                 const u32 *D = xch + (size_t)s * G::PADN;
@@ -158,8 +191,13 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
                                     X.cp.halfP, X.cp.m2);
         const u64 hi = crt_centered(res1[(c * 2 + 1) * N + p], res2[(c * 2 + 1) * N + p], X.cp.p1, X.cp.p2,
                                     X.cp.p1_inv_mod_p2, X.cp.P, X.cp.halfP, X.cp.m2);
-        out[base + i] = (cmux ? ct1[base + i] : 0) + lo + (hi << 32);
+        if (CHAIN) accs[i] += lo + (hi << 32);
+        else out[base + i] = (cmux ? ct1[base + i] : 0) + lo + (hi << 32);
     }
+    if (CHAIN) __syncthreads();  // accs and res are read again by the next step
+    }  // step
+    if (CHAIN)
+        for (int i = t; i < K1 * N; i += G::CT) out[base + i] = accs[i];
 }
 
 // unfused key layout (u64, [d][u][x]) -> fused layout (u32, [d][t][IPT4], item = t + 256 m), zero padded
@@ -190,14 +228,42 @@ static int launch_fused(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out
     static unsigned long long done_mask = 0;
     int dev = 0;
     FHE_CUDA_OK(cudaGetDevice(&dev));
-    auto kern = extprod_fused_kernel<LOGN, K1>;
+    auto kern = extprod_fused_kernel<LOGN, K1, false>;
     const int threads = G::CT;
     const size_t smem = G::SMEM;
     if (!((done_mask >> (dev & 63)) & 1ull)) {
         FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done_mask |= 1ull << (dev & 63);
     }
-    kern<<<(unsigned)batch, threads, smem, st>>>(X, ct1, ct2, out, cmux);
+    kern<<<(unsigned)batch, threads, smem, st>>>(X, ct1, ct2, out, cmux, XpChain{nullptr, nullptr, 1, 0});
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int LOGN, int K1>
+static int launch_chain(const TorusCtx &tc, const u32 *const *keys_dev, const u64 *h_dev, int steps, int negacyclic,
+                        const u64 *acc_in, u64 *acc_out, size_t batch, cudaStream_t st) {
+    typedef XpGeom<LOGN, K1> G;
+    XpParams X;
+    X.P[0] = tc.plan1->p32;
+    X.P[1] = tc.plan2->p32;
+    init_mod(X.ms[0], TORUS_P1);
+    init_mod(X.ms[1], TORUS_P2);
+    X.mu[0] = ~0ull / TORUS_P1;
+    X.mu[1] = ~0ull / TORUS_P2;
+    X.R[0] = X.R[1] = nullptr;
+    X.cp = tc.cp;
+    FHE_REQUIRE(batch <= 0x7fffffffull, "cmux chain: batch too large");
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    FHE_CUDA_OK(cudaGetDevice(&dev));
+    auto kern = extprod_fused_kernel<LOGN, K1, true>;
+    if (!((done_mask >> (dev & 63)) & 1ull)) {
+        FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_CHAIN));
+        done_mask |= 1ull << (dev & 63);
+    }
+    kern<<<(unsigned)batch, G::CT, G::SMEM_CHAIN, st>>>(X, acc_in, nullptr, acc_out, 1, XpChain{keys_dev, h_dev, steps, negacyclic});
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -241,6 +307,17 @@ int extprod_fused_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *ou
     FHE_XP_SHAPES(F)
 #undef F
     set_error("internal: fused external product called for an unsupported shape");
+    return -1;
+}
+
+// acc_out[b] = chain of `steps` CMuxes over acc_in[b]; keys_dev = device array [steps][2] of fused key layouts
+int cmux_chain_fused_device(const TorusCtx &tc, int k1, const u32 *const *keys_dev, const u64 *h_dev, int steps,
+                            int negacyclic, const u64 *acc_in, u64 *acc_out, size_t batch, cudaStream_t st) {
+    const int logn = tc.logn;
+#define F(L, K) if (logn == L && k1 == K) return launch_chain<L, K>(tc, keys_dev, h_dev, steps, negacyclic, acc_in, acc_out, batch, st);
+    FHE_XP_SHAPES(F)
+#undef F
+    set_error("internal: fused CMux chain called for an unsupported shape");
     return -1;
 }
 

@@ -161,4 +161,45 @@ int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *ta
     return finish_all({&bt, &bc, &bo}, st);
 }
 
+
+// Extension: blind rotation with one TGGSW per mask element, as a CMux chain kept on chip.
+int fhe_bootstrap_chain(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, uint64_t steps, int mode, const fhe_ksk *ksk,
+                        const uint64_t *table, const uint64_t *ct, uint64_t c_kn, uint64_t *out, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(table && ct && out && (steps == 0 || bsk), "fhe_bootstrap_chain: null pointer");
+    FHE_REQUIRE(n >= 2 && k >= 1 && (n & (n - 1)) == 0, "fhe_bootstrap_chain: n must be a power of two");
+    FHE_REQUIRE(steps <= c_kn, "fhe_bootstrap_chain: more TGGSWs than mask elements");
+    FHE_REQUIRE(ksk == nullptr || ksk->k.kn_in == k * n, "fhe_bootstrap_chain: KSK input dimension must be k*n");
+    std::vector<const Tggsw *> gs(steps);
+    for (uint64_t j = 0; j < steps; j++) {
+        FHE_REQUIRE(bsk[j] != nullptr && bsk[j]->n == n && bsk[j]->g.k == k, "fhe_bootstrap_chain: bad TGGSW handle");
+        gs[j] = &bsk[j]->g;
+    }
+    cudaStream_t st = current_stream();
+    const size_t glwe = (k + 1) * n, kn = k * n, out_w = ksk ? ksk->k.kn_out + 1 : kn + 1;
+    IoBuf bt, bc, bo;
+    int rc;
+    if ((rc = bt.init(table, glwe * 8, true, false, st))) return rc;
+    if ((rc = bc.init(ct, batch * (c_kn + 1) * 8, true, false, st))) return rc;
+    if ((rc = bo.init(out, batch * out_w * 8, false, true, st))) return rc;
+    Scratch s_acc, s_acc2, s_hs, s_ext;
+    if ((rc = s_acc.alloc(batch * glwe * 8, st))) return rc;
+    if ((rc = s_acc2.alloc(batch * glwe * 8, st))) return rc;
+    if ((rc = s_hs.alloc(batch * (steps ? steps : 1) * 8, st))) return rc;
+    if (ksk && (rc = s_ext.alloc(batch * (kn + 1) * 8, st))) return rc;
+    if ((rc = chain_prepare_device(bt.ptr<u64>(), bc.ptr<u64>(), s_acc.ptr<u64>(), s_hs.ptr<u64>(), batch, (u32)n, (u32)k,
+                                   (u32)c_kn, (u32)steps, mode != 0, st)))
+        return rc;
+    const u64 *acc = s_acc.ptr<u64>();
+    if (steps) {
+        if ((rc = cmux_chain_device(gs.data(), steps, s_acc.ptr<u64>(), s_hs.ptr<u64>(), mode != 0, s_acc2.ptr<u64>(), batch, st)))
+            return rc;
+        acc = s_acc2.ptr<u64>();
+    }
+    u64 *ext = ksk ? s_ext.ptr<u64>() : bo.ptr<u64>();
+    if ((rc = sample_extract_device(acc, ext, batch, (u32)n, (u32)k, 0, st))) return rc;
+    if (ksk && (rc = key_switch_device(ksk->k, ext, bo.ptr<u64>(), batch, st))) return rc;
+    return finish_all({&bt, &bc, &bo}, st);
+}
+
 }  // extern "C"

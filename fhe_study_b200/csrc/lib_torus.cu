@@ -1,6 +1,7 @@
 // lib_torus.cu -- C-ABI entry points of the torus (q = 2^64) path: Tn arithmetic, TGGSW external product, CMux.
 #include <map>
 #include <memory>
+#include <vector>
 
 #include "../../include/fhe_b200.h"
 #include "runtime.cuh"
@@ -131,6 +132,34 @@ int fhe_extprod(const fhe_tggsw *h, const uint64_t *ct, uint64_t *out, size_t ba
 }
 int fhe_cmux(const fhe_tggsw *h, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out, size_t batch) {
     return extprod_entry(h, ct1, ct2, out, batch, true);
+}
+
+
+int fhe_cmux_chain(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, uint64_t steps, int negacyclic,
+                   const uint64_t *acc_in, const uint64_t *h, uint64_t *acc_out, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(acc_in && acc_out && (steps == 0 || (bsk && h)), "fhe_cmux_chain: null pointer");
+    FHE_REQUIRE(n >= 2 && (n & (n - 1)) == 0 && k >= 1, "fhe_cmux_chain: n must be a power of two");
+    std::vector<const Tggsw *> gs(steps);
+    for (uint64_t j = 0; j < steps; j++) {
+        FHE_REQUIRE(bsk[j] != nullptr && bsk[j]->n == n && bsk[j]->g.k == k, "fhe_cmux_chain: bad TGGSW handle");
+        gs[j] = &bsk[j]->g;
+    }
+    cudaStream_t st = current_stream();
+    const size_t bytes = batch * (k + 1) * n * sizeof(u64);
+    IoBuf bi, bh, bo;
+    int rc;
+    if ((rc = bi.init(acc_in, bytes, true, false, st))) return rc;
+    if ((rc = bh.init(steps ? h : nullptr, batch * steps * sizeof(u64), true, false, st))) return rc;
+    if ((rc = bo.init(acc_out, bytes, false, true, st))) return rc;
+    if (steps == 0) {
+        if (bo.ptr<u64>() != bi.ptr<u64>())
+            FHE_CUDA_OK(cudaMemcpyAsync(bo.ptr<u64>(), bi.ptr<u64>(), bytes, cudaMemcpyDeviceToDevice, st));
+    } else if ((rc = cmux_chain_device(gs.data(), steps, bi.ptr<u64>(), bh.ptr<u64>(), negacyclic != 0, bo.ptr<u64>(), batch,
+                                       st))) {
+        return rc;
+    }
+    return finish_all({&bi, &bh, &bo}, st);
 }
 
 }  // extern "C"

@@ -20,6 +20,8 @@ int key_switch_mma_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, c
 int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_out, size_t batch, u32 n, u32 k, u32 c_kn,
                           cudaStream_t st);
+int chain_prepare_device(const u64 *table, const u64 *ct, u64 *acc0, u64 *hs, size_t batch, u32 n, u32 k, u32 c_kn,
+                         u32 steps, int mode, cudaStream_t st);
 int sample_extract_device(const u64 *ct, u64 *out, size_t batch, u32 n, u32 k, u32 h, cudaStream_t st);
 int shift_right_device(const u64 *a, u64 *out, size_t len, u32 shift, cudaStream_t st);
 

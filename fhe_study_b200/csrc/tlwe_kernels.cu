@@ -132,6 +132,33 @@ __global__ void rotate_extract_kernel(const u64 *__restrict__ table, const u64 *
     }
 }
 
+// Start of a CMux-chain blind rotation (extension of tlwe.rs:121-148, see fhe_bootstrap_chain): per ciphertext
+// acc0 = X^{-b'} table and the per-step rotation amounts hs[b][j] from the mod-switched mask.
+//   mode 0 (as written): c' = c >> shift (mod_switch to k*n), left_rotate semantics (h mod n), hs = c'.a[j]
+//   mode 1 (working PBS): mod_switch to 2n, true negacyclic rotation, hs = (2n - c'.a[j]) mod 2n
+__global__ void chain_prepare_kernel(const u64 *__restrict__ table, const u64 *__restrict__ ct, u64 *__restrict__ acc0,
+                                     u64 *__restrict__ hs, size_t batch, u32 n, u32 k, u32 c_kn, u32 steps, u32 shift,
+                                     int mode) {
+    const size_t glwe = (size_t)(k + 1) * n;
+    const size_t tot = batch * glwe;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < tot; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / glwe;
+        const u32 r = (u32)(idx % glwe), i = r / n, c = r % n;
+        const u64 body = ct[b * (size_t)(c_kn + 1) + c_kn];
+        const u64 hb = shift >= 64 ? body : body >> shift;
+        const u64 v = rotated_coeff(table + (size_t)i * n, n, (u32)(hb % n), c);
+        acc0[idx] = (mode && ((hb / n) & 1)) ? (u64)0 - v : v;
+    }
+    const size_t toth = batch * (size_t)steps;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < toth; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / steps;
+        const u32 j = (u32)(idx % steps);
+        const u64 a = ct[b * (size_t)(c_kn + 1) + j];
+        const u64 am = shift >= 64 ? a : a >> shift;
+        hs[idx] = mode ? (2ull * n - am) % (2ull * n) : am;
+    }
+}
+
 // TGLWE::sample_extraction(h) (tglwe.rs:89-115) for `batch` TGLWEs, one common h
 __global__ void sample_extract_kernel(const u64 *__restrict__ ct, u64 *__restrict__ out, size_t batch, u32 n, u32 k,
                                       u32 h) {
@@ -168,6 +195,16 @@ int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_ou
     const u32 shift = 64 - log2kn;  // torus.rs:58-66 (release-mode shift; kn >= 2 in every caller)
     rotate_extract_kernel<<<grid_for(batch * (size_t)((k + 1) * n)), 256, 0, st>>>(table, ct, ext, acc_out, batch, n, k,
                                                                                   c_kn, shift);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int chain_prepare_device(const u64 *table, const u64 *ct, u64 *acc0, u64 *hs, size_t batch, u32 n, u32 k, u32 c_kn,
+                         u32 steps, int mode, cudaStream_t st) {
+    const u64 q2 = mode ? 2ull * n : (u64)k * n;
+    const u32 shift = 64 - (63 - __builtin_clzll(q2));  // torus.rs:58-66
+    chain_prepare_kernel<<<grid_for(batch * (size_t)((k + 1) * n)), 256, 0, st>>>(table, ct, acc0, hs, batch, n, k, c_kn,
+                                                                                 steps, shift, mode);
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;

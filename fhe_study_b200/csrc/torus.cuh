@@ -72,6 +72,12 @@ int extprod_fused_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *ou
 int tggsw_precompute(Tggsw &g, const u64 *rows_dev, cudaStream_t st);
 int tn_addsub_device(const u64 *a, const u64 *b, u64 *c, size_t len, int op, cudaStream_t st);
 int tn_left_rotate_device(const u64 *a, u64 *out, size_t polys, u32 n, const u64 *hs, u64 h_const, u32 group,
-                          cudaStream_t st);
+                          cudaStream_t st, size_t hs_stride = 1, int negacyclic = 0);
+int cmux_chain_fused_device(const TorusCtx &tc, int k1, const u32 *const *keys_dev, const u64 *h_dev, int steps,
+                            int negacyclic, const u64 *acc_in, u64 *acc_out, size_t batch, cudaStream_t st);
+// acc_out[b] = cmux(gs[steps-1], .., cmux(gs[0], acc_in[b], X^{-h[b][0]} acc_in[b]) ..): fused persistent kernel when
+// every TGGSW has the fused layout, otherwise one rotate + CMux launch pair per step.  h = [batch][steps].
+int cmux_chain_device(const Tggsw *const *gs, size_t steps, const u64 *acc_in, const u64 *h, int negacyclic, u64 *acc_out,
+                      size_t batch, cudaStream_t st);
 
 }  // namespace fhe

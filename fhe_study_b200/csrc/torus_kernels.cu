@@ -18,6 +18,8 @@
 #include "runtime.cuh"
 #include "torus.cuh"
 
+#include <vector>
+
 #include <stdlib.h>
 
 namespace fhe {
@@ -134,15 +136,20 @@ __global__ void tn_addsub_kernel(const u64 *a, const u64 *b, u64 *c, size_t len,
 }
 // Tn::left_rotate(h) (ring_torus.rs:118-132): out = [c_h..c_{n-1}, -c_0..-c_{h-1}], h reduced mod n.
 // One rotation amount per polynomial group: h = hs[poly / group] (hs == nullptr: h_const).
+// hs_stride: distance between consecutive groups' amounts in hs.  negacyclic != 0 (extension, no reference
+// counterpart): h is taken mod 2n and h >= n negates, i.e. the true multiplication by X^{-h}.
 __global__ void tn_left_rotate_kernel(const u64 *__restrict__ a, u64 *__restrict__ out, size_t polys, u32 n,
-                                      const u64 *__restrict__ hs, u64 h_const, u32 group) {
+                                      const u64 *__restrict__ hs, u64 h_const, u32 group, size_t hs_stride,
+                                      int negacyclic) {
     const size_t total = polys * n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t poly = i / n;
         const u32 c = (u32)(i % n);
-        const u32 h = (u32)((hs ? hs[poly / group] : h_const) % n);
+        const u64 hraw = hs ? hs[(poly / group) * hs_stride] : h_const;
+        const u32 h = (u32)(hraw % n);
         const u32 src = c + h;
-        out[i] = src < n ? a[poly * n + src] : (u64)0 - a[poly * n + (src - n)];
+        const u64 v = src < n ? a[poly * n + src] : (u64)0 - a[poly * n + (src - n)];
+        out[i] = (negacyclic && ((hraw / n) & 1)) ? (u64)0 - v : v;
     }
 }
 
@@ -296,9 +303,54 @@ int tn_addsub_device(const u64 *a, const u64 *b, u64 *c, size_t len, int op, cud
     FHE_CUDA_OK(cudaGetLastError());
     return 0;
 }
+int cmux_chain_device(const Tggsw *const *gs, size_t steps, const u64 *acc_in, const u64 *h, int negacyclic, u64 *acc_out,
+                      size_t batch, cudaStream_t st) {
+    FHE_REQUIRE(steps <= 0x7fffffffull, "cmux chain: too many steps");
+    FHE_REQUIRE(steps >= 1, "cmux chain: internal, zero steps are handled by the caller");
+    const TorusCtx &tc = *gs[0]->tc;
+    const u32 n = (u32)tc.n, k1 = (u32)gs[0]->k + 1;
+    const size_t glwe = (size_t)k1 * n;
+    bool all_fused = true;
+    for (size_t j = 0; j < steps; j++) {
+        FHE_REQUIRE(gs[j]->tc == &tc && gs[j]->k + 1 == k1, "cmux chain: every TGGSW must share (n, k)");
+        all_fused = all_fused && gs[j]->R1f != nullptr;
+    }
+    const char *force = getenv("FHE_EXTPROD_PATH");
+    if (force && strncmp(force, "fused", 5) == 0 && !all_fused) {
+        set_error("FHE_EXTPROD_PATH=fused but this (n, k) has no fused instantiation");
+        return -1;
+    }
+    int rc;
+    if (all_fused && !(force && strcmp(force, "unfused") == 0)) {
+        std::vector<const u32 *> keys(2 * steps);
+        for (size_t j = 0; j < steps; j++) {
+            keys[2 * j] = gs[j]->R1f;
+            keys[2 * j + 1] = gs[j]->R2f;
+        }
+        Scratch s_keys;
+        if ((rc = s_keys.alloc(keys.size() * sizeof(void *), st))) return rc;
+        // pageable source: the copy is staged before the call returns, so `keys` may die with this frame
+        FHE_CUDA_OK(cudaMemcpyAsync(s_keys.ptr<void>(), keys.data(), keys.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
+        return cmux_chain_fused_device(tc, (int)k1, s_keys.ptr<const u32 *>(), h, (int)steps, negacyclic, acc_in, acc_out,
+                                       batch, st);
+    }
+    Scratch s_rot, s_a, s_b;
+    if ((rc = s_rot.alloc(batch * glwe * 8, st))) return rc;
+    if ((rc = s_a.alloc(batch * glwe * 8, st))) return rc;
+    if ((rc = s_b.alloc(batch * glwe * 8, st))) return rc;
+    u64 *rot = s_rot.ptr<u64>(), *pp[2] = {s_a.ptr<u64>(), s_b.ptr<u64>()};
+    const u64 *cur = acc_in;
+    for (size_t j = 0; j < steps; j++) {
+        if ((rc = tn_left_rotate_device(cur, rot, batch * k1, n, h + j, 0, k1, st, steps, negacyclic))) return rc;
+        if ((rc = extprod_device(*gs[j], cur, rot, pp[j & 1], batch, st))) return rc;  // cmux(gs[j], acc, rot)
+        cur = pp[j & 1];
+    }
+    FHE_CUDA_OK(cudaMemcpyAsync(acc_out, cur, batch * glwe * 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
 int tn_left_rotate_device(const u64 *a, u64 *out, size_t polys, u32 n, const u64 *hs, u64 h_const, u32 group,
-                          cudaStream_t st) {
-    tn_left_rotate_kernel<<<grid_for(polys * n), 256, 0, st>>>(a, out, polys, n, hs, h_const, group);
+                          cudaStream_t st, size_t hs_stride, int negacyclic) {
+    tn_left_rotate_kernel<<<grid_for(polys * n), 256, 0, st>>>(a, out, polys, n, hs, h_const, group, hs_stride, negacyclic);
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -99,6 +99,17 @@ FHE_API int fhe_extprod(const fhe_tggsw *handle, const uint64_t *ct, uint64_t *o
 /* TGGSW::cmux (tggsw.rs:39-41): out_b = ct1_b + tggsw (x) (ct2_b - ct1_b). */
 FHE_API int fhe_cmux(const fhe_tggsw *handle, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out, size_t batch);
 
+/* CMux chain -- the loop blind_rotation spells out (tlwe.rs:138-147) for `steps` TGGSWs, composed from
+ * TGGSW::cmux (tggsw.rs:39-41) and TGLWE::left_rotate (tglwe.rs:116-119):
+ *   acc_b <- cmux(bsk[j], acc_b, X^{-h[b*steps+j]} * acc_b)   for j = 0 .. steps-1.
+ * negacyclic == 0: the rotation is left_rotate (h reduced mod n, ring_torus.rs:118-132);
+ * negacyclic != 0: h is taken mod 2n and h >= n also negates (the true product by X^{-h}; the reference has no
+ * such rotation, a working blind rotation needs it).  EXTENSION: no reference execution runs a
+ * chain; parity is against the composition of the reference's own primitives.  When (n, k) has a fused kernel
+ * the accumulator stays on chip for the whole chain (one HBM round trip per chain). */
+FHE_API int fhe_cmux_chain(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, uint64_t steps, int negacyclic,
+                           const uint64_t *acc_in, const uint64_t *h, uint64_t *acc_out, size_t batch);
+
 /* ---- TLWE key switch / bootstrapping (tfhe/src/tlwe.rs, tfhe/src/tglwe.rs) ------------------------------ */
 typedef struct fhe_ksk fhe_ksk;
 /* KSK(Vec<TLev>) (tlwe.rs:84-100, tlev.rs:53-77): kn_in * l TLWE rows of kn_out+1 words, resident in HBM. */
@@ -120,6 +131,18 @@ FHE_API int fhe_blind_rotate(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk
  * table: one TGLWE ((k+1)*n words, e.g. compute_lookup_table's); ct: `batch` TLWEs of c_kn+1 words. */
 FHE_API int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *table, const uint64_t *ct, uint64_t c_kn,
                           uint64_t *out, size_t batch);
+
+/* Bootstrapping with one TGGSW per mask element (bsk: `steps` handles, steps <= c_kn) -- the blind rotation the
+ * reference's loop is evidently meant to be (EXTENSION, see fhe_cmux_chain):
+ *   mode 0 "as written": c' = mod_switch(c, k*n); acc = table.left_rotate(c'.b);
+ *                        acc = cmux(bsk[j], acc, acc.left_rotate(c'.a[j])) for j < steps
+ *   mode 1 "working":    c' = mod_switch(c, 2n); acc = X^{-c'.b} table; acc = cmux(bsk[j], acc, X^{+c'.a[j]} acc),
+ *                        true negacyclic rotations, so acc = X^{-(b - <a,s>)} table when bsk[j] encrypts bit s_j
+ * then sample_extraction(0) and, when ksk != NULL, key_switch (kn_in = k*n).  out: k*n+1 words per ciphertext
+ * (ksk == NULL) or kn_out+1. */
+FHE_API int fhe_bootstrap_chain(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, uint64_t steps, int mode,
+                                const fhe_ksk *ksk, const uint64_t *table, const uint64_t *ct, uint64_t c_kn, uint64_t *out,
+                                size_t batch);
 
 /* ---- BFV ciphertext multiplication (bfv/src/lib.rs) ----------------------------------------------------------- */
 /* RLWE::tensor (lib.rs:59-85): a, b = `batch` RLWEs (2n words) -> c0|c1|c2 (3n words each). */

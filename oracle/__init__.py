@@ -127,6 +127,8 @@ def _declare(L):
     d("orc_tlwe_encrypt_s", None, U64, U64, D, P, U64, I, P)
     d("orc_tlwe_decrypt", U64, U64, P, P)
     d("orc_tlwe_new_ksk", None, U64, U64, U64, U32, D, P, P, I, P)
+    d("orc_cmux_chain", None, U64, U64, U64, P, P, P, I, P)
+    d("orc_bootstrap_chain", None, U64, U64, U64, P, P, P, P, U64, I, P)
     d("orc_bfv_keygen", None, U64, U64, U64, P, P)
     d("orc_bfv_encrypt", None, U64, U64, U64, U64, P, P, P)
     d("orc_bfv_decrypt", None, U64, U64, U64, P, P, P)
@@ -247,6 +249,31 @@ def bootstrapping(n: int, k: int, ksk, table, c, c_kn: int, threads: int = 1) ->
     batch = c.size // (c_kn + 1)
     out = np.empty(batch * (k * n + 1), dtype=np.uint64)
     lib().orc_bootstrapping_batch(n, k, ptr(ksk), ptr(table), ptr(c), c_kn, ptr(out), batch, threads)
+    return out
+
+
+def cmux_chain(n: int, k: int, bsk, acc, h, negacyclic: bool = False) -> np.ndarray:
+    """acc_b <- cmux(bsk[j], acc_b, rotate(acc_b, h[b][j])) for j < steps; bsk = steps flat TGGSWs, h = [batch][steps]."""
+    bsk, acc, h = u64(bsk), u64(acc), u64(h)
+    glwe = (k + 1) * n
+    batch = acc.size // glwe
+    steps = h.size // batch
+    out = np.empty_like(acc)
+    for i in range(batch):
+        lib().orc_cmux_chain(n, k, steps, ptr(bsk), ptr(acc.reshape(-1)[i * glwe:]), ptr(h.reshape(-1)[i * steps:]),
+                             int(negacyclic), ptr(out.reshape(-1)[i * glwe:]))
+    return out
+
+
+def bootstrap_chain(n: int, k: int, steps: int, bsk, ksk, table, c, c_kn: int, mode: int) -> np.ndarray:
+    bsk, table, c = u64(bsk), u64(table), u64(c)
+    ksk = u64(ksk) if ksk is not None else None
+    kn = k * n
+    batch = c.size // (c_kn + 1)
+    out = np.empty((batch, kn + 1), dtype=np.uint64)
+    for i in range(batch):
+        lib().orc_bootstrap_chain(n, k, steps, ptr(bsk), ptr(ksk) if ksk is not None else None, ptr(table),
+                                  ptr(c.reshape(-1)[i * (c_kn + 1):]), c_kn, mode, ptr(out[i]))
     return out
 
 

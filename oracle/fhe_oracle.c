@@ -632,6 +632,55 @@ API void orc_blind_rotation_as_written(u64 n, u64 k, const u64 *c, u64 c_kn, con
     }
     free(rot);
 }
+/* X^{-h} acting on a TGLWE.  negacyclic = 0: exactly TGLWE::left_rotate (tglwe.rs:116-119 -> ring_torus.rs:118-132,
+ * h reduced mod n, so the sign never flips twice).  negacyclic = 1: h is taken mod 2n and h >= n means
+ * -(left_rotate(h - n)), i.e. the true multiplication by X^{-h} in T[X]/(X^n+1) that a working blind rotation
+ * needs.  The reference has no such function; mode 1 is an extension. */
+static void tglwe_rotate_mode(u64 n, u64 k, const u64 *ct, u64 h, int negacyclic, u64 *out) {
+    if (!negacyclic) { orc_tglwe_left_rotate(n, k, ct, h, out); return; }
+    h %= 2 * n;
+    orc_tglwe_left_rotate(n, k, ct, h % n, out);
+    if (h >= n) for (u64 x = 0; x < (k + 1) * n; x++) out[x] = (u64)0 - out[x];
+}
+/* CMux chain -- the loop blind_rotation spells out (tlwe.rs:138-147: c_j = cmux(btk[j], c_j, c_j.left_rotate(a_j)))
+ * composed for `steps` TGGSWs (bsk = steps flat TGGSWs), rotation amounts h[0..steps).  Extension oracle:
+ * composition of the reference's own cmux (tggsw.rs:39-41) and left_rotate; no reference execution runs it. */
+API void orc_cmux_chain(u64 n, u64 k, u64 steps, const u64 *bsk, const u64 *acc_in, const u64 *h, int negacyclic,
+                        u64 *out) {
+    u64 glwe = (k + 1) * n;
+    u64 tggsw_sz = (k + 1) * 64 * glwe;
+    u64 *rot = (u64 *)malloc(sizeof(u64) * 2 * glwe), *nxt = rot + glwe;
+    memcpy(out, acc_in, sizeof(u64) * glwe);
+    for (u64 j = 0; j < steps; j++) {
+        tglwe_rotate_mode(n, k, out, h[j], negacyclic, rot);
+        tggsw_cmux(n, k, bsk + j * tggsw_sz, out, rot, nxt, 1);
+        memcpy(out, nxt, sizeof(u64) * glwe);
+    }
+    free(rot);
+}
+/* Bootstrapping with one TGGSW per mask element of the input TLWE (bsk = steps TGGSWs, steps <= c_kn), i.e. the
+ * blind rotation the reference's loop is evidently meant to be.  Extension; composition of reference primitives.
+ *  mode 0 ("as written"): c' = mod_switch(c, k*n); acc = table.left_rotate(c'.b); h_j = c'.a[j]; left_rotate.
+ *  mode 1 ("working PBS"): c' = mod_switch(c, 2n); acc = X^{-c'.b} * table; h_j = (2n - c'.a[j]) mod 2n, true
+ *          negacyclic rotation, so that acc ends as X^{-(b - <a,s>)} * table when bsk[j] encrypts the bit s_j.
+ * then sample_extraction(0) and, when ksk != NULL, key_switch(2, 64, ksk) (kn -> kn). */
+API void orc_bootstrap_chain(u64 n, u64 k, u64 steps, const u64 *bsk, const u64 *ksk, const u64 *table, const u64 *c,
+                             u64 c_kn, int mode, u64 *out) {
+    u64 glwe = (k + 1) * n, kn = k * n;
+    u64 q2 = mode ? 2 * n : kn;
+    u64 *acc = (u64 *)malloc(sizeof(u64) * (2 * glwe + kn + 1)), *acc2 = acc + glwe, *ext = acc2 + glwe;
+    u64 *h = (u64 *)malloc(sizeof(u64) * (steps ? steps : 1));
+    tglwe_rotate_mode(n, k, table, orc_t64_mod_switch(c[c_kn], q2), mode, acc);
+    for (u64 j = 0; j < steps; j++) {
+        u64 a = orc_t64_mod_switch(c[j], q2);
+        h[j] = mode ? (2 * n - a) % (2 * n) : a;
+    }
+    orc_cmux_chain(n, k, steps, bsk, acc, h, mode, acc2);
+    orc_tglwe_sample_extraction(n, k, acc2, 0, ext);
+    if (ksk) orc_tlwe_key_switch(kn, kn, 64, ksk, ext, out);
+    else memcpy(out, ext, sizeof(u64) * (kn + 1));
+    free(acc); free(h);
+}
 /* tfhe/src/tlwe.rs:150-161 as executed: blind_rotation -> sample_extraction(0) -> key_switch(2,64) */
 API void orc_bootstrapping(u64 n, u64 k, const u64 *ksk, const u64 *table, const u64 *c, u64 c_kn, u64 *out) {
     u64 glwe = (k + 1) * n, kn = k * n;

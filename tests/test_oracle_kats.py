@@ -312,3 +312,51 @@ def test_bfv_mul_relin_functional(orc):
         L.orc_r_mul_to_rq(n, orc.ptr(orc.i64(m1)), orc.ptr(orc.i64(m2)), t, orc.ptr(expect))
         ok += int(np.array_equal(m3, expect))
     assert ok == trials
+
+
+# ---- CMux chain / blind rotation with one TGGSW per mask element (extension of tlwe.rs:138-147) ----------
+def pbs_fixture(orc, n=64, k=1, m_lwe=6, t=4, seed=77, sigma=3.2):
+    """Binary LWE key s, GLWE key z, bsk[j] = TGGSW_z(s_j), table = identity LUT, inputs encrypting 0..t-1."""
+    L = orc.lib()
+    s = (orc.uniform(seed, m_lwe) & np.uint64(1)).astype(np.uint64)
+    z = (orc.uniform(seed + 1, k * n) & np.uint64(1)).astype(np.uint64)
+    glwe = (k + 1) * n
+    bsk = np.zeros((m_lwe, (k + 1) * 64 * glwe), dtype=np.uint64)
+    for j in range(m_lwe):
+        msg = np.zeros(n, dtype=np.uint64)
+        msg[0] = s[j]
+        L.orc_tggsw_encrypt_s(seed + 10 + j, n, k, sigma, orc.ptr(z), orc.ptr(msg), 1, orc.ptr(bsk[j]))
+    table = orc.lookup_table(n, k, t)
+    delta_n = n // t
+    cts = np.zeros((t, m_lwe + 1), dtype=np.uint64)
+    for m in range(t):
+        phase = (m * delta_n + delta_n // 2) * (2**64 // (2 * n))  # centre of the m-th window of the LUT
+        L.orc_tlwe_encrypt_s(seed + 100 + m, m_lwe, sigma, orc.ptr(s), phase, 1, orc.ptr(cts[m]))
+    return s, z, bsk, table, cts
+
+
+def test_bootstrap_chain_recovers_message(orc):
+    n, k, m_lwe, t = 64, 1, 6, 4
+    s, z, bsk, table, cts = pbs_fixture(orc, n, k, m_lwe, t)
+    out = orc.bootstrap_chain(n, k, m_lwe, bsk, None, table, cts, m_lwe, mode=1)  # TLWE of dimension k*n under z
+    delta = (2**64 - 1) // t
+    for m in range(t):
+        phase = int(orc.lib().orc_tlwe_decrypt(k * n, orc.ptr(z), orc.ptr(out[m])))
+        assert round(phase / delta) % t == m
+
+
+def test_cmux_chain_is_composition_of_cmux_and_left_rotate(orc):
+    n, k, steps = 16, 2, 3
+    glwe = (k + 1) * n
+    bsk = orc.uniform(5, steps * (k + 1) * 64 * glwe)
+    acc = orc.uniform(6, glwe)
+    for neg in (False, True):
+        h = np.array([3, n + 5, 2 * n + 1], dtype=np.uint64)
+        want = acc.copy()
+        for j in range(steps):
+            hj = int(h[j])
+            rot = np.concatenate([orc.tn_left_rotate(n, want[c * n:(c + 1) * n], hj % n) for c in range(k + 1)])
+            if neg and (hj % (2 * n)) >= n:
+                rot = np.uint64(0) - rot
+            want = orc.cmux(n, k, bsk[j * (k + 1) * 64 * glwe:(j + 1) * (k + 1) * 64 * glwe], want, rot, fast=False)
+        assert np.array_equal(orc.cmux_chain(n, k, bsk, acc, h, negacyclic=neg).reshape(-1), want)
