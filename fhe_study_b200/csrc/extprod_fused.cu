@@ -45,7 +45,8 @@ struct XpParams {
     NttParams<Lazy32> P[2];   // plans of p1, p2 (device-order tables, n^-1 constants)
     Small32 ms[2];            // same moduli, csub-free forward butterflies
     u64 mu[2];                // floor(2^64 / p_r): Barrett constant for the 64-bit accumulators
-    const u32 *R[2];          // fused key layout: R[r][d][t*IPT4 + m] = NTT value of item t + 256 m of digit d
+    const u32 *R[2];          // fused key layout: R[r][d][v][t][j] = NTT value of item t + 256 (4v + j) of digit d
+                              // (one uint4 per thread and v: every warp load is 512 contiguous bytes)
     CrtParams cp;
 };
 
@@ -66,21 +67,39 @@ __device__ __forceinline__ u32 reduce64(u64 acc, u32 p, u64 mu) {
 }
 
 // NTT of digit polynomial d = (i, j) of the decomposed input under prime r, left in `sm` (padded position
-// order, values in [0, 2p)): bit 63-j of x_i (Tn::decompose, torus.rs:43-52) -> register-blocked forward NTT.
+// order, values < 2^28): bit 63-j of x_i (Tn::decompose, torus.rs:43-52) -> register-blocked forward NTT.
+//  * stage 0 works on bits: V = b*S is a select (mask & S), no multiplication;
+//  * the csub-free butterflies leave values < (2*LOGN+1)*p < 2^32; the final partial reduction
+//    x - (x >> 27)*p = (x mod 2^27) + (x >> 27)*(2^27 - p) < 2^27 + 21*2^21 < 2^28 costs one shift and one IMAD
+//    (the MAC then adds at most (k+1)*64 <= 320 products < 2^28 * 2^27: below 2^64).
 template <int LOGN>
 __device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32> &twf, int d, const u64 *xin, u32 *sm,
                                           int tid) {
     constexpr int LOGE = LOGN < 5 ? LOGN : 5;
     typedef NttShape<LOGN, LOGE> S;
     constexpr int LAST = S::P - 1;
+    constexpr int G0 = 1 << S::g(0), H0 = G0 >> 1;
+    static_assert(S::g(0) >= 2, "digit_ntt: pass 0 needs at least two stages");
     const u64 *xi = xin + (size_t)(d >> 6) * S::N;
     const int sh = 63 - (d & 63);
     u32 x[S::E];
 #pragma unroll
     for (int e = 0; e < S::E; e++) x[e] = (u32)(xi[S::pos(0, tid, e)] >> sh) & 1u;
-    fwd_chain<Small32, LOGN, LOGE>(x, sm, tid, ms, twf);
+    {   // stage 0 (ntt.rs:56-60 with U, V in {0,1}): x = U + V*S, y = U - V*S (+2p), S = roots[1]
+        const u32 S1 = twf.c0[1].w;
 #pragma unroll
-    for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = ms.mul_tw(x[e], ms.one);
+        for (int qi = 0; qi < (S::E >> S::g(0)); qi++)
+#pragma unroll
+            for (int lo = 0; lo < H0; lo++) {
+                const u32 U = x[qi * G0 + lo], V = (0u - x[qi * G0 + lo + H0]) & S1;
+                x[qi * G0 + lo] = U + V;
+                x[qi * G0 + lo + H0] = U + ms.q2 - V;
+            }
+    }
+    fwd_pass<Small32, LOGN, LOGE, 0, 1>(x, tid, ms, twf);
+    if constexpr (S::P > 1) fwd_chain<Small32, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
+#pragma unroll
+    for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = x[e] - (x[e] >> 27) * ms.q;
 }
 
 template <int LOGN, int K1, bool CHAIN>
@@ -141,14 +160,14 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
             }
             __syncthreads();
             const int nslots = min(G::SLOTS, G::ND - round * G::SLOTS);
-            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr + ((size_t)round * G::SLOTS * G::CT + t) * G::IPT4);
+            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr) + (size_t)round * G::SLOTS * (G::IPT4 / 4) * G::CT + t;
 #pragma unroll 2
             for (int s = 0; s < nslots; s++) {
                 const u32 *D = xch + (size_t)s * G::PADN;
                 u32 rv[G::IPT4];
 #pragma unroll
                 for (int v = 0; v < G::IPT4 / 4; v++) {
-                    const uint4 q4 = __ldg(Rt + (size_t)s * G::CT * (G::IPT4 / 4) + v);
+                    const uint4 q4 = __ldg(Rt + (size_t)(s * (G::IPT4 / 4) + v) * G::CT);
                     rv[4 * v] = q4.x; rv[4 * v + 1] = q4.y; rv[4 * v + 2] = q4.z; rv[4 * v + 3] = q4.w;
                 }
 #pragma unroll
@@ -200,11 +219,13 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
         for (int i = t; i < K1 * N; i += G::CT) out[base + i] = accs[i];
 }
 
-// unfused key layout (u64, [d][u][x]) -> fused layout (u32, [d][t][IPT4], item = t + 256 m), zero padded
+// unfused key layout (u64, [d][u][x]) -> fused layout (u32, [d][v][t][j], item = t + 256 (4v + j)), zero padded
 __global__ void tggsw_fused_layout_kernel(const u64 *__restrict__ R, u32 *__restrict__ Rf, int nd, int items, int ipt4) {
     const size_t total = (size_t)nd * 256 * ipt4;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int m = (int)(idx % ipt4), t = (int)((idx / ipt4) % 256), d = (int)(idx / ((size_t)ipt4 * 256));
+        const int j = (int)(idx & 3), t = (int)((idx >> 2) & 255), v = (int)((idx >> 10) % (ipt4 / 4));
+        const int d = (int)(idx / ((size_t)ipt4 * 256));
+        const int m = 4 * v + j;
         const int item = t + 256 * m;
         Rf[idx] = item < items ? (u32)R[(size_t)d * items + item] : 0u;
     }
