@@ -35,8 +35,12 @@ template <int LOGN, int K1> struct XpGeom {
     static constexpr int ITEMS = UNITS * N;
     static constexpr int IPT = (ITEMS + CT - 1) / CT;   // MAC items per thread
     static constexpr int IPT4 = (IPT + 3) / 4 * 4;      // padded to whole uint4 loads
-    static constexpr size_t SMEM = (size_t)K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)2 * UNITS * N * 4;
-    static constexpr size_t SMEM_CHAIN = SMEM + (size_t)K1 * N * 8;  // + the accumulator, resident across steps
+    // slots whose threads run an inverse transform (whole warps do): the slots behind them are free for the
+    // residues of the second prime
+    static constexpr int LIVE_SLOTS = S::T >= 32 ? UNITS : ((UNITS * S::T + 31) / 32) * (32 / S::T);
+    static constexpr size_t SMEM = (size_t)K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)UNITS * N * 4;
+    static constexpr size_t SMEM_CHAIN = SMEM;
+    static_assert((SLOTS - LIVE_SLOTS) * PADN >= UNITS * N, "no room for the second prime's residues in the exchange area");
     static_assert(UNITS <= SLOTS, "need a slot per inverse transform");
     static_assert(S::T <= 32, "one digit NTT must fit a warp (N <= 1024) in this kernel");
 };
@@ -105,39 +109,37 @@ __device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32
 template <int LOGN, int K1, bool CHAIN>
 __global__ void __launch_bounds__(256, 2)
 extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__ ct1, const u64 *__restrict__ ct2,
-                     u64 *__restrict__ out, int cmux, const XpChain ch) {
+                     u64 *out, int cmux, const XpChain ch) {
     typedef XpGeom<LOGN, K1> G;
     typedef typename G::S S;
     constexpr int LOGE = G::LOGE, N = G::N, LAST = S::P - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *xin = reinterpret_cast<u64 *>(smem_raw);                         // [K1][N] decomposed input
     u32 *xch = reinterpret_cast<u32 *>(xin + (size_t)K1 * N);             // [SLOTS][PADN] exchange / NTT(digit)
-    u32 *res = xch + (size_t)G::SLOTS * G::PADN;                          // [2][UNITS][N] residues of the result
-    u64 *accs = reinterpret_cast<u64 *>(res + (size_t)2 * G::UNITS * N);  // [K1][N] chain accumulator (CHAIN only)
+    u32 *res1 = xch + (size_t)G::SLOTS * G::PADN;                         // [UNITS][N] residues mod p1
+    u32 *res2 = xch + (size_t)G::LIVE_SLOTS * G::PADN;                    // [UNITS][N] residues mod p2 (free slots of xch)
     const int t = threadIdx.x;
     const int slot = t / S::T, tid = t % S::T;
     u32 *sm = xch + (size_t)slot * G::PADN;
     const size_t base = (size_t)blockIdx.x * K1 * N;
 
     const int steps = CHAIN ? ch.steps : 1;
-    if (CHAIN) {
-        for (int i = t; i < K1 * N; i += G::CT) accs[i] = ct1[base + i];
-        __syncthreads();
-    }
 #pragma unroll 1
     for (int step = 0; step < steps; step++) {
     // input of the external product: ct (extprod), ct2 - ct1 (TGGSW::cmux, tggsw.rs:39-41), or for the chain
-    // X^{-h} acc - acc (the CMux of tlwe.rs:140-146 with ct2 = acc.left_rotate(h))
+    // X^{-h} acc - acc (the CMux of tlwe.rs:140-146 with ct2 = acc.left_rotate(h)).  The chain's accumulator
+    // lives in this CTA's own output row between steps (16 KB, L2-resident; every HBM line is written once).
     if (CHAIN) {
+        const u64 *acc_g = step == 0 ? ct1 : out;
         const u64 hraw = ch.h[(size_t)blockIdx.x * steps + step];
         const u32 h = (u32)(hraw & (N - 1));
         const bool flip = ch.negacyclic && ((hraw >> LOGN) & 1);
         for (int i = t; i < K1 * N; i += G::CT) {
             const int c = i >> LOGN, p = i & (N - 1);
             const u32 src = (u32)p + h;
-            u64 v = src < (u32)N ? accs[(c << LOGN) + src] : (u64)0 - accs[(c << LOGN) + src - N];
+            u64 v = src < (u32)N ? acc_g[base + (c << LOGN) + src] : (u64)0 - acc_g[base + (c << LOGN) + src - N];
             if (flip) v = (u64)0 - v;
-            xin[i] = v - accs[i];
+            xin[i] = v - acc_g[base + i];
         }
     } else {
         for (int i = t; i < K1 * N; i += G::CT) xin[i] = cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
@@ -179,7 +181,9 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
             }
             __syncthreads();
         }
-        // accumulators -> inverse-transform inputs (slot u, padded position order)
+        // accumulators -> inverse-transform inputs (slot u, padded position order).  (Parking the accumulators in
+        // shared memory during the transforms removes the MOVs ptxas spends on re-pairing them in the MAC loop,
+        // but measured slower: the MAC phase is latency-, not issue-bound.)
 #pragma unroll
         for (int m = 0; m < G::IPT; m++) {
             const int item = t + G::CT * m;
@@ -195,7 +199,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
             for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(LAST, tid, e))];
             inv_chain<Lazy32, LOGN, LOGE, LAST>(x, sm, tid, ml, twi, X.P[r].ninv, X.P[r].s_ninv);
             if (slot < G::UNITS) {
-                u32 *R = res + ((size_t)r * G::UNITS + slot) * N;
+                u32 *R = (r == 0 ? res1 : res2) + (size_t)slot * N;
 #pragma unroll
                 for (int e = 0; e < S::E; e++) R[S::pos(0, tid, e)] = ml.canon2(x[e]);
             }
@@ -203,20 +207,17 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
         __syncthreads();
     }
     // CRT lift, recombination, addend
-    const u32 *res1 = res, *res2 = res + (size_t)G::UNITS * N;
     for (int i = t; i < K1 * N; i += G::CT) {
         const int c = i >> LOGN, p = i & (N - 1);
         const u64 lo = crt_centered(res1[(c * 2) * N + p], res2[(c * 2) * N + p], X.cp.p1, X.cp.p2, X.cp.p1_inv_mod_p2, X.cp.P,
                                     X.cp.halfP, X.cp.m2);
         const u64 hi = crt_centered(res1[(c * 2 + 1) * N + p], res2[(c * 2 + 1) * N + p], X.cp.p1, X.cp.p2,
                                     X.cp.p1_inv_mod_p2, X.cp.P, X.cp.halfP, X.cp.m2);
-        if (CHAIN) accs[i] += lo + (hi << 32);
-        else out[base + i] = (cmux ? ct1[base + i] : 0) + lo + (hi << 32);
+        const u64 addend = CHAIN ? (step == 0 ? ct1[base + i] : out[base + i]) : (cmux ? ct1[base + i] : 0);
+        out[base + i] = addend + lo + (hi << 32);
     }
-    if (CHAIN) __syncthreads();  // accs and res are read again by the next step
+    if (CHAIN) __syncthreads();  // the next step reads this CTA's output row (and reuses xch / res1)
     }  // step
-    if (CHAIN)
-        for (int i = t; i < K1 * N; i += G::CT) out[base + i] = accs[i];
 }
 
 // unfused key layout (u64, [d][u][x]) -> fused layout (u32, [d][v][t][j], item = t + 256 (4v + j)), zero padded
