@@ -273,6 +273,46 @@ def blind_rotate(n, k, table, ct, c_kn, bsk=None, as_written=False, out=None):
     return out
 
 
+class RqGlev:
+    """Device-resident rows of GLWE<Rq> ciphertexts, transformed once at load: a GLev (rows = l, gfhe/src/glev.rs:14)
+    or a key-switching key (rows = k*l, gfhe/src/glwe.rs:99-125)."""
+
+    def __init__(self, plan: "NttPlan", k, rows, glwes):
+        self.plan, self.k, self.rows, self.n = plan, int(k), int(rows), plan.n
+        _check_u64(glwes)
+        if _numel(glwes) != self.rows * (self.k + 1) * self.n:
+            raise ValueError("expected rows * (k+1) * n words")
+        h = C.c_void_p()
+        check(lib.fhe_rq_glev_load(plan._h, self.k, self.rows, ptr(glwes), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.fhe_rq_glev_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mul(self, v, out=None):
+        """impl Mul<Vec<R>> for GLev<R> (glev.rs:67-80): v = batch x rows polynomials -> batch GLWEs."""
+        batch = _numel(v) // (self.rows * self.n)
+        out = _new(v, (batch, (self.k + 1) * self.n)) if out is None else out
+        _check_u64(v, out)
+        check(lib.fhe_rq_glev_mul(self._h, ptr(v), ptr(out), batch))
+        return out
+
+    def key_switch(self, beta, l, ct, out=None):
+        """GLWE<Rq>::key_switch (glwe.rs:126-137)."""
+        out = _empty_like(ct) if out is None else out
+        _check_u64(ct, out)
+        check(lib.fhe_glwe_rq_key_switch(self._h, int(beta), int(l), ptr(ct), ptr(out), _numel(ct) // ((self.k + 1) * self.n)))
+        return out
+
+
 def _handles(bsk):
     return (C.c_void_p * max(len(bsk), 1))(*[b._h for b in bsk])
 

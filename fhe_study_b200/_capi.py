@@ -63,6 +63,10 @@ SIGNATURES = {
     "fhe_sample_extract": (I, [U64, U64, P, U64, P, SZ]),
     "fhe_blind_rotate": (I, [U64, U64, P, I, P, P, U64, P, SZ]),
     "fhe_bootstrap": (I, [U64, U64, P, P, P, U64, P, SZ]),
+    "fhe_rq_glev_load": (I, [P, U64, U64, P, C.POINTER(P)]),
+    "fhe_rq_glev_destroy": (None, [P]),
+    "fhe_rq_glev_mul": (I, [P, P, P, SZ]),
+    "fhe_glwe_rq_key_switch": (I, [P, C.c_uint32, C.c_uint32, P, P, SZ]),
     "fhe_cmux_chain": (I, [U64, U64, P, U64, I, P, P, P, SZ]),
     "fhe_bootstrap_chain": (I, [U64, U64, P, U64, I, P, P, P, U64, P, SZ]),
     "fhe_bfv_tensor": (I, [U64, U64, U64, P, P, P, SZ]),

@@ -191,6 +191,14 @@ int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 
 }
 }  // namespace
 
+namespace fhe {
+// device-pointer transform launch for the other translation units (glwe_rq.cu)
+int plan_launch(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
+                int flags, cudaStream_t st) {
+    return launch_plan(plan, mode, a, b, c, c_evals, batch, flags, st);
+}
+}  // namespace fhe
+
 extern "C" {
 
 const char *fhe_last_error(void) { return t_error.c_str(); }

@@ -144,6 +144,20 @@ FHE_API int fhe_bootstrap_chain(uint64_t n, uint64_t k, const fhe_tggsw *const *
                                 const fhe_ksk *ksk, const uint64_t *table, const uint64_t *ct, uint64_t c_kn, uint64_t *out,
                                 size_t batch);
 
+/* ---- gfhe over Rq: GLev product and GLWE key switch (gfhe/src/glev.rs, gfhe/src/glwe.rs) -- SURVEY 8f rank 2 ------- */
+typedef struct fhe_rq_glev fhe_rq_glev;
+/* Uploads `rows` GLWE<Rq> ciphertexts ((k+1) polynomials of n words each: mask, then body) and keeps their NTT images
+ * resident: a GLev (rows = l, glev.rs:14) or a KSK (rows = k*l, KSK[i][j] at row i*l + j; glwe.rs:99-125). */
+FHE_API int fhe_rq_glev_load(const fhe_ntt_plan *plan, uint64_t k, uint64_t rows, const uint64_t *glwes, fhe_rq_glev **handle);
+FHE_API void fhe_rq_glev_destroy(fhe_rq_glev *handle);
+/* impl Mul<Vec<R>> for GLev<R> (glev.rs:67-80) with GLWE * R (glwe.rs:263-280): out_b = sum_r row_r * v_{b,r};
+ * v: batch x rows polynomials, out: batch GLWEs. */
+FHE_API int fhe_rq_glev_mul(const fhe_rq_glev *handle, const uint64_t *v, uint64_t *out, size_t batch);
+/* GLWE<Rq>::key_switch(beta, l, ksk) (glwe.rs:126-137): (0, b) - sum_i ksk_i * a_i.decompose(beta, l), digits as
+ * Zq::decompose (zq.rs:140-186, saturation branch included).  The handle must hold k*l rows. */
+FHE_API int fhe_glwe_rq_key_switch(const fhe_rq_glev *ksk, uint32_t beta, uint32_t l, const uint64_t *ct, uint64_t *out,
+                                   size_t batch);
+
 /* ---- BFV ciphertext multiplication (bfv/src/lib.rs) ----------------------------------------------------------- */
 /* RLWE::tensor (lib.rs:59-85): a, b = `batch` RLWEs (2n words) -> c0|c1|c2 (3n words each). */
 FHE_API int fhe_bfv_tensor(uint64_t q, uint64_t n, uint64_t t, const uint64_t *a, const uint64_t *b, uint64_t *c012, size_t batch);

@@ -129,6 +129,13 @@ def _declare(L):
     d("orc_tlwe_new_ksk", None, U64, U64, U64, U32, D, P, P, I, P)
     d("orc_cmux_chain", None, U64, U64, U64, P, P, P, I, P)
     d("orc_bootstrap_chain", None, U64, U64, U64, P, P, P, P, U64, I, P)
+    d("orc_glev_rq_mul", None, U64, U64, U64, U64, P, P, P)
+    d("orc_glwe_rq_key_switch", None, U64, U64, U64, U32, U32, P, P, P)
+    d("orc_glwe_rq_mod_switch", None, U64, U64, U64, P, U64, P)
+    d("orc_glwe_rq_keygen", None, U64, U64, U64, U64, P)
+    d("orc_glwe_rq_encrypt_s", None, U64, U64, U64, U64, D, P, P, P)
+    d("orc_glwe_rq_decrypt", None, U64, U64, U64, P, P, P)
+    d("orc_glwe_rq_new_ksk", None, U64, U64, U64, U64, U32, U32, D, P, P, P)
     d("orc_bfv_keygen", None, U64, U64, U64, P, P)
     d("orc_bfv_encrypt", None, U64, U64, U64, U64, P, P, P)
     d("orc_bfv_decrypt", None, U64, U64, U64, P, P, P)
@@ -274,6 +281,26 @@ def bootstrap_chain(n: int, k: int, steps: int, bsk, ksk, table, c, c_kn: int, m
     for i in range(batch):
         lib().orc_bootstrap_chain(n, k, steps, ptr(bsk), ptr(ksk) if ksk is not None else None, ptr(table),
                                   ptr(c.reshape(-1)[i * (c_kn + 1):]), c_kn, mode, ptr(out[i]))
+    return out
+
+
+def glwe_rq_key_switch(q: int, n: int, k: int, beta: int, l: int, ksk, ct) -> np.ndarray:
+    """GLWE<Rq>::key_switch (gfhe/src/glwe.rs:126-137) for a batch of GLWEs of (k+1)*n words."""
+    ksk, ct = u64(ksk), u64(ct)
+    glwe = (k + 1) * n
+    out = np.empty_like(ct)
+    for i in range(ct.size // glwe):
+        lib().orc_glwe_rq_key_switch(q, n, k, beta, l, ptr(ksk), ptr(ct.reshape(-1)[i * glwe:]), ptr(out.reshape(-1)[i * glwe:]))
+    return out
+
+
+def glev_rq_mul(q: int, n: int, k: int, l: int, glev, v) -> np.ndarray:
+    """impl Mul<Vec<R>> for GLev<R> (gfhe/src/glev.rs:67-80), R = Rq; v = batch x l polys."""
+    glev, v = u64(glev), u64(v)
+    batch = v.size // (l * n)
+    out = np.empty((batch, (k + 1) * n), dtype=np.uint64)
+    for i in range(batch):
+        lib().orc_glev_rq_mul(q, n, k, l, ptr(glev), ptr(v.reshape(-1)[i * l * n:]), ptr(out[i]))
     return out
 
 

@@ -834,6 +834,95 @@ API void orc_tlwe_new_ksk(u64 seed, u64 kn_in, u64 kn_out, uint32_t l, double si
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * gfhe: GLWE<Rq> / GLev<Rq> (gfhe/src/glwe.rs, gfhe/src/glev.rs) -- SURVEY 8f rank 2.
+ * GLWE<Rq> flat layout: (k+1) polys of n (mask a_0..a_{k-1}, then body b).  KSK = k GLevs of l GLWEs:
+ * ksk[(i*l + j)*(k+1)*n ...].
+ * ---------------------------------------------------------------------------------------------- */
+/* impl Mul<Vec<R>> for GLev<R> (glev.rs:67-80) with GLWE * R (glwe.rs:263-280) and the Sum fold
+ * (glwe.rs:236-244): out = sum_j glev[j] * v[j], every component an Rq product (ring_nq.rs:586-607). */
+API void orc_glev_rq_mul(u64 q, u64 n, u64 k, u64 l, const u64 *glev, const u64 *v, u64 *out) {
+    u64 glwe = (k + 1) * n;
+    u64 *term = (u64 *)malloc(sizeof(u64) * n);
+    for (u64 j = 0; j < l; j++)
+        for (u64 c = 0; c <= k; c++) {
+            orc_rq_mul(q, n, glev + j * glwe + c * n, v + j * n, term, 0, 0, NULL);
+            if (j == 0) memcpy(out + c * n, term, sizeof(u64) * n);
+            else orc_rq_addsub(q, n, out + c * n, term, out + c * n, 0);
+        }
+    free(term);
+}
+/* GLWE<R>::key_switch (glwe.rs:126-137) for R = Rq: (0, b) - sum_i ksk_i * a_i.decompose(beta, l) */
+API void orc_glwe_rq_key_switch(u64 q, u64 n, u64 k, uint32_t beta, uint32_t l, const u64 *ksk, const u64 *ct, u64 *out) {
+    u64 glwe = (k + 1) * n;
+    u64 *dec = (u64 *)malloc(sizeof(u64) * l * n);
+    u64 *lev = (u64 *)malloc(sizeof(u64) * 2 * glwe), *rhs = lev + glwe;
+    for (u64 i = 0; i < k; i++) {
+        orc_rq_decompose(q, n, ct + i * n, beta, l, dec);
+        orc_glev_rq_mul(q, n, k, l, ksk + i * l * glwe, dec, lev);
+        if (i == 0) memcpy(rhs, lev, sizeof(u64) * glwe);
+        else for (u64 c = 0; c <= k; c++) orc_rq_addsub(q, n, rhs + c * n, lev + c * n, rhs + c * n, 0);
+    }
+    for (u64 c = 0; c < k; c++) orc_rq_addsub(q, n, rhs + c * n, NULL, out + c * n, 2); /* 0 - rhs.a */
+    orc_rq_addsub(q, n, ct + k * n, rhs + k * n, out + k * n, 1);                        /* b - rhs.b */
+    free(dec); free(lev);
+}
+/* GLWE<Rq>::mod_switch (glwe.rs:197-204): every coefficient through Zq::mod_switch */
+API void orc_glwe_rq_mod_switch(u64 q, u64 n, u64 k, const u64 *ct, u64 p, u64 *out) {
+    orc_rq_mod_switch(q, (k + 1) * n, ct, p, out);
+}
+/* keygen / encrypt_s / decrypt / new_ksk for GLWE<Rq> (glwe.rs:76-92,99-125,140-156,175-179; glev.rs:36-54) */
+static void rq_rand_f64(orc_rng *r, u64 q, u64 n, int kind, double sigma, u64 *out) {
+    for (u64 i = 0; i < n; i++)
+        out[i] = orc_zq_from_f64(q, kind == 0 ? rng_uniform(r, 0.0, 2.0) : kind == 1 ? rng_normal(r, sigma) : rng_uniform(r, 0.0, (double)q));
+}
+API void orc_glwe_rq_keygen(u64 seed, u64 q, u64 n, u64 k, u64 *sk) {
+    orc_rng r = { seed };
+    rq_rand_f64(&r, q, k * n, 0, 0.0, sk);
+}
+static void glwe_rq_encrypt_s(orc_rng *r, u64 q, u64 n, u64 k, double sigma, const u64 *sk, const u64 *m, u64 *ct) {
+    u64 *tmp = (u64 *)malloc(sizeof(u64) * n), *b = ct + k * n;
+    rq_rand_f64(r, q, k * n, 0, 0.0, ct);                 /* a <- Xi_key (glwe.rs:146-149) */
+    for (u64 i = 0; i < k; i++) {                          /* TR dot product */
+        orc_rq_mul(q, n, ct + i * n, sk + i * n, tmp, 0, 0, NULL);
+        if (i == 0) memcpy(b, tmp, sizeof(u64) * n);
+        else orc_rq_addsub(q, n, b, tmp, b, 0);
+    }
+    orc_rq_addsub(q, n, b, m, b, 0);
+    rq_rand_f64(r, q, n, 1, sigma, tmp);
+    orc_rq_addsub(q, n, b, tmp, b, 0);
+    free(tmp);
+}
+API void orc_glwe_rq_encrypt_s(u64 seed, u64 q, u64 n, u64 k, double sigma, const u64 *sk, const u64 *m, u64 *ct) {
+    orc_rng r = { seed };
+    glwe_rq_encrypt_s(&r, q, n, k, sigma, sk, m, ct);
+}
+API void orc_glwe_rq_decrypt(u64 q, u64 n, u64 k, const u64 *sk, const u64 *ct, u64 *p) {
+    u64 *tmp = (u64 *)malloc(sizeof(u64) * 2 * n), *acc = tmp + n;
+    for (u64 i = 0; i < k; i++) {
+        orc_rq_mul(q, n, ct + i * n, sk + i * n, tmp, 0, 0, NULL);
+        if (i == 0) memcpy(acc, tmp, sizeof(u64) * n);
+        else orc_rq_addsub(q, n, acc, tmp, acc, 0);
+    }
+    orc_rq_addsub(q, n, ct + k * n, acc, p, 1);
+    free(tmp);
+}
+API void orc_glwe_rq_new_ksk(u64 seed, u64 q, u64 n, u64 k, uint32_t beta, uint32_t l, double sigma, const u64 *sk,
+                             const u64 *new_sk, u64 *ksk) {
+    orc_rng r = { seed };
+    u64 glwe = (k + 1) * n;
+    u64 *aux = (u64 *)malloc(sizeof(u64) * n);
+    for (u64 i = 0; i < k; i++) {
+        u64 bp = 1;
+        for (uint32_t lv = 1; lv <= l; lv++) {
+            bp *= beta;                                  /* beta.pow(i) is u32 arithmetic (glev.rs:49) */
+            orc_rq_mul_u64(q, n, sk + i * n, q / (u64)(uint32_t)bp, aux);
+            glwe_rq_encrypt_s(&r, q, n, k, sigma, new_sk, aux, ksk + (i * l + (lv - 1)) * glwe);
+        }
+    }
+    free(aux);
+}
+
 /* BFV keygen / encrypt / decrypt / rlk (bfv/src/lib.rs:120-178,202-225), Rq ops through orc_rq_mul */
 API void orc_bfv_keygen(u64 seed, u64 q, u64 n, u64 *sk, u64 *pk /* 2n */) {
     orc_rng r = { seed };

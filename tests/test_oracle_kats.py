@@ -360,3 +360,38 @@ def test_cmux_chain_is_composition_of_cmux_and_left_rotate(orc):
                 rot = np.uint64(0) - rot
             want = orc.cmux(n, k, bsk[j * (k + 1) * 64 * glwe:(j + 1) * (k + 1) * 64 * glwe], want, rot, fast=False)
         assert np.array_equal(orc.cmux_chain(n, k, bsk, acc, h, negacyclic=neg).reshape(-1), want)
+
+
+# ---- gfhe/src/glwe.rs:580-624 (test_key_switch) re-run inside the oracle -----------------------------------------
+def glwe_rq_fixture(orc, q=Q, n=128, k=16, t=2, beta=2, l=16, seed=5, batch=2):
+    L = orc.lib()
+    glwe = (k + 1) * n
+    sk, sk2 = np.empty(k * n, dtype=np.uint64), np.empty(k * n, dtype=np.uint64)
+    L.orc_glwe_rq_keygen(seed, q, n, k, orc.ptr(sk))
+    L.orc_glwe_rq_keygen(seed + 1, q, n, k, orc.ptr(sk2))
+    ksk = np.empty(k * l * glwe, dtype=np.uint64)
+    L.orc_glwe_rq_new_ksk(seed + 2, q, n, k, beta, l, 3.2, orc.ptr(sk), orc.ptr(sk2), orc.ptr(ksk))
+    msgs = orc.uniform(seed + 3, (batch, n), t)
+    cts = np.empty((batch, glwe), dtype=np.uint64)
+    for i in range(batch):
+        p = (msgs[i] * np.uint64(q // t)) % np.uint64(q)  # GLWE::encode, glwe.rs:183-189
+        L.orc_glwe_rq_encrypt_s(seed + 10 + i, q, n, k, 3.2, orc.ptr(sk), orc.ptr(p), orc.ptr(cts[i]))
+    return sk, sk2, ksk, msgs, cts
+
+
+def glwe_rq_decode(orc, q, n, k, t, sk, ct):
+    L = orc.lib()
+    p = np.empty(n, dtype=np.uint64)
+    L.orc_glwe_rq_decrypt(q, n, k, orc.ptr(sk), orc.ptr(np.ascontiguousarray(ct)), orc.ptr(p))
+    r = np.empty(n, dtype=np.uint64)
+    L.orc_rq_mul_div_round(q, n, orc.ptr(p), t, q, orc.ptr(r))  # GLWE::decode, glwe.rs:191-195
+    return r % np.uint64(t)
+
+
+def test_glwe_rq_key_switch_functional(orc):
+    q, n, k, t, beta, l = Q, 128, 16, 2, 2, 16
+    sk, sk2, ksk, msgs, cts = glwe_rq_fixture(orc, q, n, k, t, beta, l)
+    out = orc.glwe_rq_key_switch(q, n, k, beta, l, ksk, cts)
+    for i in range(len(msgs)):
+        assert np.array_equal(glwe_rq_decode(orc, q, n, k, t, sk, cts[i]), msgs[i])       # sanity: decrypts under sk
+        assert np.array_equal(glwe_rq_decode(orc, q, n, k, t, sk2, out[i]), msgs[i])      # and under sk2 after the switch
