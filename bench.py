@@ -279,26 +279,34 @@ def main():
     value = world * batch * args.steps / (total_ms_max * 1e-3)
 
     # ---- end to end through the C ABI with pinned host buffers ---------------------------------------
+    # Two wire formats of the same call: u64 words (fhe_rq_mul) and packed u32 words (fhe_rq_mul_u32, q <= 2^32:
+    # half the PCIe bytes; the Rust shim gathers Vec<Zq>.v into either layout at the same cost).  The step is
+    # PCIe-bound in both, so the packed one is the end-to-end headline and the u64 one is reported beside it.
     e2e_steps = max(3, min(args.steps, 10))
-    ha = torch.empty((batch, N), dtype=torch.int64).pin_memory()
-    hb = torch.empty((batch, N), dtype=torch.int64).pin_memory()
-    hc = torch.empty((batch, N), dtype=torch.int64).pin_memory()
-    ha.copy_(a)
-    hb.copy_(b)
-    plan.mul(ha, hb, out=hc)  # warm the staging pool
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        plan.mul(ha, hb, out=hc)  # H2D(a,b) -> kernel -> D2H(c); returns when c is on the host
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop()  # sampled across both timed regions (device-resident steps and end-to-end steps)
-    e2e_value = world * batch * e2e_steps / (float(t.item()) * 1e-3)
-    same = bool(torch.equal(hc.to(dev), c))
+
+    def e2e_run(host_dtype, call):
+        ha = torch.empty((batch, N), dtype=host_dtype).pin_memory()
+        hb = torch.empty((batch, N), dtype=host_dtype).pin_memory()
+        hc = torch.empty((batch, N), dtype=host_dtype).pin_memory()
+        ha.copy_(a)
+        hb.copy_(b)
+        call(ha, hb, hc)  # warm the staging pool
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            call(ha, hb, hc)  # H2D(a,b) -> kernel -> D2H(c); returns when c is on the host
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = bool(torch.equal(hc.to(dev).to(torch.int64), c))
+        return world * batch * e2e_steps / (float(t.item()) * 1e-3), ok
+
+    e2e64_value, same64 = e2e_run(torch.int64, lambda x, y, z: plan.mul(x, y, out=z))
+    e2e_value, same = e2e_run(torch.int32, lambda x, y, z: plan.mul_u32(x, y, out=z))
+    clocks = sampler.stop()  # sampled across the timed regions (device-resident steps and end-to-end steps)
 
     boot = measure_bootstrap(fhe, torch, dist, dev, rank, world, quick=args.steps < 20)
 
@@ -328,8 +336,14 @@ def main():
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
         },
         "e2e": {
-            "value": e2e_value, "unit": "polymul/s", "h2d_bytes_per_step": 2 * N * 8 * batch,
-            "d2h_bytes_per_step": N * 8 * batch, "steps": e2e_steps, "matches_device_result": same,
+            "value": e2e_value, "unit": "polymul/s", "h2d_bytes_per_step": 2 * N * 4 * batch,
+            "d2h_bytes_per_step": N * 4 * batch, "steps": e2e_steps, "matches_device_result": same,
+            "call": "fhe_rq_mul_u32 (packed 32-bit wire, q <= 2^32), pinned host buffers",
+        },
+        "e2e_u64_wire": {
+            "value": e2e64_value, "unit": "polymul/s", "h2d_bytes_per_step": 2 * N * 8 * batch,
+            "d2h_bytes_per_step": N * 8 * batch, "steps": e2e_steps, "matches_device_result": same64,
+            "call": "fhe_rq_mul (u64 words), pinned host buffers",
         },
         "gpu_launches": int(launches),
         "clocks": clocks,

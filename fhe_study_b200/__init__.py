@@ -46,6 +46,20 @@ def _check_u64(*xs):
                 raise TypeError("numpy buffers must be C-contiguous uint64")
 
 
+def _check_u32(*xs):
+    for x in xs:
+        if x is None:
+            continue
+        if _is_torch(x):
+            import torch
+
+            if x.dtype not in (torch.int32, torch.uint32) or not x.is_contiguous():
+                raise TypeError("torch buffers must be contiguous int32/uint32 (bit patterns of u32)")
+        else:
+            if x.dtype != np.uint32 or not x.flags["C_CONTIGUOUS"]:
+                raise TypeError("numpy buffers must be C-contiguous uint32")
+
+
 def set_device(device: int) -> None:
     check(lib.fhe_set_device(int(device)))
 
@@ -128,6 +142,28 @@ class NttPlan:
         if _numel(a) != _numel(b):
             raise ValueError("operand sizes differ")
         check(lib.fhe_rq_mul(self._h, ptr(a), ptr(b), ptr(out), self._batch(a), int(flags), ptr(evals_out)))
+        return out
+
+
+    # packed 32-bit wire format (q <= 2^32): same values, half the bytes over PCIe
+    def ntt_u32(self, a, out=None):
+        out = _empty_like(a) if out is None else out
+        _check_u32(a, out)
+        check(lib.fhe_ntt_fwd_u32(self._h, ptr(a), ptr(out), self._batch(a)))
+        return out
+
+    def intt_u32(self, a, out=None):
+        out = _empty_like(a) if out is None else out
+        _check_u32(a, out)
+        check(lib.fhe_ntt_inv_u32(self._h, ptr(a), ptr(out), self._batch(a)))
+        return out
+
+    def mul_u32(self, a, b, out=None, flags: int = 0, evals_out=None):
+        out = _empty_like(a) if out is None else out
+        _check_u32(a, b, out, evals_out)
+        if _numel(a) != _numel(b):
+            raise ValueError("operand sizes differ")
+        check(lib.fhe_rq_mul_u32(self._h, ptr(a), ptr(b), ptr(out), self._batch(a), int(flags), ptr(evals_out)))
         return out
 
 

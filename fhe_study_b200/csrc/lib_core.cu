@@ -191,6 +191,89 @@ int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 
 }
 }  // namespace
 
+namespace {
+// ---- packed 32-bit wire format (q <= 2^32): halves the PCIe bytes of the host-buffer path ------------------------
+__global__ void widen_u32_kernel(const u32 *__restrict__ in, u64 *__restrict__ out, size_t len4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len4; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = reinterpret_cast<const uint4 *>(in)[i];
+        reinterpret_cast<ulonglong2 *>(out)[2 * i] = make_ulonglong2(v.x, v.y);
+        reinterpret_cast<ulonglong2 *>(out)[2 * i + 1] = make_ulonglong2(v.z, v.w);
+    }
+}
+__global__ void narrow_u64_kernel(const u64 *__restrict__ in, u32 *__restrict__ out, size_t len4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len4; i += (size_t)gridDim.x * blockDim.x) {
+        const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(in)[2 * i], b = reinterpret_cast<const ulonglong2 *>(in)[2 * i + 1];
+        reinterpret_cast<uint4 *>(out)[i] = make_uint4((u32)a.x, (u32)a.y, (u32)b.x, (u32)b.y);
+    }
+}
+inline unsigned grid_for_len(size_t work) {
+    size_t g = (work + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    return (unsigned)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+// Chunked, double-buffered: [copy u32 in] -> widen -> transform -> narrow -> [copy u32 out]; host or device pointers.
+int run_ntt_wire32(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *b, u32 *c, u32 *c_evals, size_t batch,
+                   int flags) {
+    FHE_REQUIRE(plan != nullptr, "null plan");
+    if (batch == 0) return 0;
+    FHE_REQUIRE(a != nullptr && c != nullptr && (mode != MODE_MUL || b != nullptr), "null polynomial pointer");
+    FHE_REQUIRE(plan->host.q <= (1ull << 32), "the 32-bit wire format needs q <= 2^32");
+    FHE_REQUIRE(plan->host.n % 4 == 0, "the 32-bit wire format needs n >= 4");
+    if (mode != MODE_MUL) b = nullptr;
+    cudaStream_t st = current_stream();
+    int rc = t_pipe.init();
+    if (rc) return rc;
+    PipeStreams &ps = t_pipe;
+    const size_t n = plan->host.n;
+    const size_t chunk = std::min(batch, std::max<size_t>(1, (32ull << 20) / (n * sizeof(u32))));
+    const size_t w = chunk * n;  // words per chunk buffer
+    const bool host = is_host_ptr(a) || (b && is_host_ptr(b)) || is_host_ptr(c) || (c_evals && is_host_ptr(c_evals));
+    // per parity: u64 A, B, C, E and u32 a, b, c, e  (unused ones still reserved; at most ~0.8 GB)
+    Scratch s64, s32;
+    if ((rc = s64.alloc(2 * 4 * w * sizeof(u64), st))) return rc;
+    if ((rc = s32.alloc(2 * 4 * w * sizeof(u32), st))) return rc;
+    FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch is used from the side streams as well
+    auto b64 = [&](int which, int par) { return s64.ptr<u64>() + ((size_t)par * 4 + which) * w; };
+    auto b32 = [&](int which, int par) { return s32.ptr<u32>() + ((size_t)par * 4 + which) * w; };
+    size_t i = 0;
+    for (size_t off = 0; off < batch && !rc; off += chunk, i++) {
+        const size_t nb = std::min(chunk, batch - off), words = nb * n, bytes = words * sizeof(u32);
+        const int par = (int)(i & 1);
+        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // staging of chunk i-2 consumed
+        FHE_CUDA_OK(cudaMemcpyAsync(b32(0, par), a + off * n, bytes, cudaMemcpyDefault, ps.h2d));
+        if (b) FHE_CUDA_OK(cudaMemcpyAsync(b32(1, par), b + off * n, bytes, cudaMemcpyDefault, ps.h2d));
+        FHE_CUDA_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
+        FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.h2d_done[par], 0));
+        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
+        widen_u32_kernel<<<grid_for_len(words / 4), 256, 0, st>>>(b32(0, par), b64(0, par), words / 4);
+        if (b) widen_u32_kernel<<<grid_for_len(words / 4), 256, 0, st>>>(b32(1, par), b64(1, par), words / 4);
+        count_launch(b ? 2 : 1);
+        if ((rc = launch_plan(plan, mode, b64(0, par), b ? b64(1, par) : nullptr, b64(2, par), c_evals ? b64(3, par) : nullptr,
+                              nb, flags, st)))
+            break;
+        narrow_u64_kernel<<<grid_for_len(words / 4), 256, 0, st>>>(b64(2, par), b32(2, par), words / 4);
+        if (c_evals) narrow_u64_kernel<<<grid_for_len(words / 4), 256, 0, st>>>(b64(3, par), b32(3, par), words / 4);
+        count_launch(c_evals ? 2 : 1);
+        FHE_CUDA_OK(cudaGetLastError());
+        FHE_CUDA_OK(cudaEventRecord(ps.comp_done[par], st));
+        FHE_CUDA_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
+        FHE_CUDA_OK(cudaMemcpyAsync(c + off * n, b32(2, par), bytes, cudaMemcpyDefault, ps.d2h));
+        if (c_evals) FHE_CUDA_OK(cudaMemcpyAsync(c_evals + off * n, b32(3, par), bytes, cudaMemcpyDefault, ps.d2h));
+        FHE_CUDA_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
+    }
+    // the side streams own part of the work: the call returns with everything complete (also for device pointers)
+    cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st);
+    (void)host;
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        set_error(std::string("32-bit wire path failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+        return -2;
+    }
+    return 0;
+}
+}  // namespace
+
 namespace fhe {
 // device-pointer transform launch for the other translation units (glwe_rq.cu)
 int plan_launch(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
@@ -289,6 +372,16 @@ int fhe_ntt_inv(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *out, siz
 int fhe_rq_mul(const fhe_ntt_plan *plan, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, int flags,
                uint64_t *c_evals) {
     return run_ntt(plan, MODE_MUL, a, b, c, c_evals, batch, flags);
+}
+int fhe_ntt_fwd_u32(const fhe_ntt_plan *plan, const uint32_t *in, uint32_t *out, size_t batch) {
+    return run_ntt_wire32(plan, MODE_FWD, in, nullptr, out, nullptr, batch, 0);
+}
+int fhe_ntt_inv_u32(const fhe_ntt_plan *plan, const uint32_t *in, uint32_t *out, size_t batch) {
+    return run_ntt_wire32(plan, MODE_INV, in, nullptr, out, nullptr, batch, 0);
+}
+int fhe_rq_mul_u32(const fhe_ntt_plan *plan, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch, int flags,
+                   uint32_t *c_evals) {
+    return run_ntt_wire32(plan, MODE_MUL, a, b, c, c_evals, batch, flags);
 }
 
 }  // extern "C"

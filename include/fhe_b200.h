@@ -75,6 +75,14 @@ FHE_API int fhe_ntt_inv(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *
 #define FHE_B_IS_EVALS 2
 FHE_API int fhe_rq_mul(const fhe_ntt_plan *plan, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, int flags,
                uint64_t *c_evals);
+/* Packed 32-bit wire format of the three calls above for q <= 2^32 (the reference's only NTT modulus is 65537):
+ * every polynomial is n uint32_t words.  Same values, half the PCIe bytes on the host-buffer path; the Rust shim
+ * gathers Vec<Zq>.v (16-byte AoS, zq.rs:7-10) into either layout at the same cost.  Host or device pointers;
+ * the call returns with the result complete. */
+FHE_API int fhe_ntt_fwd_u32(const fhe_ntt_plan *plan, const uint32_t *in, uint32_t *out, size_t batch);
+FHE_API int fhe_ntt_inv_u32(const fhe_ntt_plan *plan, const uint32_t *in, uint32_t *out, size_t batch);
+FHE_API int fhe_rq_mul_u32(const fhe_ntt_plan *plan, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch, int flags,
+                           uint32_t *c_evals);
 
 /* ---- Tn = T_q[X]/(X^n+1), q = 2^64 (arith/src/ring_torus.rs) ------------------------------------------- */
 /* impl Mul<Tn> for Tn -> naive_poly_mul (ring_torus.rs:251-298): exact negacyclic product mod 2^64. */
