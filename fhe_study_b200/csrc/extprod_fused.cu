@@ -29,19 +29,24 @@ template <int LOGN, int K1> struct XpGeom {
     static constexpr int CT = 256;
     static constexpr int SLOTS = CT / S::T;             // concurrent NTTs
     static constexpr int ND = K1 * 64;                  // digit polynomials per accumulator
-    static constexpr int ROUNDS = (ND + SLOTS - 1) / SLOTS;
     static constexpr int PADN = N + (N >> 5);
     static constexpr int UNITS = K1 * 2;                // (component, limb)
     static constexpr int ITEMS = UNITS * N;
-    static constexpr int IPT = (ITEMS + CT - 1) / CT;   // MAC items per thread
+    static constexpr int IPT = (ITEMS + CT - 1) / CT;   // MAC items per thread (per accumulator)
     static constexpr int IPT4 = (IPT + 3) / 4 * 4;      // padded to whole uint4 loads
+    // Accumulators per CTA.  The MAC streams the whole transformed TGGSW (2 * ND * ITEMS * 4 B) from L2 once per
+    // CTA; small rings leave registers and shared memory for several accumulators, which then share every key load
+    // (n = 64, k = 4: 1.6 MB of key per 2.5 KB accumulator -- L2 bandwidth, not arithmetic, was the limit).
+    static constexpr int A = LOGN <= 7 ? 4 : (LOGN <= 9 && ITEMS <= 2048) ? 2 : 1;
+    static constexpr int DPR = SLOTS / A;               // digits per round (each for all A accumulators)
+    static constexpr int ROUNDS = (ND + DPR - 1) / DPR;
     // slots whose threads run an inverse transform (whole warps do): the slots behind them are free for the
     // residues of the second prime
-    static constexpr int LIVE_SLOTS = S::T >= 32 ? UNITS : ((UNITS * S::T + 31) / 32) * (32 / S::T);
-    static constexpr size_t SMEM = (size_t)K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)UNITS * N * 4;
+    static constexpr int LIVE_SLOTS = S::T >= 32 ? A * UNITS : ((A * UNITS * S::T + 31) / 32) * (32 / S::T);
+    static constexpr size_t SMEM = (size_t)A * K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)A * UNITS * N * 4;
     static constexpr size_t SMEM_CHAIN = SMEM;
-    static_assert((SLOTS - LIVE_SLOTS) * PADN >= UNITS * N, "no room for the second prime's residues in the exchange area");
-    static_assert(UNITS <= SLOTS, "need a slot per inverse transform");
+    static_assert(SLOTS % A == 0 && A * UNITS <= SLOTS, "need a slot per inverse transform");
+    static_assert((SLOTS - LIVE_SLOTS) * PADN >= A * UNITS * N, "no room for the second prime's residues in the exchange area");
     static_assert(S::T <= 32, "one digit NTT must fit a warp (N <= 1024) in this kernel");
 };
 
@@ -109,40 +114,48 @@ __device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32
 template <int LOGN, int K1, bool CHAIN>
 __global__ void __launch_bounds__(256, 2)
 extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__ ct1, const u64 *__restrict__ ct2,
-                     u64 *out, int cmux, const XpChain ch) {
+                     u64 *out, int cmux, const XpChain ch, size_t batch) {
     typedef XpGeom<LOGN, K1> G;
     typedef typename G::S S;
-    constexpr int LOGE = G::LOGE, N = G::N, LAST = S::P - 1;
+    constexpr int LOGE = G::LOGE, N = G::N, LAST = S::P - 1, A = G::A, GLWE = K1 * N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *xin = reinterpret_cast<u64 *>(smem_raw);                         // [K1][N] decomposed input
-    u32 *xch = reinterpret_cast<u32 *>(xin + (size_t)K1 * N);             // [SLOTS][PADN] exchange / NTT(digit)
-    u32 *res1 = xch + (size_t)G::SLOTS * G::PADN;                         // [UNITS][N] residues mod p1
-    u32 *res2 = xch + (size_t)G::LIVE_SLOTS * G::PADN;                    // [UNITS][N] residues mod p2 (free slots of xch)
+    u64 *xin = reinterpret_cast<u64 *>(smem_raw);                         // [A][K1][N] decomposed inputs
+    u32 *xch = reinterpret_cast<u32 *>(xin + (size_t)A * GLWE);           // [SLOTS][PADN] exchange / NTT(digit)
+    u32 *res1 = xch + (size_t)G::SLOTS * G::PADN;                         // [A][UNITS][N] residues mod p1
+    u32 *res2 = xch + (size_t)G::LIVE_SLOTS * G::PADN;                    // [A][UNITS][N] residues mod p2 (free slots of xch)
     const int t = threadIdx.x;
     const int slot = t / S::T, tid = t % S::T;
+    const int s_acc = slot % A, s_dig = slot / A;   // forward phase: which accumulator, which digit of the round
     u32 *sm = xch + (size_t)slot * G::PADN;
-    const size_t base = (size_t)blockIdx.x * K1 * N;
+    const size_t acc0 = (size_t)blockIdx.x * A;     // first accumulator of this CTA
+    const int na = (int)(batch - acc0 < (size_t)A ? batch - acc0 : (size_t)A);
+    const size_t base = acc0 * GLWE;
 
     const int steps = CHAIN ? ch.steps : 1;
 #pragma unroll 1
     for (int step = 0; step < steps; step++) {
     // input of the external product: ct (extprod), ct2 - ct1 (TGGSW::cmux, tggsw.rs:39-41), or for the chain
     // X^{-h} acc - acc (the CMux of tlwe.rs:140-146 with ct2 = acc.left_rotate(h)).  The chain's accumulator
-    // lives in this CTA's own output row between steps (16 KB, L2-resident; every HBM line is written once).
-    if (CHAIN) {
-        const u64 *acc_g = step == 0 ? ct1 : out;
-        const u64 hraw = ch.h[(size_t)blockIdx.x * steps + step];
-        const u32 h = (u32)(hraw & (N - 1));
-        const bool flip = ch.negacyclic && ((hraw >> LOGN) & 1);
-        for (int i = t; i < K1 * N; i += G::CT) {
-            const int c = i >> LOGN, p = i & (N - 1);
-            const u32 src = (u32)p + h;
-            u64 v = src < (u32)N ? acc_g[base + (c << LOGN) + src] : (u64)0 - acc_g[base + (c << LOGN) + src - N];
-            if (flip) v = (u64)0 - v;
-            xin[i] = v - acc_g[base + i];
+    // lives in this CTA's own output rows between steps (L2-resident; every HBM line is written once).
+    for (int i = t; i < A * GLWE; i += G::CT) {
+        const int aa = i / GLWE, rem = i % GLWE;
+        u64 v = 0;
+        if (aa < na) {
+            if (CHAIN) {
+                const u64 *acc_g = (step == 0 ? ct1 : out) + base + (size_t)aa * GLWE;
+                const u64 hraw = ch.h[(acc0 + aa) * steps + step];
+                const u32 h = (u32)(hraw & (N - 1));
+                const bool flip = ch.negacyclic && ((hraw >> LOGN) & 1);
+                const int c = rem >> LOGN, p = rem & (N - 1);
+                const u32 src = (u32)p + h;
+                v = src < (u32)N ? acc_g[(c << LOGN) + src] : (u64)0 - acc_g[(c << LOGN) + src - N];
+                if (flip) v = (u64)0 - v;
+                v -= acc_g[rem];
+            } else {
+                v = cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
+            }
         }
-    } else {
-        for (int i = t; i < K1 * N; i += G::CT) xin[i] = cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
+        xin[i] = v;
     }
     __syncthreads();
 
@@ -150,55 +163,63 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     for (int r = 0; r < 2; r++) {
         const u32 *Rr = CHAIN ? ch.R[2 * step + r] : X.R[r];
         const Lazy32 &ml = X.P[r].mod;
-        u64 acc[G::IPT];
+        u64 acc[A][G::IPT];
 #pragma unroll
-        for (int m = 0; m < G::IPT; m++) acc[m] = 0;
+        for (int aa = 0; aa < A; aa++)
+#pragma unroll
+            for (int m = 0; m < G::IPT; m++) acc[aa][m] = 0;
 #pragma unroll 1
         for (int round = 0; round < G::ROUNDS; round++) {
-            const int d = round * G::SLOTS + slot;
+            const int d = round * G::DPR + s_dig;
             if (d < G::ND) {
                 const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
-                digit_ntt<LOGN>(X.ms[r], twf, d, xin, sm, tid);
+                digit_ntt<LOGN>(X.ms[r], twf, d, xin + (size_t)s_acc * GLWE, sm, tid);
             }
             __syncthreads();
-            const int nslots = min(G::SLOTS, G::ND - round * G::SLOTS);
-            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr) + (size_t)round * G::SLOTS * (G::IPT4 / 4) * G::CT + t;
+            const int nd = min(G::DPR, G::ND - round * G::DPR);
+            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr) + (size_t)round * G::DPR * (G::IPT4 / 4) * G::CT + t;
 #pragma unroll 2
-            for (int s = 0; s < nslots; s++) {
-                const u32 *D = xch + (size_t)s * G::PADN;
+            for (int dd = 0; dd < nd; dd++) {
                 u32 rv[G::IPT4];
 #pragma unroll
                 for (int v = 0; v < G::IPT4 / 4; v++) {
-                    const uint4 q4 = __ldg(Rt + (size_t)(s * (G::IPT4 / 4) + v) * G::CT);
+                    const uint4 q4 = __ldg(Rt + (size_t)(dd * (G::IPT4 / 4) + v) * G::CT);
                     rv[4 * v] = q4.x; rv[4 * v + 1] = q4.y; rv[4 * v + 2] = q4.z; rv[4 * v + 3] = q4.w;
                 }
 #pragma unroll
-                for (int m = 0; m < G::IPT; m++) {
-                    const int item = t + G::CT * m;
-                    const u32 dv = D[pad_idx(item & (N - 1))];
-                    acc[m] += (u64)dv * rv[m];  // item >= ITEMS only when ITEMS % 256 != 0: key padding is zero
+                for (int aa = 0; aa < A; aa++) {
+                    const u32 *D = xch + (size_t)(dd * A + aa) * G::PADN;
+#pragma unroll
+                    for (int m = 0; m < G::IPT; m++) {
+                        const int item = t + G::CT * m;
+                        const u32 dv = D[pad_idx(item & (N - 1))];
+                        acc[aa][m] += (u64)dv * rv[m];  // item >= ITEMS only when ITEMS % 256 != 0: key padding is zero
+                    }
                 }
             }
             __syncthreads();
         }
-        // accumulators -> inverse-transform inputs (slot u, padded position order).  (Parking the accumulators in
-        // shared memory during the transforms removes the MOVs ptxas spends on re-pairing them in the MAC loop,
-        // but measured slower: the MAC phase is latency-, not issue-bound.)
+        // accumulators -> inverse-transform inputs (slot aa*UNITS + u, padded position order).  (Parking the
+        // accumulators in shared memory during the transforms removes the MOVs ptxas spends on re-pairing them in
+        // the MAC loop, but measured slower: the MAC phase is latency-, not issue-bound.)
 #pragma unroll
-        for (int m = 0; m < G::IPT; m++) {
-            const int item = t + G::CT * m;
-            if (item < G::ITEMS) xch[(size_t)(item >> LOGN) * G::PADN + pad_idx(item & (N - 1))] = reduce64(acc[m], ml.q, X.mu[r]);
-        }
+        for (int aa = 0; aa < A; aa++)
+#pragma unroll
+            for (int m = 0; m < G::IPT; m++) {
+                const int item = t + G::CT * m;
+                if (item < G::ITEMS)
+                    xch[(size_t)(aa * G::UNITS + (item >> LOGN)) * G::PADN + pad_idx(item & (N - 1))] = reduce64(acc[aa][m], ml.q, X.mu[r]);
+            }
         __syncthreads();
         // warp-uniform condition: every lane of a warp that owns at least one live slot runs the transform
         // (the exchanges inside synchronise whole warps); lanes of dead slots compute on scratch and store nothing
-        if ((t & ~31) / S::T < G::UNITS) {
+        if ((t & ~31) / S::T < A * G::UNITS) {
             const TwSrc<Lazy32> twi = {X.P[r].c_inv, X.P[r].inv};
             u32 x[S::E];
 #pragma unroll
             for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(LAST, tid, e))];
             inv_chain<Lazy32, LOGN, LOGE, LAST>(x, sm, tid, ml, twi, X.P[r].ninv, X.P[r].s_ninv);
-            if (slot < G::UNITS) {
+            if (slot < A * G::UNITS) {
                 u32 *R = (r == 0 ? res1 : res2) + (size_t)slot * N;
 #pragma unroll
                 for (int e = 0; e < S::E; e++) R[S::pos(0, tid, e)] = ml.canon2(x[e]);
@@ -207,16 +228,17 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
         __syncthreads();
     }
     // CRT lift, recombination, addend
-    for (int i = t; i < K1 * N; i += G::CT) {
-        const int c = i >> LOGN, p = i & (N - 1);
-        const u64 lo = crt_centered(res1[(c * 2) * N + p], res2[(c * 2) * N + p], X.cp.p1, X.cp.p2, X.cp.p1_inv_mod_p2, X.cp.P,
-                                    X.cp.halfP, X.cp.m2);
-        const u64 hi = crt_centered(res1[(c * 2 + 1) * N + p], res2[(c * 2 + 1) * N + p], X.cp.p1, X.cp.p2,
-                                    X.cp.p1_inv_mod_p2, X.cp.P, X.cp.halfP, X.cp.m2);
+    for (int i = t; i < A * GLWE; i += G::CT) {
+        const int aa = i / GLWE, rem = i % GLWE;
+        if (aa >= na) continue;
+        const int c = rem >> LOGN, p = rem & (N - 1);
+        const int u0 = (aa * G::UNITS + c * 2) * N + p, u1 = u0 + N;
+        const u64 lo = crt_centered(res1[u0], res2[u0], X.cp.p1, X.cp.p2, X.cp.p1_inv_mod_p2, X.cp.P, X.cp.halfP, X.cp.m2);
+        const u64 hi = crt_centered(res1[u1], res2[u1], X.cp.p1, X.cp.p2, X.cp.p1_inv_mod_p2, X.cp.P, X.cp.halfP, X.cp.m2);
         const u64 addend = CHAIN ? (step == 0 ? ct1[base + i] : out[base + i]) : (cmux ? ct1[base + i] : 0);
         out[base + i] = addend + lo + (hi << 32);
     }
-    if (CHAIN) __syncthreads();  // the next step reads this CTA's output row (and reuses xch / res1)
+    if (CHAIN) __syncthreads();  // the next step reads this CTA's output rows (and reuses xch / res1)
     }  // step
 }
 
@@ -257,7 +279,7 @@ static int launch_fused(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out
         FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done_mask |= 1ull << (dev & 63);
     }
-    kern<<<(unsigned)batch, threads, smem, st>>>(X, ct1, ct2, out, cmux, XpChain{nullptr, nullptr, 1, 0});
+    kern<<<(unsigned)((batch + G::A - 1) / G::A), threads, smem, st>>>(X, ct1, ct2, out, cmux, XpChain{nullptr, nullptr, 1, 0}, batch);
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -285,7 +307,8 @@ static int launch_chain(const TorusCtx &tc, const u32 *const *keys_dev, const u6
         FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_CHAIN));
         done_mask |= 1ull << (dev & 63);
     }
-    kern<<<(unsigned)batch, G::CT, G::SMEM_CHAIN, st>>>(X, acc_in, nullptr, acc_out, 1, XpChain{keys_dev, h_dev, steps, negacyclic});
+    kern<<<(unsigned)((batch + G::A - 1) / G::A), G::CT, G::SMEM_CHAIN, st>>>(X, acc_in, nullptr, acc_out, 1,
+                                                                              XpChain{keys_dev, h_dev, steps, negacyclic}, batch);
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;
