@@ -141,7 +141,12 @@ def run_reference(args, emit):
         "impl": "reference", "metric": "NTT polymul/s", "value": v, "unit": "polymul/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"Rq negacyclic NTT polymul N={N} q={Q}", "batch_per_step": per_step},
+        "config": {
+            "workload": f"BASELINE configs[1]: batched Rq negacyclic NTT polymul, N={N}, q={Q}, batch {BATCH} per GPU",
+            "n": N, "q": Q, "batch_per_step_sampled": per_step,
+            "note": "CPU arm: each step is a bounded sample of the workload (the full 65536-polymul batch takes ~0.4 s "
+                    "per step on these cores); throughput is per polymul, so the sample size does not change the metric",
+        },
         "cpu_baseline": {"value": v, "unit": "polymul/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} polymuls per step, oracle C port of arith/src/ntt.rs + ring_nq.rs"},
         "e2e": {"value": v, "unit": "polymul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

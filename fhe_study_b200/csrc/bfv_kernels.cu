@@ -12,28 +12,31 @@ namespace fhe {
 
 // Rust `f64 as i64`: saturating, NaN -> 0 (cvt.rzi.s64.f64 has exactly these semantics)
 __device__ __forceinline__ i64 f64_as_i64(double x) { return __double2ll_rz(x); }
-// Zq::from_f64 (zq.rs:32-40)
-__device__ __forceinline__ u64 zq_from_f64(u64 q, double e) {
+// Zq::from_f64 (zq.rs:32-40): r = round(e) as i64; out of [0, q): ((r % q) + q) % q with the signed remainder,
+// i.e. the mathematical r mod q.  Nearly every scaled coefficient takes that branch (t*v/q >> q), and two software
+// 64-bit divisions per coefficient were the bulk of the kernel: |r| mod q is one Barrett step with
+// mu = floor((2^64 - 1) / q) (quotient estimate low by at most two for any 64-bit operand), the sign is applied after.
+__device__ __forceinline__ u64 zq_from_f64(u64 q, u64 mu, double e) {
     const i64 ei = f64_as_i64(round(e));
-    const i64 qi = (i64)q;
-    if (ei < 0 || ei >= qi) {
-        const u64 v = (u64)(((ei % qi) + qi) % qi);
-        return v >= q ? v % q : v;  // Zq::from_u64 (zq.rs:21-31)
-    }
-    return (u64)ei;
+    if (ei >= 0 && (u64)ei < q) return (u64)ei;
+    const u64 mag = ei < 0 ? (u64)0 - (u64)ei : (u64)ei;  // |r| (2^63 for i64::MIN)
+    u64 r = mag - __umul64hi(mag, mu) * q;                 // quotient estimate low by at most 2: r in [0, 3q)
+    if (r >= q) r -= q;
+    if (r >= q) r -= q;
+    return (ei < 0 && r != 0) ? q - r : r;
 }
 // one coefficient of ring_n::mul_div_round (ring_n.rs:130-138): round((num as f64 * v as f64) / den as f64) -> Zq
-__device__ __forceinline__ u64 scale_round(u64 q, i64 v, double num, double den) {
-    return zq_from_f64(q, __ddiv_rn(__dmul_rn(num, __ll2double_rn(v)), den));
+__device__ __forceinline__ u64 scale_round(u64 q, u64 mu, i64 v, double num, double den) {
+    return zq_from_f64(q, mu, __ddiv_rn(__dmul_rn(num, __ll2double_rn(v)), den));
 }
 __device__ __forceinline__ u64 zq_sub(u64 q, u64 a, u64 b) { return a >= b ? a - b : (q + a) - b; }  // zq.rs:259-277
 __device__ __forceinline__ u64 zq_add(u64 q, u64 a, u64 b) { u64 v = a + b; return v >= q ? v - q : v; }  // zq.rs:219-231
 
 // fold of the scaled pair (ring_nq.rs:132-141): res[c] = f(conv[c]) - f(conv[c+n]); index c+n exists for c <= n-2
-__device__ __forceinline__ u64 scale_fold(u64 q, u32 n, u32 c, u64 lo, u64 hi, double num, double den) {
-    const u64 x = scale_round(q, (i64)lo, num, den);
+__device__ __forceinline__ u64 scale_fold(u64 q, u64 mu, u32 n, u32 c, u64 lo, u64 hi, double num, double den) {
+    const u64 x = scale_round(q, mu, (i64)lo, num, den);
     if (c + 1 >= n) return x;
-    return zq_sub(q, x, scale_round(q, (i64)hi, num, den));
+    return zq_sub(q, x, scale_round(q, mu, (i64)hi, num, den));
 }
 
 // mode 0: RLWE::tensor only (out = c0|c1|c2, 3n words) ; 1: RLWE::mul (tensor + relinearize_204, out 2n words) ;
@@ -53,6 +56,7 @@ __global__ void bfv_mul_kernel(const u64 *__restrict__ a, const u64 *__restrict_
     CT *s = reinterpret_cast<CT *>(k1 + n) + (size_t)slot * 5 * n;
     CT *a0 = s, *a1 = s + n, *b0 = s + 2 * n, *b1 = s + 3 * n, *c2s = s + 4 * n;
     const double dq = __ull2double_rn(q), dt = __ull2double_rn(t);
+    const u64 mu = ~0ull / q;  // floor((2^64 - 1) / q)
     u64 c0 = 0, c1 = 0, c2 = 0;
     if (mode != 0) {
         for (u32 i = threadIdx.x; i < 2 * n; i += blockDim.x) k0[i] = rlk[i];
@@ -80,9 +84,9 @@ __global__ void bfv_mul_kernel(const u64 *__restrict__ a, const u64 *__restrict_
             }
             j = j == 0 ? n - 1 : j - 1;
         }
-        c0 = scale_fold(q, n, c, l00, h00, dt, dq);
-        c1 = scale_fold(q, n, c, l01, h01, dt, dq);
-        c2 = scale_fold(q, n, c, l11, h11, dt, dq);
+        c0 = scale_fold(q, mu, n, c, l00, h00, dt, dq);
+        c1 = scale_fold(q, mu, n, c, l01, h01, dt, dq);
+        c2 = scale_fold(q, mu, n, c, l11, h11, dt, dq);
     }
     if (mode == 0) {
         if (valid) {
@@ -103,8 +107,8 @@ __global__ void bfv_mul_kernel(const u64 *__restrict__ a, const u64 *__restrict_
             if (i <= c) { l0 += x * y0; l1 += x * y1; } else { h0 += x * y0; h1 += x * y1; }
             j = j == 0 ? n - 1 : j - 1;
         }
-        const u64 r0 = scale_fold(q, n, c, l0, h0, 1.0, dp);
-        const u64 r1 = scale_fold(q, n, c, l1, h1, 1.0, dp);
+        const u64 r0 = scale_fold(q, mu, n, c, l0, h0, 1.0, dp);
+        const u64 r1 = scale_fold(q, mu, n, c, l1, h1, 1.0, dp);
         u64 *po = out + ct * 2 * n;
         po[c] = zq_add(q, c0, r0);
         po[n + c] = zq_add(q, c1, r1);

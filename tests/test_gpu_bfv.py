@@ -128,3 +128,17 @@ def test_rq_coefficientwise_known_answers(fhe, orc):
             want = np.empty(l * n, dtype=np.uint64)
             L.orc_rq_decompose(q, n, orc.ptr(np.ascontiguousarray(x[p])), beta, l, orc.ptr(want))
             assert (got[p].reshape(-1) == want).all(), (beta, l)
+
+
+@pytest.mark.parametrize("q,p,n,t", [(2**16, 2**8, 16, 2), (3, 9, 8, 2), (2**61 - 1, 4, 16, 5), (2**32, 2**16, 4, 3),
+                                      (2**63 - 25, 1, 8, 2)])
+def test_mul_relin_modulus_edge_cases(fhe, orc, q, p, n, t):
+    # power-of-two and near-2^63 moduli: Zq::from_f64's reduction of negative / huge rounded values (zq.rs:32-40)
+    pq = p * q
+    a = orc.uniform(11, (9, 2 * n), q)
+    b = orc.uniform(12, (9, 2 * n), q)
+    a[0, :] = q - 1
+    b[0, :] = q - 1
+    rlk = orc.uniform(13, 2 * n, pq)
+    want = orc.bfv_mul(q, n, t, pq, rlk, a.reshape(-1), b.reshape(-1)).reshape(9, 2 * n)
+    assert (fhe.bfv_mul_relin(q, n, t, pq, rlk, a, b) == want).all()
