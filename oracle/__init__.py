@@ -204,8 +204,9 @@ def rq_addsub(q: int, n: int, a, b, op: int) -> np.ndarray:
     a = u64(a)
     b = u64(b) if b is not None else a
     c = np.empty_like(a)
+    af, bf, cf = a.reshape(-1), b.reshape(-1), c.reshape(-1)
     for i in range(a.size // n):
-        lib().orc_rq_addsub(q, n, ptr(a[i * n:]), ptr(b[i * n:]), ptr(c[i * n:]), op)
+        lib().orc_rq_addsub(q, n, ptr(af[i * n:]), ptr(bf[i * n:]), ptr(cf[i * n:]), op)
     return c
 
 
@@ -227,9 +228,10 @@ def extprod(n: int, k: int, tggsw, ct, fast: bool = True) -> np.ndarray:
     tggsw, ct = u64(tggsw), u64(ct)
     glwe = (k + 1) * n
     out = np.empty_like(ct)
+    cf, of = ct.reshape(-1), out.reshape(-1)  # any batch shape: rows are addressed on the flat views
     f = lib().orc_tggsw_extprod_fast if fast else lib().orc_tggsw_extprod
     for i in range(ct.size // glwe):
-        f(n, k, ptr(tggsw), ptr(ct[i * glwe:]), ptr(out[i * glwe:]))
+        f(n, k, ptr(tggsw), ptr(cf[i * glwe:]), ptr(of[i * glwe:]))
     return out
 
 
@@ -237,9 +239,10 @@ def cmux(n: int, k: int, tggsw, ct1, ct2, fast: bool = True) -> np.ndarray:
     tggsw, ct1, ct2 = u64(tggsw), u64(ct1), u64(ct2)
     glwe = (k + 1) * n
     out = np.empty_like(ct1)
+    f1, f2, of = ct1.reshape(-1), ct2.reshape(-1), out.reshape(-1)
     f = lib().orc_tggsw_cmux_fast if fast else lib().orc_tggsw_cmux
     for i in range(ct1.size // glwe):
-        f(n, k, ptr(tggsw), ptr(ct1[i * glwe:]), ptr(ct2[i * glwe:]), ptr(out[i * glwe:]))
+        f(n, k, ptr(tggsw), ptr(f1[i * glwe:]), ptr(f2[i * glwe:]), ptr(of[i * glwe:]))
     return out
 
 

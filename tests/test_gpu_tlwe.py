@@ -160,3 +160,21 @@ def test_key_switch_full_size_both_paths(fhe, orc, p5, monkeypatch):
         monkeypatch.setenv("FHE_KS_PATH", path)
         assert (K.key_switch(ct) == want).all(), path
     monkeypatch.delenv("FHE_KS_PATH")
+
+
+def test_bootstrap_at_baseline_batch_spot_checked(fhe, orc, p5):
+    # BASELINE configs[4] size (8192 TLWE inputs per GPU): every tile of the tensor-core key switch is exercised;
+    # 48 rows spread over the batch (first and last tile included) are compared with the oracle, and the whole
+    # batch must be invariant under a permutation of its rows (independent units: no cross-row leakage)
+    n, k, kn = p5["n"], p5["k"], p5["kn"]
+    batch = 8192
+    K = fhe.Ksk(kn, kn, 64, p5["ksk"])
+    table = orc.uniform(501, (k + 1) * n)
+    cts = orc.uniform(502, (batch, kn + 1))
+    got = fhe.bootstrap(n, k, K, table, cts, kn)
+    rows = np.unique(np.concatenate([np.arange(8), batch - 1 - np.arange(8), orc.uniform(503, 32, batch).astype(np.int64)]))
+    want = orc.bootstrapping(n, k, p5["ksk"], table, np.ascontiguousarray(cts[rows]).reshape(-1), kn, threads=8)
+    assert np.array_equal(got[rows].reshape(-1), want)
+    perm = np.argsort(orc.uniform(504, batch))
+    got_p = fhe.bootstrap(n, k, K, table, np.ascontiguousarray(cts[perm]), kn)
+    assert np.array_equal(got_p, got[perm])

@@ -194,3 +194,21 @@ def test_extprod_device_buffers_and_linearity(fhe, orc):
     assert torch.equal(full, parts)
     got = full[:3].cpu().numpy().view(np.uint64)
     assert (got.reshape(-1) == orc.extprod(n, k, tggsw, x[:3].reshape(-1))).all()
+
+
+@pytest.mark.parametrize("n,k,batch", [(1024, 1, 1024), (64, 4, 8191)])
+def test_cmux_at_baseline_batch_spot_checked(fhe, orc, n, k, batch):
+    # BASELINE configs[3] sizes ("batched accumulators" sharing one TGGSW), ragged for the multi-accumulator CTAs:
+    # rows spread over the batch against the oracle + row-permutation invariance of the whole batch
+    glwe = (k + 1) * n
+    tggsw = orc.uniform(601, (k + 1) * 64 * glwe)
+    ct1, ct2 = orc.uniform(602, (batch, glwe)), orc.uniform(603, (batch, glwe))
+    g = fhe.Tggsw(n, k, tggsw)
+    got = g.cmux(ct1, ct2)
+    rows = np.unique(np.concatenate([np.arange(5), batch - 1 - np.arange(5), orc.uniform(604, 6, batch).astype(np.int64)]))
+    want = orc.cmux(n, k, tggsw, np.ascontiguousarray(ct1[rows]), np.ascontiguousarray(ct2[rows]))
+    assert np.array_equal(got[rows], want)
+    perm = np.argsort(orc.uniform(605, batch))
+    assert np.array_equal(g.cmux(np.ascontiguousarray(ct1[perm]), np.ascontiguousarray(ct2[perm])), got[perm])
+    # cmux(g, x, x) = x for any TGGSW (the external product of zero is zero)
+    assert np.array_equal(g.cmux(ct1, ct1), ct1)
