@@ -107,6 +107,13 @@ def tfhe_paths(fhe, dev, quick, cpu=True):
         ms_c = _time(lambda: g.cmux(ct1, ct2, out=out), reps, warm=1)
         row = {"n": n, "k": k, "batch": batch, "extprod_per_s": batch / (ms_e * 1e-3), "cmux_per_s": batch / (ms_c * 1e-3),
                "extprod_ms": ms_e, "cmux_ms": ms_c}
+        # integer roofline (limb-NTT formulation): 2 primes x [(k+1)*64 forward + 2(k+1) inverse
+        # transforms] + 2 primes x (k+1)*64 digits x 2(k+1) units x n MACs, against the measured Shoup-modmul peak
+        logn = n.bit_length() - 1
+        modmul = 2 * ((k + 1) * 64 * (n // 2) * logn + 2 * (k + 1) * ((n // 2) * logn + n)) + 2 * (k + 1) * 64 * 2 * (k + 1) * n
+        row["modmul_per_unit"] = modmul
+        row["int_roofline_frac"] = row["extprod_per_s"] * modmul / fhe.int_peak(1)
+        row["hbm_frac"] = row["extprod_per_s"] * 2 * (k + 1) * n * 8 / (_hbm_peak() * 1e9)
         if cpu:
             sample = max(1, min(batch, cores * (4 if n <= 64 else 1)))
             hg = tggsw.cpu().numpy().view(np.uint64)
@@ -134,6 +141,9 @@ def tfhe_paths(fhe, dev, quick, cpu=True):
     row = {"n": n, "k": k, "l": l, "batch": batch, "bootstraps_per_s": batch / (ms_b * 1e-3), "bootstrap_ms": ms_b,
            "key_switch_per_s": batch / (ms_k * 1e-3), "ksk_bytes": int(ksk.numel() * 8),
            "u64_mac_per_s": batch * kn * l * (kn + 1) / (ms_b * 1e-3)}
+    # tensor roofline: every u64 MAC is 8 byte-plane int8 MACs on the tensor cores (ks_tc.cu) = 16 int8 ops
+    row["int8_pops"] = row["u64_mac_per_s"] * 16 / 1e15
+    row["tensor_roofline_frac_vs_4.5_pops_nominal"] = row["int8_pops"] / 4.5
     if cpu:
         sample = cores * 2
         hk = ksk.cpu().numpy().view(np.uint64)

@@ -64,6 +64,8 @@ struct fhe_tggsw {
 namespace fhe {
 
 int tn_mul_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t batch, cudaStream_t st);
+bool tn_mul_fused_supported(int logn);
+int tn_mul_fused_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t batch, cudaStream_t st);
 // out = g (x) ct1 (ct2 == nullptr)  or  ct1 + g (x) (ct2 - ct1)  (CMux)
 int extprod_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, cudaStream_t st);
 bool extprod_fused_supported(int logn, int k1);

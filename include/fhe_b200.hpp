@@ -8,6 +8,7 @@
 //   tfhe::TGLWE / TGGSW         tfhe/src/tglwe.rs:30,89-119 ; tfhe/src/tggsw.rs:14,39-62
 //   tfhe::TLWE / KSK / bootstrapping   tfhe/src/tlwe.rs:37-40,101-161
 //   bfv::RLWE / RLK             bfv/src/lib.rs:35-47,59-90,251-271
+//   gfhe::GLWE<Rq> / GLev<Rq> / KSK<Rq>   gfhe/src/glwe.rs:57-66,126-137,197-204,263-280 ; gfhe/src/glev.rs:14,67-80
 // Header-only; link with -lfhe_b200.
 #pragma once
 #include <cstdint>
@@ -252,6 +253,83 @@ inline TLWE bootstrapping(size_t n, size_t k, const KSK &ksk, const TGLWE &table
     check(fhe_bootstrap(n, k, ksk.handle(), table.data.data(), c.data.data(), c.kn(), out.data(), 1));
     return TLWE(std::move(out));
 }
+
+// blind rotation with one TGGSW per mask element: the loop tlwe.rs:138-147 spells out (extension, see fhe_b200.h)
+inline TGLWE cmux_chain(const std::vector<TGGSW> &bsk, const TGLWE &acc, const std::vector<uint64_t> &h, bool negacyclic) {
+    if (h.size() != bsk.size()) throw std::runtime_error("fhe_b200: cmux_chain needs one rotation per TGGSW");
+    std::vector<const fhe_tggsw *> hs;
+    for (const TGGSW &g : bsk) hs.push_back(g.handle());
+    TGLWE r(acc.n, acc.k);
+    check(fhe_cmux_chain(acc.n, acc.k, hs.data(), hs.size(), negacyclic ? 1 : 0, acc.data.data(), h.data(), r.data.data(), 1));
+    return r;
+}
+inline TLWE bootstrapping_chain(size_t n, size_t k, const std::vector<TGGSW> &bsk, int mode, const KSK *ksk, const TGLWE &table,
+                                const TLWE &c) {
+    std::vector<const fhe_tggsw *> hs;
+    for (const TGGSW &g : bsk) hs.push_back(g.handle());
+    std::vector<uint64_t> out((ksk ? ksk->kn_out : k * n) + 1);
+    check(fhe_bootstrap_chain(n, k, hs.data(), hs.size(), mode, ksk ? ksk->handle() : nullptr, table.data.data(), c.data.data(),
+                              c.kn(), out.data(), 1));
+    return TLWE(std::move(out));
+}
+
+// ---- gfhe over Rq -------------------------------------------------------------------------------------------
+struct GLWE {  // GLWE<Rq>(TR<Rq>, Rq) (gfhe/src/glwe.rs:57): k mask polynomials, then the body
+    RingParam param;
+    size_t k;
+    std::vector<uint64_t> data;  // (k+1)*n words
+    GLWE(RingParam p, size_t k_) : param(p), k(k_), data((k_ + 1) * p.n, 0) {}
+    GLWE(RingParam p, size_t k_, std::vector<uint64_t> d) : param(p), k(k_), data(std::move(d)) {
+        if (data.size() != (k + 1) * p.n) throw std::runtime_error("fhe_b200: GLWE needs (k+1)*n words");
+    }
+    bool operator==(const GLWE &o) const { return param == o.param && k == o.k && data == o.data; }
+    GLWE operator+(const GLWE &o) const { detail::same(param, o.param); GLWE r(param, k); check(fhe_rq_add(param.q, data.data(), o.data.data(), r.data.data(), data.size())); return r; }
+    GLWE operator-(const GLWE &o) const { detail::same(param, o.param); GLWE r(param, k); check(fhe_rq_sub(param.q, data.data(), o.data.data(), r.data.data(), data.size())); return r; }
+    GLWE mod_switch(uint64_t p) const {  // glwe.rs:197-204
+        GLWE r(RingParam{p, param.n}, k);
+        check(fhe_rq_mod_switch(param.q, data.data(), p, r.data.data(), data.size()));
+        return r;
+    }
+    GLWE operator*(const Rq &plaintext) const {  // impl Mul<R> for GLWE<R> (glwe.rs:263-280): every component times the plaintext
+        detail::same(param, plaintext.param);
+        GLWE r(param, k);
+        std::vector<uint64_t> rhs;
+        for (size_t c = 0; c <= k; c++) rhs.insert(rhs.end(), plaintext.coeffs.begin(), plaintext.coeffs.end());
+        check(fhe_rq_mul(detail::plan(param).get(), data.data(), rhs.data(), r.data.data(), k + 1, 0, nullptr));
+        return r;
+    }
+};
+class GLev {  // GLev<Rq>(Vec<GLWE<Rq>>) (gfhe/src/glev.rs:14), or the k*l rows of a KSK<Rq> (glwe.rs:99-125)
+  public:
+    RingParam param;
+    size_t k, rows;
+    GLev(RingParam p, size_t k_, const std::vector<GLWE> &glwes) : param(p), k(k_), rows(glwes.size()) {
+        std::vector<uint64_t> flat;
+        for (const GLWE &g : glwes) { detail::same(p, g.param); flat.insert(flat.end(), g.data.begin(), g.data.end()); }
+        plan_ = detail::plan(p);
+        fhe_rq_glev *h = nullptr;
+        check(fhe_rq_glev_load(plan_.get(), k, rows, flat.data(), &h));
+        h_.reset(h, [](fhe_rq_glev *x) { fhe_rq_glev_destroy(x); });
+    }
+    GLWE operator*(const std::vector<Rq> &v) const {  // impl Mul<Vec<R>> for GLev<R> (glev.rs:67-80)
+        if (v.size() != rows) throw std::runtime_error("fhe_b200: GLev * Vec<R> needs one polynomial per level");
+        std::vector<uint64_t> flat;
+        for (const Rq &x : v) { detail::same(param, x.param); flat.insert(flat.end(), x.coeffs.begin(), x.coeffs.end()); }
+        GLWE r(param, k);
+        check(fhe_rq_glev_mul(h_.get(), flat.data(), r.data.data(), 1));
+        return r;
+    }
+    GLWE key_switch(const GLWE &ct, uint32_t beta, uint32_t l) const {  // GLWE::key_switch (glwe.rs:126-137), *this = the KSK
+        detail::same(param, ct.param);
+        GLWE r(param, k);
+        check(fhe_glwe_rq_key_switch(h_.get(), beta, l, ct.data.data(), r.data.data(), 1));
+        return r;
+    }
+
+  private:
+    std::shared_ptr<fhe_ntt_plan> plan_;
+    std::shared_ptr<fhe_rq_glev> h_;
+};
 
 // ---- BFV --------------------------------------------------------------------------------------------------
 struct RLWE {  // bfv/src/lib.rs:35-47

@@ -91,6 +91,40 @@ int main() {
         TGLWE zero(n, k);
         EXPECT((g * zero).data == zero.data);
     }
+    {   // CMux chain (the loop of tlwe.rs:138-147): equals applying TGGSW::cmux + left_rotate step by step
+        const size_t n = 64, k = 1, steps = 3;
+        std::mt19937_64 rng(3);
+        std::vector<TGGSW> bsk;
+        for (size_t j = 0; j < steps; j++) {
+            std::vector<uint64_t> rows((k + 1) * 64 * (k + 1) * n);
+            for (auto &x : rows) x = rng();
+            bsk.emplace_back(n, k, rows);
+        }
+        std::vector<uint64_t> c((k + 1) * n), h = {5, 0, 63};
+        for (auto &x : c) x = rng();
+        TGLWE acc(n, k, c), step = acc;
+        for (size_t j = 0; j < steps; j++) step = TGGSW::cmux(bsk[j], step, step.left_rotate(h[j]));
+        EXPECT(cmux_chain(bsk, acc, h, false).data == step.data);
+    }
+    {   // gfhe over Rq: GLev * Vec<Rq> equals the sum of GLWE * Rq (glev.rs:67-80), and key_switch with an all-zero
+        // key is (0, b) (glwe.rs:126-137)
+        RingParam p{Q, 16};
+        const size_t k = 2, l = 3;
+        std::mt19937_64 rng(4);
+        auto rnd = [&](size_t len) { std::vector<uint64_t> v(len); for (auto &x : v) x = rng() % Q; return v; };
+        std::vector<GLWE> rows;
+        std::vector<Rq> v;
+        for (size_t j = 0; j < l; j++) { rows.emplace_back(p, k, rnd((k + 1) * p.n)); v.emplace_back(p, rnd(p.n)); }
+        GLWE want = rows[0] * v[0];
+        for (size_t j = 1; j < l; j++) want = want + rows[j] * v[j];
+        EXPECT((GLev(p, k, rows) * v) == want);
+        std::vector<GLWE> zero_rows(k * 4, GLWE(p, k));
+        GLWE ct(p, k, rnd((k + 1) * p.n));
+        GLWE ks = GLev(p, k, zero_rows).key_switch(ct, 2, 4);
+        GLWE expect(p, k);
+        std::copy(ct.data.begin() + k * p.n, ct.data.end(), expect.data.begin() + k * p.n);
+        EXPECT(ks == expect);
+    }
     std::printf(failures ? "%d FAILURES\n" : "ALL OK\n", failures);
     return failures ? 1 : 0;
 }

@@ -30,9 +30,9 @@ def test_left_rotate_known_answers(fhe):
     assert list(fhe.tn_left_rotate(4, f, np.array([4 + 1], dtype=np.uint64))) == neg64([3, -4, -1, -2])  # h % n
 
 
-@pytest.mark.parametrize("n", [2, 4, 64, 128, 1024, 4096])
-def test_tn_mul_matches_schoolbook(fhe, orc, n):
-    batch = 3 if n >= 1024 else 9
+@pytest.mark.parametrize("n", [2, 4, 64, 128, 256, 512, 1024, 4096])
+def test_tn_mul_matches_schoolbook(fhe, orc, n, monkeypatch):
+    batch = 3 if n >= 1024 else 37  # ragged against the products-per-CTA grouping of the fused kernel
     a = orc.uniform(n + 1, (batch, n))
     b = orc.uniform(n + 2, (batch, n))
     a[0, :] = M64 - 1  # worst case for the exactness bound of the CRT lift
@@ -41,6 +41,9 @@ def test_tn_mul_matches_schoolbook(fhe, orc, n):
     b[2, :] = 1
     want = orc.tn_mul(n, a, b, threads=8)
     assert (fhe.tn_mul(n, a, b) == want).all()
+    monkeypatch.setenv("FHE_TN_PATH", "unfused")  # building-block path (the only one outside 64 <= n <= 1024)
+    assert (fhe.tn_mul(n, a, b) == want).all()
+    monkeypatch.delenv("FHE_TN_PATH")
 
 
 def test_tn_elementwise(fhe, orc):
