@@ -322,8 +322,8 @@ int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
     std::string why = build_host_tables(q, n, p->host);
     FHE_REQUIRE(why.empty(), "fhe_ntt_plan_create: " + why);
     p->device = dev;
-    p->kind = modulus_kind(q);
     p->logn = hp_ilog2(n);
+    p->kind = modulus_kind(q, p->logn);
     FHE_REQUIRE(p->logn <= ((p->kind == 0 || p->kind == 3) ? 15 : 14),
                 "fhe_ntt_plan_create: n too large (max 2^15 for q < 2^30, 2^14 for larger q)");
     // coefficients per thread: the library default, or FHE_NTT_LOGE (a tuning knob; only values that were

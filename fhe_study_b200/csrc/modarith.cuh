@@ -81,6 +81,9 @@ struct Lazy32 {
         x = mul_tw(s, ninv);
         y = mul_tw(d, s_ninv);
     }
+    // K = number of inverse stages already executed (only the csub-free Small32 policy needs it)
+    template <int K> FHE_HD void inv_k(u32 &x, u32 &y, T t) const { inv(x, y, t); }
+    template <int K> FHE_HD void inv_last_k(u32 &x, u32 &y, T ninv, T s_ninv) const { inv_last(x, y, ninv, s_ninv); }
     FHE_HD u32 canon4(u32 x) const { return csub(csub(x, q2), q); }  // [0,4q) -> [0,q)
     FHE_HD u32 canon2(u32 x) const { return csub(x, q); }            // [0,2q) -> [0,q)
     // a*b mod q for canonical a,b (Barrett on the 2k-bit product), result in [0,q).
@@ -131,6 +134,9 @@ struct Lazy64 {
         x = mul_tw(s, ninv);
         y = mul_tw(d, s_ninv);
     }
+    // K = number of inverse stages already executed (only the csub-free Small32 policy needs it)
+    template <int K> FHE_HD void inv_k(u64 &x, u64 &y, T t) const { inv(x, y, t); }
+    template <int K> FHE_HD void inv_last_k(u64 &x, u64 &y, T ninv, T s_ninv) const { inv_last(x, y, ninv, s_ninv); }
     FHE_HD u64 canon4(u64 x) const { return csub(csub(x, q2), q); }
     FHE_HD u64 canon2(u64 x) const { return csub(x, q); }
     // Montgomery product a*b*2^-64 mod q in [0,q) (a*b < q*2^64).
@@ -184,6 +190,9 @@ struct Strict64 {
         x = mul_tw(s, ninv);
         y = mul_tw(d, s_ninv);
     }
+    // K = number of inverse stages already executed (only the csub-free Small32 policy needs it)
+    template <int K> FHE_HD void inv_k(u64 &x, u64 &y, T t) const { inv(x, y, t); }
+    template <int K> FHE_HD void inv_last_k(u64 &x, u64 &y, T ninv, T s_ninv) const { inv_last(x, y, ninv, s_ninv); }
     FHE_HD u64 canon4(u64 x) const { return x; }
     FHE_HD u64 canon2(u64 x) const { return x; }
     FHE_HD u64 mont(u64 a, u64 b) const {
@@ -203,7 +212,7 @@ struct Strict64 {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// Small32: q < 2^22 (the reference's only NTT modulus, 65537, lives here).  With so much headroom in a
+// Small32: q < 2^22 and 2q * n <= 2^32 (the reference's only NTT modulus, 65537, lives here for every n <= 2^14).  With so much headroom in a
 // 32-bit word the forward butterfly needs no conditional subtraction at all: x' = x + V, y' = x - V + 2q
 // grows by at most 2q per stage, so after LOGN <= 15 stages values stay below 31q < 2^27.  The pointwise
 // product of two such lazy values (a*b < 961 q^2 < q*2^32) is one Montgomery reduction, whose 2^-32 factor
@@ -216,6 +225,7 @@ struct Small32 {
     u32 qinv_neg;  // -q^-1 mod 2^32
     Tw32 one;      // w = 1           : mul_tw(x, one) = x mod q in [0,2q) for any 32-bit x
     Tw32 r;        // w = 2^32 mod q  : undoes the Montgomery factor
+    u32 qk[16];    // 2q << K: offset of the K-th executed inverse stage (read from the constant bank by IADD3)
     static constexpr bool PW_SCALED = true;
 
     FHE_HD u32 mul_tw(u32 y, T t) const { return y * t.w - mulhi_u32(y, t.wp) * q; }
@@ -234,6 +244,22 @@ struct Small32 {
     FHE_HD void inv_last(u32 &x, u32 &y, T ninv, T s_ninv) const {
         u32 s = x + y;
         u32 d = x - y + q2;
+        x = mul_tw(s, ninv);
+        y = mul_tw(d, s_ninv);
+    }
+    // csub-free inverse butterflies: the sum path doubles its bound every stage (values < 2q * 2^K before the
+    // (K+1)-th executed stage), the difference is offset by that bound (a multiple of q) and goes through mul_tw,
+    // which takes any 32-bit word.  Needs 2q * 2^LOGN <= 2^32: plan_host.hpp: modulus_kind() only selects this
+    // policy when that holds.
+    template <int K> FHE_HD void inv_k(u32 &x, u32 &y, T t) const {
+        u32 s = x + y;
+        u32 d = x - y + qk[K];
+        x = s;
+        y = mul_tw(d, t);
+    }
+    template <int K> FHE_HD void inv_last_k(u32 &x, u32 &y, T ninv, T s_ninv) const {
+        u32 s = x + y;
+        u32 d = x - y + qk[K];
         x = mul_tw(s, ninv);
         y = mul_tw(d, s_ninv);
     }

@@ -111,6 +111,7 @@ FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
     typedef NttShape<LOGN, LOGE> S;
     constexpr int g = S::g(PASS), s0 = S::s0(PASS), nL = S::nL(PASS), G = 1 << g;
     constexpr int half = 1 << (g - 1 - LS);
+    constexpr int K = LOGN - 1 - (s0 + LS);  // inverse stages already executed (stages run from LOGN-1 down to 0)
 #pragma unroll
     for (int qi = 0; qi < (S::E >> g); qi++) {
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
@@ -118,14 +119,15 @@ FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
         for (int hi = 0; hi < (1 << LS); hi++) {
             if constexpr (PASS == 0 && LS == 0) {
 #pragma unroll
-                for (int lo = 0; lo < half; lo++) m.inv_last(x[qi * G + lo], x[qi * G + lo + half], ninv, s_ninv);
+                for (int lo = 0; lo < half; lo++)
+                    m.template inv_last_k<K>(x[qi * G + lo], x[qi * G + lo + half], ninv, s_ninv);
             } else {
                 const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
                 const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
 #pragma unroll
                 for (int lo = 0; lo < half; lo++) {
                     const int ru = (hi << (g - LS)) | lo;
-                    m.inv(x[qi * G + ru], x[qi * G + ru + half], t);
+                    m.template inv_k<K>(x[qi * G + ru], x[qi * G + ru + half], t);
                 }
             }
         }

@@ -134,10 +134,15 @@ inline void init_mod(Small32 &m, u64 q) {
     m.qinv_neg = neg_inv32((u32)q);
     m.one = make_tw((u32)1, (u32)q, (Tw32 *)nullptr);
     m.r = make_tw((u32)((1ull << 32) % q), (u32)q, (Tw32 *)nullptr);
+    for (int k = 0; k < 16; k++) m.qk[k] = (u32)((2 * q) << k);  // wraps only where the policy is not selected
 }
 
-// 3: Small32 (q < 2^22), 0: Lazy32 (q < 2^30), 1: Lazy64 (q < 2^62), 2: Strict64 (q < 2^63)
-inline int modulus_kind(u64 q) { return q < (1ull << 22) ? 3 : q < (1ull << 30) ? 0 : q < (1ull << 62) ? 1 : 2; }
+// 3: Small32 (q < 2^22 and 2q*n <= 2^32: both transforms free of conditional subtractions), 0: Lazy32 (q < 2^30),
+// 1: Lazy64 (q < 2^62), 2: Strict64 (q < 2^63)
+inline int modulus_kind(u64 q, int logn) {
+    if (q < (1ull << 22) && ((2 * q) << logn) <= (1ull << 32)) return 3;
+    return q < (1ull << 30) ? 0 : q < (1ull << 62) ? 1 : 2;
+}
 
 // Shoup-expanded tables for policy M.
 template <class M> struct ExpandedTables {

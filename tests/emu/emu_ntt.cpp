@@ -120,10 +120,12 @@ extern "C" {
 // kind: -1 auto (as the library picks), 0 Lazy32, 1 Lazy64, 2 Strict64, 3 Small32 ; mode 0 fwd, 1 inv, 2 mul
 int emu_ntt(int kind, uint64_t q, uint64_t n, int loge, int mode, const uint64_t *a, const uint64_t *b, uint64_t *c,
             uint64_t *c_evals, int flags) {
-    if (kind < 0) kind = modulus_kind(q);
+    int logn = 0;
+    while ((1ull << logn) < n) logn++;
+    if (kind < 0) kind = modulus_kind(q, logn);
     if (kind == 0) return q < (1ull << 30) ? emu_any<Lazy32>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
     if (kind == 1) return q < (1ull << 62) ? emu_any<Lazy64>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
-    if (kind == 3) return q < (1ull << 22) ? emu_any<Small32>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
+    if (kind == 3) return modulus_kind(q, logn) == 3 ? emu_any<Small32>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
     return emu_any<Strict64>(q, n, loge, mode, a, b, c, c_evals, flags);
 }
 int emu_plan(uint64_t q, uint64_t n, uint64_t *psi, uint64_t *n_inv, uint64_t *roots, uint64_t *roots_inv) {

@@ -44,10 +44,18 @@ def test_lazy32_all_sizes(emu, orc, logn):
 @pytest.mark.parametrize("logn", range(1, 16))
 def test_small32_all_sizes(emu, orc, logn):
     # q < 2^22: csub-free forward butterflies, Montgomery pointwise with the factor folded into n^-1
+    # and csub-free inverse butterflies, which need 2q*n <= 2^32 (that is what selects the policy)
     n = 1 << logn
+    small = lambda q: (2 * q) << logn <= 2**32
     for loge in (0, 3, 4):
-        _check(emu, orc, 3, Q17, n, loge)
-    _check(emu, orc, 3, Q22, n, 0)
+        if small(Q17):
+            _check(emu, orc, 3, Q17, n, loge)
+    if small(Q22):
+        _check(emu, orc, 3, Q22, n, 0)
+    else:  # the library must refuse the policy there (and pick Lazy32 on its own)
+        a = orc.uniform(1, n, Q22)
+        assert emu.emu_ntt(3, Q22, n, 0, 0, orc.ptr(a), None, orc.ptr(a.copy()), None, 0) == -2
+        _check(emu, orc, -1, Q22, n, 0)
     _check(emu, orc, -1, Q17, n, 0)  # the policy the library picks for the reference's modulus
 
 
@@ -83,3 +91,17 @@ def test_modmul_policies(emu):
         cases += [(int(x), int(y)) for x, y in zip(rng.integers(0, q, 5000, dtype=np.uint64), rng.integers(0, q, 5000, dtype=np.uint64))]
         for a, b in cases:
             assert emu.emu_modmul(kind, q, a, b) == a * b % q
+
+
+@pytest.mark.parametrize("q,logn", [(Q17, 14), (Q17, 10), (Q22, 9), (417793, 12), (1032193, 11), (163841, 13)])
+def test_small32_inverse_worst_case_growth(emu, orc, q, logn):
+    # csub-free inverse: the sum path reaches 2q*n - 1 when every input is q-1 (and, for the polymul, 2q-1 after the
+    # lazy pointwise product); must still equal the oracle at the largest (q, n) the policy accepts
+    n = 1 << logn
+    for fill in (q - 1, 0, 1):
+        a = np.full(n, fill, dtype=np.uint64)
+        out = np.empty(n, dtype=np.uint64)
+        assert emu.emu_ntt(3, q, n, 0, 1, orc.ptr(a), None, orc.ptr(out), None, 0) == 0
+        assert np.array_equal(out, orc.ntt(q, n, a, inverse=True))
+        assert emu.emu_ntt(3, q, n, 0, 2, orc.ptr(a), orc.ptr(a), orc.ptr(out), None, 0) == 0
+        assert np.array_equal(out, orc.rq_mul_batch(q, n, a, a))
