@@ -18,7 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--fmad=false",
-]
+] + os.environ.get("FHE_EXTRA_NVCC_FLAGS", "").split()  # tuning experiments only (e.g. -DFHE_A_SMEM_MINB=6)
 
 
 def _sources():

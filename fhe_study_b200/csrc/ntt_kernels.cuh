@@ -89,8 +89,19 @@ __device__ __forceinline__ void store_poly(typename M::W (&x)[1 << LOGE], u64 *_
     }
 }
 
+// Polymul with NTT(a) parked in shared memory while b is transformed (instead of 32 more live registers): lets more
+// CTAs be resident.  Only for one-warp transforms on 32-bit words.  FHE_A_SMEM_MINB = resident CTAs asked of ptxas.
+#ifndef FHE_A_SMEM_MINB
+#define FHE_A_SMEM_MINB 0
+#endif
+template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
+    static constexpr bool on = FHE_A_SMEM_MINB > 0 && MODE == MODE_MUL && sizeof(typename M::W) == 4 &&
+                               NttShape<LOGN, LOGE>::T <= 32 && LOGN == 10;
+    static constexpr int minb = on ? FHE_A_SMEM_MINB : 1;
+};
+
 template <class M, int LOGN, int LOGE, int MODE>
-__global__ void __launch_bounds__(KernelGeom<LOGN, LOGE>::CT)
+__global__ void __launch_bounds__(KernelGeom<LOGN, LOGE>::CT, ASmem<M, LOGN, LOGE, MODE>::minb)
 ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, const u64 *__restrict__ b,
            u64 *__restrict__ c, u64 *__restrict__ c_evals, size_t batch, int flags) {
     typedef NttShape<LOGN, LOGE> S;
@@ -123,7 +134,9 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
     } else {
         const TwSrc<M> twf = {P.c_fwd, P.fwd};
         const TwSrc<M> twi = {P.c_inv, P.inv};
-        W A[S::E];
+        constexpr bool PARK = ASmem<M, LOGN, LOGE, MODE>::on;
+        W A[PARK ? 1 : S::E];
+        W *sA = reinterpret_cast<W *>(smem_raw) + (size_t)G::PPC * G::PADN + (size_t)slot * S::N;  // PARK only
         // both operands run through ONE copy of the forward-transform code (the fully unrolled transform is
         // the bulk of the kernel's instruction footprint; see profiles/: no_instruction stalls)
 #pragma unroll 1
@@ -138,16 +151,27 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
                 for (int e = 0; e < S::E; e++) x[e] = m.fwd_out(x[e]);
             }
             if (op == 0) {
+                if constexpr (PARK) {
 #pragma unroll
-                for (int e = 0; e < S::E; e++) A[e] = x[e];
+                    for (int e = 0; e < S::E; e++) sA[e * S::T + tid] = x[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < S::E; e++) A[e] = x[e];
+                }
             }
         }
+        if constexpr (PARK) {
 #pragma unroll
-        for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(A[e], x[e]);
+            for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(sA[e * S::T + tid], x[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(A[e], x[e]);
+        }
         if (c_evals != nullptr) {  // ring_nq.rs:606 -- the product keeps its evals
+            W ev[S::E];
 #pragma unroll
-            for (int e = 0; e < S::E; e++) A[e] = m.pw_evals(x[e]);
-            store_poly<M, LOGN, LOGE, LAST>(A, c_evals + off, valid, sm, tid);
+            for (int e = 0; e < S::E; e++) ev[e] = m.pw_evals(x[e]);
+            store_poly<M, LOGN, LOGE, LAST>(ev, c_evals + off, valid, sm, tid);
         }
         inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, twi, P.ninv_pw, P.s_ninv_pw);
 #pragma unroll
@@ -161,7 +185,7 @@ int launch_one(const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c
                cudaStream_t st) {
     typedef KernelGeom<LOGN, LOGE> G;
     auto kern = ntt_kernel<M, LOGN, LOGE, MODE>;
-    const size_t smem = (size_t)G::PPC * G::PADN * sizeof(typename M::W);
+    const size_t smem = (size_t)G::PPC * (G::PADN + (ASmem<M, LOGN, LOGE, MODE>::on ? G::S::N : 0)) * sizeof(typename M::W);
     if (smem > 48 * 1024) {  // opt in once per device (and per instantiation)
         static unsigned long long done_mask = 0;
         int dev = 0;
