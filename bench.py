@@ -200,7 +200,30 @@ def measure_bootstrap(fhe, torch, dist, dev, rank, world, quick):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # end to end through fhe_bootstrap with pinned HOST buffers (chunked H2D / compute / D2H overlap inside the call)
+    hct = torch.empty(cts.shape, dtype=torch.int64).pin_memory()
+    hout = torch.empty(cts.shape, dtype=torch.int64).pin_memory()
+    hct.copy_(cts)
+    fhe.bootstrap(n, k, K, table, hct, kn, out=hout)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fhe.bootstrap(n, k, K, table, hct, kn, out=hout)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e_ok = bool(torch.equal(hout.to(dev), out))
     return {
+        "e2e": {"value": world * batch * steps / (ms_e2e * 1e-3), "unit": "bootstraps/s",
+                "h2d_bytes_per_step": batch * (kn + 1) * 8, "d2h_bytes_per_step": batch * (kn + 1) * 8,
+                "matches_device_result": e2e_ok},
         "metric": "TFHE bootstraps/s (as executed: mod_switch + rotate + sample_extract + key_switch)",
         "value": world * batch * steps / (ms * 1e-3), "unit": "bootstraps/s", "n_gpus": world,
         "batch_per_gpu": batch, "steps": steps, "ms_per_step": ms / steps, "scaling": "weak",

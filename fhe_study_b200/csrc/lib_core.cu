@@ -90,37 +90,7 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, 
     return rc;
 }
 
-bool is_host_ptr(const void *p) {
-    if (p == nullptr) return false;
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
-        cudaGetLastError();
-        return true;
-    }
-    return !(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
-}
 
-// Host-buffer path for large batches: the batch is cut into chunks and H2D copies, kernels and D2H copies of
-// consecutive chunks overlap on three streams (PCIe is full duplex), double-buffered on the device.
-struct PipeStreams {
-    cudaStream_t h2d = nullptr, d2h = nullptr;
-    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
-    int device = -1;
-    int init() {
-        int dev = 0;
-        FHE_CUDA_OK(cudaGetDevice(&dev));
-        if (device == dev) return 0;
-        FHE_CUDA_OK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
-        FHE_CUDA_OK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            FHE_CUDA_OK(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
-            FHE_CUDA_OK(cudaEventCreateWithFlags(&comp_done[i], cudaEventDisableTiming));
-            FHE_CUDA_OK(cudaEventCreateWithFlags(&d2h_done[i], cudaEventDisableTiming));
-        }
-        device = dev;
-        return 0;
-    }
-};
 thread_local PipeStreams t_pipe;
 
 int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
@@ -275,6 +245,16 @@ int run_ntt_wire32(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *
 }  // namespace
 
 namespace fhe {
+bool is_host_ptr(const void *p) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return !(attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+}
+PipeStreams &thread_pipe() { return t_pipe; }
 // device-pointer transform launch for the other translation units (glwe_rq.cu)
 int plan_launch(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
                 int flags, cudaStream_t st) {

@@ -1,5 +1,6 @@
 // lib_tlwe.cu -- C-ABI entry points of the TLWE path: key switch, sample extraction, mod switch, blind rotation
 // and bootstrapping (tfhe/src/tlwe.rs:101-161, tfhe/src/tglwe.rs:89-119).
+#include <algorithm>
 #include <memory>
 #include <vector>
 
@@ -58,6 +59,12 @@ int fhe_key_switch(const fhe_ksk *h, const uint64_t *ct, uint64_t *out, size_t b
     if (batch == 0) return 0;
     FHE_REQUIRE(ct && out, "null ciphertext pointer");
     cudaStream_t st = current_stream();
+    const size_t chunk = std::max<size_t>(256, ((16u << 20) / ((h->k.kn_in + 1) * 8)) / 256 * 256);  // ~16 MB stages
+    if (batch >= 4 * chunk && is_host_ptr(ct) && is_host_ptr(out))  // all-host call: copies and kernels overlap
+        return run_host_pipelined(ct, (h->k.kn_in + 1) * 8, out, (h->k.kn_out + 1) * 8, batch, chunk, st,
+                                  [&](const void *din, void *dout, size_t nb, cudaStream_t s) {
+                                      return key_switch_device(h->k, (const u64 *)din, (u64 *)dout, nb, s);
+                                  });
     IoBuf bi, bo;
     int rc;
     if ((rc = bi.init(ct, batch * (h->k.kn_in + 1) * 8, true, false, st))) return rc;
@@ -151,6 +158,20 @@ int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *ta
     IoBuf bt, bc, bo;
     int rc;
     if ((rc = bt.init(table, (k + 1) * n * 8, true, false, st))) return rc;
+    const size_t chunk = 2048;  // ~17 MB of ciphertexts per stage
+    if (batch >= 4 * chunk && is_host_ptr(ct) && is_host_ptr(out)) {
+        // all-host call: H2D, rotate+extract+key switch and D2H of consecutive chunks overlap
+        Scratch ext;
+        if ((rc = ext.alloc(chunk * (k * n + 1) * 8, st))) return rc;
+        const u64 *tab = bt.ptr<u64>();
+        rc = run_host_pipelined(ct, (c_kn + 1) * 8, out, (ksk->k.kn_out + 1) * 8, batch, chunk, st,
+                                [&](const void *din, void *dout, size_t nb, cudaStream_t s) {
+                                    int r = rotate_extract_device(tab, (const u64 *)din, ext.ptr<u64>(), nullptr, nb, (u32)n, (u32)k,
+                                                                  (u32)c_kn, s);
+                                    return r ? r : key_switch_device(ksk->k, ext.ptr<u64>(), (u64 *)dout, nb, s);
+                                });
+        return rc;
+    }
     if ((rc = bc.init(ct, batch * (c_kn + 1) * 8, true, false, st))) return rc;
     if ((rc = bo.init(out, batch * (ksk->k.kn_out + 1) * 8, false, true, st))) return rc;
     Scratch ext;
@@ -160,7 +181,6 @@ int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *ta
     if (rc) return rc;
     return finish_all({&bt, &bc, &bo}, st);
 }
-
 
 // Extension: blind rotation with one TGGSW per mask element, as a CMux chain kept on chip.
 int fhe_bootstrap_chain(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, uint64_t steps, int mode, const fhe_ksk *ksk,

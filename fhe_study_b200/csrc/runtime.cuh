@@ -77,6 +77,67 @@ class Scratch {
     cudaStream_t st_ = nullptr;
 };
 
+// Host-buffer path for large batches: the batch is cut into chunks and H2D copies, kernels and D2H copies of
+// consecutive chunks overlap on three streams (PCIe is full duplex), double-buffered on the device.
+struct PipeStreams {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+    int device = -1;
+    int init() {
+        int dev = 0;
+        FHE_CUDA_OK(cudaGetDevice(&dev));
+        if (device == dev) return 0;
+        FHE_CUDA_OK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        FHE_CUDA_OK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            FHE_CUDA_OK(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
+            FHE_CUDA_OK(cudaEventCreateWithFlags(&comp_done[i], cudaEventDisableTiming));
+            FHE_CUDA_OK(cudaEventCreateWithFlags(&d2h_done[i], cudaEventDisableTiming));
+        }
+        device = dev;
+        return 0;
+    }
+};
+PipeStreams &thread_pipe();  // per host thread (lib_core.cu)
+
+// Host-buffer batches: `batch` independent units cut into chunks; H2D copy of chunk i+1, fn(dev_in, dev_out, nb, st)
+// of chunk i and D2H copy of chunk i-1 overlap (double-buffered device staging).  Returns with `out` complete.
+template <class F>
+int run_host_pipelined(const void *in, size_t in_unit, void *out, size_t out_unit, size_t batch, size_t chunk, cudaStream_t st,
+                       F fn) {
+    PipeStreams &ps = thread_pipe();
+    int rc = ps.init();
+    if (rc) return rc;
+    Scratch sin, sout;
+    if ((rc = sin.alloc(2 * chunk * in_unit, st))) return rc;
+    if ((rc = sout.alloc(2 * chunk * out_unit, st))) return rc;
+    FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch is used from the side streams as well
+    size_t i = 0;
+    for (size_t off = 0; off < batch && !rc; off += chunk, i++) {
+        const size_t nb = batch - off < chunk ? batch - off : chunk;
+        const int par = (int)(i & 1);
+        char *din = sin.ptr<char>() + (size_t)par * chunk * in_unit, *dout = sout.ptr<char>() + (size_t)par * chunk * out_unit;
+        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // staging of chunk i-2 consumed
+        FHE_CUDA_OK(cudaMemcpyAsync(din, (const char *)in + off * in_unit, nb * in_unit, cudaMemcpyHostToDevice, ps.h2d));
+        FHE_CUDA_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
+        FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.h2d_done[par], 0));
+        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
+        if ((rc = fn(din, dout, nb, st))) break;
+        FHE_CUDA_OK(cudaEventRecord(ps.comp_done[par], st));
+        FHE_CUDA_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
+        FHE_CUDA_OK(cudaMemcpyAsync((char *)out + off * out_unit, dout, nb * out_unit, cudaMemcpyDeviceToHost, ps.d2h));
+        FHE_CUDA_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        set_error(std::string("pipelined transfer failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+        return -2;
+    }
+    return 0;
+}
+bool is_host_ptr(const void *p);
+
 // Scope helper: finish() every buffer, and synchronise the stream iff any of them lives on the host
 // (the call then has the reference's blocking semantics; all-device calls stay asynchronous).
 inline int finish_all(std::initializer_list<IoBuf *> bufs, cudaStream_t st) {
