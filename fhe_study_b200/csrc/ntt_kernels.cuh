@@ -97,7 +97,30 @@ __device__ __forceinline__ void store_poly(typename M::W (&x)[1 << LOGE], u64 *_
 template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
     static constexpr bool on = FHE_A_SMEM_MINB > 0 && MODE == MODE_MUL && sizeof(typename M::W) == 4 &&
                                NttShape<LOGN, LOGE>::T <= 32 && LOGN == 10;
-    static constexpr int minb = on ? FHE_A_SMEM_MINB : 1;
+#ifndef FHE_MUL_MINB
+#define FHE_MUL_MINB 5
+#endif
+    // 0 = no minimum (ptxas' own choice; an explicit 1 makes it spend up to 65536/CT registers and lose occupancy).
+    // The 32-bit polymul on 128-thread CTAs asks for five resident CTAs (<= 102 registers, no spills): measured
+    // 0.775 of HBM peak at N=1024 against 0.74 with ptxas' unconstrained 139 registers (three CTAs).
+    // measured (q = 65537, hbm fraction before -> after): polymul N=1024 0.74 -> 0.78 (CT=128, five CTAs); NTT N=16384
+    // 0.47 -> 0.57 (CT=512, two CTAs of 64 registers instead of one of ~100); CT=256: NTT slower when bounded
+    // (0.80 -> 0.73), polymul about even
+    static constexpr int CT_ = KernelGeom<LOGN, LOGE>::CT;
+    static constexpr bool W32 = sizeof(typename M::W) == 4;
+#ifndef FHE_NTT_MINB_256
+#define FHE_NTT_MINB_256 0
+#endif
+#ifndef FHE_NTT_MINB_512
+#define FHE_NTT_MINB_512 2
+#endif
+#ifndef FHE_MUL_MINB_256
+#define FHE_MUL_MINB_256 3
+#endif
+    static constexpr int minb = on ? FHE_A_SMEM_MINB
+                                : !W32 ? 0
+                                : MODE == MODE_MUL ? (CT_ == 128 ? FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0)
+                                : (CT_ == 256 ? FHE_NTT_MINB_256 : CT_ == 512 ? FHE_NTT_MINB_512 : 0);
 };
 
 template <class M, int LOGN, int LOGE, int MODE>

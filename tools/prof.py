@@ -1,5 +1,5 @@
 """Tiny driver for ncu captures: runs one hot-path op a few times on cuda:0 (device-resident buffers).
-  python tools/prof.py polymul|ntt|intt [logn] [q] [batch] [reps]"""
+  python tools/prof.py polymul|ntt|intt [logn] [q] [batch] [reps] | tn [n] [batch] | extprod [n k batch] | bootstrap [batch]"""
 import os
 import sys
 
@@ -16,6 +16,18 @@ batch = int(sys.argv[4]) if len(sys.argv) > 4 else (1 << 26) // n
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 torch.cuda.set_device(0)
 fhe.use_torch_stream()
+if op == "tn":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    batch = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randint(-(2**63), 2**63 - 1, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    b = torch.randint(-(2**63), 2**63 - 1, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    c = torch.empty_like(a)
+    for _ in range(3):
+        fhe.tn_mul(n, a, b, out=c)
+    torch.cuda.synchronize()
+    print("done tn", n, batch)
+    sys.exit(0)
 if op in ("bootstrap", "extprod"):
     g = torch.Generator(device="cuda").manual_seed(1)
     r = lambda *shape: torch.randint(-(2**63), 2**63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
