@@ -38,6 +38,9 @@ template <int LOGN, int K1> struct XpGeom {
     // CTA; small rings leave registers and shared memory for several accumulators, which then share every key load
     // (n = 64, k = 4: 1.6 MB of key per 2.5 KB accumulator -- L2 bandwidth, not arithmetic, was the limit).
     static constexpr int A = LOGN <= 7 ? 4 : (LOGN <= 9 && ITEMS <= 2048) ? 2 : 1;
+    // resident CTAs asked of ptxas: three 80-register CTAs help the small rings (n=64,k=4: 6.0 -> 6.6 M/s), while at
+    // n=1024 two 128-register CTAs are faster (1.44 vs 1.27 M/s; the chain even 1.28 vs 0.91 M CMux/s)
+    static constexpr int MINB = LOGN <= 7 ? 3 : 2;
     static constexpr int DPR = SLOTS / A;               // digits per round (each for all A accumulators)
     static constexpr int ROUNDS = (ND + DPR - 1) / DPR;
     // slots whose threads run an inverse transform (whole warps do): the slots behind them are free for the
@@ -112,7 +115,7 @@ __device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32
 }
 
 template <int LOGN, int K1, bool CHAIN>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, XpGeom<LOGN, K1>::MINB)
 extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__ ct1, const u64 *__restrict__ ct2,
                      u64 *out, int cmux, const XpChain ch, size_t batch) {
     typedef XpGeom<LOGN, K1> G;

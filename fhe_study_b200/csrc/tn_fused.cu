@@ -42,7 +42,10 @@ __device__ __forceinline__ u32 tn_reduce64(u64 acc, u32 p, u64 mu) {  // acc mod
 }
 
 template <int LOGN>
-__global__ void __launch_bounds__(256, 2)
+#ifndef FHE_TN_MINB
+#define FHE_TN_MINB 3
+#endif
+__global__ void __launch_bounds__(256, FHE_TN_MINB)
 tn_mul_fused_kernel(const __grid_constant__ TnParams X, const u64 *__restrict__ a, const u64 *__restrict__ b,
                     u64 *__restrict__ c, size_t batch) {
     typedef TnGeom<LOGN> G;
