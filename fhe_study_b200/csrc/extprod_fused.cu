@@ -37,19 +37,23 @@ template <int LOGN, int K1> struct XpGeom {
     // Accumulators per CTA.  The MAC streams the whole transformed TGGSW (2 * ND * ITEMS * 4 B) from L2 once per
     // CTA; small rings leave registers and shared memory for several accumulators, which then share every key load
     // (n = 64, k = 4: 1.6 MB of key per 2.5 KB accumulator -- L2 bandwidth, not arithmetic, was the limit).
-    static constexpr int A = LOGN <= 7 ? 4 : (LOGN <= 9 && ITEMS <= 2048) ? 2 : 1;
+#ifndef FHE_XP_A10
+#define FHE_XP_A10 1
+#endif
+    static constexpr int A = LOGN <= 7 ? 4 : (LOGN <= 9 && ITEMS <= 2048) ? 2 : (LOGN == 10 && K1 == 2) ? FHE_XP_A10 : 1;
     // resident CTAs asked of ptxas: three 80-register CTAs help the small rings (n=64,k=4: 6.0 -> 6.6 M/s), while at
     // n=1024 two 128-register CTAs are faster (1.44 vs 1.27 M/s; the chain even 1.28 vs 0.91 M CMux/s)
-    static constexpr int MINB = LOGN <= 7 ? 3 : 2;
+    static constexpr int MINB = LOGN <= 7 ? 3 : (LOGN == 10 && A > 1) ? 1 : 2;
     static constexpr int DPR = SLOTS / A;               // digits per round (each for all A accumulators)
     static constexpr int ROUNDS = (ND + DPR - 1) / DPR;
     // slots whose threads run an inverse transform (whole warps do): the slots behind them are free for the
     // residues of the second prime
     static constexpr int LIVE_SLOTS = S::T >= 32 ? A * UNITS : ((A * UNITS * S::T + 31) / 32) * (32 / S::T);
-    static constexpr size_t SMEM = (size_t)A * K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)A * UNITS * N * 4;
+    // the second prime's residues live in the free exchange slots when there are enough of them
+    static constexpr bool RES2_IN_XCH = (SLOTS - LIVE_SLOTS) * PADN >= A * UNITS * N;
+    static constexpr size_t SMEM = (size_t)A * K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)(RES2_IN_XCH ? 1 : 2) * A * UNITS * N * 4;
     static constexpr size_t SMEM_CHAIN = SMEM;
     static_assert(SLOTS % A == 0 && A * UNITS <= SLOTS, "need a slot per inverse transform");
-    static_assert((SLOTS - LIVE_SLOTS) * PADN >= A * UNITS * N, "no room for the second prime's residues in the exchange area");
     static_assert(S::T <= 32, "one digit NTT must fit a warp (N <= 1024) in this kernel");
 };
 
@@ -125,7 +129,8 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     u64 *xin = reinterpret_cast<u64 *>(smem_raw);                         // [A][K1][N] decomposed inputs
     u32 *xch = reinterpret_cast<u32 *>(xin + (size_t)A * GLWE);           // [SLOTS][PADN] exchange / NTT(digit)
     u32 *res1 = xch + (size_t)G::SLOTS * G::PADN;                         // [A][UNITS][N] residues mod p1
-    u32 *res2 = xch + (size_t)G::LIVE_SLOTS * G::PADN;                    // [A][UNITS][N] residues mod p2 (free slots of xch)
+    u32 *res2 = G::RES2_IN_XCH ? xch + (size_t)G::LIVE_SLOTS * G::PADN    // [A][UNITS][N] residues mod p2 (free slots of xch)
+                               : res1 + (size_t)A * G::UNITS * N;
     const int t = threadIdx.x;
     const int slot = t / S::T, tid = t % S::T;
     const int s_acc = slot % A, s_dig = slot / A;   // forward phase: which accumulator, which digit of the round
