@@ -16,6 +16,8 @@
 //     slice, fragments through ldmatrix.x4.  One __syncthreads per K step.
 //   * Epilogue: an n-tile of 8 columns is exactly one key word; the 8 plane sums are shifted, reduced over
 //     the 4 lanes of a quad by shuffles and subtracted from (0,..,0,b) (tlwe.rs:111).
+#include <algorithm>
+
 #include "../../include/fhe_b200.h"
 #include "runtime.cuh"
 #include "tlwe.cuh"
@@ -214,9 +216,21 @@ ks_mma_kernel(const unsigned char *__restrict__ blocks, const u64 *__restrict__ 
     }
 }
 
+__global__ void ksk_gather_bcol_kernel(const u64 *__restrict__ rows, u64 *__restrict__ bcol, size_t nrows, u32 w) {
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < nrows; r += (size_t)gridDim.x * blockDim.x)
+        bcol[r] = rows[r * w + (w - 1)];
+}
+
 int ksk_build_mma_layout(Ksk &k, cudaStream_t st) {
     const u32 w = (u32)k.kn_out + 1;
-    k.mma_n_tiles = (w + 31) / 32;
+    const bool split_b = k.kn_out % 32 == 0;  // see tlwe.cuh: Ksk::bcol
+    k.mma_n_tiles = split_b ? (u32)(k.kn_out / 32) : (w + 31) / 32;
+    if (split_b) {
+        const size_t nrows = (size_t)k.kn_in * k.l;
+        FHE_CUDA_OK(cudaMalloc((void **)&k.bcol, nrows * sizeof(u64)));
+        ksk_gather_bcol_kernel<<<(unsigned)std::min<size_t>((nrows + 255) / 256, (size_t)num_sms() * 8), 256, 0, st>>>(k.rows, k.bcol, nrows, w);
+        count_launch(1);
+    }
     const size_t bytes = (size_t)k.mma_n_tiles * (k.kn_in / 2) * KM_BBYTES;
     FHE_CUDA_OK(cudaMalloc((void **)&k.mma_blocks, bytes));
     const size_t chunks = bytes / 16;

@@ -41,6 +41,8 @@ int fhe_ksk_load(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *ro
         int rc = ksk_build_mma_layout(h->k, st);
         if (rc) {
             cudaFree(h->k.rows);
+            cudaFree(h->k.mma_blocks);
+            cudaFree(h->k.bcol);
             return rc;
         }
     }
@@ -51,6 +53,7 @@ void fhe_ksk_destroy(fhe_ksk *h) {
     if (!h) return;
     cudaFree(h->k.rows);
     cudaFree(h->k.mma_blocks);
+    cudaFree(h->k.bcol);
     delete h;
 }
 

@@ -12,11 +12,16 @@ struct Ksk {
     // swizzled 32 KB blocks [n_tile][k_tile]
     unsigned char *mma_blocks = nullptr;
     u32 mma_n_tiles = 0;
+    // when kn_out is a multiple of 32 the body column (index kn_out) would cost a 33rd, almost empty column tile
+    // (1056 instead of 1024 CTAs at n=1024, batch 8192: an eighth wave on 148 SMs): the GEMM then covers the
+    // kn_out mask columns only and the body column is a separate bit-vector x column product (ks_bcol_kernel)
+    u64 *bcol = nullptr;  // [kn_in*l] = rows[r][kn_out], contiguous
 };
 
 int ksk_build_mma_layout(Ksk &k, cudaStream_t st);
 int key_switch_tc_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int key_switch_mma_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
+int key_switch_bcol_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_out, size_t batch, u32 n, u32 k, u32 c_kn,
                           cudaStream_t st);

@@ -4,6 +4,8 @@
 //   out = (0,..,0, b) - sum_{i<kn_in} sum_{j<l} bit_{l-1-j}(a_i) * KSK[i][j][:]      (tlwe.rs:101-112,
 //   tlev.rs:95-105, tlwe.rs:269-279, torus.rs:43-52)
 // with a kn_in*l*(kn_out+1)*8-byte key resident in HBM (537 MB for n=1024, k=1, l=64).
+#include <algorithm>
+
 #include "../../include/fhe_b200.h"
 #include "runtime.cuh"
 #include "tlwe.cuh"
@@ -66,6 +68,47 @@ key_switch_kernel(const u64 *__restrict__ ksk, const u64 *__restrict__ ct, u64 *
     }
 }
 
+// Body column of the key switch when the GEMM covers the mask columns only (Ksk::bcol):
+//   out[b][kn_out] = ct[b][kn_in] - sum_{i,j} bit_{l-1-j}(ct[b][i]) * bcol[i*l + j]      (tlwe.rs:101-112, column kn_out)
+// Block = 32 ciphertexts (one per lane) x 8 warps striding the mask words of this block's K slice; the column
+// entries are warp-uniform loads.  Partial sums are combined with 64-bit atomic adds (wrapping adds commute).
+__global__ void __launch_bounds__(256)
+ks_bcol_kernel(const u64 *__restrict__ bcol, const u64 *__restrict__ ct, u64 *__restrict__ out, size_t batch, u32 kn_in,
+               u32 kn_out, u32 l) {
+    __shared__ u64 red[8][32];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t b = (size_t)blockIdx.x * 32 + lane;
+    const u32 per = (kn_in + gridDim.y - 1) / gridDim.y;
+    const u32 i0 = blockIdx.y * per, i1 = min(kn_in, i0 + per);
+    const u64 *cp = ct + b * (size_t)(kn_in + 1);
+    u64 acc = 0;
+    for (u32 i = i0 + warp; i < i1; i += 8) {
+        const u64 a = b < batch ? __ldg(cp + i) : 0;
+        const u64 *kb = bcol + (size_t)i * l;
+#pragma unroll 8
+        for (u32 j = 0; j < l; j++) acc += ((a >> (l - 1 - j)) & 1ull) ? __ldg(kb + j) : 0ull;
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && b < batch) {
+        u64 s = 0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; w8++) s += red[w8][lane];
+        const u64 v = (blockIdx.y == 0 ? __ldg(cp + kn_in) : 0ull) - s;
+        atomicAdd(reinterpret_cast<unsigned long long *>(out + b * (size_t)(kn_out + 1) + kn_out), (unsigned long long)v);
+    }
+}
+int key_switch_bcol_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
+    const size_t w = k.kn_out + 1;
+    FHE_CUDA_OK(cudaMemset2DAsync(out + k.kn_out, w * sizeof(u64), 0, sizeof(u64), batch, st));
+    const unsigned ksplit = (unsigned)std::max<size_t>(1, std::min<size_t>(k.kn_in / 8, ((size_t)num_sms() * 8 * 32 + batch - 1) / batch));
+    dim3 grid((unsigned)((batch + 31) / 32), std::min(ksplit, 64u));
+    ks_bcol_kernel<<<grid, 256, 0, st>>>(k.bcol, ct, out, batch, (u32)k.kn_in, (u32)k.kn_out, (u32)k.l);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
     // path selection (l == 64 keys carry the byte-plane tensor-core layout): tcgen05 GEMM for batches that fill
     // an MMA tile, the mma.sync GEMM for small batches, CUDA cores otherwise.  FHE_KS_PATH=tc|mma|cuda forces
@@ -78,6 +121,10 @@ int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaS
             set_error("FHE_KS_PATH asks for a tensor-core path but this key has no byte-plane layout (needs l == 64, even kn_in)");
             return -1;
         }
+    }
+    if (path != 0 && k.bcol != nullptr) {  // the GEMMs cover the mask columns only
+        int rc = key_switch_bcol_device(k, ct, out, batch, st);
+        if (rc) return rc;
     }
     if (path == 2) return key_switch_tc_device(k, ct, out, batch, st);
     if (path == 1) return key_switch_mma_device(k, ct, out, batch, st);
