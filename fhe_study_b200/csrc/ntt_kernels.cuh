@@ -117,8 +117,14 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 #ifndef FHE_MUL_MINB_256
 #define FHE_MUL_MINB_256 3
 #endif
+#ifndef FHE_MUL64_MINB
+#define FHE_MUL64_MINB 0
+#endif
+#ifndef FHE_NTT64_MINB
+#define FHE_NTT64_MINB 0
+#endif
     static constexpr int minb = on ? FHE_A_SMEM_MINB
-                                : !W32 ? 0
+                                : !W32 ? (CT_ == 128 ? (MODE == MODE_MUL ? FHE_MUL64_MINB : FHE_NTT64_MINB) : 0)
                                 : MODE == MODE_MUL ? (CT_ == 128 ? FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0)
                                 : (CT_ == 256 ? FHE_NTT_MINB_256 : CT_ == 512 ? FHE_NTT_MINB_512 : 0);
 };
