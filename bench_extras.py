@@ -222,10 +222,44 @@ def tn_mul_path(fhe, dev, quick):
     return res
 
 
+def gfhe_path(fhe, dev, quick, cpu=True):
+    """SURVEY 8f rank 2: GLWE<Rq>::key_switch at the reference's test parameters (gfhe/src/glwe.rs:582-594:
+    q=65537, n=128, k=16, beta=2, l=16), batched, with a CPU sample of the oracle port beside it."""
+    import time
+
+    import numpy as np
+    import torch
+
+    import oracle
+
+    q, n, k, beta, l = Q17, 128, 16, 2, 16
+    batch = 256 if quick else 2048
+    glwe = (k + 1) * n
+    g = torch.Generator(device=dev).manual_seed(21)
+    ksk = torch.randint(0, q, (k * l * glwe,), dtype=torch.int64, device=dev, generator=g)
+    ct = torch.randint(0, q, (batch, glwe), dtype=torch.int64, device=dev, generator=g)
+    K = fhe.RqGlev(fhe.NttPlan(q, n), k, k * l, ksk)
+    out = torch.empty_like(ct)
+    ms = _time(lambda: K.key_switch(beta, l, ct, out=out), 2 if quick else 5, warm=1)
+    row = {"q": q, "n": n, "k": k, "beta": beta, "l": l, "batch": batch, "key_switch_per_s": batch / (ms * 1e-3), "ms": ms}
+    if cpu:
+        sample = min(batch, 4 * (os.cpu_count() or 1))
+        hk = ksk.cpu().numpy().view(np.uint64)
+        hc = ct[:sample].cpu().numpy().view(np.uint64).copy()
+        t0 = time.perf_counter()
+        want = oracle.glwe_rq_key_switch(q, n, k, beta, l, hk, hc)
+        dt = time.perf_counter() - t0
+        row["cpu_key_switch_per_s"] = sample / dt
+        row["cpu_sample"] = f"{sample} key switches, oracle port (single thread: the reference is sequential), {dt:.2f} s"
+        row["gpu_matches_cpu_sample"] = bool((out[:sample].cpu().numpy().view(np.uint64) == want).all())
+    return row
+
+
 def run(fhe, dev, quick=False, cpu=True):
     res = {}
     for name, fn in (("ntt", lambda: ntt_sweep(fhe, dev, quick)), ("tfhe", lambda: tfhe_paths(fhe, dev, quick, cpu)),
-                     ("bfv", lambda: bfv_path(fhe, dev, quick, cpu)), ("tn_mul", lambda: tn_mul_path(fhe, dev, quick))):
+                     ("bfv", lambda: bfv_path(fhe, dev, quick, cpu)), ("tn_mul", lambda: tn_mul_path(fhe, dev, quick)),
+                     ("gfhe", lambda: gfhe_path(fhe, dev, quick, cpu))):
         try:
             res[name] = fn()
         except Exception as ex:  # one failing extra must not hide the others

@@ -14,5 +14,6 @@ fhe.use_torch_stream()
 dev = torch.device("cuda", 0)
 what = sys.argv[1] if len(sys.argv) > 1 else "tfhe"
 fn = {"tfhe": lambda: bench_extras.tfhe_paths(fhe, dev, False, cpu=False), "bfv": lambda: bench_extras.bfv_path(fhe, dev, False, cpu=False),
-      "tn": lambda: bench_extras.tn_mul_path(fhe, dev, False), "ntt": lambda: bench_extras.ntt_sweep(fhe, dev, False)}[what]
+      "tn": lambda: bench_extras.tn_mul_path(fhe, dev, False), "ntt": lambda: bench_extras.ntt_sweep(fhe, dev, False),
+      "gfhe": lambda: bench_extras.gfhe_path(fhe, dev, False, cpu=True)}[what]
 print(json.dumps(fn(), indent=1))
