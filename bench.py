@@ -233,6 +233,26 @@ def measure_bootstrap(fhe, torch, dist, dev, rank, world, quick):
     }
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the end-to-end
+    legs are allocated on (and copied from) the NUMA node the GPU hangs off.  Best effort; returns a note."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {index}"
+    except Exception as ex:  # no NVML, no permission: keep the inherited affinity
+        return f"unbound ({type(ex).__name__})"
+    return "unbound"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -262,6 +282,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa(local) if world > 1 else "single rank: inherited affinity"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import fhe_study_b200 as fhe
@@ -356,6 +377,7 @@ def main():
             "batch_per_gpu": batch, "n": N, "q": Q,
             "l2_policy": f"inputs+outputs {alg_bytes / 2**20:.0f} MiB per step, larger than the 126 MB L2",
             "parallelism": f"independent polynomials sharded over {world} GPU(s), no collective",
+            "host_affinity": numa_note,
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
