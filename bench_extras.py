@@ -56,6 +56,17 @@ def ntt_sweep(fhe, dev, quick):
                 row[name] = {"per_s": batch / (ms * 1e-3), "ms": ms, "hbm_gbs": gbs, "hbm_frac": gbs / peak}
             out.append(row)
             del a, b, c
+    # batch sweep at N=1024 (BASELINE configs[1]: batch 1..64k), device-resident; small batches are launch-latency bound
+    plan = fhe.NttPlan(Q17, 1024)
+    batch_sweep = []
+    for batch in (1, 16, 256, 4096, 65536):
+        a = torch.randint(0, Q17, (batch, 1024), dtype=torch.int64, device=dev)
+        b = torch.randint(0, Q17, (batch, 1024), dtype=torch.int64, device=dev)
+        c = torch.empty_like(a)
+        ms = _time(lambda: plan.mul(a, b, out=c), 20 if batch >= 4096 else 100, warm=5)
+        batch_sweep.append({"batch": batch, "us_per_call": ms * 1e3, "polymul_per_s": batch / (ms * 1e-3),
+                            "note": "working set fits the 126 MB L2" if batch * 3 * 8192 < 100e6 else "HBM-resident"})
+        del a, b, c
     # batch-1 latency (BASELINE configs[0]: the crate's own test path), device-resident
     plan = fhe.NttPlan(Q17, 1024)
     a = torch.randint(0, Q17, (1, 1024), dtype=torch.int64, device=dev)
@@ -70,7 +81,7 @@ def ntt_sweep(fhe, dev, quick):
         for name in ("ntt", "intt", "polymul"):
             row[name]["modmul_frac"] = row[name]["per_s"] * work[name] / pk
             row[name]["roofline_frac"] = max(row[name]["hbm_frac"], row[name]["modmul_frac"])
-    return {"sweep": out, "polymul_n1024_batch1_us": lat * 1e3, "int_peaks": peaks}
+    return {"sweep": out, "batch_sweep_n1024": batch_sweep, "polymul_n1024_batch1_us": lat * 1e3, "int_peaks": peaks}
 
 
 
