@@ -65,7 +65,7 @@ def ntt_sweep(fhe, dev, quick):
         c = torch.empty_like(a)
         ms = _time(lambda: plan.mul(a, b, out=c), 20 if batch >= 4096 else 100, warm=5)
         batch_sweep.append({"batch": batch, "us_per_call": ms * 1e3, "polymul_per_s": batch / (ms * 1e-3),
-                            "note": "working set fits the 126 MB L2" if batch * 3 * 8192 < 100e6 else "HBM-resident"})
+                            "note": "working set fits the 126 MB L2" if batch * 3 * 8192 < 126e6 else "HBM-resident"})
         del a, b, c
     # batch-1 latency (BASELINE configs[0]: the crate's own test path), device-resident
     plan = fhe.NttPlan(Q17, 1024)

@@ -114,6 +114,9 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 #ifndef FHE_NTT_MINB_512
 #define FHE_NTT_MINB_512 2
 #endif
+#ifndef FHE_INV_MINB_256
+#define FHE_INV_MINB_256 3
+#endif
 #ifndef FHE_MUL_MINB_256
 #define FHE_MUL_MINB_256 3
 #endif
@@ -126,7 +129,8 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
     static constexpr int minb = on ? FHE_A_SMEM_MINB
                                 : !W32 ? (CT_ == 128 ? (MODE == MODE_MUL ? FHE_MUL64_MINB : FHE_NTT64_MINB) : 0)
                                 : MODE == MODE_MUL ? (CT_ == 128 ? FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0)
-                                : (CT_ == 256 ? FHE_NTT_MINB_256 : CT_ == 512 ? FHE_NTT_MINB_512 : 0);
+                                : (CT_ == 256 ? (MODE == MODE_INV ? FHE_INV_MINB_256 : FHE_NTT_MINB_256)
+                                   : CT_ == 512 ? FHE_NTT_MINB_512 : 0);
 };
 
 template <class M, int LOGN, int LOGE, int MODE>
