@@ -61,6 +61,16 @@ mod gpu {
         sys::check(unsafe { sys::fhe_rq_mul(plan(&p), fa.as_ptr(), fb.as_ptr(), c.as_mut_ptr(), a.len(), 0, std::ptr::null_mut()) });
         c.chunks(p.n).map(|v| Rq { param: p, coeffs: zqs(p.q, v.to_vec()), evals: None }).collect()
     }
+    /// same, over the packed 32-bit wire (q <= 2^32: half the PCIe bytes; 5.7 M vs 3.0 M polymul/s end to end)
+    pub fn mul_batch_u32(a: &[Rq], b: &[Rq]) -> Vec<Rq> {
+        let p = a[0].param;
+        assert!(p.q <= 1u64 << 32);
+        let fa: Vec<u32> = a.iter().flat_map(|x| x.coeffs.iter().map(|z| z.v as u32)).collect();
+        let fb: Vec<u32> = b.iter().flat_map(|x| x.coeffs.iter().map(|z| z.v as u32)).collect();
+        let mut c = vec![0u32; fa.len()];
+        sys::check(unsafe { sys::fhe_rq_mul_u32(plan(&p), fa.as_ptr(), fb.as_ptr(), c.as_mut_ptr(), a.len(), 0, std::ptr::null_mut()) });
+        c.chunks(p.n).map(|v| Rq { param: p, coeffs: v.iter().map(|&x| Zq { q: p.q, v: x as u64 }).collect(), evals: None }).collect()
+    }
     /// replaces ring_torus::naive_poly_mul (arith/src/ring_torus.rs:266-298); T64 needs #[repr(transparent)]
     pub fn tn_mul(a: &Tn, b: &Tn) -> Tn {
         let n = a.param.n;
@@ -80,3 +90,6 @@ mod gpu {
 //   tfhe/src/tlwe.rs:101  TLWE::key_switch           -> fhe_ksk_load (once) + fhe_key_switch
 //   tfhe/src/tlwe.rs:150  bootstrapping              -> fhe_bootstrap
 //   bfv/src/lib.rs:87     RLWE::mul                  -> fhe_bfv_mul_relin
+//   gfhe/src/glwe.rs:126  GLWE<Rq>::key_switch       -> fhe_rq_glev_load (once, k*l rows) + fhe_glwe_rq_key_switch
+//   gfhe/src/glev.rs:67   GLev<Rq> * Vec<Rq>         -> fhe_rq_glev_load (once, l rows) + fhe_rq_glev_mul
+//   tfhe/src/tlwe.rs:138  the CMux loop of blind_rotation, if a maintainer makes it run -> fhe_cmux_chain
