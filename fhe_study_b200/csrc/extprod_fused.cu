@@ -54,6 +54,7 @@ template <int LOGN, int K1> struct XpGeom {
     static constexpr size_t SMEM = (size_t)A * K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)(RES2_IN_XCH ? 1 : 2) * A * UNITS * N * 4;
     static constexpr size_t SMEM_CHAIN = SMEM;
     static_assert(SLOTS % A == 0 && A * UNITS <= SLOTS, "need a slot per inverse transform");
+    static_assert(ND % DPR == 0, "every round must be full: the digit transforms synchronise whole warps");
     static_assert(S::T <= 32, "one digit NTT must fit a warp (N <= 1024) in this kernel");
 };
 

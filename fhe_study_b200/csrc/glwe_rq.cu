@@ -6,6 +6,9 @@
 // once, the sum is taken in the NTT domain and only (k+1) inverse transforms are run per ciphertext.
 #include <memory>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "../../include/fhe_b200.h"
 #include "plan.cuh"
 #include "runtime.cuh"
@@ -20,6 +23,7 @@ struct fhe_rq_glev {
     fhe_ntt_plan *plan = nullptr;  // owned reference
     u64 k = 0, rows = 0;
     u64 *evals = nullptr;          // [rows][k+1][n] NTT images of the rows (reference order, canonical)
+    u32 *evals_f = nullptr;        // fused-kernel layout [row][v][thread][4] (item = t + 256 (4v + j)), when instantiated
 };
 
 namespace {
@@ -99,6 +103,221 @@ int gadget_product_device(const fhe_rq_glev *h, const u64 *v, u64 *out, size_t b
     return plan_launch(h->plan, 1 /* inverse */, acc, nullptr, out, nullptr, batch * k1, 0, st);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused GLWE<Rq>::key_switch for beta = 2 under the Small32 policy (q < 2^22, 2q*n <= 2^32: the reference's 65537):
+// one CTA handles A ciphertexts; decompose -> digit NTTs -> MAC against the resident NTT images of the KSK rows ->
+// k+1 inverse NTTs -> (0, b) - rhs, one HBM round trip.  Same structure as extprod_fused.cu with a single modulus:
+// slots of T = n/32 threads run the digit transforms (csub-free butterflies, stage 0 on bits is a select), all 256
+// threads then MAC the round's digits into 64-bit register accumulators (key loads shared by the A ciphertexts),
+// finally the sums are reduced mod q and inverse-transformed.
+// ---------------------------------------------------------------------------------------------------------------
+template <int LOGN, int K1> struct KsGeom {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int LOGE = LOGN < 5 ? LOGN : 5;
+    typedef NttShape<LOGN, LOGE> S;
+    static constexpr int CT = 256;
+    static constexpr int SLOTS = CT / S::T;
+    static constexpr int PADN = N + (N >> 5);
+    static constexpr int ITEMS = K1 * N;                 // (component, position)
+    static constexpr int IPT = (ITEMS + CT - 1) / CT;
+    static constexpr int IPT4 = (IPT + 3) / 4 * 4;
+    static constexpr int A = IPT <= 4 ? 4 : IPT <= 12 ? 2 : 1;   // ciphertexts per CTA (A * IPT 64-bit accumulators)
+    static constexpr int DPR = SLOTS / A;                // digits per round
+    static constexpr size_t SMEM = (size_t)A * (K1 - 1) * N * 4 + (size_t)SLOTS * PADN * 4;
+    static_assert(S::T <= 32 && SLOTS % A == 0 && A * K1 <= SLOTS, "unsupported shape for the fused key switch");
+};
+
+struct KsParams {
+    NttParams<Small32> P;
+    u64 mu;            // floor(2^64 / q)
+    const u32 *Rf;     // fused key layout
+    u32 l, nd;         // levels, digits per ciphertext = k*l
+};
+
+template <int LOGN, int K1>
+__global__ void __launch_bounds__(256, 2)
+glwe_ks_fused_kernel(const __grid_constant__ KsParams X, const u64 *__restrict__ ct, u64 *__restrict__ out, size_t batch) {
+    typedef KsGeom<LOGN, K1> G;
+    typedef typename G::S S;
+    constexpr int LOGE = G::LOGE, N = G::N, LAST = S::P - 1, A = G::A, K = K1 - 1, GLWE = K1 * N;
+    constexpr int G0 = 1 << S::g(0), H0 = G0 >> 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32 *xin = reinterpret_cast<u32 *>(smem_raw);              // [A][K][N] mask coefficients (canonical, < q < 2^22)
+    u32 *xch = xin + (size_t)A * K * N;                        // [SLOTS][PADN]
+    const Small32 &ms = X.P.mod;
+    const int t = threadIdx.x;
+    const int slot = t / S::T, tid = t % S::T;
+    const int s_acc = slot % A, s_dig = slot / A;
+    u32 *sm = xch + (size_t)slot * G::PADN;
+    const size_t acc0 = (size_t)blockIdx.x * A;
+    const int na = (int)(batch - acc0 < (size_t)A ? batch - acc0 : (size_t)A);
+    const u32 l = X.l;
+    const u32 sat_thr = l >= 32 ? 0xffffffffu : (1u << l);     // Zq::decompose: v >= 2^l -> every digit is 1 (zq.rs:174-186)
+
+    for (int i = t; i < A * K * N; i += G::CT) {
+        const int aa = i / (K * N), rem = i % (K * N);
+        xin[i] = aa < na ? (u32)ct[(acc0 + aa) * GLWE + rem] : 0u;
+    }
+    __syncthreads();
+
+    u64 acc[A][G::IPT];
+#pragma unroll
+    for (int aa = 0; aa < A; aa++)
+#pragma unroll
+        for (int m = 0; m < G::IPT; m++) acc[aa][m] = 0;
+    const TwSrc<Small32> twf = {X.P.c_fwd, X.P.fwd};
+    const int rounds = (int)((X.nd + G::DPR - 1) / G::DPR);
+#pragma unroll 1
+    for (int round = 0; round < rounds; round++) {
+        const u32 d = (u32)round * G::DPR + s_dig;
+        {   // every slot runs the transform (the exchanges inside synchronise whole warps, and k*l need not fill the
+            // last round): slots past the last digit transform zeros into their own slot, which the MAC never reads
+            const bool live = d < X.nd;
+            const u32 dc = live ? d : 0;
+            const u32 *xi = xin + ((size_t)s_acc * K + dc / l) * N;
+            const u32 sh = l - 1 - dc % l;
+            u32 x[S::E];
+#pragma unroll
+            for (int e = 0; e < S::E; e++) {
+                const u32 v = xi[S::pos(0, tid, e)];
+                const u32 bit = (l < 32 && v >= sat_thr) ? 1u : (sh < 32 ? (v >> sh) & 1u : 0u);
+                x[e] = live ? bit : 0u;
+            }
+            {   // stage 0 on bits: V = b*S is a select
+                const u32 S1 = twf.c0[1].w;
+#pragma unroll
+                for (int qi = 0; qi < (S::E >> S::g(0)); qi++)
+#pragma unroll
+                    for (int lo = 0; lo < H0; lo++) {
+                        const u32 U = x[qi * G0 + lo], V = (0u - x[qi * G0 + lo + H0]) & S1;
+                        x[qi * G0 + lo] = U + V;
+                        x[qi * G0 + lo + H0] = U + ms.q2 - V;
+                    }
+            }
+            fwd_pass<Small32, LOGN, LOGE, 0, 1>(x, tid, ms, twf);
+            if constexpr (S::P > 1) fwd_chain<Small32, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
+#pragma unroll
+            for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = x[e];  // < (2 LOGN + 1) q: no reduction needed
+        }
+        __syncthreads();
+        const int nd = min(G::DPR, (int)X.nd - round * G::DPR);
+        const uint4 *Rt = reinterpret_cast<const uint4 *>(X.Rf) + (size_t)round * G::DPR * (G::IPT4 / 4) * G::CT + t;
+#pragma unroll 2
+        for (int dd = 0; dd < nd; dd++) {
+            u32 rv[G::IPT4];
+#pragma unroll
+            for (int v = 0; v < G::IPT4 / 4; v++) {
+                const uint4 q4 = __ldg(Rt + (size_t)(dd * (G::IPT4 / 4) + v) * G::CT);
+                rv[4 * v] = q4.x; rv[4 * v + 1] = q4.y; rv[4 * v + 2] = q4.z; rv[4 * v + 3] = q4.w;
+            }
+#pragma unroll
+            for (int aa = 0; aa < A; aa++) {
+                const u32 *D = xch + (size_t)(dd * A + aa) * G::PADN;
+#pragma unroll
+                for (int m = 0; m < G::IPT; m++) {
+                    const int item = t + G::CT * m;
+                    acc[aa][m] += (u64)D[pad_idx(item & (N - 1))] * rv[m];  // key padding beyond ITEMS is zero
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // sums -> inverse-transform inputs (slot aa*K1 + c)
+#pragma unroll
+    for (int aa = 0; aa < A; aa++)
+#pragma unroll
+        for (int m = 0; m < G::IPT; m++) {
+            const int item = t + G::CT * m;
+            if (item < G::ITEMS) {
+                const u64 a = acc[aa][m];
+                u64 r = a - __umul64hi(a, X.mu) * ms.q;
+                if (r >= ms.q) r -= ms.q;
+                xch[(size_t)(aa * K1 + (item >> LOGN)) * G::PADN + pad_idx(item & (N - 1))] = (u32)r;
+            }
+        }
+    __syncthreads();
+    if ((t & ~31) / S::T < A * K1) {  // whole warps run the transform (see extprod_fused.cu)
+        const TwSrc<Small32> twi = {X.P.c_inv, X.P.inv};
+        u32 x[S::E];
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(LAST, tid, e))];
+        inv_chain<Small32, LOGN, LOGE, LAST>(x, sm, tid, ms, twi, X.P.ninv, X.P.s_ninv);
+        const int aa = slot / K1, c = slot % K1;
+        if (slot < A * K1 && aa < na) {
+            // GLWE::key_switch's last line (glwe.rs:136): (0, .., 0, b) - rhs, Zq::sub (zq.rs:259-277)
+            const size_t row = (acc0 + aa) * GLWE + (size_t)c * N;
+#pragma unroll
+            for (int e = 0; e < S::E; e++) {
+                const int p = S::pos(0, tid, e);
+                const u64 y = ms.canon2(x[e]);
+                const u64 xv = c == K ? ct[row + p] : 0;
+                out[row + p] = xv >= y ? xv - y : (ms.q + xv) - y;
+            }
+        }
+    }
+}
+
+// evals [row][c][x] (u64) -> fused layout (u32 [row][v][t][4], item = c*N + x = t + 256 (4v + j)), zero padded
+__global__ void glev_fused_layout_kernel(const u64 *__restrict__ E, u32 *__restrict__ Ef, size_t rows, int items, int ipt4) {
+    const size_t total = rows * 256 * (size_t)ipt4;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx & 3), t = (int)((idx >> 2) & 255), v = (int)((idx >> 10) % (ipt4 / 4));
+        const size_t r = idx / ((size_t)ipt4 * 256);
+        const int item = t + 256 * (4 * v + j);
+        Ef[idx] = item < items ? (u32)E[r * items + item] : 0u;
+    }
+}
+
+#define FHE_KS_SHAPES(F) F(7, 17) F(10, 2) F(9, 2) F(8, 2) F(6, 2) F(6, 5) F(7, 2) F(8, 3)
+
+bool ks_fused_supported(const fhe_ntt_plan *plan, u64 k, u64 rows) {
+    if (plan->kind != 3) return false;  // Small32 only
+    const u64 q = plan->host.q;
+    // exactness of the 64-bit sums: rows * (2 logn + 1) q * q < 2^64
+    if ((u128)rows * (2 * plan->logn + 1) * q * q >= ((u128)1 << 64)) return false;
+#define F(L, K) if (plan->logn == L && (int)k + 1 == K) return true;
+    FHE_KS_SHAPES(F)
+#undef F
+    return false;
+}
+int ks_fused_ipt4(int logn, int k1) {
+    const int ipt = (k1 * (1 << logn) + 255) / 256;
+    return (ipt + 3) / 4 * 4;
+}
+
+template <int LOGN, int K1>
+int launch_ks_fused(const fhe_rq_glev *h, u32 l, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
+    typedef KsGeom<LOGN, K1> G;
+    KsParams X;
+    X.P = h->plan->psm;
+    X.mu = ~0ull / h->plan->host.q;
+    X.Rf = h->evals_f;
+    X.l = l;
+    X.nd = (u32)h->rows;
+    auto kern = glwe_ks_fused_kernel<LOGN, K1>;
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    FHE_CUDA_OK(cudaGetDevice(&dev));
+    if (!((done_mask >> (dev & 63)) & 1ull)) {
+        FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        done_mask |= 1ull << (dev & 63);
+    }
+    const size_t grid = (batch + G::A - 1) / G::A;
+    FHE_REQUIRE(grid <= 0x7fffffffull, "key switch: batch too large");
+    kern<<<(unsigned)grid, G::CT, G::SMEM, st>>>(X, ct, out, batch);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int ks_fused_device(const fhe_rq_glev *h, u32 l, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
+    const int logn = h->plan->logn, k1 = (int)h->k + 1;
+#define F(L, K) if (logn == L && k1 == K) return launch_ks_fused<L, K>(h, l, ct, out, batch, st);
+    FHE_KS_SHAPES(F)
+#undef F
+    set_error("internal: fused key switch called for an unsupported shape");
+    return -1;
+}
 }  // namespace
 
 extern "C" {
@@ -125,11 +344,29 @@ int fhe_rq_glev_load(const fhe_ntt_plan *plan, uint64_t k, uint64_t rows, const 
         fhe_ntt_plan_destroy(h->plan);
         return rc ? rc : -2;
     }
+    if (ks_fused_supported(h->plan, k, rows)) {  // fused key-switch layout (used when the call asks for beta = 2)
+        const int items = (int)((k + 1) * plan->host.n), ipt4 = ks_fused_ipt4(h->plan->logn, (int)k + 1);
+        const size_t words = rows * 256 * (size_t)ipt4;
+        e = cudaMalloc((void **)&h->evals_f, words * sizeof(u32));
+        if (e == cudaSuccess) {
+            glev_fused_layout_kernel<<<grid_for(words), 256, 0, st>>>(h->evals, h->evals_f, rows, items, ipt4);
+            count_launch(1);
+            e = cudaStreamSynchronize(st);
+        }
+        if (e != cudaSuccess) {
+            set_error(std::string("fhe_rq_glev_load: ") + cudaGetErrorString(e));
+            cudaFree(h->evals_f);
+            cudaFree(h->evals);
+            fhe_ntt_plan_destroy(h->plan);
+            return -2;
+        }
+    }
     *out = h.release();
     return 0;
 }
 void fhe_rq_glev_destroy(fhe_rq_glev *h) {
     if (!h) return;
+    cudaFree(h->evals_f);
     cudaFree(h->evals);
     fhe_ntt_plan_destroy(h->plan);
     delete h;
@@ -167,6 +404,14 @@ int fhe_glwe_rq_key_switch(const fhe_rq_glev *ksk, uint32_t beta, uint32_t l, co
     int rc;
     if ((rc = bi.init(ct, batch * k1 * n * 8, true, false, st))) return rc;
     if ((rc = bo.init(out, batch * k1 * n * 8, false, true, st))) return rc;
+    {   // fused kernel (beta = 2, shapes instantiated, Small32 modulus); FHE_GLWE_KS_PATH=unfused forces the blocks below
+        const char *force = getenv("FHE_GLWE_KS_PATH");
+        if (ksk->evals_f != nullptr && beta == 2 && l <= 63 && bi.ptr<u64>() != bo.ptr<u64>() &&
+            !(force && strcmp(force, "unfused") == 0)) {
+            if ((rc = ks_fused_device(ksk, l, bi.ptr<u64>(), bo.ptr<u64>(), batch, st))) return rc;
+            return finish_all({&bi, &bo}, st);
+        }
+    }
     if ((rc = sd.alloc(batch * k * l * n * 8, st))) return rc;
     if ((rc = sr.alloc(batch * k1 * n * 8, st))) return rc;
     // digits of the mask polynomials: [b][i][j][n]  (a_i.decompose(beta, l), ring_nq.rs:67-77); the body is skipped

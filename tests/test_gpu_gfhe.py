@@ -31,14 +31,20 @@ def test_key_switch_reference_params_functional(fhe, orc):
 
 
 @pytest.mark.parametrize("q,n,k,beta,l,batch", [(Q, 16, 2, 2, 16, 5), (Q, 8, 1, 4, 8, 3), (Q, 1024, 1, 2, 17, 2),
-                                                  (Q, 64, 3, 3, 10, 4), (Q62, 32, 2, 2, 62, 2), (12289, 512, 2, 2, 10, 3)])
-def test_key_switch_random_inputs(fhe, orc, q, n, k, beta, l, batch):
+                                                  (Q, 64, 3, 3, 10, 4), (Q62, 32, 2, 2, 62, 2), (12289, 512, 2, 2, 10, 3),
+                                                  (Q, 128, 16, 2, 16, 5), (Q, 1024, 1, 2, 16, 3), (Q, 64, 4, 2, 40, 9),
+                                                  (Q, 256, 1, 2, 5, 6), (12289, 512, 1, 2, 14, 7), (Q, 64, 1, 2, 33, 5)])
+def test_key_switch_random_inputs(fhe, orc, monkeypatch, q, n, k, beta, l, batch):
     glwe = (k + 1) * n
     ksk = orc.uniform(q % 1000 + n, k * l * glwe, q)
     cts = orc.uniform(n + k, (batch, glwe), q)
     cts[0, :n] = q - 1  # beta = 2 with 2^l <= q-1, or beta^l <= q-1: the saturating branch of Zq::decompose
     K = fhe.RqGlev(fhe.NttPlan(q, n), k, k * l, ksk)
-    assert np.array_equal(K.key_switch(beta, l, cts), orc.glwe_rq_key_switch(q, n, k, beta, l, ksk, cts))
+    want = orc.glwe_rq_key_switch(q, n, k, beta, l, ksk, cts)
+    assert np.array_equal(K.key_switch(beta, l, cts), want)          # fused kernel where (n, k, q, beta) allow it
+    monkeypatch.setenv("FHE_GLWE_KS_PATH", "unfused")
+    assert np.array_equal(K.key_switch(beta, l, cts), want)          # building-block path
+    monkeypatch.delenv("FHE_GLWE_KS_PATH")
 
 
 @pytest.mark.parametrize("q,n,k,l,batch", [(Q, 128, 16, 16, 2), (Q, 4, 1, 1, 7), (Q62, 64, 2, 5, 3)])
