@@ -340,6 +340,8 @@ static int fused_ipt4(int logn, int k1) {
 int tggsw_build_fused_layout(Tggsw &g, cudaStream_t st) {
     const int logn = g.tc->logn, k1 = (int)g.k + 1;
     if (!extprod_fused_supported(logn, k1)) return 0;
+    // the fused kernels read the plans' twiddle tables in the device order of 32 coefficients per thread
+    if (g.tc->plan1->loge != (logn < 5 ? logn : 5) || g.tc->plan2->loge != g.tc->plan1->loge) return 0;
     const int nd = k1 * 64, items = k1 * 2 * (1 << logn), ipt4 = fused_ipt4(logn, k1);
     const size_t words = (size_t)nd * 256 * ipt4;
     FHE_CUDA_OK(cudaMalloc((void **)&g.R1f, words * sizeof(u32)));

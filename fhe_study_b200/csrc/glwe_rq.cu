@@ -273,6 +273,7 @@ __global__ void glev_fused_layout_kernel(const u64 *__restrict__ E, u32 *__restr
 
 bool ks_fused_supported(const fhe_ntt_plan *plan, u64 k, u64 rows) {
     if (plan->kind != 3) return false;  // Small32 only
+    if (plan->loge != (plan->logn < 5 ? plan->logn : 5)) return false;  // table order of 32 coefficients per thread
     const u64 q = plan->host.q;
     // exactness of the 64-bit sums: rows * (2 logn + 1) q * q < 2^64
     if ((u128)rows * (2 * plan->logn + 1) * q * q >= ((u128)1 << 64)) return false;

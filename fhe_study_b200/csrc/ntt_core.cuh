@@ -61,9 +61,13 @@ inline u64 tw_slot(int logn, int loge, u64 ref_index) {
 }
 // coefficients per thread (log2): 32 for 32-bit words, 16 for 64-bit words (register budget of the
 // polymul kernel, which keeps NTT(a) in registers while transforming b)
+// Measured on B200 (q = 65537, fraction of HBM peak, 16 vs 32 coefficients per thread): N=2048 NTT 0.96 vs 0.86 and
+// polymul 0.59 vs 0.52; N=4096 polymul 0.52 vs 0.50 -- hence 16 per thread for those two degrees.
 template <class M> struct LogE {
     static constexpr int MAXE = sizeof(typename M::W) == 4 ? 5 : 4;
-    static constexpr int of(int logn) { return logn < MAXE ? logn : MAXE; }
+    static constexpr int of(int logn) {
+        return (sizeof(typename M::W) == 4 && (logn == 11 || logn == 12)) ? 4 : logn < MAXE ? logn : MAXE;
+    }
 };
 
 // Twiddle source: pass 0 twiddles are identical for every thread (H = 0), so they are taken from a

@@ -247,13 +247,23 @@ int launch_modes(int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u6
 
 // `loge` must be a value ntt_loge_supported() accepts for (M, logn): the default LogE<M>::of(logn), or, for
 // the tunable degrees, one of the alternatives instantiated below.
+// tunable degrees of the 32-bit policies: which coefficients-per-thread settings are instantiated
+constexpr bool ntt_alt_loge(int logn, int loge, int wbytes) {
+    return wbytes == 4 && ((logn >= 10 && logn <= 12 && loge >= 3 && loge <= 5) || (logn >= 13 && logn <= 14 && loge >= 4 && loge <= 5));
+}
 template <class M, int LOGN>
 int launch_logn(int loge, int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals,
                 size_t batch, int flags, cudaStream_t st) {
     constexpr int DEF = LogE<M>::of(LOGN);
-    if constexpr (LOGN >= 10 && LOGN <= 12 && sizeof(typename M::W) == 4) {
+    constexpr int WB = (int)sizeof(typename M::W);
+    if constexpr (ntt_alt_loge(LOGN, 3, WB) && DEF != 3) {
         if (loge == 3) return launch_modes<M, LOGN, 3>(mode, P, a, b, c, c_evals, batch, flags, st);
+    }
+    if constexpr (ntt_alt_loge(LOGN, 4, WB) && DEF != 4) {
         if (loge == 4) return launch_modes<M, LOGN, 4>(mode, P, a, b, c, c_evals, batch, flags, st);
+    }
+    if constexpr (ntt_alt_loge(LOGN, 5, WB) && DEF != 5) {
+        if (loge == 5) return launch_modes<M, LOGN, 5>(mode, P, a, b, c, c_evals, batch, flags, st);
     }
     if (loge != DEF) {
         set_error("internal: unsupported coefficients-per-thread setting");
@@ -263,7 +273,7 @@ int launch_logn(int loge, int mode, const NttParams<M> &P, const u64 *a, const u
 }
 template <class M> bool ntt_loge_supported(int logn, int loge) {
     if (loge == LogE<M>::of(logn)) return true;
-    return sizeof(typename M::W) == 4 && logn >= 10 && logn <= 12 && (loge == 3 || loge == 4);
+    return ntt_alt_loge(logn, loge, (int)sizeof(typename M::W));
 }
 
 template <class M>

@@ -197,7 +197,8 @@ int TorusCtx::ntt(int r, int mode, const u64 *in, u64 *out, size_t polys, cudaSt
 // FHE_TN_PATH=unfused forces the building-block path below (the tests cover both).
 int tn_mul_device(const TorusCtx &tc, const u64 *a, const u64 *b, u64 *c, size_t batch, cudaStream_t st) {
     const char *force = getenv("FHE_TN_PATH");
-    if (tn_mul_fused_supported(tc.logn) && !(force && strcmp(force, "unfused") == 0))
+    if (tn_mul_fused_supported(tc.logn) && tc.plan1->loge == (tc.logn < 5 ? tc.logn : 5) && tc.plan2->loge == tc.plan1->loge &&
+        !(force && strcmp(force, "unfused") == 0))
         return tn_mul_fused_device(tc, a, b, c, batch, st);
     const u32 n = (u32)tc.n;
     const size_t plane_words = batch * 4 * (size_t)n;
