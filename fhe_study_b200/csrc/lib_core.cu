@@ -93,6 +93,17 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, 
 
 thread_local PipeStreams t_pipe;
 
+// bytes per operand and pipeline stage of the chunked host-buffer paths (FHE_PIPE_CHUNK_MB overrides; tuning knob).
+// The first H2D and the last D2H of a call are not overlapped with anything, so smaller stages shorten fill and drain.
+size_t pipe_chunk_bytes() {
+    static const size_t v = [] {
+        const char *e = getenv("FHE_PIPE_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return (size_t)(mb >= 1 && mb <= 1024 ? mb : 32) << 20;
+    }();
+    return v;
+}
+
 int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
                       int flags, cudaStream_t st, size_t chunk) {
     int rc = t_pipe.init();
@@ -144,7 +155,7 @@ int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 
     const size_t bytes = batch * plan->host.n * sizeof(u64);
     if (mode != MODE_MUL) b = nullptr;
     {   // all-host call on a batch worth pipelining (>= 4 chunks of ~32 MiB per operand)
-        const size_t chunk = std::max<size_t>(1, (32ull << 20) / (plan->host.n * sizeof(u64)));
+        const size_t chunk = std::max<size_t>(1, pipe_chunk_bytes() / (plan->host.n * sizeof(u64)));
         if (batch >= 4 * chunk && is_host_ptr(a) && (!b || is_host_ptr(b)) && is_host_ptr(c) &&
             (!c_evals || is_host_ptr(c_evals)) && a != c && b != c)
             return run_ntt_pipelined(plan, mode, a, b, c, c_evals, batch, flags, st, chunk);
@@ -196,7 +207,7 @@ int run_ntt_wire32(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *
     if (rc) return rc;
     PipeStreams &ps = t_pipe;
     const size_t n = plan->host.n;
-    const size_t chunk = std::min(batch, std::max<size_t>(1, (32ull << 20) / (n * sizeof(u32))));
+    const size_t chunk = std::min(batch, std::max<size_t>(1, pipe_chunk_bytes() / (n * sizeof(u32))));
     const size_t w = chunk * n;  // words per chunk buffer
     const bool host = is_host_ptr(a) || (b && is_host_ptr(b)) || is_host_ptr(c) || (c_evals && is_host_ptr(c_evals));
     // per parity: u64 A, B, C, E and u32 a, b, c, e  (unused ones still reserved; at most ~0.8 GB)
