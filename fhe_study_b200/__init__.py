@@ -268,6 +268,26 @@ class Ksk:
         check(lib.fhe_ksk_load(self.kn_in, self.kn_out, self.l, ptr(rows), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def generate(cls, kn_in, kn_out, l, sk, new_sk, sigma=3.2, seed=0, uniform_mask=True):
+        """TLWE::new_ksk (tfhe/src/tlwe.rs:84-100) generated on the device (counter-based sampler, see fhe_b200.h)."""
+        self = cls.__new__(cls)
+        self.kn_in, self.kn_out, self.l = int(kn_in), int(kn_out), int(l)
+        _check_u64(sk, new_sk)
+        if _numel(sk) != self.kn_in or _numel(new_sk) != self.kn_out:
+            raise ValueError("sk / new_sk must hold kn_in / kn_out words")
+        h = C.c_void_p()
+        check(lib.fhe_ksk_generate(self.kn_in, self.kn_out, self.l, ptr(sk), ptr(new_sk), float(sigma), int(seed),
+                                   int(bool(uniform_mask)), C.byref(h)))
+        self._h = h
+        return self
+
+    def export(self):
+        """The key rows as a numpy array (layout of the constructor's `rows`)."""
+        out = np.empty(self.kn_in * self.l * (self.kn_out + 1), dtype=np.uint64)
+        check(lib.fhe_ksk_export(self._h, ptr(out)))
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             lib.fhe_ksk_destroy(self._h)

@@ -60,6 +60,8 @@ SIGNATURES = {
     "fhe_extprod": (I, [P, P, P, SZ]),
     "fhe_cmux": (I, [P, P, P, P, SZ]),
     "fhe_ksk_load": (I, [U64, U64, U64, P, C.POINTER(P)]),
+    "fhe_ksk_generate": (I, [U64, U64, U64, P, P, C.c_double, U64, I, C.POINTER(P)]),
+    "fhe_ksk_export": (I, [P, P]),
     "fhe_ksk_destroy": (None, [P]),
     "fhe_key_switch": (I, [P, P, P, SZ]),
     "fhe_tlwe_mod_switch": (I, [P, U64, P, SZ]),

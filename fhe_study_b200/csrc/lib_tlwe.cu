@@ -17,6 +17,21 @@ struct fhe_ksk {
 
 extern "C" {
 
+// shared tail of fhe_ksk_load / fhe_ksk_generate: the handle owns `rows` (already on the device)
+static int ksk_finish_handle(std::unique_ptr<fhe_ksk> &h, cudaStream_t st, fhe_ksk **out) {
+    if (h->k.l == 64 && h->k.kn_in % 2 == 0 && h->k.kn_in <= 131072) {
+        int rc = ksk_build_mma_layout(h->k, st);
+        if (rc) {
+            cudaFree(h->k.rows);
+            cudaFree(h->k.mma_blocks);
+            cudaFree(h->k.bcol);
+            return rc;
+        }
+    }
+    *out = h.release();
+    return 0;
+}
+
 int fhe_ksk_load(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *rows, fhe_ksk **out) {
     FHE_REQUIRE(out && rows, "null pointer");
     *out = nullptr;
@@ -37,16 +52,43 @@ int fhe_ksk_load(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *ro
         set_error(std::string("fhe_ksk_load: ") + cudaGetErrorString(e));
         return -2;
     }
-    if (l == 64 && kn_in % 2 == 0 && kn_in <= 131072) {
-        int rc = ksk_build_mma_layout(h->k, st);
-        if (rc) {
-            cudaFree(h->k.rows);
-            cudaFree(h->k.mma_blocks);
-            cudaFree(h->k.bcol);
-            return rc;
-        }
+    return ksk_finish_handle(h, st, out);
+}
+
+// KSK generated on the device (tlwe.rs:84-100): no 537 MB upload, no CPU sampling loop.
+int fhe_ksk_generate(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *sk, const uint64_t *new_sk, double sigma,
+                     uint64_t seed, int uniform_mask, fhe_ksk **out) {
+    FHE_REQUIRE(out && sk && new_sk, "null pointer");
+    *out = nullptr;
+    FHE_REQUIRE(kn_in >= 1 && kn_out >= 1 && l >= 1 && l <= 64, "fhe_ksk_generate: need kn_in, kn_out >= 1 and 1 <= l <= 64");
+    device_init_once();
+    cudaStream_t st = current_stream();
+    IoBuf bs, bn;
+    int rc;
+    if ((rc = bs.init(sk, kn_in * 8, true, false, st))) return rc;
+    if ((rc = bn.init(new_sk, kn_out * 8, true, false, st))) return rc;
+    std::unique_ptr<fhe_ksk> h(new fhe_ksk());
+    h->k.kn_in = kn_in;
+    h->k.kn_out = kn_out;
+    h->k.l = l;
+    FHE_CUDA_OK(cudaMalloc((void **)&h->k.rows, kn_in * l * (kn_out + 1) * sizeof(u64)));
+    rc = ksk_generate_device(h->k.rows, bs.ptr<u64>(), bn.ptr<u64>(), seed, (u32)kn_in, (u32)kn_out, (u32)l, sigma,
+                             uniform_mask != 0, st);
+    cudaError_t e = rc ? cudaSuccess : cudaStreamSynchronize(st);
+    if (rc || e != cudaSuccess) {
+        cudaFree(h->k.rows);
+        if (!rc) set_error(std::string("fhe_ksk_generate: ") + cudaGetErrorString(e));
+        return rc ? rc : -2;
     }
-    *out = h.release();
+    return ksk_finish_handle(h, st, out);
+}
+// copies the key rows (kn_in * l * (kn_out + 1) words, the layout fhe_ksk_load takes) back out of a handle
+int fhe_ksk_export(const fhe_ksk *h, uint64_t *rows) {
+    FHE_REQUIRE(h != nullptr && rows != nullptr, "null pointer");
+    cudaStream_t st = current_stream();
+    const size_t bytes = h->k.kn_in * h->k.l * (h->k.kn_out + 1) * sizeof(u64);
+    FHE_CUDA_OK(cudaMemcpyAsync(rows, h->k.rows, bytes, cudaMemcpyDefault, st));
+    FHE_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }
 void fhe_ksk_destroy(fhe_ksk *h) {

@@ -21,6 +21,8 @@ struct Ksk {
 int ksk_build_mma_layout(Ksk &k, cudaStream_t st);
 int key_switch_tc_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int key_switch_mma_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
+int ksk_generate_device(u64 *rows, const u64 *sk, const u64 *new_sk, u64 seed, u32 kn_in, u32 kn_out, u32 l, double sigma,
+                        int uniform_mask, cudaStream_t st);
 int key_switch_bcol_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_out, size_t batch, u32 n, u32 k, u32 c_kn,

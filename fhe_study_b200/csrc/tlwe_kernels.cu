@@ -98,6 +98,54 @@ ks_bcol_kernel(const u64 *__restrict__ bcol, const u64 *__restrict__ ct, u64 *__
         atomicAdd(reinterpret_cast<unsigned long long *>(out + b * (size_t)(kn_out + 1) + kn_out), (unsigned long long)v);
     }
 }
+// Device-side KSK generation: structure of tlwe.rs:84-100 / tlev.rs:53-77 / glwe.rs:140-156
+// (row i*l + lv-1 = TLWE_{new_sk}(sk_i * g_lv)), counter-based SplitMix64 sampler -- the one the CPU restatement
+// (orc_tlwe_new_ksk_ctr) documents; every draw is addressed by (row, position), so rows are independent.
+// One warp per row; f64 steps with explicit IEEE intrinsics (bit-identical to the CPU restatement).
+__device__ __forceinline__ u64 ctr_draw(u64 seed, u64 pos) {
+    u64 z = seed + (pos + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double ctr_unit(u64 v) { return __dmul_rn(__ull2double_rn(v >> 11), 1.0 / 9007199254740992.0); }
+__device__ __forceinline__ u64 f64_as_u64_sat(double x) { return __double2ull_rz(x); }  // Rust `as u64`: saturating, NaN -> 0
+__global__ void __launch_bounds__(256)
+ksk_generate_kernel(u64 *__restrict__ rows, const u64 *__restrict__ sk, const u64 *__restrict__ new_sk, u64 seed, u32 kn_in,
+                    u32 kn_out, u32 l, double sigma, int uniform_mask) {
+    const u32 lane = threadIdx.x & 31;
+    const size_t nrows = (size_t)kn_in * l, per_row = (size_t)kn_out + 12, w = (size_t)kn_out + 1;
+    for (size_t r = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < nrows; r += (size_t)gridDim.x * 8) {
+        const size_t base = r * per_row;
+        u64 *row = rows + r * w;
+        u64 part = 0;
+        for (u32 x = lane; x < kn_out; x += 32) {
+            const u64 v = ctr_draw(seed, base + x);
+            const u64 a = uniform_mask ? v : f64_as_u64_sat(round(__dmul_rn(2.0, ctr_unit(v))));
+            row[x] = a;
+            part += a * new_sk[x];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) {
+            double acc = 0.0;
+            for (u32 t = 0; t < 12; t++) acc = __dadd_rn(acc, ctr_unit(ctr_draw(seed, base + kn_out + t)));
+            const u32 i = (u32)(r / l), lv = (u32)(r % l) + 1;
+            const u64 g = lv < 64 ? ~0ull / (1ull << lv) : 1ull;
+            row[kn_out] = part + sk[i] * g + f64_as_u64_sat(round(__dmul_rn(sigma, __dadd_rn(acc, -6.0))));
+        }
+    }
+}
+int ksk_generate_device(u64 *rows, const u64 *sk, const u64 *new_sk, u64 seed, u32 kn_in, u32 kn_out, u32 l, double sigma,
+                        int uniform_mask, cudaStream_t st) {
+    const size_t nrows = (size_t)kn_in * l;
+    const unsigned grid = (unsigned)std::min<size_t>((nrows + 7) / 8, (size_t)num_sms() * 16);
+    ksk_generate_kernel<<<grid, 256, 0, st>>>(rows, sk, new_sk, seed, kn_in, kn_out, l, sigma, uniform_mask);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int key_switch_bcol_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
     const size_t w = k.kn_out + 1;
     FHE_CUDA_OK(cudaMemset2DAsync(out + k.kn_out, w * sizeof(u64), 0, sizeof(u64), batch, st));

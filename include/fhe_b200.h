@@ -122,6 +122,16 @@ FHE_API int fhe_cmux_chain(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, 
 typedef struct fhe_ksk fhe_ksk;
 /* KSK(Vec<TLev>) (tlwe.rs:84-100, tlev.rs:53-77): kn_in * l TLWE rows of kn_out+1 words, resident in HBM. */
 FHE_API int fhe_ksk_load(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *rows, fhe_ksk **handle);
+/* TLWE::new_ksk (tlwe.rs:84-100 over tlev.rs:53-77 and glwe.rs:140-156) ON THE DEVICE: row i*l + lv-1 encrypts
+ * sk[i] * (u64::MAX / 2^lv) under new_sk.  The reference samples from an unseeded thread_rng that no implementation
+ * can reproduce; the sampler here is a counter-based SplitMix64 (specified in oracle/fhe_oracle.c:
+ * orc_tlwe_new_ksk_ctr, which the device output equals bit for bit): uniform_mask != 0 draws the mask uniformly from
+ * Z_2^64, 0 draws it from the key distribution as the reference does (glwe.rs:146-149); error = round(sigma * x),
+ * x an Irwin-Hall(12) approximation of N(0,1), cast like T64::rand (torus.rs:32-35).  SURVEY 8f rank 3. */
+FHE_API int fhe_ksk_generate(uint64_t kn_in, uint64_t kn_out, uint64_t l, const uint64_t *sk, const uint64_t *new_sk,
+                             double sigma, uint64_t seed, int uniform_mask, fhe_ksk **handle);
+/* Reads the key rows back (layout of fhe_ksk_load); rows may be a host or a device pointer. */
+FHE_API int fhe_ksk_export(const fhe_ksk *handle, uint64_t *rows);
 FHE_API void fhe_ksk_destroy(fhe_ksk *handle);
 /* TLWE::key_switch(param, 2, l, ksk) (tlwe.rs:101-112): `batch` TLWEs of kn_in+1 words -> kn_out+1 words. */
 FHE_API int fhe_key_switch(const fhe_ksk *handle, const uint64_t *ct, uint64_t *out, size_t batch);

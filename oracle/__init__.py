@@ -129,6 +129,7 @@ def _declare(L):
     d("orc_tlwe_new_ksk", None, U64, U64, U64, U32, D, P, P, I, P)
     d("orc_cmux_chain", None, U64, U64, U64, P, P, P, I, P)
     d("orc_bootstrap_chain", None, U64, U64, U64, P, P, P, P, U64, I, P)
+    d("orc_tlwe_new_ksk_ctr", None, U64, U64, U64, U32, D, P, P, I, P)
     d("orc_glev_rq_mul", None, U64, U64, U64, U64, P, P, P)
     d("orc_glwe_rq_key_switch", None, U64, U64, U64, U32, U32, P, P, P)
     d("orc_glwe_rq_mod_switch", None, U64, U64, U64, P, U64, P)
@@ -304,6 +305,14 @@ def glev_rq_mul(q: int, n: int, k: int, l: int, glev, v) -> np.ndarray:
     out = np.empty((batch, (k + 1) * n), dtype=np.uint64)
     for i in range(batch):
         lib().orc_glev_rq_mul(q, n, k, l, ptr(glev), ptr(v.reshape(-1)[i * l * n:]), ptr(out[i]))
+    return out
+
+
+def tlwe_new_ksk_ctr(seed: int, kn_in: int, kn_out: int, l: int, sigma: float, sk, new_sk, uniform_mask: bool = True) -> np.ndarray:
+    """KSK with the counter-based sampler the device generator reproduces (orc_tlwe_new_ksk_ctr)."""
+    sk, new_sk = u64(sk), u64(new_sk)
+    out = np.empty(kn_in * l * (kn_out + 1), dtype=np.uint64)
+    lib().orc_tlwe_new_ksk_ctr(seed, kn_in, kn_out, l, float(sigma), ptr(sk), ptr(new_sk), int(uniform_mask), ptr(out))
     return out
 
 

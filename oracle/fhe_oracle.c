@@ -834,6 +834,43 @@ API void orc_tlwe_new_ksk(u64 seed, u64 kn_in, u64 kn_out, uint32_t l, double si
     }
 }
 
+/* KSK generation with a COUNTER-BASED sampler (what the device-side generator fhe_ksk_generate reproduces bit for
+ * bit).  The reference's RNG stream is an unseeded thread_rng and cannot be reproduced, so the
+ * sampler is ours; the STRUCTURE is the reference's (tlwe.rs:84-100 -> tlev.rs:53-77 -> glwe.rs:140-156 with R = T64):
+ * row r = i*l + (lv-1) is TLWE_{new_sk}(sk_i * g_lv), g_lv = u64::MAX / 2^lv (lv < 64), 1 (lv = 64).
+ * Draw p of row r is output number r*(kn_out+12) + p + 1 of SplitMix64(seed):
+ *   p < kn_out : mask word (uniform_mask: the 64 random bits; else Xi_key as the reference does: round(2u) in {0,1,2})
+ *   then 12 uniforms for the error: e = round(sigma * (u_0 + .. + u_11 - 6)) cast like T64::rand (negative -> 0). */
+static inline u64 ctr_draw(u64 seed, u64 pos) {
+    u64 z = seed + (pos + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline double ctr_unit(u64 v) { return (double)(v >> 11) * (1.0 / 9007199254740992.0); }
+API void orc_tlwe_new_ksk_ctr(u64 seed, u64 kn_in, u64 kn_out, uint32_t l, double sigma, const u64 *sk, const u64 *new_sk,
+                              int uniform_mask, u64 *ksk) {
+    u64 w = kn_out + 1, per_row = kn_out + 12;
+#pragma omp parallel for schedule(static)
+    for (i64 r = 0; r < (i64)(kn_in * l); r++) {
+        u64 i = (u64)r / l, lv = (u64)r % l + 1;
+        u64 g = lv < 64 ? UINT64_MAX / ((u64)1 << lv) : 1;
+        u64 *row = ksk + (u64)r * w, base = (u64)r * per_row;
+        u64 b = 0;
+        for (u64 x = 0; x < kn_out; x++) {
+            u64 v = ctr_draw(seed, base + x);
+            u64 a = uniform_mask ? v : f64_as_u64(round(2.0 * ctr_unit(v)));
+            row[x] = a;
+            b += a * new_sk[x];
+        }
+        double acc = 0.0;
+        for (u64 t = 0; t < 12; t++) acc += ctr_unit(ctr_draw(seed, base + kn_out + t));
+        b += sk[i] * g;
+        b += f64_as_u64(round(sigma * (acc - 6.0)));
+        row[kn_out] = b;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * gfhe: GLWE<Rq> / GLev<Rq> (gfhe/src/glwe.rs, gfhe/src/glev.rs) -- SURVEY 8f rank 2.
  * GLWE<Rq> flat layout: (k+1) polys of n (mask a_0..a_{k-1}, then body b).  KSK = k GLevs of l GLWEs:

@@ -178,3 +178,36 @@ def test_bootstrap_at_baseline_batch_spot_checked(fhe, orc, p5):
     perm = np.argsort(orc.uniform(504, batch))
     got_p = fhe.bootstrap(n, k, K, table, np.ascontiguousarray(cts[perm]), kn)
     assert np.array_equal(got_p, got[perm])
+
+
+@pytest.mark.parametrize("kn_in,kn_out,l,uniform", [(16, 16, 64, True), (5, 33, 7, False), (64, 64, 64, False), (3, 1, 1, True)])
+def test_ksk_generated_on_device_equals_cpu_restatement(fhe, orc, kn_in, kn_out, l, uniform):
+    # TLWE::new_ksk (tlwe.rs:84-100) on the device, counter-based sampler: bit-exact against the
+    # oracle's orc_tlwe_new_ksk_ctr (masks, bodies, the f64 error path included)
+    sk = orc.uniform(1, kn_in) & np.uint64(1)
+    sk2 = orc.uniform(2, kn_out) & np.uint64(1)
+    K = fhe.Ksk.generate(kn_in, kn_out, l, sk, sk2, sigma=3.2, seed=1234 + l, uniform_mask=uniform)
+    want = orc.tlwe_new_ksk_ctr(1234 + l, kn_in, kn_out, l, 3.2, sk, sk2, uniform)
+    assert np.array_equal(K.export(), want)
+    # and the generated handle behaves like a loaded one
+    ct = orc.uniform(3, (37, kn_in + 1))
+    assert np.array_equal(K.key_switch(ct).reshape(-1), orc.key_switch(kn_in, kn_out, l, want, ct.reshape(-1)))
+
+
+def test_device_generated_ksk_switches_keys_functionally(fhe, orc):
+    # the reference's test_key_switch property (tlwe.rs:423-463) with a key that never left the GPU, at n=1024
+    L = orc.lib()
+    kn, t = 1024, 128
+    sk, sk2 = np.empty(kn, dtype=np.uint64), np.empty(kn, dtype=np.uint64)
+    L.orc_tlwe_keygen(11, kn, orc.ptr(sk))
+    L.orc_tlwe_keygen(12, kn, orc.ptr(sk2))
+    K = fhe.Ksk.generate(kn, kn, 64, sk, sk2, sigma=3.2, seed=99, uniform_mask=True)
+    delta = (2**64 - 1) // t
+    msgs = [0, 1, 77, 127]
+    cts = np.empty((len(msgs), kn + 1), dtype=np.uint64)
+    for i, m in enumerate(msgs):
+        L.orc_tlwe_encrypt_s(20 + m, kn, 3.2, orc.ptr(sk), (m * delta) % 2**64, 1, orc.ptr(cts[i]))
+    out = K.key_switch(cts)
+    for i, m in enumerate(msgs):
+        p = L.orc_tlwe_decrypt(kn, orc.ptr(sk2), orc.ptr(np.ascontiguousarray(out[i])))
+        assert L.orc_t64_mul_div_round(p, t, 2**64 - 1) % t == m

@@ -395,3 +395,21 @@ def test_glwe_rq_key_switch_functional(orc):
     for i in range(len(msgs)):
         assert np.array_equal(glwe_rq_decode(orc, q, n, k, t, sk, cts[i]), msgs[i])       # sanity: decrypts under sk
         assert np.array_equal(glwe_rq_decode(orc, q, n, k, t, sk2, out[i]), msgs[i])      # and under sk2 after the switch
+
+
+def test_counter_based_ksk_decrypts_to_gadget_multiples(orc):
+    # orc_tlwe_new_ksk_ctr (the sampler the device generator reproduces): row i*l + lv-1 must decrypt, under new_sk, to
+    # sk_i * (u64::MAX / 2^lv) up to the small non-negative error (tlev.rs:53-77)
+    L = orc.lib()
+    kn_in, kn_out, l = 6, 10, 64
+    sk = orc.uniform(1, kn_in) & np.uint64(1)
+    sk2 = orc.uniform(2, kn_out) & np.uint64(1)
+    for uniform in (True, False):
+        ksk = orc.tlwe_new_ksk_ctr(7, kn_in, kn_out, l, 3.2, sk, sk2, uniform).reshape(kn_in, l, kn_out + 1)
+        errs = []
+        for i in range(kn_in):
+            for lv in range(1, l + 1):
+                g = (2**64 - 1) // 2**lv if lv < 64 else 1
+                p = int(L.orc_tlwe_decrypt(kn_out, orc.ptr(sk2), orc.ptr(np.ascontiguousarray(ksk[i, lv - 1]))))
+                errs.append((p - int(sk[i]) * g) % 2**64)
+        assert max(errs) < 40 and len(set(errs)) > 3  # errors are small, non-negative (T64::rand's cast) and not constant
