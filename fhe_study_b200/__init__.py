@@ -227,6 +227,20 @@ class Tggsw:
         check(lib.fhe_tggsw_load(self.n, self.k, ptr(rows), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def generate(cls, n, k, sk, m, sigma=3.2, seed=0, uniform_mask=True, rows_out=None):
+        """TGGSW::encrypt_s (tfhe/src/tggsw.rs:17-33) sampled on the device; rows_out optionally receives the rows."""
+        self = cls.__new__(cls)
+        self.n, self.k = int(n), int(k)
+        _check_u64(sk, m, rows_out)
+        if _numel(sk) != self.k * self.n or _numel(m) != self.n:
+            raise ValueError("sk must hold k*n words and m n words")
+        h = C.c_void_p()
+        check(lib.fhe_tggsw_generate(self.n, self.k, ptr(sk), ptr(m), float(sigma), int(seed), int(bool(uniform_mask)),
+                                     ptr(rows_out), C.byref(h)))
+        self._h = h
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             lib.fhe_tggsw_destroy(self._h)

@@ -102,6 +102,39 @@ int fhe_tggsw_load(uint64_t n, uint64_t k, const uint64_t *rows, fhe_tggsw **out
     *out = h.release();
     return 0;
 }
+// TGGSW::encrypt_s on the device: the rows are sampled in HBM, transformed like loaded rows, and
+// optionally copied out (rows_out: host or device, may be NULL).
+int fhe_tggsw_generate(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *m, double sigma, uint64_t seed,
+                       int uniform_mask, uint64_t *rows_out, fhe_tggsw **out) {
+    FHE_REQUIRE(out != nullptr && sk != nullptr && m != nullptr, "null pointer");
+    *out = nullptr;
+    FHE_REQUIRE(k >= 1 && k <= 64, "fhe_tggsw_generate: k must be in 1..64");
+    TorusCtx *tc;
+    int rc = get_torus_ctx(n, &tc);
+    if (rc) return rc;
+    FHE_REQUIRE((unsigned __int128)(k + 1) * 64 * n * ((u64)1 << 32) < tc->cp.halfP,
+                "fhe_tggsw_generate: (k+1)*64*n too large for the exact two-prime lift");
+    std::unique_ptr<fhe_tggsw> h(new fhe_tggsw());
+    h->g.tc = tc;
+    h->g.k = k;
+    h->n = n;
+    cudaStream_t st = current_stream();
+    const size_t bytes = (k + 1) * 64 * (k + 1) * n * sizeof(u64);
+    IoBuf bs, bm, bo;
+    Scratch rows;
+    if ((rc = bs.init(sk, k * n * 8, true, false, st))) return rc;
+    if ((rc = bm.init(m, n * 8, true, false, st))) return rc;
+    if ((rc = bo.init(rows_out, rows_out ? bytes : 0, false, true, st))) return rc;
+    if ((rc = rows.alloc(bytes, st))) return rc;
+    if ((rc = tggsw_generate_device(*tc, k, bs.ptr<u64>(), bm.ptr<u64>(), sigma, seed, uniform_mask != 0, rows.ptr<u64>(), st)))
+        return rc;
+    if (rows_out) FHE_CUDA_OK(cudaMemcpyAsync(bo.ptr<u64>(), rows.ptr<u64>(), bytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = tggsw_precompute(h->g, rows.ptr<u64>(), st))) return rc;
+    if ((rc = finish_all({&bs, &bm, &bo}, st))) return rc;
+    FHE_CUDA_OK(cudaStreamSynchronize(st));
+    *out = h.release();
+    return 0;
+}
 void fhe_tggsw_destroy(fhe_tggsw *h) {
     if (!h) return;
     cudaFree(h->g.R1);

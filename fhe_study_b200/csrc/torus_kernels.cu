@@ -303,6 +303,74 @@ int tggsw_precompute(Tggsw &g, const u64 *rows_dev, cudaStream_t st) {
     return tggsw_build_fused_layout(g, st);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// TGGSW::encrypt_s on the device (tggsw.rs:17-33,100-122, glwe.rs:140-156 with R = Tn), counter-based
+// sampler of the CPU restatement (orc_tggsw_encrypt_s_ctr): draw p of row r is SplitMix64 output r*(k*n + 12n) + p + 1.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 tg_draw(u64 seed, u64 pos) {
+    u64 z = seed + (pos + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double tg_unit(u64 v) { return __dmul_rn(__ull2double_rn(v >> 11), 1.0 / 9007199254740992.0); }
+// A[(r*k + c)*n + x] = mask coefficient, S[(r*k + c)*n + x] = sk_c[x] (operands of the batched Tn product);
+// also negs[c*n + x] = -sk_c[x] and mrep[c*n + x] = m[x] for the messages -s_c * m
+__global__ void tggsw_gen_masks_kernel(u64 *__restrict__ A, u64 *__restrict__ S, u64 *__restrict__ negs, u64 *__restrict__ mrep,
+                                       const u64 *__restrict__ sk, const u64 *__restrict__ m, u64 seed, u32 n, u32 k, u32 rows,
+                                       int uniform_mask) {
+    const size_t kn = (size_t)k * n, per_row = kn + 12 * (size_t)n, total = (size_t)rows * kn;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / kn, p = idx % kn;
+        const u64 v = tg_draw(seed, r * per_row + p);
+        A[idx] = uniform_mask ? v : __double2ull_rz(round(__dmul_rn(2.0, tg_unit(v))));
+        S[idx] = sk[p];
+        if (r == 0) {
+            negs[p] = (u64)0 - sk[p];
+            mrep[p] = m[p % n];
+        }
+    }
+}
+// rows[r] = (A_r, sum_c P_{r,c} + mi_{r/64} * g_lv + e)
+__global__ void tggsw_gen_finish_kernel(u64 *__restrict__ out, const u64 *__restrict__ A, const u64 *__restrict__ P,
+                                        const u64 *__restrict__ mi, u64 seed, u32 n, u32 k, u32 rows, double sigma) {
+    const size_t kn = (size_t)k * n, per_row = kn + 12 * (size_t)n, glwe = kn + n, total = (size_t)rows * glwe;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / glwe, q = idx % glwe;
+        if (q < kn) { out[idx] = A[r * kn + q]; continue; }
+        const u32 x = (u32)(q - kn), i = (u32)(r / 64), lv = (u32)(r % 64) + 1;
+        u64 b = 0;
+        for (u32 c = 0; c < k; c++) b += P[(r * k + c) * n + x];
+        double acc = 0.0;
+        for (u32 t = 0; t < 12; t++) acc = __dadd_rn(acc, tg_unit(tg_draw(seed, r * per_row + kn + 12 * (size_t)x + t)));
+        const u64 g = lv < 64 ? ~0ull / (1ull << lv) : 1ull;
+        out[idx] = b + mi[(size_t)i * n + x] * g + __double2ull_rz(round(__dmul_rn(sigma, __dadd_rn(acc, -6.0))));
+    }
+}
+// rows_out: (k+1)*64 TGLWEs of (k+1)*n words, device pointer
+int tggsw_generate_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *m, double sigma, u64 seed, int uniform_mask,
+                          u64 *rows_out, cudaStream_t st) {
+    const u32 n = (u32)tc.n, rows = (u32)((k + 1) * 64);
+    const size_t kn = (size_t)k * n, words = (size_t)rows * kn;
+    Scratch sA, sS, sP, sN, sM, sMi;
+    int rc;
+    if ((rc = sA.alloc(words * 8, st)) || (rc = sS.alloc(words * 8, st)) || (rc = sP.alloc(words * 8, st)) ||
+        (rc = sN.alloc(kn * 8, st)) || (rc = sM.alloc(kn * 8, st)) || (rc = sMi.alloc((kn + n) * 8, st)))
+        return rc;
+    u64 *A = sA.ptr<u64>(), *S = sS.ptr<u64>(), *P = sP.ptr<u64>(), *mi = sMi.ptr<u64>();
+    tggsw_gen_masks_kernel<<<grid_for(words), 256, 0, st>>>(A, S, sN.ptr<u64>(), sM.ptr<u64>(), sk, m, seed, n, (u32)k, rows,
+                                                          uniform_mask);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    if ((rc = tn_mul_device(tc, sN.ptr<u64>(), sM.ptr<u64>(), mi, k, st))) return rc;          // mi_c = -s_c * m  (tggsw.rs:28)
+    FHE_CUDA_OK(cudaMemcpyAsync(mi + kn, m, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));       // mi_k = m
+    if ((rc = tn_mul_device(tc, A, S, P, (size_t)rows * k, st))) return rc;                     // a_{r,c} * s_c
+    tggsw_gen_finish_kernel<<<grid_for((size_t)rows * (kn + n)), 256, 0, st>>>(rows_out, A, P, mi, seed, n, (u32)k, rows, sigma);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int tn_addsub_device(const u64 *a, const u64 *b, u64 *c, size_t len, int op, cudaStream_t st) {
     tn_addsub_kernel<<<grid_for(len), 256, 0, st>>>(a, b, c, len, op);
     count_launch(1);

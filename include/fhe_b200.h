@@ -101,6 +101,13 @@ typedef struct fhe_tggsw fhe_tggsw;
 /* Uploads one TGGSW ((k+1)*64 TGLWE rows, beta=2 / l=64 as hard-coded at tggsw.rs:49-50) and transforms it
  * once; the handle keeps it resident in HBM.  rows: (k+1) * 64 * (k+1) * n words. */
 FHE_API int fhe_tggsw_load(uint64_t n, uint64_t k, const uint64_t *rows, fhe_tggsw **handle);
+/* TGGSW::encrypt_s(sk, m) (tggsw.rs:17-33 over tggsw.rs:100-122 and glwe.rs:140-156, beta = 2, l = 64) ON THE DEVICE:
+ * sk = k polynomials, m = the message polynomial (a bootstrapping key is k such calls with m = s_i, tlwe.rs:176-179).
+ * Sampler and flags as fhe_ksk_generate (counter-based SplitMix64; the CPU restatement orc_tggsw_encrypt_s_ctr gives the
+ * same rows bit for bit).  rows_out (host or device, may be NULL) receives the (k+1)*64*(k+1)*n sampled words.
+ * SURVEY 8f rank 3. */
+FHE_API int fhe_tggsw_generate(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *m, double sigma, uint64_t seed,
+                               int uniform_mask, uint64_t *rows_out, fhe_tggsw **handle);
 FHE_API void fhe_tggsw_destroy(fhe_tggsw *handle);
 /* impl Mul<TGLWE> for TGGSW (tggsw.rs:45-62): out_b = tggsw (x) ct_b for `batch` TGLWEs of (k+1)*n words. */
 FHE_API int fhe_extprod(const fhe_tggsw *handle, const uint64_t *ct, uint64_t *out, size_t batch);

@@ -130,6 +130,7 @@ def _declare(L):
     d("orc_cmux_chain", None, U64, U64, U64, P, P, P, I, P)
     d("orc_bootstrap_chain", None, U64, U64, U64, P, P, P, P, U64, I, P)
     d("orc_tlwe_new_ksk_ctr", None, U64, U64, U64, U32, D, P, P, I, P)
+    d("orc_tggsw_encrypt_s_ctr", None, U64, U64, U64, D, P, P, I, P)
     d("orc_glev_rq_mul", None, U64, U64, U64, U64, P, P, P)
     d("orc_glwe_rq_key_switch", None, U64, U64, U64, U32, U32, P, P, P)
     d("orc_glwe_rq_mod_switch", None, U64, U64, U64, P, U64, P)
@@ -313,6 +314,14 @@ def tlwe_new_ksk_ctr(seed: int, kn_in: int, kn_out: int, l: int, sigma: float, s
     sk, new_sk = u64(sk), u64(new_sk)
     out = np.empty(kn_in * l * (kn_out + 1), dtype=np.uint64)
     lib().orc_tlwe_new_ksk_ctr(seed, kn_in, kn_out, l, float(sigma), ptr(sk), ptr(new_sk), int(uniform_mask), ptr(out))
+    return out
+
+
+def tggsw_encrypt_s_ctr(seed: int, n: int, k: int, sigma: float, sk, m, uniform_mask: bool = True) -> np.ndarray:
+    """TGGSW::encrypt_s with the counter-based sampler the device generator reproduces."""
+    sk, m = u64(sk), u64(m)
+    out = np.empty((k + 1) * 64 * (k + 1) * n, dtype=np.uint64)
+    lib().orc_tggsw_encrypt_s_ctr(seed, n, k, float(sigma), ptr(sk), ptr(m), int(uniform_mask), ptr(out))
     return out
 
 

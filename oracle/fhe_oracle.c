@@ -871,6 +871,48 @@ API void orc_tlwe_new_ksk_ctr(u64 seed, u64 kn_in, u64 kn_out, uint32_t l, doubl
     }
 }
 
+/* TGGSW::encrypt_s (tggsw.rs:17-33 -> tggsw.rs:100-122 -> glwe.rs:140-156 with R = Tn) with the counter-based sampler of
+ * orc_tlwe_new_ksk_ctr: row r = i*64 + (lv-1) (i = 0..k: TGLev of -s_i*m for i < k, of m for i = k) is
+ * TGLWE_sk(mi * g_lv).  Draw p of row r is output number r*(k*n + 12*n) + p + 1 of SplitMix64(seed):
+ *   p = c*n + x (c < k)        : mask coefficient x of component c (uniform_mask, or Xi_key as the reference does)
+ *   p = k*n + 12*x + t (t < 12) : the 12 uniforms of error coefficient x.
+ * What fhe_tggsw_generate reproduces bit for bit. */
+API void orc_tggsw_encrypt_s_ctr(u64 seed, u64 n, u64 k, double sigma, const u64 *sk, const u64 *m, int uniform_mask, u64 *out) {
+    const uint32_t l = 64;
+    u64 glwe = (k + 1) * n, per_row = k * n + 12 * n;
+    u64 *mi = (u64 *)malloc(sizeof(u64) * (k + 1) * n), *negs = (u64 *)malloc(sizeof(u64) * n);
+    for (u64 i = 0; i <= k; i++) {
+        if (i < k) {
+            for (u64 x = 0; x < n; x++) negs[x] = (u64)0 - sk[i * n + x];
+            tn_mul_fast(n, negs, m, mi + i * n);
+        } else memcpy(mi + i * n, m, sizeof(u64) * n);
+    }
+#pragma omp parallel for schedule(dynamic)
+    for (i64 r = 0; r < (i64)((k + 1) * l); r++) {
+        u64 i = (u64)r / l, lv = (u64)r % l + 1, base = (u64)r * per_row;
+        u64 g = lv < 64 ? UINT64_MAX / ((u64)1 << lv) : 1;
+        u64 *row = out + (u64)r * glwe, *b = row + k * n;
+        u64 *tmp = (u64 *)malloc(sizeof(u64) * n);
+        for (u64 p = 0; p < k * n; p++) {
+            u64 v = ctr_draw(seed, base + p);
+            row[p] = uniform_mask ? v : f64_as_u64(round(2.0 * ctr_unit(v)));
+        }
+        memset(b, 0, sizeof(u64) * n);
+        for (u64 c = 0; c < k; c++) { /* TR dot product, tuple_ring.rs:117-134 */
+            tn_mul_fast(n, row + c * n, sk + c * n, tmp);
+            for (u64 x = 0; x < n; x++) b[x] += tmp[x];
+        }
+        for (u64 x = 0; x < n; x++) {
+            double acc = 0.0;
+            for (u64 t = 0; t < 12; t++) acc += ctr_unit(ctr_draw(seed, base + k * n + 12 * x + t));
+            b[x] += mi[i * n + x] * g;
+            b[x] += f64_as_u64(round(sigma * (acc - 6.0)));
+        }
+        free(tmp);
+    }
+    free(mi); free(negs);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * gfhe: GLWE<Rq> / GLev<Rq> (gfhe/src/glwe.rs, gfhe/src/glev.rs) -- SURVEY 8f rank 2.
  * GLWE<Rq> flat layout: (k+1) polys of n (mask a_0..a_{k-1}, then body b).  KSK = k GLevs of l GLWEs:

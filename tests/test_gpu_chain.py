@@ -71,3 +71,33 @@ def test_chain_argument_errors(fhe, orc):
         fhe.cmux_chain(n, k, [g, g2], acc, np.zeros(2, dtype=np.uint64))  # mismatched handle
     with pytest.raises(RuntimeError):
         fhe.bootstrap_chain(n, k, [g, g], orc.uniform(3, (k + 1) * n), orc.uniform(4, (1, 2)), 1)  # steps > c_kn
+
+
+@pytest.mark.parametrize("n,k,uniform", [(64, 1, True), (64, 4, False), (1024, 1, True), (16, 2, True)])
+def test_tggsw_generated_on_device_equals_cpu_restatement(fhe, orc, n, k, uniform):
+    # TGGSW::encrypt_s (tggsw.rs:17-33) sampled on the device; rows bit-exact against the oracle's
+    # counter-based restatement, and the resident handle behaves like a loaded one
+    sk = orc.uniform(1, k * n) & np.uint64(1)
+    m = orc.uniform(2, n) & np.uint64(1)
+    rows = np.empty((k + 1) * 64 * (k + 1) * n, dtype=np.uint64)
+    g = fhe.Tggsw.generate(n, k, sk, m, sigma=3.2, seed=77 + n, uniform_mask=uniform, rows_out=rows)
+    want = orc.tggsw_encrypt_s_ctr(77 + n, n, k, 3.2, sk, m, uniform)
+    assert np.array_equal(rows, want)
+    ct = orc.uniform(3, (2, (k + 1) * n))
+    assert np.array_equal(g.extprod(ct), fhe.Tggsw(n, k, want).extprod(ct))
+
+
+def test_bootstrap_chain_with_device_generated_keys(fhe, orc):
+    # a whole programmable bootstrap whose bootstrapping key never left the GPU recovers the message
+    n, k, m_lwe, t = 64, 1, 6, 4
+    s, z, _, table, cts = pbs_fixture(orc, n, k, m_lwe, t)
+    bsk = []
+    for j in range(m_lwe):
+        msg = np.zeros(n, dtype=np.uint64)
+        msg[0] = s[j]
+        bsk.append(fhe.Tggsw.generate(n, k, z, msg, sigma=3.2, seed=500 + j))
+    out = fhe.bootstrap_chain(n, k, bsk, table, cts, m_lwe, mode=1)
+    delta = (2**64 - 1) // t
+    for m in range(t):
+        phase = int(orc.lib().orc_tlwe_decrypt(k * n, orc.ptr(z), orc.ptr(np.ascontiguousarray(out[m]))))
+        assert round(phase / delta) % t == m
