@@ -367,6 +367,12 @@ def main():
     hbm_peak, peak_kind = peaks()
     alg_bytes = 3 * N * 8 * batch
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    # the other roofline of the north star ("the slower of the integer-mulmod and HBM rooflines"): modular
+    # multiplications per launch (1.5 N log2 N + 2N per polymul) against the Shoup-modmul rate a register-only
+    # microbenchmark reaches on this GPU at these clocks (fhe_int_peak, measured now)
+    modmul_per_polymul = 3 * (N // 2) * (N.bit_length() - 1) + 2 * N
+    modmul_peak = fhe.int_peak(1)
+    modmul_rate = modmul_per_polymul * batch / (kern_ms * 1e-3)
     line = {
         "metric": "NTT polymul/s", "value": value, "unit": "polymul/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
@@ -384,6 +390,11 @@ def main():
             "traffic": NCU_TRAFFIC_BYTES if batch == BATCH else None, "traffic_source": NCU_TRAFFIC_SOURCE,
             "peak_source": peak_kind, "kernel": "ntt_kernel<Small32,10,5,MUL>",
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+        },
+        "roofline_int": {
+            "bound": "int32 Shoup modmul (3 IMAD)", "achieved": modmul_rate / 1e12, "peak": modmul_peak / 1e12,
+            "unit": "T modmul/s", "frac": modmul_rate / modmul_peak, "modmul_per_polymul": modmul_per_polymul,
+            "peak_source": "fhe_int_peak microbenchmark, this run",
         },
         "e2e": {
             "value": e2e_value, "unit": "polymul/s", "h2d_bytes_per_step": 2 * N * 4 * batch,
