@@ -14,6 +14,7 @@ from ._capi import FheError, check, lib, ptr  # noqa: F401
 
 A_IS_EVALS = 1
 B_IS_EVALS = 2
+B_BROADCAST = 4
 
 
 def _is_torch(x) -> bool:
@@ -139,7 +140,7 @@ class NttPlan:
         """ring_nq::mul (arith/src/ring_nq.rs:586-607); `evals_out` receives the product's cached evals."""
         out = _empty_like(a) if out is None else out
         _check_u64(a, b, out, evals_out)
-        if _numel(a) != _numel(b):
+        if _numel(b) != (self.n if int(flags) & B_BROADCAST else _numel(a)):
             raise ValueError("operand sizes differ")
         check(lib.fhe_rq_mul(self._h, ptr(a), ptr(b), ptr(out), self._batch(a), int(flags), ptr(evals_out)))
         return out
@@ -447,6 +448,15 @@ def bfv_mul_relin(q, n, t, pq, rlk, a, b, out=None):
     out = _empty_like(a) if out is None else out
     _check_u64(rlk, a, b, out)
     check(lib.fhe_bfv_mul_relin(int(q), int(n), int(t), int(pq), ptr(rlk), ptr(a), ptr(b), ptr(out), _numel(a) // (2 * int(n))))
+    return out
+
+
+def bfv_decrypt(plan: NttPlan, t, sk, ct, out=None):
+    """BFV::decrypt (bfv/src/lib.rs:164-178) for a batch of RLWEs (2n words each) under one secret key."""
+    batch = _numel(ct) // (2 * plan.n)
+    out = _new(ct, (batch, plan.n)) if out is None else out
+    _check_u64(sk, ct, out)
+    check(lib.fhe_bfv_decrypt(plan._h, plan.q, plan.n, int(t), ptr(sk), ptr(ct), ptr(out), batch))
     return out
 
 

@@ -5,6 +5,8 @@
 // coefficient, by f64 round((num*v)/den) (ring_n.rs:130-138), Zq::from_f64 (zq.rs:32-40), and only then the
 // X^n+1 fold as a Zq subtraction (ring_nq.rs:132-141).  The f64 steps use explicit IEEE round-to-nearest
 // intrinsics (no FMA contraction) so they match the CPU's arithmetic.
+#include <algorithm>
+
 #include "../../include/fhe_b200.h"
 #include "runtime.cuh"
 
@@ -151,10 +153,63 @@ static int bfv_launch(int mode, u64 q, u64 n, u64 t, u64 pq, const u64 *rlk, con
     return finish_all({&ba, &bb, &bk, &bo}, st);
 }
 
+// ---- BFV::decrypt (bfv/src/lib.rs:164-178): m = ((c0 + c1*s) . mul_div_round(t, q)) . remodule(t) -----------------
+// c1 polynomials of `batch` RLWEs gathered contiguously (the transform kernels take dense batches)
+__global__ void bfv_gather_c1_kernel(const u64 *__restrict__ ct, u64 *__restrict__ c1, size_t batch, u32 n) {
+    const size_t total = batch * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        c1[i] = ct[(i / n) * 2 * n + n + i % n];
+}
+// cs = c0 + c1s (Zq::add, zq.rs:219-231); r = Zq::from_f64(round((t * cs) / q)) (ring_nq.rs:106-113); m = from_u64(t, r)
+__global__ void bfv_decrypt_finish_kernel(const u64 *__restrict__ ct, const u64 *__restrict__ c1s, u64 *__restrict__ m,
+                                          size_t batch, u32 n, u64 q, u64 t) {
+    const size_t total = batch * n;
+    const double dq = __ull2double_rn(q), dt = __ull2double_rn(t);
+    const u64 mu = ~0ull / q;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const u64 cs = zq_add(q, ct[(i / n) * 2 * n + i % n], c1s[i]);
+        const u64 r = zq_from_f64(q, mu, __ddiv_rn(__dmul_rn(dt, __ull2double_rn(cs)), dq));
+        m[i] = r >= t ? r % t : r;
+    }
+}
+
 }  // namespace fhe
+
+struct fhe_ntt_plan;
+namespace fhe {
+int plan_launch(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch, int flags,
+                cudaStream_t st);  // lib_core.cu
+}
 
 using namespace fhe;
 extern "C" {
+int fhe_bfv_decrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, uint64_t t, const uint64_t *sk, const uint64_t *ct,
+                    uint64_t *m, size_t batch) {
+    FHE_REQUIRE(plan != nullptr, "null plan");
+    if (batch == 0) return 0;
+    FHE_REQUIRE(sk && ct && m, "fhe_bfv_decrypt: null pointer");
+    FHE_REQUIRE(t >= 1 && q >= 2 && n >= 1, "fhe_bfv_decrypt: need t >= 1");
+    cudaStream_t st = current_stream();
+    IoBuf bs, bc, bm;
+    Scratch c1, c1s;
+    int rc;
+    if ((rc = bs.init(sk, n * 8, true, false, st))) return rc;
+    if ((rc = bc.init(ct, batch * 2 * n * 8, true, false, st))) return rc;
+    if ((rc = bm.init(m, batch * n * 8, false, true, st))) return rc;
+    if ((rc = c1.alloc(batch * n * 8, st))) return rc;
+    if ((rc = c1s.alloc(batch * n * 8, st))) return rc;
+    const unsigned grid = (unsigned)std::min<size_t>((batch * n + 255) / 256, (size_t)num_sms() * 16);
+    bfv_gather_c1_kernel<<<grid, 256, 0, st>>>(bc.ptr<u64>(), c1.ptr<u64>(), batch, (u32)n);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    // c1 * s: every product shares the one secret-key polynomial (its transform is recomputed per CTA, n <= 2^15 words)
+    if ((rc = plan_launch(plan, 2 /* MODE_MUL */, c1.ptr<u64>(), bs.ptr<u64>(), c1s.ptr<u64>(), nullptr, batch, 4 /* B_BROADCAST */, st)))
+        return rc;
+    bfv_decrypt_finish_kernel<<<grid, 256, 0, st>>>(bc.ptr<u64>(), c1s.ptr<u64>(), bm.ptr<u64>(), batch, (u32)n, q, t);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return finish_all({&bs, &bc, &bm}, st);
+}
 int fhe_bfv_tensor(uint64_t q, uint64_t n, uint64_t t, const uint64_t *a, const uint64_t *b, uint64_t *c012, size_t batch) {
     return bfv_launch(0, q, n, t, 0, nullptr, a, b, c012, batch);
 }

@@ -154,7 +154,8 @@ int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 
     cudaStream_t st = current_stream();
     const size_t bytes = batch * plan->host.n * sizeof(u64);
     if (mode != MODE_MUL) b = nullptr;
-    {   // all-host call on a batch worth pipelining (>= 4 chunks of ~32 MiB per operand)
+    const bool bcast = mode == MODE_MUL && (flags & B_BROADCAST);
+    if (!bcast) {   // all-host call on a batch worth pipelining (>= 4 chunks of ~32 MiB per operand)
         const size_t chunk = std::max<size_t>(1, pipe_chunk_bytes() / (plan->host.n * sizeof(u64)));
         if (batch >= 4 * chunk && is_host_ptr(a) && (!b || is_host_ptr(b)) && is_host_ptr(c) &&
             (!c_evals || is_host_ptr(c_evals)) && a != c && b != c)
@@ -163,7 +164,7 @@ int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 
     IoBuf ba, bb, bc, be;
     int rc;
     if ((rc = ba.init(a, bytes, true, false, st))) return rc;
-    if ((rc = bb.init(mode == MODE_MUL ? b : nullptr, bytes, true, false, st))) return rc;
+    if ((rc = bb.init(mode == MODE_MUL ? b : nullptr, bcast ? plan->host.n * sizeof(u64) : bytes, true, false, st))) return rc;
     if ((rc = bc.init(c, bytes, false, true, st))) return rc;
     if ((rc = be.init(c_evals, bytes, false, true, st))) return rc;
     rc = launch_plan(plan, mode, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(), be.ptr<u64>(), batch, flags, st);
@@ -201,6 +202,7 @@ int run_ntt_wire32(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *
     FHE_REQUIRE(a != nullptr && c != nullptr && (mode != MODE_MUL || b != nullptr), "null polynomial pointer");
     FHE_REQUIRE(plan->host.q <= (1ull << 32), "the 32-bit wire format needs q <= 2^32");
     FHE_REQUIRE(plan->host.n % 4 == 0, "the 32-bit wire format needs n >= 4");
+    FHE_REQUIRE(!(flags & B_BROADCAST), "FHE_B_BROADCAST is not supported on the 32-bit wire");
     if (mode != MODE_MUL) b = nullptr;
     cudaStream_t st = current_stream();
     int rc = t_pipe.init();

@@ -24,7 +24,7 @@ template <class M> struct NttParams {
 };
 
 enum NttMode { MODE_FWD = 0, MODE_INV = 1, MODE_MUL = 2 };
-enum MulFlags { A_IS_EVALS = 1, B_IS_EVALS = 2 };
+enum MulFlags { A_IS_EVALS = 1, B_IS_EVALS = 2, B_BROADCAST = 4 };  // B_BROADCAST: b is ONE polynomial, used for every product
 
 template <int LOGN, int LOGE> struct KernelGeom {
     typedef NttShape<LOGN, LOGE> S;
@@ -174,7 +174,7 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
         // the bulk of the kernel's instruction footprint; see profiles/: no_instruction stalls)
 #pragma unroll 1
         for (int op = 0; op < 2; op++) {
-            const u64 *src = (op == 0 ? a : b) + off;
+            const u64 *src = op == 0 ? a + off : (flags & B_BROADCAST) ? b : b + off;
             if (flags & (op == 0 ? A_IS_EVALS : B_IS_EVALS)) {
                 load_poly<M, LOGN, LOGE, LAST>(x, src, valid, sm, tid);
             } else {

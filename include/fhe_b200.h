@@ -73,6 +73,7 @@ FHE_API int fhe_ntt_inv(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *
  * the reference caches on the product (ring_nq.rs:606). */
 #define FHE_A_IS_EVALS 1
 #define FHE_B_IS_EVALS 2
+#define FHE_B_BROADCAST 4 /* b is ONE polynomial (n words) multiplied into every a_i: GLWE * R (gfhe/src/glwe.rs:263-280) */
 FHE_API int fhe_rq_mul(const fhe_ntt_plan *plan, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, int flags,
                uint64_t *c_evals);
 /* Packed 32-bit wire format of the three calls above for q <= 2^32 (the reference's only NTT modulus is 65537):
@@ -192,6 +193,11 @@ FHE_API int fhe_bfv_relinearize(uint64_t q, uint64_t n, uint64_t pq, const uint6
 /* RLWE::mul (lib.rs:87-90) = tensor + relinearize_204, fused. */
 FHE_API int fhe_bfv_mul_relin(uint64_t q, uint64_t n, uint64_t t, uint64_t pq, const uint64_t *rlk, const uint64_t *a,
                               const uint64_t *b, uint64_t *out, size_t batch);
+/* BFV::decrypt (lib.rs:164-178): m_b = ((c0 + c1 * s).mul_div_round(t, q)).remodule(t) for `batch` RLWEs (2n words each);
+ * sk = the secret polynomial (n words), plan = the (q, n) plan (q and n are checked against it by the caller's types in the
+ * reference; here they are passed so that the map kernels need no plan internals).  m: batch * n words. */
+FHE_API int fhe_bfv_decrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, uint64_t t, const uint64_t *sk, const uint64_t *ct,
+                            uint64_t *m, size_t batch);
 
 /* ---- coefficient-wise Rq / Tn operations (arith/src/ring_nq.rs, ring_torus.rs, zq.rs, torus.rs) ------------- */
 /* Add / Sub / Neg / mul_by_u64 (ring_nq.rs:267-281,406-561) on `len` coefficients mod q (any q < 2^63). */

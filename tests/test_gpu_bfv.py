@@ -142,3 +142,35 @@ def test_mul_relin_modulus_edge_cases(fhe, orc, q, p, n, t):
     rlk = orc.uniform(13, 2 * n, pq)
     want = orc.bfv_mul(q, n, t, pq, rlk, a.reshape(-1), b.reshape(-1)).reshape(9, 2 * n)
     assert (fhe.bfv_mul_relin(q, n, t, pq, rlk, a, b) == want).all()
+
+
+@pytest.mark.parametrize("q,n,t,batch", [(Q, 512, 32, 9), (Q, 128, 32, 40), (Q, 16, 2, 4096), (0x3FFC0001, 64, 5, 7)])
+def test_bfv_decrypt_batched(fhe, orc, q, n, t, batch):
+    # BFV::decrypt (bfv/src/lib.rs:164-178) at the reference's parameter sets (lib.rs:283-290: n=512, t=32; :311-318:
+    # n=128; :559-564: n=16, t=2): real encryptions decrypt to their messages, random ciphertexts match the oracle
+    L = orc.lib()
+    sk, pk = np.empty(n, dtype=np.uint64), np.empty(2 * n, dtype=np.uint64)
+    L.orc_bfv_keygen(31, q, n, orc.ptr(sk), orc.ptr(pk))
+    msgs = orc.uniform(32, (batch, n), t)
+    cts = np.empty((batch, 2 * n), dtype=np.uint64)
+    for i in range(min(batch, 50)):
+        L.orc_bfv_encrypt(100 + i, q, n, t, orc.ptr(pk), orc.ptr(np.ascontiguousarray(msgs[i])), orc.ptr(cts[i]))
+    cts[50:] = orc.uniform(33, (max(batch - 50, 0), 2 * n), q)
+    plan = fhe.NttPlan(q, n)
+    got = fhe.bfv_decrypt(plan, t, sk, cts)
+    want = np.empty((batch, n), dtype=np.uint64)
+    for i in range(batch):
+        L.orc_bfv_decrypt(q, n, t, orc.ptr(sk), orc.ptr(np.ascontiguousarray(cts[i])), orc.ptr(want[i]))
+    assert np.array_equal(got, want)
+    k = min(batch, 50)
+    assert np.array_equal(got[:k], msgs[:k])  # decrypt(encrypt(m)) == m (lib.rs:281-307)
+
+
+def test_rq_mul_broadcast_operand(fhe, orc):
+    # FHE_B_BROADCAST: one right operand for the whole batch (GLWE * R, gfhe/src/glwe.rs:263-280)
+    q, n, batch = Q, 256, 11
+    plan = fhe.NttPlan(q, n)
+    a, b = orc.uniform(1, (batch, n), q), orc.uniform(2, n, q)
+    want = orc.rq_mul_batch(q, n, a, np.tile(b, batch))
+    assert np.array_equal(plan.mul(a, b, flags=fhe.B_BROADCAST), want)
+    assert np.array_equal(plan.mul(a, plan.ntt(b), flags=fhe.B_BROADCAST | fhe.B_IS_EVALS), want)
