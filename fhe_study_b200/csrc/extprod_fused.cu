@@ -22,11 +22,18 @@
 
 namespace fhe {
 
+// threads per CTA: 256, or (tuning experiment FHE_XP_CT512) 512 at n = 1024, k = 1 with two accumulators per CTA that
+// share every key load at unchanged occupancy (16 warps, 128 registers, 132 KB shared memory per SM)
+#ifndef FHE_XP_CT512
+#define FHE_XP_CT512 0
+#endif
+__host__ __device__ constexpr int xp_ct(int logn, int k1) { return (logn == 10 && k1 == 2 && FHE_XP_CT512) ? 512 : 256; }
+
 template <int LOGN, int K1> struct XpGeom {
     static constexpr int N = 1 << LOGN;
     static constexpr int LOGE = LOGN < 5 ? LOGN : 5;
     typedef NttShape<LOGN, LOGE> S;
-    static constexpr int CT = 256;
+    static constexpr int CT = xp_ct(LOGN, K1);
     static constexpr int SLOTS = CT / S::T;             // concurrent NTTs
     static constexpr int ND = K1 * 64;                  // digit polynomials per accumulator
     static constexpr int PADN = N + (N >> 5);
@@ -40,10 +47,10 @@ template <int LOGN, int K1> struct XpGeom {
 #ifndef FHE_XP_A10
 #define FHE_XP_A10 1
 #endif
-    static constexpr int A = LOGN <= 7 ? 4 : (LOGN <= 9 && ITEMS <= 2048) ? 2 : (LOGN == 10 && K1 == 2) ? FHE_XP_A10 : 1;
+    static constexpr int A = CT == 512 ? 2 : LOGN <= 7 ? 4 : (LOGN <= 9 && ITEMS <= 2048) ? 2 : (LOGN == 10 && K1 == 2) ? FHE_XP_A10 : 1;
     // resident CTAs asked of ptxas: three 80-register CTAs help the small rings (n=64,k=4: 6.0 -> 6.6 M/s), while at
     // n=1024 two 128-register CTAs are faster (1.44 vs 1.27 M/s; the chain even 1.28 vs 0.91 M CMux/s)
-    static constexpr int MINB = LOGN <= 7 ? 3 : (LOGN == 10 && A > 1) ? 1 : 2;
+    static constexpr int MINB = CT == 512 ? 1 : LOGN <= 7 ? 3 : (LOGN == 10 && A > 1) ? 1 : 2;
     static constexpr int DPR = SLOTS / A;               // digits per round (each for all A accumulators)
     static constexpr int ROUNDS = (ND + DPR - 1) / DPR;
     // slots whose threads run an inverse transform (whole warps do): the slots behind them are free for the
@@ -120,7 +127,7 @@ __device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32
 }
 
 template <int LOGN, int K1, bool CHAIN>
-__global__ void __launch_bounds__(256, XpGeom<LOGN, K1>::MINB)
+__global__ void __launch_bounds__(XpGeom<LOGN, K1>::CT, XpGeom<LOGN, K1>::MINB)
 extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__ ct1, const u64 *__restrict__ ct2,
                      u64 *out, int cmux, const XpChain ch, size_t batch) {
     typedef XpGeom<LOGN, K1> G;
@@ -252,13 +259,13 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
 }
 
 // unfused key layout (u64, [d][u][x]) -> fused layout (u32, [d][v][t][j], item = t + 256 (4v + j)), zero padded
-__global__ void tggsw_fused_layout_kernel(const u64 *__restrict__ R, u32 *__restrict__ Rf, int nd, int items, int ipt4) {
-    const size_t total = (size_t)nd * 256 * ipt4;
+__global__ void tggsw_fused_layout_kernel(const u64 *__restrict__ R, u32 *__restrict__ Rf, int nd, int items, int ipt4, int ct) {
+    const size_t total = (size_t)nd * ct * ipt4;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(idx & 3), t = (int)((idx >> 2) & 255), v = (int)((idx >> 10) % (ipt4 / 4));
-        const int d = (int)(idx / ((size_t)ipt4 * 256));
+        const int j = (int)(idx & 3), t = (int)((idx >> 2) % ct), v = (int)((idx / (4 * (size_t)ct)) % (ipt4 / 4));
+        const int d = (int)(idx / ((size_t)ipt4 * ct));
         const int m = 4 * v + j;
-        const int item = t + 256 * m;
+        const int item = t + ct * m;
         Rf[idx] = item < items ? (u32)R[(size_t)d * items + item] : 0u;
     }
 }
@@ -332,7 +339,7 @@ bool extprod_fused_supported(int logn, int k1) {
     return false;
 }
 static int fused_ipt4(int logn, int k1) {
-    const int items = k1 * 2 * (1 << logn), ipt = (items + 255) / 256;
+    const int items = k1 * 2 * (1 << logn), ct = xp_ct(logn, k1), ipt = (items + ct - 1) / ct;
     return (ipt + 3) / 4 * 4;
 }
 
@@ -343,13 +350,14 @@ int tggsw_build_fused_layout(Tggsw &g, cudaStream_t st) {
     // the fused kernels read the plans' twiddle tables in the device order of 32 coefficients per thread
     if (g.tc->plan1->loge != (logn < 5 ? logn : 5) || g.tc->plan2->loge != g.tc->plan1->loge) return 0;
     const int nd = k1 * 64, items = k1 * 2 * (1 << logn), ipt4 = fused_ipt4(logn, k1);
-    const size_t words = (size_t)nd * 256 * ipt4;
+    const int ct = xp_ct(logn, k1);
+    const size_t words = (size_t)nd * ct * ipt4;
     FHE_CUDA_OK(cudaMalloc((void **)&g.R1f, words * sizeof(u32)));
     FHE_CUDA_OK(cudaMalloc((void **)&g.R2f, words * sizeof(u32)));
     size_t grid = (words + 255) / 256;
     if (grid > (size_t)num_sms() * 32) grid = (size_t)num_sms() * 32;
-    tggsw_fused_layout_kernel<<<(unsigned)grid, 256, 0, st>>>(g.R1, g.R1f, nd, items, ipt4);
-    tggsw_fused_layout_kernel<<<(unsigned)grid, 256, 0, st>>>(g.R2, g.R2f, nd, items, ipt4);
+    tggsw_fused_layout_kernel<<<(unsigned)grid, 256, 0, st>>>(g.R1, g.R1f, nd, items, ipt4, ct);
+    tggsw_fused_layout_kernel<<<(unsigned)grid, 256, 0, st>>>(g.R2, g.R2f, nd, items, ipt4, ct);
     count_launch(2);
     FHE_CUDA_OK(cudaGetLastError());
     FHE_CUDA_OK(cudaStreamSynchronize(st));
