@@ -107,7 +107,7 @@ int fhe_key_switch(const fhe_ksk *h, const uint64_t *ct, uint64_t *out, size_t b
     const size_t chunk = std::max<size_t>(256, ((16u << 20) / ((h->k.kn_in + 1) * 8)) / 256 * 256);  // ~16 MB stages
     if (batch >= 4 * chunk && is_host_ptr(ct) && is_host_ptr(out))  // all-host call: copies and kernels overlap
         return run_host_pipelined(ct, (h->k.kn_in + 1) * 8, out, (h->k.kn_out + 1) * 8, batch, chunk, st,
-                                  [&](const void *din, void *dout, size_t nb, cudaStream_t s) {
+                                  [&](const void *din, void *dout, size_t nb, cudaStream_t s, int) {
                                       return key_switch_device(h->k, (const u64 *)din, (u64 *)dout, nb, s);
                                   });
     IoBuf bi, bo;
@@ -203,17 +203,18 @@ int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *ta
     IoBuf bt, bc, bo;
     int rc;
     if ((rc = bt.init(table, (k + 1) * n * 8, true, false, st))) return rc;
-    const size_t chunk = 2048;  // ~17 MB of ciphertexts per stage
+    const size_t chunk = 1024;  // ~8 MB of ciphertexts per stage; consecutive chunks compute on two streams
     if (batch >= 4 * chunk && is_host_ptr(ct) && is_host_ptr(out)) {
         // all-host call: H2D, rotate+extract+key switch and D2H of consecutive chunks overlap
         Scratch ext;
-        if ((rc = ext.alloc(chunk * (k * n + 1) * 8, st))) return rc;
+        const size_t ext_words = chunk * (k * n + 1);
+        if ((rc = ext.alloc(2 * ext_words * 8, st))) return rc;
         const u64 *tab = bt.ptr<u64>();
         rc = run_host_pipelined(ct, (c_kn + 1) * 8, out, (ksk->k.kn_out + 1) * 8, batch, chunk, st,
-                                [&](const void *din, void *dout, size_t nb, cudaStream_t s) {
-                                    int r = rotate_extract_device(tab, (const u64 *)din, ext.ptr<u64>(), nullptr, nb, (u32)n, (u32)k,
-                                                                  (u32)c_kn, s);
-                                    return r ? r : key_switch_device(ksk->k, ext.ptr<u64>(), (u64 *)dout, nb, s);
+                                [&](const void *din, void *dout, size_t nb, cudaStream_t s, int par) {
+                                    u64 *e = ext.ptr<u64>() + (size_t)par * ext_words;
+                                    int r = rotate_extract_device(tab, (const u64 *)din, e, nullptr, nb, (u32)n, (u32)k, (u32)c_kn, s);
+                                    return r ? r : key_switch_device(ksk->k, e, (u64 *)dout, nb, s);
                                 });
         return rc;
     }

@@ -80,7 +80,7 @@ class Scratch {
 // Host-buffer path for large batches: the batch is cut into chunks and H2D copies, kernels and D2H copies of
 // consecutive chunks overlap on three streams (PCIe is full duplex), double-buffered on the device.
 struct PipeStreams {
-    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaStream_t h2d = nullptr, d2h = nullptr, comp2 = nullptr;  // comp2: second compute stream (odd chunks)
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
     int device = -1;
     int init() {
@@ -89,6 +89,7 @@ struct PipeStreams {
         if (device == dev) return 0;
         FHE_CUDA_OK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
         FHE_CUDA_OK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        FHE_CUDA_OK(cudaStreamCreateWithFlags(&comp2, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
             FHE_CUDA_OK(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
             FHE_CUDA_OK(cudaEventCreateWithFlags(&comp_done[i], cudaEventDisableTiming));
@@ -100,8 +101,10 @@ struct PipeStreams {
 };
 PipeStreams &thread_pipe();  // per host thread (lib_core.cu)
 
-// Host-buffer batches: `batch` independent units cut into chunks; H2D copy of chunk i+1, fn(dev_in, dev_out, nb, st)
-// of chunk i and D2H copy of chunk i-1 overlap (double-buffered device staging).  Returns with `out` complete.
+// Host-buffer batches: `batch` independent units cut into chunks; H2D copy of chunk i+1, fn(dev_in, dev_out, nb, stream, parity)
+// of chunk i and D2H copy of chunk i-1 overlap (double-buffered device staging).  Even and odd chunks compute on two
+// different streams, so the tail of one chunk's kernels (a partial last wave) overlaps the head of the next chunk's.
+// fn must keep any scratch it uses per parity.  Returns with `out` complete.
 template <class F>
 int run_host_pipelined(const void *in, size_t in_unit, void *out, size_t out_unit, size_t batch, size_t chunk, cudaStream_t st,
                        F fn) {
@@ -111,27 +114,30 @@ int run_host_pipelined(const void *in, size_t in_unit, void *out, size_t out_uni
     Scratch sin, sout;
     if ((rc = sin.alloc(2 * chunk * in_unit, st))) return rc;
     if ((rc = sout.alloc(2 * chunk * out_unit, st))) return rc;
-    FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch is used from the side streams as well
+    FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch (and the caller's) is used from the side streams as well
     size_t i = 0;
     for (size_t off = 0; off < batch && !rc; off += chunk, i++) {
         const size_t nb = batch - off < chunk ? batch - off : chunk;
         const int par = (int)(i & 1);
+        cudaStream_t cs = par ? ps.comp2 : st;
         char *din = sin.ptr<char>() + (size_t)par * chunk * in_unit, *dout = sout.ptr<char>() + (size_t)par * chunk * out_unit;
         if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // staging of chunk i-2 consumed
         FHE_CUDA_OK(cudaMemcpyAsync(din, (const char *)in + off * in_unit, nb * in_unit, cudaMemcpyHostToDevice, ps.h2d));
         FHE_CUDA_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
-        FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.h2d_done[par], 0));
-        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
-        if ((rc = fn(din, dout, nb, st))) break;
-        FHE_CUDA_OK(cudaEventRecord(ps.comp_done[par], st));
+        FHE_CUDA_OK(cudaStreamWaitEvent(cs, ps.h2d_done[par], 0));
+        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(cs, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
+        if ((rc = fn(din, dout, nb, cs, par))) break;
+        FHE_CUDA_OK(cudaEventRecord(ps.comp_done[par], cs));
         FHE_CUDA_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
         FHE_CUDA_OK(cudaMemcpyAsync((char *)out + off * out_unit, dout, nb * out_unit, cudaMemcpyDeviceToHost, ps.d2h));
         FHE_CUDA_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
     }
-    cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st);
+    cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st),
+                e4 = cudaStreamSynchronize(ps.comp2);
     if (rc) return rc;
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-        set_error(std::string("pipelined transfer failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+        set_error(std::string("pipelined transfer failed: ") +
+                  cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4));
         return -2;
     }
     return 0;
