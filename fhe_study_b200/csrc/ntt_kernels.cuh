@@ -28,7 +28,10 @@ enum MulFlags { A_IS_EVALS = 1, B_IS_EVALS = 2, B_BROADCAST = 4 };  // B_BROADCA
 
 template <int LOGN, int LOGE> struct KernelGeom {
     typedef NttShape<LOGN, LOGE> S;
-    static constexpr int CT = S::T > 128 ? S::T : 128;   // threads per CTA
+#ifndef FHE_NTT_MIN_CT
+#define FHE_NTT_MIN_CT 128
+#endif
+    static constexpr int CT = S::T > FHE_NTT_MIN_CT ? S::T : FHE_NTT_MIN_CT;   // threads per CTA
     static constexpr int PPC = CT / S::T;                // polynomials per CTA
     static constexpr int PADN = S::N + (S::N >> 5);      // padded words per polynomial in smem
 };
@@ -128,7 +131,7 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 #endif
     static constexpr int minb = on ? FHE_A_SMEM_MINB
                                 : !W32 ? (CT_ == 128 ? (MODE == MODE_MUL ? FHE_MUL64_MINB : FHE_NTT64_MINB) : 0)
-                                : MODE == MODE_MUL ? (CT_ == 128 ? FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0)
+                                : MODE == MODE_MUL ? (CT_ == 128 ? FHE_MUL_MINB : CT_ == 64 ? 2 * FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0)
                                 : (CT_ == 256 ? (MODE == MODE_INV ? FHE_INV_MINB_256 : FHE_NTT_MINB_256)
                                    : CT_ == 512 ? FHE_NTT_MINB_512 : 0);
 };
