@@ -47,10 +47,13 @@ template <int LOGN, int K1> struct XpGeom {
 #ifndef FHE_XP_A10
 #define FHE_XP_A10 1
 #endif
-    static constexpr int A = CT == 512 ? 2 : LOGN <= 7 ? 4 : (LOGN <= 9 && ITEMS <= 2048) ? 2 : (LOGN == 10 && K1 == 2) ? FHE_XP_A10 : 1;
+#ifndef FHE_XP_A_SMALL
+#define FHE_XP_A_SMALL 4
+#endif
+    static constexpr int A = CT == 512 ? 2 : LOGN <= 7 ? FHE_XP_A_SMALL : (LOGN <= 9 && ITEMS <= 2048) ? 2 : (LOGN == 10 && K1 == 2) ? FHE_XP_A10 : 1;
     // resident CTAs asked of ptxas: three 80-register CTAs help the small rings (n=64,k=4: 6.0 -> 6.6 M/s), while at
     // n=1024 two 128-register CTAs are faster (1.44 vs 1.27 M/s; the chain even 1.28 vs 0.91 M CMux/s)
-    static constexpr int MINB = CT == 512 ? 1 : LOGN <= 7 ? 3 : (LOGN == 10 && A > 1) ? 1 : 2;
+    static constexpr int MINB = CT == 512 ? 1 : LOGN <= 7 ? (FHE_XP_A_SMALL > 4 ? 2 : 3) : (LOGN == 10 && A > 1) ? 1 : 2;
     static constexpr int DPR = SLOTS / A;               // digits per round (each for all A accumulators)
     static constexpr int ROUNDS = (ND + DPR - 1) / DPR;
     // slots whose threads run an inverse transform (whole warps do): the slots behind them are free for the
