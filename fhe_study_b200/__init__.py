@@ -412,6 +412,29 @@ def bootstrap_chain(n, k, bsk, table, ct, c_kn, mode=1, ksk: Ksk = None, out=Non
     return out
 
 
+def tlwe_decrypt(kn, sk, ct, out=None):
+    """TLWE::decrypt (tfhe/src/tlwe.rs:80-82): the phase b - <a, sk> of every ciphertext."""
+    batch = _numel(ct) // (int(kn) + 1)
+    out = _new(ct, (batch,)) if out is None else out
+    _check_u64(sk, ct, out)
+    check(lib.fhe_tlwe_decrypt(int(kn), ptr(sk), ptr(ct), ptr(out), batch))
+    return out
+
+
+def tglwe_decrypt(n, k, sk, ct, out=None):
+    """TGLWE::decrypt (tfhe/src/tglwe.rs:86-88): b - sum_i a_i * sk_i."""
+    batch = _numel(ct) // ((int(k) + 1) * int(n))
+    out = _new(ct, (batch, int(n))) if out is None else out
+    _check_u64(sk, ct, out)
+    check(lib.fhe_tglwe_decrypt(int(n), int(k), ptr(sk), ptr(ct), ptr(out), batch))
+    return out
+
+
+def torus_decode(p, t):
+    """TLWE::decode / TGLWE::decode (tlwe.rs:60-63, tglwe.rs:59-63): round(t * p / u64::MAX) reduced mod t."""
+    return rq_remodule(tn_mul_div_round(p, int(t), 2**64 - 1), int(t))
+
+
 def sample_extract(n, k, ct, h, out=None):
     batch = _numel(ct) // ((int(k) + 1) * int(n))
     out = _new(ct, (batch, int(k) * int(n) + 1)) if out is None else out

@@ -118,6 +118,21 @@ int fhe_key_switch(const fhe_ksk *h, const uint64_t *ct, uint64_t *out, size_t b
     return finish_all({&bi, &bo}, st);
 }
 
+// TLWE::decrypt for `batch` TLWEs under one secret key: phases, not yet decoded
+int fhe_tlwe_decrypt(uint64_t kn, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(sk && ct && p, "fhe_tlwe_decrypt: null pointer");
+    FHE_REQUIRE(kn >= 1 && kn < (1ull << 31), "fhe_tlwe_decrypt: kn out of range");
+    cudaStream_t st = current_stream();
+    IoBuf bs, bc, bo;
+    int rc;
+    if ((rc = bs.init(sk, kn * 8, true, false, st))) return rc;
+    if ((rc = bc.init(ct, batch * (kn + 1) * 8, true, false, st))) return rc;
+    if ((rc = bo.init(p, batch * 8, false, true, st))) return rc;
+    if ((rc = tlwe_decrypt_device(bs.ptr<u64>(), bc.ptr<u64>(), bo.ptr<u64>(), batch, (u32)kn, st))) return rc;
+    return finish_all({&bs, &bc, &bo}, st);
+}
+
 int fhe_tlwe_mod_switch(const uint64_t *ct, uint64_t q2, uint64_t *out, size_t len) {
     if (len == 0) return 0;
     FHE_REQUIRE(ct && out, "null pointer");

@@ -135,6 +135,22 @@ int fhe_tggsw_generate(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_
     *out = h.release();
     return 0;
 }
+// TGLWE::decrypt for `batch` TGLWEs under one secret key (k polynomials): phases, not yet decoded
+int fhe_tglwe_decrypt(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(sk && ct && p, "fhe_tglwe_decrypt: null pointer");
+    FHE_REQUIRE(k >= 1, "fhe_tglwe_decrypt: k must be >= 1");
+    TorusCtx *tc;
+    int rc = get_torus_ctx(n, &tc);
+    if (rc) return rc;
+    cudaStream_t st = current_stream();
+    IoBuf bs, bc, bo;
+    if ((rc = bs.init(sk, k * n * 8, true, false, st))) return rc;
+    if ((rc = bc.init(ct, batch * (k + 1) * n * 8, true, false, st))) return rc;
+    if ((rc = bo.init(p, batch * n * 8, false, true, st))) return rc;
+    if ((rc = tglwe_decrypt_device(*tc, k, bs.ptr<u64>(), bc.ptr<u64>(), bo.ptr<u64>(), batch, st))) return rc;
+    return finish_all({&bs, &bc, &bo}, st);
+}
 void fhe_tggsw_destroy(fhe_tggsw *h) {
     if (!h) return;
     cudaFree(h->g.R1);

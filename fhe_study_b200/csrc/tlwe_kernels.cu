@@ -294,6 +294,27 @@ int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_ou
     FHE_CUDA_OK(cudaGetLastError());
     return 0;
 }
+// TLWE::decrypt (tlwe.rs:80-82 -> glwe.rs:175-179 with R = T64): phase_b = ct_b.b - <ct_b.a, sk>, one warp per ciphertext
+__global__ void __launch_bounds__(256)
+tlwe_decrypt_kernel(const u64 *__restrict__ sk, const u64 *__restrict__ ct, u64 *__restrict__ out, size_t batch, u32 kn) {
+    const u32 lane = threadIdx.x & 31;
+    for (size_t b = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < batch; b += (size_t)gridDim.x * 8) {
+        const u64 *c = ct + b * (size_t)(kn + 1);
+        u64 part = 0;
+        for (u32 i = lane; i < kn; i += 32) part += c[i] * sk[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) out[b] = c[kn] - part;
+    }
+}
+int tlwe_decrypt_device(const u64 *sk, const u64 *ct, u64 *out, size_t batch, u32 kn, cudaStream_t st) {
+    const unsigned grid = (unsigned)std::min<size_t>((batch + 7) / 8, (size_t)num_sms() * 16);
+    tlwe_decrypt_kernel<<<grid, 256, 0, st>>>(sk, ct, out, batch, kn);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int chain_prepare_device(const u64 *table, const u64 *ct, u64 *acc0, u64 *hs, size_t batch, u32 n, u32 k, u32 c_kn,
                          u32 steps, int mode, cudaStream_t st) {
     const u64 q2 = mode ? 2ull * n : (u64)k * n;

@@ -72,6 +72,7 @@ bool extprod_fused_supported(int logn, int k1);
 int tggsw_build_fused_layout(Tggsw &g, cudaStream_t st);
 int extprod_fused_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, int cmux, cudaStream_t st);
 int tggsw_precompute(Tggsw &g, const u64 *rows_dev, cudaStream_t st);
+int tglwe_decrypt_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int tggsw_generate_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *m, double sigma, u64 seed, int uniform_mask,
                           u64 *rows_out, cudaStream_t st);
 int tn_addsub_device(const u64 *a, const u64 *b, u64 *c, size_t len, int op, cudaStream_t st);

@@ -371,6 +371,43 @@ int tggsw_generate_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *m
     return 0;
 }
 
+// TGLWE::decrypt (tglwe.rs:86-88 -> glwe.rs:175-179 with R = Tn): p_b = ct_b.b - sum_i ct_b.a_i * sk_i
+__global__ void tglwe_dec_gather_kernel(const u64 *__restrict__ ct, const u64 *__restrict__ sk, u64 *__restrict__ A,
+                                        u64 *__restrict__ S, size_t batch, u32 n, u32 k) {
+    const size_t kn = (size_t)k * n, total = batch * kn;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / kn, p = idx % kn;
+        A[idx] = ct[b * (kn + n) + p];
+        S[idx] = sk[p];
+    }
+}
+__global__ void tglwe_dec_finish_kernel(const u64 *__restrict__ ct, const u64 *__restrict__ P, u64 *__restrict__ out,
+                                        size_t batch, u32 n, u32 k) {
+    const size_t kn = (size_t)k * n, total = batch * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / n;
+        const u32 x = (u32)(idx % n);
+        u64 acc = 0;
+        for (u32 i = 0; i < k; i++) acc += P[b * kn + (size_t)i * n + x];
+        out[idx] = ct[b * (kn + n) + kn + x] - acc;
+    }
+}
+int tglwe_decrypt_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
+    const u32 n = (u32)tc.n;
+    const size_t words = batch * k * n;
+    Scratch sA, sS, sP;
+    int rc;
+    if ((rc = sA.alloc(words * 8, st)) || (rc = sS.alloc(words * 8, st)) || (rc = sP.alloc(words * 8, st))) return rc;
+    tglwe_dec_gather_kernel<<<grid_for(words), 256, 0, st>>>(ct, sk, sA.ptr<u64>(), sS.ptr<u64>(), batch, n, (u32)k);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    if ((rc = tn_mul_device(tc, sA.ptr<u64>(), sS.ptr<u64>(), sP.ptr<u64>(), batch * k, st))) return rc;
+    tglwe_dec_finish_kernel<<<grid_for(batch * n), 256, 0, st>>>(ct, sP.ptr<u64>(), out, batch, n, (u32)k);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int tn_addsub_device(const u64 *a, const u64 *b, u64 *c, size_t len, int op, cudaStream_t st) {
     tn_addsub_kernel<<<grid_for(len), 256, 0, st>>>(a, b, c, len, op);
     count_launch(1);

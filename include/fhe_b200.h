@@ -143,6 +143,12 @@ FHE_API int fhe_ksk_export(const fhe_ksk *handle, uint64_t *rows);
 FHE_API void fhe_ksk_destroy(fhe_ksk *handle);
 /* TLWE::key_switch(param, 2, l, ksk) (tlwe.rs:101-112): `batch` TLWEs of kn_in+1 words -> kn_out+1 words. */
 FHE_API int fhe_key_switch(const fhe_ksk *handle, const uint64_t *ct, uint64_t *out, size_t batch);
+/* TLWE::decrypt (tlwe.rs:80-82 over glwe.rs:175-179): p_b = ct_b.b - <ct_b.a, sk> for `batch` TLWEs of kn+1 words; the
+ * phases are decoded with fhe_tn_mul_div_round(p, t, u64::MAX) and a reduction mod t (TLWE::decode, tlwe.rs:60-63). */
+FHE_API int fhe_tlwe_decrypt(uint64_t kn, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch);
+/* TGLWE::decrypt (tglwe.rs:86-88 over glwe.rs:175-179): p_b = ct_b.b - sum_i ct_b.a_i * sk_i for `batch` TGLWEs; sk = k
+ * polynomials, p = batch * n words (decode as above, TGLWE::decode tglwe.rs:59-63). */
+FHE_API int fhe_tglwe_decrypt(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch);
 /* TLWE::mod_switch(q2) (tlwe.rs:114-118, torus.rs:58-66): every word >> (64 - log2 q2); q2 a power of two. */
 FHE_API int fhe_tlwe_mod_switch(const uint64_t *ct, uint64_t q2, uint64_t *out, size_t len);
 /* TGLWE::sample_extraction(h) (tglwe.rs:89-115): `batch` TGLWEs ((k+1)*n) -> TLWEs (k*n+1). */

@@ -211,3 +211,39 @@ def test_device_generated_ksk_switches_keys_functionally(fhe, orc):
     for i, m in enumerate(msgs):
         p = L.orc_tlwe_decrypt(kn, orc.ptr(sk2), orc.ptr(np.ascontiguousarray(out[i])))
         assert L.orc_t64_mul_div_round(p, t, 2**64 - 1) % t == m
+
+
+def test_tlwe_and_tglwe_decrypt_decode(fhe, orc):
+    # TLWE / TGLWE decrypt + decode (tlwe.rs:60-63,80-82; tglwe.rs:59-63,86-88) batched on the device: bit-exact phases
+    # against the oracle and the reference's functional property decode(decrypt(encrypt(m))) == m
+    L = orc.lib()
+    kn, t, batch = 1024, 128, 70
+    sk = np.empty(kn, dtype=np.uint64)
+    L.orc_tlwe_keygen(1, kn, orc.ptr(sk))
+    delta = (2**64 - 1) // t
+    msgs = orc.uniform(2, batch, t)
+    cts = np.empty((batch, kn + 1), dtype=np.uint64)
+    for i in range(batch):
+        L.orc_tlwe_encrypt_s(10 + i, kn, 3.2, orc.ptr(sk), (int(msgs[i]) * delta) % 2**64, 0, orc.ptr(cts[i]))
+    cts[-1] = orc.uniform(3, kn + 1)  # a random one: parity without any structure
+    ph = fhe.tlwe_decrypt(kn, sk, cts)
+    want = np.array([L.orc_tlwe_decrypt(kn, orc.ptr(sk), orc.ptr(np.ascontiguousarray(cts[i]))) for i in range(batch)], dtype=np.uint64)
+    assert np.array_equal(ph, want)
+    assert np.array_equal(fhe.torus_decode(ph, t)[:-1], msgs[:-1])
+    for n, k in ((64, 4), (1024, 1), (16, 2)):
+        glwe = (k + 1) * n
+        skp = np.empty(k * n, dtype=np.uint64)
+        L.orc_tglwe_keygen(4, n, k, orc.ptr(skp))
+        m = orc.uniform(5, (6, n), t)
+        ct = np.empty((6, glwe), dtype=np.uint64)
+        for i in range(6):
+            pt = np.empty(n, dtype=np.uint64)
+            L.orc_tglwe_encode(n, t, orc.ptr(np.ascontiguousarray(m[i])), orc.ptr(pt))
+            L.orc_tglwe_encrypt_s(20 + i, n, k, 3.2, orc.ptr(skp), orc.ptr(pt), 0, orc.ptr(ct[i]))
+        ct[-1] = orc.uniform(6, glwe)
+        p = fhe.tglwe_decrypt(n, k, skp, ct)
+        wantp = np.empty((6, n), dtype=np.uint64)
+        for i in range(6):
+            L.orc_tglwe_decrypt(n, k, orc.ptr(skp), orc.ptr(np.ascontiguousarray(ct[i])), orc.ptr(wantp[i]))
+        assert np.array_equal(p, wantp)
+        assert np.array_equal(fhe.torus_decode(p, t)[:-1], m[:-1])
