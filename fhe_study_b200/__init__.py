@@ -412,6 +412,15 @@ def bootstrap_chain(n, k, bsk, table, ct, c_kn, mode=1, ksk: Ksk = None, out=Non
     return out
 
 
+def tlwe_encrypt(kn, sk, msgs, sigma=3.2, seed=0, uniform_mask=True, out=None):
+    """TLWE::encrypt_s (tfhe/src/tlwe.rs:71-74) of already-encoded messages, sampled on the device."""
+    batch = _numel(msgs)
+    out = _new(msgs, (batch, int(kn) + 1)) if out is None else out
+    _check_u64(sk, msgs, out)
+    check(lib.fhe_tlwe_encrypt(int(kn), ptr(sk), ptr(msgs), float(sigma), int(seed), int(bool(uniform_mask)), ptr(out), batch))
+    return out
+
+
 def tlwe_decrypt(kn, sk, ct, out=None):
     """TLWE::decrypt (tfhe/src/tlwe.rs:80-82): the phase b - <a, sk> of every ciphertext."""
     batch = _numel(ct) // (int(kn) + 1)

@@ -56,6 +56,7 @@ SIGNATURES = {
     "fhe_tn_neg": (I, [P, P, SZ]),
     "fhe_tn_left_rotate": (I, [U64, P, P, U64, P, SZ]),
     "fhe_tggsw_load": (I, [U64, U64, P, C.POINTER(P)]),
+    "fhe_tlwe_encrypt": (I, [U64, P, P, C.c_double, U64, I, P, SZ]),
     "fhe_tlwe_decrypt": (I, [U64, P, P, P, SZ]),
     "fhe_tglwe_decrypt": (I, [U64, U64, P, P, P, SZ]),
     "fhe_tggsw_generate": (I, [U64, U64, P, P, C.c_double, U64, I, P, C.POINTER(P)]),

@@ -118,6 +118,23 @@ int fhe_key_switch(const fhe_ksk *h, const uint64_t *ct, uint64_t *out, size_t b
     return finish_all({&bi, &bo}, st);
 }
 
+// TLWE::encrypt_s for `batch` already-encoded messages (counter-based sampler, row b of the stream = ciphertext b)
+int fhe_tlwe_encrypt(uint64_t kn, const uint64_t *sk, const uint64_t *msgs, double sigma, uint64_t seed, int uniform_mask,
+                     uint64_t *ct, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(sk && msgs && ct, "fhe_tlwe_encrypt: null pointer");
+    FHE_REQUIRE(kn >= 1 && kn < (1ull << 31), "fhe_tlwe_encrypt: kn out of range");
+    cudaStream_t st = current_stream();
+    IoBuf bs, bm, bo;
+    int rc;
+    if ((rc = bs.init(sk, kn * 8, true, false, st))) return rc;
+    if ((rc = bm.init(msgs, batch * 8, true, false, st))) return rc;
+    if ((rc = bo.init(ct, batch * (kn + 1) * 8, false, true, st))) return rc;
+    if ((rc = tlwe_encrypt_device(bo.ptr<u64>(), bs.ptr<u64>(), bm.ptr<u64>(), batch, seed, (u32)kn, sigma, uniform_mask != 0, st)))
+        return rc;
+    return finish_all({&bs, &bm, &bo}, st);
+}
+
 // TLWE::decrypt for `batch` TLWEs under one secret key: phases, not yet decoded
 int fhe_tlwe_decrypt(uint64_t kn, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch) {
     if (batch == 0) return 0;

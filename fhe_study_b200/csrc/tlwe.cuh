@@ -27,6 +27,8 @@ int key_switch_bcol_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, 
 int key_switch_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int rotate_extract_device(const u64 *table, const u64 *ct, u64 *ext, u64 *acc_out, size_t batch, u32 n, u32 k, u32 c_kn,
                           cudaStream_t st);
+int tlwe_encrypt_device(u64 *out, const u64 *sk, const u64 *msgs, size_t batch, u64 seed, u32 kn, double sigma, int uniform_mask,
+                        cudaStream_t st);
 int tlwe_decrypt_device(const u64 *sk, const u64 *ct, u64 *out, size_t batch, u32 kn, cudaStream_t st);
 int chain_prepare_device(const u64 *table, const u64 *ct, u64 *acc0, u64 *hs, size_t batch, u32 n, u32 k, u32 c_kn,
                          u32 steps, int mode, cudaStream_t st);

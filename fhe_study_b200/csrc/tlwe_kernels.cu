@@ -112,9 +112,10 @@ __device__ __forceinline__ double ctr_unit(u64 v) { return __dmul_rn(__ull2doubl
 __device__ __forceinline__ u64 f64_as_u64_sat(double x) { return __double2ull_rz(x); }  // Rust `as u64`: saturating, NaN -> 0
 __global__ void __launch_bounds__(256)
 ksk_generate_kernel(u64 *__restrict__ rows, const u64 *__restrict__ sk, const u64 *__restrict__ new_sk, u64 seed, u32 kn_in,
-                    u32 kn_out, u32 l, double sigma, int uniform_mask) {
+                    u32 kn_out, u32 l, double sigma, int uniform_mask, const u64 *__restrict__ msgs, size_t nmsgs) {
+    // msgs != nullptr: plain batch encryption, row r = TLWE_{new_sk}(msgs[r]) (TLWE::encrypt_s, tlwe.rs:71-74)
     const u32 lane = threadIdx.x & 31;
-    const size_t nrows = (size_t)kn_in * l, per_row = (size_t)kn_out + 12, w = (size_t)kn_out + 1;
+    const size_t nrows = msgs ? nmsgs : (size_t)kn_in * l, per_row = (size_t)kn_out + 12, w = (size_t)kn_out + 1;
     for (size_t r = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < nrows; r += (size_t)gridDim.x * 8) {
         const size_t base = r * per_row;
         u64 *row = rows + r * w;
@@ -130,9 +131,14 @@ ksk_generate_kernel(u64 *__restrict__ rows, const u64 *__restrict__ sk, const u6
         if (lane == 0) {
             double acc = 0.0;
             for (u32 t = 0; t < 12; t++) acc = __dadd_rn(acc, ctr_unit(ctr_draw(seed, base + kn_out + t)));
-            const u32 i = (u32)(r / l), lv = (u32)(r % l) + 1;
-            const u64 g = lv < 64 ? ~0ull / (1ull << lv) : 1ull;
-            row[kn_out] = part + sk[i] * g + f64_as_u64_sat(round(__dmul_rn(sigma, __dadd_rn(acc, -6.0))));
+            u64 msg;
+            if (msgs) {
+                msg = msgs[r];
+            } else {
+                const u32 i = (u32)(r / l), lv = (u32)(r % l) + 1;
+                msg = sk[i] * (lv < 64 ? ~0ull / (1ull << lv) : 1ull);
+            }
+            row[kn_out] = part + msg + f64_as_u64_sat(round(__dmul_rn(sigma, __dadd_rn(acc, -6.0))));
         }
     }
 }
@@ -140,7 +146,15 @@ int ksk_generate_device(u64 *rows, const u64 *sk, const u64 *new_sk, u64 seed, u
                         int uniform_mask, cudaStream_t st) {
     const size_t nrows = (size_t)kn_in * l;
     const unsigned grid = (unsigned)std::min<size_t>((nrows + 7) / 8, (size_t)num_sms() * 16);
-    ksk_generate_kernel<<<grid, 256, 0, st>>>(rows, sk, new_sk, seed, kn_in, kn_out, l, sigma, uniform_mask);
+    ksk_generate_kernel<<<grid, 256, 0, st>>>(rows, sk, new_sk, seed, kn_in, kn_out, l, sigma, uniform_mask, nullptr, 0);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int tlwe_encrypt_device(u64 *out, const u64 *sk, const u64 *msgs, size_t batch, u64 seed, u32 kn, double sigma, int uniform_mask,
+                        cudaStream_t st) {
+    const unsigned grid = (unsigned)std::min<size_t>((batch + 7) / 8, (size_t)num_sms() * 16);
+    ksk_generate_kernel<<<grid, 256, 0, st>>>(out, nullptr, sk, seed, 0, kn, 1, sigma, uniform_mask, msgs, batch);
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;

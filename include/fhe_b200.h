@@ -143,6 +143,11 @@ FHE_API int fhe_ksk_export(const fhe_ksk *handle, uint64_t *rows);
 FHE_API void fhe_ksk_destroy(fhe_ksk *handle);
 /* TLWE::key_switch(param, 2, l, ksk) (tlwe.rs:101-112): `batch` TLWEs of kn_in+1 words -> kn_out+1 words. */
 FHE_API int fhe_key_switch(const fhe_ksk *handle, const uint64_t *ct, uint64_t *out, size_t batch);
+/* TLWE::encrypt_s (tlwe.rs:71-74 over glwe.rs:140-156) for `batch` already-encoded messages (TLWE::encode, tlwe.rs:52-59:
+ * m * (u64::MAX / t)), sampled on the device with the counter-based sampler of fhe_ksk_generate: ciphertext b is row b of
+ * the stream (the CPU restatement orc_tlwe_encrypt_ctr gives the same words). */
+FHE_API int fhe_tlwe_encrypt(uint64_t kn, const uint64_t *sk, const uint64_t *msgs, double sigma, uint64_t seed,
+                             int uniform_mask, uint64_t *ct, size_t batch);
 /* TLWE::decrypt (tlwe.rs:80-82 over glwe.rs:175-179): p_b = ct_b.b - <ct_b.a, sk> for `batch` TLWEs of kn+1 words; the
  * phases are decoded with fhe_tn_mul_div_round(p, t, u64::MAX) and a reduction mod t (TLWE::decode, tlwe.rs:60-63). */
 FHE_API int fhe_tlwe_decrypt(uint64_t kn, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch);

@@ -871,6 +871,24 @@ API void orc_tlwe_new_ksk_ctr(u64 seed, u64 kn_in, u64 kn_out, uint32_t l, doubl
     }
 }
 
+/* TLWE::encrypt_s (tlwe.rs:71-74) of `batch` encoded messages with the same counter-based sampler: ciphertext b uses
+ * the draws of row b (what fhe_tlwe_encrypt reproduces). */
+API void orc_tlwe_encrypt_ctr(u64 seed, u64 kn, double sigma, const u64 *sk, const u64 *msgs, u64 batch, int uniform_mask, u64 *ct) {
+    u64 w = kn + 1, per_row = kn + 12;
+    for (u64 r = 0; r < batch; r++) {
+        u64 *row = ct + r * w, base = r * per_row, b = 0;
+        for (u64 x = 0; x < kn; x++) {
+            u64 v = ctr_draw(seed, base + x);
+            u64 a = uniform_mask ? v : f64_as_u64(round(2.0 * ctr_unit(v)));
+            row[x] = a;
+            b += a * sk[x];
+        }
+        double acc = 0.0;
+        for (u64 t = 0; t < 12; t++) acc += ctr_unit(ctr_draw(seed, base + kn + t));
+        row[kn] = b + msgs[r] + f64_as_u64(round(sigma * (acc - 6.0)));
+    }
+}
+
 /* TGGSW::encrypt_s (tggsw.rs:17-33 -> tggsw.rs:100-122 -> glwe.rs:140-156 with R = Tn) with the counter-based sampler of
  * orc_tlwe_new_ksk_ctr: row r = i*64 + (lv-1) (i = 0..k: TGLev of -s_i*m for i < k, of m for i = k) is
  * TGLWE_sk(mi * g_lv).  Draw p of row r is output number r*(k*n + 12*n) + p + 1 of SplitMix64(seed):

@@ -247,3 +247,17 @@ def test_tlwe_and_tglwe_decrypt_decode(fhe, orc):
             L.orc_tglwe_decrypt(n, k, orc.ptr(skp), orc.ptr(np.ascontiguousarray(ct[i])), orc.ptr(wantp[i]))
         assert np.array_equal(p, wantp)
         assert np.array_equal(fhe.torus_decode(p, t)[:-1], m[:-1])
+
+
+def test_tlwe_encrypt_on_device_roundtrip(fhe, orc):
+    # TLWE::encrypt_s on the device (counter-based sampler): bit-exact against the oracle, and decrypt+decode gives m back
+    kn, t, batch = 630, 16, 333
+    sk = orc.uniform(1, kn) & np.uint64(1)
+    msgs = orc.uniform(2, batch, t)
+    enc = msgs * np.uint64((2**64 - 1) // t)
+    for uniform in (True, False):
+        ct = fhe.tlwe_encrypt(kn, sk, enc, sigma=3.2, seed=42, uniform_mask=uniform)
+        want = np.empty((batch, kn + 1), dtype=np.uint64)
+        orc.lib().orc_tlwe_encrypt_ctr(42, kn, 3.2, orc.ptr(sk), orc.ptr(enc), batch, int(uniform), orc.ptr(want))
+        assert np.array_equal(ct, want)
+        assert np.array_equal(fhe.torus_decode(fhe.tlwe_decrypt(kn, sk, ct), t), msgs)
