@@ -101,3 +101,28 @@ def test_bootstrap_chain_with_device_generated_keys(fhe, orc):
     for m in range(t):
         phase = int(orc.lib().orc_tlwe_decrypt(k * n, orc.ptr(z), orc.ptr(np.ascontiguousarray(out[m]))))
         assert round(phase / delta) % t == m
+
+
+def test_whole_tfhe_pipeline_on_the_gpu(fhe, orc):
+    # keys sampled on the device (fhe_tggsw_generate, fhe_ksk_generate), inputs encrypted on the device (fhe_tlwe_encrypt),
+    # programmable bootstrap = CMux chain + sample extraction + key switch, outputs decrypted and decoded on the device:
+    # the messages come back (the functional property of tfhe/src/tlwe.rs:465-504 for a blind rotation that really runs)
+    n, k, m_lwe, t, batch = 64, 1, 8, 4, 40
+    kn = n * k
+    s = orc.uniform(1, m_lwe) & np.uint64(1)       # input LWE key
+    z = orc.uniform(2, kn) & np.uint64(1)          # GLWE key (k polynomials) = extracted TLWE key
+    s2 = orc.uniform(3, kn) & np.uint64(1)         # key after the key switch
+    bsk = []
+    for j in range(m_lwe):
+        msg = np.zeros(n, dtype=np.uint64)
+        msg[0] = s[j]
+        bsk.append(fhe.Tggsw.generate(n, k, z, msg, sigma=3.2, seed=100 + j))
+    K = fhe.Ksk.generate(kn, kn, 64, z, s2, sigma=3.2, seed=200)
+    table = orc.lookup_table(n, k, t)
+    msgs = orc.uniform(4, batch, t)
+    delta_n = n // t
+    enc = (msgs * np.uint64(delta_n) + np.uint64(delta_n // 2)) * np.uint64(2**64 // (2 * n))  # centre of the LUT window
+    cts = fhe.tlwe_encrypt(m_lwe, s, enc, sigma=3.2, seed=300)
+    out = fhe.bootstrap_chain(n, k, bsk, table, cts, m_lwe, mode=1, ksk=K)
+    got = fhe.torus_decode(fhe.tlwe_decrypt(kn, s2, out), t)
+    assert np.array_equal(got, msgs)
