@@ -430,6 +430,15 @@ def tlwe_decrypt(kn, sk, ct, out=None):
     return out
 
 
+def tglwe_encrypt(n, k, sk, msgs, sigma=3.2, seed=0, uniform_mask=True, out=None):
+    """TGLWE::encrypt_s (tfhe/src/tglwe.rs:76-79) of already-encoded message polynomials, sampled on the device."""
+    batch = _numel(msgs) // int(n)
+    out = _new(msgs, (batch, (int(k) + 1) * int(n))) if out is None else out
+    _check_u64(sk, msgs, out)
+    check(lib.fhe_tglwe_encrypt(int(n), int(k), ptr(sk), ptr(msgs), float(sigma), int(seed), int(bool(uniform_mask)), ptr(out), batch))
+    return out
+
+
 def tglwe_decrypt(n, k, sk, ct, out=None):
     """TGLWE::decrypt (tfhe/src/tglwe.rs:86-88): b - sum_i a_i * sk_i."""
     batch = _numel(ct) // ((int(k) + 1) * int(n))

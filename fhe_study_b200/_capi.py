@@ -58,6 +58,7 @@ SIGNATURES = {
     "fhe_tggsw_load": (I, [U64, U64, P, C.POINTER(P)]),
     "fhe_tlwe_encrypt": (I, [U64, P, P, C.c_double, U64, I, P, SZ]),
     "fhe_tlwe_decrypt": (I, [U64, P, P, P, SZ]),
+    "fhe_tglwe_encrypt": (I, [U64, U64, P, P, C.c_double, U64, I, P, SZ]),
     "fhe_tglwe_decrypt": (I, [U64, U64, P, P, P, SZ]),
     "fhe_tggsw_generate": (I, [U64, U64, P, P, C.c_double, U64, I, P, C.POINTER(P)]),
     "fhe_tggsw_destroy": (None, [P]),

@@ -135,6 +135,24 @@ int fhe_tggsw_generate(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_
     *out = h.release();
     return 0;
 }
+// TGLWE::encrypt_s for `batch` already-encoded message polynomials (counter-based sampler)
+int fhe_tglwe_encrypt(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *msgs, double sigma, uint64_t seed,
+                      int uniform_mask, uint64_t *ct, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(sk && msgs && ct, "fhe_tglwe_encrypt: null pointer");
+    FHE_REQUIRE(k >= 1, "fhe_tglwe_encrypt: k must be >= 1");
+    TorusCtx *tc;
+    int rc = get_torus_ctx(n, &tc);
+    if (rc) return rc;
+    cudaStream_t st = current_stream();
+    IoBuf bs, bm, bo;
+    if ((rc = bs.init(sk, k * n * 8, true, false, st))) return rc;
+    if ((rc = bm.init(msgs, batch * n * 8, true, false, st))) return rc;
+    if ((rc = bo.init(ct, batch * (k + 1) * n * 8, false, true, st))) return rc;
+    if ((rc = tglwe_encrypt_device(*tc, k, bs.ptr<u64>(), bm.ptr<u64>(), batch, sigma, seed, uniform_mask != 0, bo.ptr<u64>(), st)))
+        return rc;
+    return finish_all({&bs, &bm, &bo}, st);
+}
 // TGLWE::decrypt for `batch` TGLWEs under one secret key (k polynomials): phases, not yet decoded
 int fhe_tglwe_decrypt(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch) {
     if (batch == 0) return 0;

@@ -72,6 +72,8 @@ bool extprod_fused_supported(int logn, int k1);
 int tggsw_build_fused_layout(Tggsw &g, cudaStream_t st);
 int extprod_fused_device(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, int cmux, cudaStream_t st);
 int tggsw_precompute(Tggsw &g, const u64 *rows_dev, cudaStream_t st);
+int tglwe_encrypt_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *msgs, size_t batch, double sigma, u64 seed,
+                         int uniform_mask, u64 *out, cudaStream_t st);
 int tglwe_decrypt_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *ct, u64 *out, size_t batch, cudaStream_t st);
 int tggsw_generate_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *m, double sigma, u64 seed, int uniform_mask,
                           u64 *rows_out, cudaStream_t st);

@@ -332,8 +332,10 @@ __global__ void tggsw_gen_masks_kernel(u64 *__restrict__ A, u64 *__restrict__ S,
     }
 }
 // rows[r] = (A_r, sum_c P_{r,c} + mi_{r/64} * g_lv + e)
+// msgs != nullptr: plain batch encryption, row r = TGLWE_sk(msgs[r]) (TGLWE::encrypt_s, tglwe.rs:76-79)
 __global__ void tggsw_gen_finish_kernel(u64 *__restrict__ out, const u64 *__restrict__ A, const u64 *__restrict__ P,
-                                        const u64 *__restrict__ mi, u64 seed, u32 n, u32 k, u32 rows, double sigma) {
+                                        const u64 *__restrict__ mi, u64 seed, u32 n, u32 k, u32 rows, double sigma,
+                                        const u64 *__restrict__ msgs) {
     const size_t kn = (size_t)k * n, per_row = kn + 12 * (size_t)n, glwe = kn + n, total = (size_t)rows * glwe;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t r = idx / glwe, q = idx % glwe;
@@ -344,7 +346,8 @@ __global__ void tggsw_gen_finish_kernel(u64 *__restrict__ out, const u64 *__rest
         double acc = 0.0;
         for (u32 t = 0; t < 12; t++) acc = __dadd_rn(acc, tg_unit(tg_draw(seed, r * per_row + kn + 12 * (size_t)x + t)));
         const u64 g = lv < 64 ? ~0ull / (1ull << lv) : 1ull;
-        out[idx] = b + mi[(size_t)i * n + x] * g + __double2ull_rz(round(__dmul_rn(sigma, __dadd_rn(acc, -6.0))));
+        const u64 msg = msgs ? msgs[r * n + x] : mi[(size_t)i * n + x] * g;
+        out[idx] = b + msg + __double2ull_rz(round(__dmul_rn(sigma, __dadd_rn(acc, -6.0))));
     }
 }
 // rows_out: (k+1)*64 TGLWEs of (k+1)*n words, device pointer
@@ -365,7 +368,30 @@ int tggsw_generate_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *m
     if ((rc = tn_mul_device(tc, sN.ptr<u64>(), sM.ptr<u64>(), mi, k, st))) return rc;          // mi_c = -s_c * m  (tggsw.rs:28)
     FHE_CUDA_OK(cudaMemcpyAsync(mi + kn, m, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));       // mi_k = m
     if ((rc = tn_mul_device(tc, A, S, P, (size_t)rows * k, st))) return rc;                     // a_{r,c} * s_c
-    tggsw_gen_finish_kernel<<<grid_for((size_t)rows * (kn + n)), 256, 0, st>>>(rows_out, A, P, mi, seed, n, (u32)k, rows, sigma);
+    tggsw_gen_finish_kernel<<<grid_for((size_t)rows * (kn + n)), 256, 0, st>>>(rows_out, A, P, mi, seed, n, (u32)k, rows, sigma,
+                                                                              nullptr);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+// out[b] = TGLWE_sk(msgs[b]) for `batch` message polynomials (same sampler: ciphertext b uses the draws of row b)
+int tglwe_encrypt_device(const TorusCtx &tc, u64 k, const u64 *sk, const u64 *msgs, size_t batch, double sigma, u64 seed,
+                         int uniform_mask, u64 *out, cudaStream_t st) {
+    const u32 n = (u32)tc.n;
+    FHE_REQUIRE(batch < (1ull << 31), "tglwe encrypt: batch too large");
+    const size_t kn = (size_t)k * n, words = batch * kn;
+    Scratch sA, sS, sP, sN, sM;
+    int rc;
+    if ((rc = sA.alloc(words * 8, st)) || (rc = sS.alloc(words * 8, st)) || (rc = sP.alloc(words * 8, st)) ||
+        (rc = sN.alloc(kn * 8, st)) || (rc = sM.alloc(kn * 8, st)))
+        return rc;
+    tggsw_gen_masks_kernel<<<grid_for(words), 256, 0, st>>>(sA.ptr<u64>(), sS.ptr<u64>(), sN.ptr<u64>(), sM.ptr<u64>(), sk, msgs, seed,
+                                                          n, (u32)k, (u32)batch, uniform_mask);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    if ((rc = tn_mul_device(tc, sA.ptr<u64>(), sS.ptr<u64>(), sP.ptr<u64>(), batch * k, st))) return rc;
+    tggsw_gen_finish_kernel<<<grid_for(batch * (kn + n)), 256, 0, st>>>(out, sA.ptr<u64>(), sP.ptr<u64>(), nullptr, seed, n, (u32)k,
+                                                                       (u32)batch, sigma, msgs);
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -151,6 +151,11 @@ FHE_API int fhe_tlwe_encrypt(uint64_t kn, const uint64_t *sk, const uint64_t *ms
 /* TLWE::decrypt (tlwe.rs:80-82 over glwe.rs:175-179): p_b = ct_b.b - <ct_b.a, sk> for `batch` TLWEs of kn+1 words; the
  * phases are decoded with fhe_tn_mul_div_round(p, t, u64::MAX) and a reduction mod t (TLWE::decode, tlwe.rs:60-63). */
 FHE_API int fhe_tlwe_decrypt(uint64_t kn, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch);
+/* TGLWE::encrypt_s (tglwe.rs:76-79 over glwe.rs:140-156) for `batch` already-encoded message polynomials (TGLWE::encode,
+ * tglwe.rs:49-58), sampled on the device: ciphertext b uses the draws of row b of the stream of fhe_tggsw_generate (the CPU
+ * restatement orc_tglwe_encrypt_ctr gives the same words). */
+FHE_API int fhe_tglwe_encrypt(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *msgs, double sigma, uint64_t seed,
+                              int uniform_mask, uint64_t *ct, size_t batch);
 /* TGLWE::decrypt (tglwe.rs:86-88 over glwe.rs:175-179): p_b = ct_b.b - sum_i ct_b.a_i * sk_i for `batch` TGLWEs; sk = k
  * polynomials, p = batch * n words (decode as above, TGLWE::decode tglwe.rs:59-63). */
 FHE_API int fhe_tglwe_decrypt(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch);

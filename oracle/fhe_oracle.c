@@ -931,6 +931,32 @@ API void orc_tggsw_encrypt_s_ctr(u64 seed, u64 n, u64 k, double sigma, const u64
     free(mi); free(negs);
 }
 
+/* TGLWE::encrypt_s (tglwe.rs:76-79) of `batch` encoded message polynomials, sampler and draw addressing of
+ * orc_tggsw_encrypt_s_ctr with row = ciphertext index (what fhe_tglwe_encrypt reproduces). */
+API void orc_tglwe_encrypt_ctr(u64 seed, u64 n, u64 k, double sigma, const u64 *sk, const u64 *msgs, u64 batch, int uniform_mask,
+                               u64 *ct) {
+    u64 glwe = (k + 1) * n, per_row = k * n + 12 * n;
+    u64 *tmp = (u64 *)malloc(sizeof(u64) * n);
+    for (u64 r = 0; r < batch; r++) {
+        u64 *row = ct + r * glwe, *b = row + k * n, base = r * per_row;
+        for (u64 p = 0; p < k * n; p++) {
+            u64 v = ctr_draw(seed, base + p);
+            row[p] = uniform_mask ? v : f64_as_u64(round(2.0 * ctr_unit(v)));
+        }
+        memset(b, 0, sizeof(u64) * n);
+        for (u64 c = 0; c < k; c++) {
+            tn_mul_fast(n, row + c * n, sk + c * n, tmp);
+            for (u64 x = 0; x < n; x++) b[x] += tmp[x];
+        }
+        for (u64 x = 0; x < n; x++) {
+            double acc = 0.0;
+            for (u64 t = 0; t < 12; t++) acc += ctr_unit(ctr_draw(seed, base + k * n + 12 * x + t));
+            b[x] += msgs[r * n + x] + f64_as_u64(round(sigma * (acc - 6.0)));
+        }
+    }
+    free(tmp);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * gfhe: GLWE<Rq> / GLev<Rq> (gfhe/src/glwe.rs, gfhe/src/glev.rs) -- SURVEY 8f rank 2.
  * GLWE<Rq> flat layout: (k+1) polys of n (mask a_0..a_{k-1}, then body b).  KSK = k GLevs of l GLWEs:

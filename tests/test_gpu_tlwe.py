@@ -261,3 +261,17 @@ def test_tlwe_encrypt_on_device_roundtrip(fhe, orc):
         orc.lib().orc_tlwe_encrypt_ctr(42, kn, 3.2, orc.ptr(sk), orc.ptr(enc), batch, int(uniform), orc.ptr(want))
         assert np.array_equal(ct, want)
         assert np.array_equal(fhe.torus_decode(fhe.tlwe_decrypt(kn, sk, ct), t), msgs)
+
+
+@pytest.mark.parametrize("n,k", [(64, 4), (1024, 1), (16, 2)])
+def test_tglwe_encrypt_on_device_roundtrip(fhe, orc, n, k):
+    t, batch = 16, 9
+    sk = orc.uniform(1, k * n) & np.uint64(1)
+    msgs = orc.uniform(2, (batch, n), t)
+    enc = msgs * np.uint64((2**64 - 1) // t)  # TGLWE::encode (tglwe.rs:49-58)
+    for uniform in (True, False):
+        ct = fhe.tglwe_encrypt(n, k, sk, enc, sigma=3.2, seed=7, uniform_mask=uniform)
+        want = np.empty((batch, (k + 1) * n), dtype=np.uint64)
+        orc.lib().orc_tglwe_encrypt_ctr(7, n, k, 3.2, orc.ptr(sk), orc.ptr(enc), batch, int(uniform), orc.ptr(want))
+        assert np.array_equal(ct, want)
+        assert np.array_equal(fhe.torus_decode(fhe.tglwe_decrypt(n, k, sk, ct), t), msgs)
