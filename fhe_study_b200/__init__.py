@@ -492,6 +492,15 @@ def bfv_mul_relin(q, n, t, pq, rlk, a, b, out=None):
     return out
 
 
+def bfv_encrypt(plan: NttPlan, t, pk, m, sigma=3.2, seed=0, out=None):
+    """BFV::encrypt (bfv/src/lib.rs:142-160) of a batch of messages mod t, sampled on the device."""
+    batch = _numel(m) // plan.n
+    out = _new(m, (batch, 2 * plan.n)) if out is None else out
+    _check_u64(pk, m, out)
+    check(lib.fhe_bfv_encrypt(plan._h, plan.q, plan.n, int(t), ptr(pk), ptr(m), float(sigma), int(seed), ptr(out), batch))
+    return out
+
+
 def bfv_decrypt(plan: NttPlan, t, sk, ct, out=None):
     """BFV::decrypt (bfv/src/lib.rs:164-178) for a batch of RLWEs (2n words each) under one secret key."""
     batch = _numel(ct) // (2 * plan.n)

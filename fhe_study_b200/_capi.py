@@ -82,6 +82,7 @@ SIGNATURES = {
     "fhe_bfv_tensor": (I, [U64, U64, U64, P, P, P, SZ]),
     "fhe_bfv_relinearize": (I, [U64, U64, U64, P, P, P, SZ]),
     "fhe_bfv_mul_relin": (I, [U64, U64, U64, U64, P, P, P, P, SZ]),
+    "fhe_bfv_encrypt": (I, [P, U64, U64, U64, P, P, C.c_double, U64, P, SZ]),
     "fhe_bfv_decrypt": (I, [P, U64, U64, U64, P, P, P, SZ]),
     "fhe_rq_add": (I, [U64, P, P, P, SZ]),
     "fhe_rq_sub": (I, [U64, P, P, P, SZ]),

@@ -173,6 +173,46 @@ __global__ void bfv_decrypt_finish_kernel(const u64 *__restrict__ ct, const u64 
     }
 }
 
+// ---- BFV::encrypt (bfv/src/lib.rs:142-160) with a counter-based sampler (the CPU restatement orc_bfv_encrypt_ctr) -------
+// draw p of ciphertext r is SplitMix64 output r*25n + p + 1: p < n -> u_x = from_f64(-1 + 2 unit) (Uniform(-1,1), lib.rs:149);
+// n + 12x + t -> e1_x, 13n + 12x + t -> e2_x, each from_f64(sigma * (sum of 12 units - 6)) (Normal(0, sigma) stand-in)
+__device__ __forceinline__ u64 bfv_draw(u64 seed, u64 pos) {
+    u64 z = seed + (pos + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double bfv_unit(u64 v) { return __dmul_rn(__ull2double_rn(v >> 11), 1.0 / 9007199254740992.0); }
+__global__ void bfv_sample_u_kernel(u64 *__restrict__ U, size_t batch, u32 n, u64 q, u64 seed) {
+    const size_t total = batch * n;
+    const u64 mu = ~0ull / q;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / n;
+        const u32 x = (u32)(i % n);
+        U[i] = zq_from_f64(q, mu, __dadd_rn(-1.0, __dmul_rn(2.0, bfv_unit(bfv_draw(seed, r * 25 * (size_t)n + x)))));
+    }
+}
+__global__ void bfv_encrypt_finish_kernel(const u64 *__restrict__ P0, const u64 *__restrict__ P1, const u64 *__restrict__ m,
+                                          u64 *__restrict__ ct, size_t batch, u32 n, u64 q, u64 t, double sigma, u64 seed) {
+    const size_t total = batch * n;
+    const u64 mu = ~0ull / q, delta = q / t, dq = delta >= q ? delta % q : delta;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / n, base = r * 25 * (size_t)n;
+        const u32 x = (u32)(i % n);
+        double a1 = 0.0, a2 = 0.0;
+        for (u32 k = 0; k < 12; k++) {
+            a1 = __dadd_rn(a1, bfv_unit(bfv_draw(seed, base + n + 12 * (size_t)x + k)));
+            a2 = __dadd_rn(a2, bfv_unit(bfv_draw(seed, base + 13 * (size_t)n + 12 * (size_t)x + k)));
+        }
+        const u64 e1 = zq_from_f64(q, mu, __dmul_rn(sigma, __dadd_rn(a1, -6.0)));
+        const u64 e2 = zq_from_f64(q, mu, __dmul_rn(sigma, __dadd_rn(a2, -6.0)));
+        const u64 mv = m[i] >= q ? m[i] % q : m[i];                                     // m.remodule(q), ring_nq.rs:82-88
+        const u64 md = (u64)(((unsigned __int128)mv * dq) % q);                         // m * floor(q/t), ring_nq.rs:274-281
+        ct[r * 2 * n + x] = zq_add(q, zq_add(q, P0[i], e1), md);                        // &pk.0 * &u + e_1 + m*delta
+        ct[r * 2 * n + n + x] = zq_add(q, P1[i], e2);                                   // &pk.1 * &u + e_2
+    }
+}
+
 }  // namespace fhe
 
 struct fhe_ntt_plan;
@@ -183,6 +223,33 @@ int plan_launch(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, 
 
 using namespace fhe;
 extern "C" {
+int fhe_bfv_encrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, uint64_t t, const uint64_t *pk, const uint64_t *m,
+                    double sigma, uint64_t seed, uint64_t *ct, size_t batch) {
+    FHE_REQUIRE(plan != nullptr, "null plan");
+    if (batch == 0) return 0;
+    FHE_REQUIRE(pk && m && ct, "fhe_bfv_encrypt: null pointer");
+    FHE_REQUIRE(t >= 1 && q >= 2 && n >= 1, "fhe_bfv_encrypt: need t >= 1");
+    cudaStream_t st = current_stream();
+    IoBuf bp, bm, bc;
+    Scratch U, P0, P1;
+    int rc;
+    if ((rc = bp.init(pk, 2 * n * 8, true, false, st))) return rc;
+    if ((rc = bm.init(m, batch * n * 8, true, false, st))) return rc;
+    if ((rc = bc.init(ct, batch * 2 * n * 8, false, true, st))) return rc;
+    if ((rc = U.alloc(batch * n * 8, st)) || (rc = P0.alloc(batch * n * 8, st)) || (rc = P1.alloc(batch * n * 8, st))) return rc;
+    const unsigned grid = (unsigned)std::min<size_t>((batch * n + 255) / 256, (size_t)num_sms() * 16);
+    bfv_sample_u_kernel<<<grid, 256, 0, st>>>(U.ptr<u64>(), batch, (u32)n, q, seed);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    // pk.0 * u and pk.1 * u: one public-key polynomial against every u (Rq products are commutative: exact in Z_q)
+    if ((rc = plan_launch(plan, 2, U.ptr<u64>(), bp.ptr<u64>(), P0.ptr<u64>(), nullptr, batch, 4, st))) return rc;
+    if ((rc = plan_launch(plan, 2, U.ptr<u64>(), bp.ptr<u64>() + n, P1.ptr<u64>(), nullptr, batch, 4, st))) return rc;
+    bfv_encrypt_finish_kernel<<<grid, 256, 0, st>>>(P0.ptr<u64>(), P1.ptr<u64>(), bm.ptr<u64>(), bc.ptr<u64>(), batch, (u32)n, q, t,
+                                                  sigma, seed);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return finish_all({&bp, &bm, &bc}, st);
+}
 int fhe_bfv_decrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, uint64_t t, const uint64_t *sk, const uint64_t *ct,
                     uint64_t *m, size_t batch) {
     FHE_REQUIRE(plan != nullptr, "null plan");

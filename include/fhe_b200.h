@@ -209,6 +209,11 @@ FHE_API int fhe_bfv_relinearize(uint64_t q, uint64_t n, uint64_t pq, const uint6
 /* RLWE::mul (lib.rs:87-90) = tensor + relinearize_204, fused. */
 FHE_API int fhe_bfv_mul_relin(uint64_t q, uint64_t n, uint64_t t, uint64_t pq, const uint64_t *rlk, const uint64_t *a,
                               const uint64_t *b, uint64_t *out, size_t batch);
+/* BFV::encrypt (lib.rs:142-160) for `batch` messages (n words mod t each) under the public key pk = (pk0, pk1) (2n words),
+ * sampled on the device: c0 = pk0*u + e1 + m*floor(q/t), c1 = pk1*u + e2 with u from Uniform(-1,1) and e from a
+ * Normal(0, sigma) stand-in, counter-based sampler (the CPU restatement orc_bfv_encrypt_ctr gives the same words). */
+FHE_API int fhe_bfv_encrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, uint64_t t, const uint64_t *pk, const uint64_t *m,
+                            double sigma, uint64_t seed, uint64_t *ct, size_t batch);
 /* BFV::decrypt (lib.rs:164-178): m_b = ((c0 + c1 * s).mul_div_round(t, q)).remodule(t) for `batch` RLWEs (2n words each);
  * sk = the secret polynomial (n words), plan = the (q, n) plan (q and n are checked against it by the caller's types in the
  * reference; here they are passed so that the map kernels need no plan internals).  m: batch * n words. */

@@ -131,6 +131,7 @@ def _declare(L):
     d("orc_bootstrap_chain", None, U64, U64, U64, P, P, P, P, U64, I, P)
     d("orc_tlwe_new_ksk_ctr", None, U64, U64, U64, U32, D, P, P, I, P)
     d("orc_tlwe_encrypt_ctr", None, U64, U64, D, P, P, U64, I, P)
+    d("orc_bfv_encrypt_ctr", None, U64, U64, U64, U64, D, P, P, U64, P)
     d("orc_tglwe_encrypt_ctr", None, U64, U64, U64, D, P, P, U64, I, P)
     d("orc_tggsw_encrypt_s_ctr", None, U64, U64, U64, D, P, P, I, P)
     d("orc_glev_rq_mul", None, U64, U64, U64, U64, P, P, P)

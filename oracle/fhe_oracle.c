@@ -1073,6 +1073,32 @@ API void orc_bfv_encrypt(u64 seed, u64 q, u64 n, u64 t, const u64 *pk, const u64
     orc_rq_addsub(q, n, ct + n, e2, ct + n, 0);
     free(u);
 }
+/* BFV::encrypt (lib.rs:142-160) with the counter-based sampler the device reproduces (fhe_bfv_encrypt): draw p of ciphertext r
+ * is SplitMix64 output r*25n + p + 1; p < n: u_x; n + 12x + t: e1_x; 13n + 12x + t: e2_x (ctr_draw / ctr_unit above). */
+API void orc_bfv_encrypt_ctr(u64 seed, u64 q, u64 n, u64 t, double sigma, const u64 *pk, const u64 *msgs, u64 batch, u64 *ct) {
+    u64 *u = (u64 *)malloc(sizeof(u64) * 4 * n), *e1 = u + n, *e2 = e1 + n, *md = e2 + n;
+    for (u64 r = 0; r < batch; r++) {
+        u64 base = r * 25 * n, *c = ct + r * 2 * n;
+        for (u64 x = 0; x < n; x++) {
+            u[x] = orc_zq_from_f64(q, -1.0 + 2.0 * ctr_unit(ctr_draw(seed, base + x)));
+            double a1 = 0.0, a2 = 0.0;
+            for (u64 k = 0; k < 12; k++) {
+                a1 += ctr_unit(ctr_draw(seed, base + n + 12 * x + k));
+                a2 += ctr_unit(ctr_draw(seed, base + 13 * n + 12 * x + k));
+            }
+            e1[x] = orc_zq_from_f64(q, sigma * (a1 - 6.0));
+            e2[x] = orc_zq_from_f64(q, sigma * (a2 - 6.0));
+        }
+        orc_rq_remodule(n, msgs + r * n, q, md);
+        orc_rq_mul_u64(q, n, md, q / t, md);
+        orc_rq_mul(q, n, pk, u, c, 0, 0, NULL);
+        orc_rq_addsub(q, n, c, e1, c, 0);
+        orc_rq_addsub(q, n, c, md, c, 0);
+        orc_rq_mul(q, n, pk + n, u, c + n, 0, 0, NULL);
+        orc_rq_addsub(q, n, c + n, e2, c + n, 0);
+    }
+    free(u);
+}
 API void orc_bfv_decrypt(u64 q, u64 n, u64 t, const u64 *sk, const u64 *ct, u64 *m) {
     u64 *cs = (u64 *)malloc(sizeof(u64) * n);
     orc_rq_mul(q, n, ct + n, sk, cs, 0, 0, NULL);

@@ -174,3 +174,19 @@ def test_rq_mul_broadcast_operand(fhe, orc):
     want = orc.rq_mul_batch(q, n, a, np.tile(b, batch))
     assert np.array_equal(plan.mul(a, b, flags=fhe.B_BROADCAST), want)
     assert np.array_equal(plan.mul(a, plan.ntt(b), flags=fhe.B_BROADCAST | fhe.B_IS_EVALS), want)
+
+
+@pytest.mark.parametrize("q,n,t,batch", [(Q, 512, 32, 6), (Q, 128, 32, 25), (Q, 16, 2, 300), (0x3FFC0001, 64, 5, 7)])
+def test_bfv_encrypt_on_device_roundtrip(fhe, orc, q, n, t, batch):
+    # BFV::encrypt (bfv/src/lib.rs:142-160) sampled on the device: bit-exact against the oracle's counter-based restatement,
+    # and decrypt(encrypt(m)) == m as in test_encrypt_decrypt (lib.rs:281-307)
+    L = orc.lib()
+    sk, pk = np.empty(n, dtype=np.uint64), np.empty(2 * n, dtype=np.uint64)
+    L.orc_bfv_keygen(41, q, n, orc.ptr(sk), orc.ptr(pk))
+    msgs = orc.uniform(42, (batch, n), t)
+    plan = fhe.NttPlan(q, n)
+    ct = fhe.bfv_encrypt(plan, t, pk, msgs, sigma=3.2, seed=9)
+    want = np.empty((batch, 2 * n), dtype=np.uint64)
+    L.orc_bfv_encrypt_ctr(9, q, n, t, 3.2, orc.ptr(pk), orc.ptr(msgs), batch, orc.ptr(want))
+    assert np.array_equal(ct, want)
+    assert np.array_equal(fhe.bfv_decrypt(plan, t, sk, ct), msgs)
