@@ -190,3 +190,25 @@ def test_bfv_encrypt_on_device_roundtrip(fhe, orc, q, n, t, batch):
     L.orc_bfv_encrypt_ctr(9, q, n, t, 3.2, orc.ptr(pk), orc.ptr(msgs), batch, orc.ptr(want))
     assert np.array_equal(ct, want)
     assert np.array_equal(fhe.bfv_decrypt(plan, t, sk, ct), msgs)
+
+
+def test_bfv_pipeline_on_the_gpu(fhe, orc):
+    # encrypt -> ciphertext multiply + relinearise -> decrypt, all batched on the device, at the reference's test_mul_relin
+    # parameters (bfv/src/lib.rs:557-601): the decrypted product equals m1 * m2 in Z_t[X]/(X^n+1)
+    L = orc.lib()
+    q, n, t, batch = Q, 16, 2, 500
+    p = q * q
+    pq = p * q
+    sk, pk, rlk = np.empty(n, dtype=np.uint64), np.empty(2 * n, dtype=np.uint64), np.empty(2 * n, dtype=np.uint64)
+    L.orc_bfv_keygen(51, q, n, orc.ptr(sk), orc.ptr(pk))
+    L.orc_bfv_rlk_key(52, q, n, p, orc.ptr(sk), orc.ptr(rlk))
+    m1, m2 = orc.uniform(53, (batch, n), t), orc.uniform(54, (batch, n), t)
+    plan = fhe.NttPlan(q, n)
+    c1 = fhe.bfv_encrypt(plan, t, pk, m1, seed=1)
+    c2 = fhe.bfv_encrypt(plan, t, pk, m2, seed=2)
+    m3 = fhe.bfv_decrypt(plan, t, sk, fhe.bfv_mul_relin(q, n, t, pq, rlk, c1, c2))
+    want = np.empty((batch, n), dtype=np.uint64)
+    for i in range(batch):
+        L.orc_r_mul_to_rq(n, orc.ptr(orc.i64(m1[i])), orc.ptr(orc.i64(m2[i])), t, orc.ptr(want[i]))
+    # the reference's own test tolerates nothing: every coefficient of every product must match
+    assert np.array_equal(m3, want)
