@@ -179,6 +179,12 @@ struct TGLWE {  // GLWE<Tn>: k mask polynomials then the body, flat (tfhe/src/tg
         check(fhe_tn_left_rotate(n, data.data(), &h, k + 1, r.data.data(), k + 1));
         return r;
     }
+    Tn decrypt(const std::vector<uint64_t> &sk) const {  // tglwe.rs:86-88: b - sum_i a_i * sk_i (sk = k polynomials, flat)
+        if (sk.size() != k * n) throw std::runtime_error("fhe_b200: TGLWE::decrypt needs k*n key words");
+        Tn p = Tn::zero(RingParam{~0ull, n});
+        check(fhe_tglwe_decrypt(n, k, sk.data(), data.data(), p.coeffs.data(), 1));
+        return p;
+    }
     std::vector<uint64_t> sample_extraction(uint64_t h) const {  // tglwe.rs:89-115 -> TLWE of dimension k*n
         std::vector<uint64_t> out(k * n + 1);
         check(fhe_sample_extract(n, k, data.data(), h, out.data(), 1));
@@ -234,6 +240,18 @@ struct TLWE {  // GLWE<T64>: kn mask words then b (tfhe/src/tlwe.rs:37-40)
         std::vector<uint64_t> out(ksk.kn_out + 1);
         check(fhe_key_switch(ksk.handle(), data.data(), out.data(), 1));
         return TLWE(std::move(out));
+    }
+    uint64_t decrypt(const std::vector<uint64_t> &sk) const {  // tlwe.rs:80-82: the phase b - <a, sk>
+        if (sk.size() != kn()) throw std::runtime_error("fhe_b200: TLWE::decrypt needs a key of the ciphertext's dimension");
+        uint64_t p = 0;
+        check(fhe_tlwe_decrypt(kn(), sk.data(), data.data(), &p, 1));
+        return p;
+    }
+    static uint64_t decode(uint64_t t, uint64_t p) {  // tlwe.rs:60-63
+        uint64_t r = 0, m = 0;
+        check(fhe_tn_mul_div_round(&p, t, ~0ull, &r, 1));
+        check(fhe_rq_remodule(&r, t, &m, 1));
+        return m;
     }
     TLWE mod_switch(uint64_t q2) const {  // tlwe.rs:114-118
         std::vector<uint64_t> out(data.size());
@@ -334,6 +352,16 @@ class GLev {  // GLev<Rq>(Vec<GLWE<Rq>>) (gfhe/src/glev.rs:14), or the k*l rows 
 // ---- BFV --------------------------------------------------------------------------------------------------
 struct RLWE {  // bfv/src/lib.rs:35-47
     Rq c0, c1;
+    // BFV::decrypt (lib.rs:164-178): ((c0 + c1*s).mul_div_round(t, q)).remodule(t)
+    static Rq decrypt(uint64_t t, const Rq &sk, const RLWE &c) {
+        detail::same(sk.param, c.c0.param);
+        const RingParam p = c.c0.param;
+        std::vector<uint64_t> flat(c.c0.coeffs);
+        flat.insert(flat.end(), c.c1.coeffs.begin(), c.c1.coeffs.end());
+        Rq m = Rq::zero(RingParam{t, p.n});
+        check(fhe_bfv_decrypt(detail::plan(p).get(), p.q, p.n, t, sk.coeffs.data(), flat.data(), m.coeffs.data(), 1));
+        return m;
+    }
     // RLWE::mul (lib.rs:87-90) = tensor + relinearize_204; rlk = (rlk0, rlk1) with coefficients mod pq
     static RLWE mul(uint64_t t, uint64_t pq, const std::pair<std::vector<uint64_t>, std::vector<uint64_t>> &rlk, const RLWE &a,
                     const RLWE &b) {

@@ -125,6 +125,22 @@ int main() {
         std::copy(ct.data.begin() + k * p.n, ct.data.end(), expect.data.begin() + k * p.n);
         EXPECT(ks == expect);
     }
+    {   // decrypt entry points: a trivial TLWE (zero mask) decrypts to its body; a trivial TGLWE to its body polynomial;
+        // a BFV ciphertext (m * floor(q/t), 0) to m
+        std::vector<uint64_t> c(9, 0), sk(8, 1);
+        c[8] = 5 * (~0ull / 16);
+        TLWE tl(c);
+        EXPECT(tl.decrypt(sk) == c[8] && TLWE::decode(16, tl.decrypt(sk)) == 5);
+        TGLWE tg(64, 1);
+        for (size_t x = 0; x < 64; x++) tg.data[64 + x] = x * (~0ull / 128);
+        std::vector<uint64_t> z(64, 1);
+        EXPECT(tg.decrypt(z).coeffs == std::vector<uint64_t>(tg.data.begin() + 64, tg.data.end()));
+        RingParam p{Q, 16};
+        std::vector<uint64_t> m(16), c0(16);
+        for (size_t x = 0; x < 16; x++) { m[x] = x % 8; c0[x] = m[x] * (Q / 8); }
+        RLWE ct{Rq(p, c0), Rq::zero(p)};
+        EXPECT(RLWE::decrypt(8, Rq(p, std::vector<uint64_t>(16, 1)), ct).coeffs == m);
+    }
     std::printf(failures ? "%d FAILURES\n" : "ALL OK\n", failures);
     return failures ? 1 : 0;
 }
