@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfhe_b200.so")
+# FHE_B200_LIB: a tuning variant of the same CUDA library (see build.py), for A/B measurements only.
+LIB_PATH = os.environ.get("FHE_B200_LIB") or os.path.join(_HERE, "libfhe_b200.so")
 
 U64 = C.c_uint64
 SZ = C.c_size_t

@@ -12,8 +12,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libfhe_b200.so")
+# FHE_BUILD_DIR / FHE_LIB_OUT: build a tuning variant (with FHE_EXTRA_NVCC_FLAGS) beside the product library;
+# FHE_B200_LIB (see _capi.py) then selects it for an A/B measurement.
+OBJ = os.environ.get("FHE_BUILD_DIR") or os.path.join(HERE, "_build")
+LIB = os.environ.get("FHE_LIB_OUT") or os.path.join(HERE, "libfhe_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -20,6 +20,8 @@
 
 namespace fhe {
 
+FHE_HD constexpr bool ntt_extra_at_back(int P, int rem) { return P >= 3 && rem == P - 1; }
+
 template <int LOGN, int LOGE> struct NttShape {
     static_assert(LOGE >= 1 && LOGE <= LOGN, "need 1 <= LOGE <= LOGN");
     static constexpr int N = 1 << LOGN;
@@ -27,8 +29,12 @@ template <int LOGN, int LOGE> struct NttShape {
     static constexpr int T = N / E;                         // threads per polynomial
     static constexpr int P = (LOGN + LOGE - 1) / LOGE;      // passes
     static constexpr int BASE = LOGN / P, REM = LOGN % P;
-    FHE_HD static constexpr int g(int p) { return BASE + (p < REM ? 1 : 0); }
-    FHE_HD static constexpr int s0(int p) { return p * BASE + (p < REM ? p : REM); }
+    // The REM passes that get one extra stage: the first REM, except when that would leave the last two passes
+    // unequal (REM == P-1, P >= 3) -- then the last REM.  Equal last passes make the exchange between them a
+    // transposition inside 2^g <= 32 consecutive threads, i.e. inside one warp (ntt_kernels.cuh: exch_in_warp).
+    static constexpr bool BACK = ntt_extra_at_back(P, REM);
+    FHE_HD static constexpr int g(int p) { return BASE + ((BACK ? p >= 1 : p < REM) ? 1 : 0); }
+    FHE_HD static constexpr int s0(int p) { return p * BASE + (BACK ? (p >= 1 ? p - 1 : 0) : (p < REM ? p : REM)); }
     FHE_HD static constexpr int nL(int p) { return LOGN - s0(p) - g(p); }
     // position of register slot e of thread tid in the layout of pass p
     FHE_HD static constexpr int pos(int p, int tid, int e) {
@@ -46,6 +52,7 @@ template <int LOGN, int LOGE> struct NttShape {
 inline int ntt_num_passes(int logn, int loge) { return (logn + loge - 1) / loge; }
 inline int ntt_pass_s0(int logn, int loge, int p) {
     const int P = ntt_num_passes(logn, loge), base = logn / P, rem = logn % P;
+    if (ntt_extra_at_back(P, rem)) return p * base + (p >= 1 ? p - 1 : 0);
     return p * base + (p < rem ? p : rem);
 }
 inline u64 tw_slot(int logn, int loge, u64 ref_index) {

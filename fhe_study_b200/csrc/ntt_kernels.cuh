@@ -41,33 +41,54 @@ template <int T> __device__ __forceinline__ void group_sync() {
     if (T <= 32) __syncwarp(); else __syncthreads();
 }
 
-// registers (layout of pass FROM) -> shared -> registers (layout of pass TO)
-template <class M, int LOGN, int LOGE, int FROM, int TO>
+// An exchange between ADJACENT passes a < b touches, per thread, a closed set of partners: the threads that share
+// the s0(a) high bits H and the nL(b) low bits of the butterfly-group index.  When g(a) == g(b) the g bits that
+// vary sit at [nL(b), nL(a)) in both layouts; with nL(a) <= 5 they are lane bits, so every partner is in the same
+// warp and __syncwarp orders the exchange (always the case for the LAST two passes once they are equal).
+template <int LOGN, int LOGE, int FROM, int TO> struct ExchScope {
+    typedef NttShape<LOGN, LOGE> S;
+    static constexpr int A = FROM < TO ? FROM : TO, B = FROM < TO ? TO : FROM;
+    static constexpr bool in_warp = S::T <= 32 || (B == A + 1 && S::g(A) == S::g(B) && S::nL(A) <= 5 && S::T % 32 == 0);
+};
+
+// registers (layout of pass FROM) -> shared -> registers (layout of pass TO).
+// LEAD = false drops the barrier in front of the writes: allowed when this thread's previous access to `sm` was
+// the read side of an exchange INTO layout FROM (it then overwrites exactly the words it read itself, so there is
+// no other reader to wait for) -- i.e. for every exchange of a chain but the first.
+template <class M, int LOGN, int LOGE, int FROM, int TO, bool LEAD = true>
 __device__ __forceinline__ void exchange(typename M::W (&x)[1 << LOGE], typename M::W *sm, int tid) {
     typedef NttShape<LOGN, LOGE> S;
-    group_sync<S::T>();  // earlier readers of sm are done
+#ifdef FHE_NTT_FULL_SYNC  // the conservative scheme (two CTA-wide barriers per exchange), kept for A/B measurements
+    group_sync<S::T>();
+#else
+    if constexpr (LEAD) group_sync<S::T>();  // earlier readers of sm are done
+#endif
 #pragma unroll
     for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(FROM, tid, e))] = x[e];
+#ifdef FHE_NTT_FULL_SYNC
     group_sync<S::T>();
+#else
+    if constexpr (ExchScope<LOGN, LOGE, FROM, TO>::in_warp) __syncwarp(); else __syncthreads();
+#endif
 #pragma unroll
     for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(TO, tid, e))];
 }
 
-template <class M, int LOGN, int LOGE, int PASS = 0>
+template <class M, int LOGN, int LOGE, int PASS = 0, bool FIRST = true>
 __device__ __forceinline__ void fwd_chain(typename M::W (&x)[1 << LOGE], typename M::W *sm, int tid, const M &m,
                                           const TwSrc<M> &tw) {
     typedef NttShape<LOGN, LOGE> S;
-    if constexpr (PASS > 0) exchange<M, LOGN, LOGE, PASS - 1, PASS>(x, sm, tid);
+    if constexpr (PASS > 0) exchange<M, LOGN, LOGE, PASS - 1, PASS, FIRST>(x, sm, tid);
     fwd_pass<M, LOGN, LOGE, PASS>(x, tid, m, tw);
-    if constexpr (PASS + 1 < S::P) fwd_chain<M, LOGN, LOGE, PASS + 1>(x, sm, tid, m, tw);
+    if constexpr (PASS + 1 < S::P) fwd_chain<M, LOGN, LOGE, PASS + 1, (FIRST && PASS == 0)>(x, sm, tid, m, tw);
 }
-template <class M, int LOGN, int LOGE, int PASS>
+template <class M, int LOGN, int LOGE, int PASS, bool FIRST = true>
 __device__ __forceinline__ void inv_chain(typename M::W (&x)[1 << LOGE], typename M::W *sm, int tid, const M &m,
                                           const TwSrc<M> &tw, typename M::T ninv, typename M::T s_ninv) {
     inv_pass<M, LOGN, LOGE, PASS>(x, tid, m, tw, ninv, s_ninv);
     if constexpr (PASS > 0) {
-        exchange<M, LOGN, LOGE, PASS, PASS - 1>(x, sm, tid);
-        inv_chain<M, LOGN, LOGE, PASS - 1>(x, sm, tid, m, tw, ninv, s_ninv);
+        exchange<M, LOGN, LOGE, PASS, PASS - 1, FIRST>(x, sm, tid);
+        inv_chain<M, LOGN, LOGE, PASS - 1, false>(x, sm, tid, m, tw, ninv, s_ninv);
     }
 }
 
@@ -80,12 +101,12 @@ __device__ __forceinline__ void load_poly(typename M::W (&x)[1 << LOGE], const u
     for (int e = 0; e < S::E; e++) x[e] = valid ? M::load(__ldg(g + S::pos(0, tid, e))) : (typename M::W)0;
     if constexpr (TO != 0) exchange<M, LOGN, LOGE, 0, TO>(x, sm, tid);
 }
-// registers in the layout of pass FROM -> global (coalesced)
-template <class M, int LOGN, int LOGE, int FROM>
+// registers in the layout of pass FROM -> global (coalesced).  LEAD as in exchange().
+template <class M, int LOGN, int LOGE, int FROM, bool LEAD = true>
 __device__ __forceinline__ void store_poly(typename M::W (&x)[1 << LOGE], u64 *__restrict__ g, bool valid,
                                            typename M::W *sm, int tid) {
     typedef NttShape<LOGN, LOGE> S;
-    if constexpr (FROM != 0) exchange<M, LOGN, LOGE, FROM, 0>(x, sm, tid);
+    if constexpr (FROM != 0) exchange<M, LOGN, LOGE, FROM, 0, LEAD>(x, sm, tid);
     if (valid) {
 #pragma unroll
         for (int e = 0; e < S::E; e++) g[S::pos(0, tid, e)] = M::store(x[e]);
@@ -159,7 +180,7 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
         fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, tw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.fwd_canon(x[e]);
-        store_poly<M, LOGN, LOGE, LAST>(x, c + off, valid, sm, tid);
+        store_poly<M, LOGN, LOGE, LAST, false>(x, c + off, valid, sm, tid);  // last smem access: own reads in layout LAST
     } else if constexpr (MODE == MODE_INV) {
         const TwSrc<M> tw = {P.c_inv, P.inv};
         load_poly<M, LOGN, LOGE, LAST>(x, a + off, valid, sm, tid);
@@ -207,9 +228,11 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
             W ev[S::E];
 #pragma unroll
             for (int e = 0; e < S::E; e++) ev[e] = m.pw_evals(x[e]);
-            store_poly<M, LOGN, LOGE, LAST>(ev, c_evals + off, valid, sm, tid);
+            // b's last smem access (end of its chain, or load_poly<LAST>) was this thread's reads in layout LAST
+            store_poly<M, LOGN, LOGE, LAST, false>(ev, c_evals + off, valid, sm, tid);
+            if constexpr (S::P > 1) group_sync<S::T>();  // the evals store read layout 0: foreign words
         }
-        inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, twi, P.ninv_pw, P.s_ninv_pw);
+        inv_chain<M, LOGN, LOGE, LAST, false>(x, sm, tid, m, twi, P.ninv_pw, P.s_ninv_pw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
         store_poly<M, LOGN, LOGE, 0>(x, c + off, valid, sm, tid);
