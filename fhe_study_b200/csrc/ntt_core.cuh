@@ -20,7 +20,13 @@
 
 namespace fhe {
 
-FHE_HD constexpr bool ntt_extra_at_back(int P, int rem) { return P >= 3 && rem == P - 1; }
+// Pass split.  Up to two passes: stages divided evenly, the odd one in front.  Three or more: every pass after the
+// first takes LOGE stages and pass 0 the remainder.  That (a) makes every layout the exchanges touch conflict-free
+// in shared memory under the i + (i >> 5) padding of 4-byte words (i + (i >> 4) for 8-byte words) -- a pass whose
+// butterfly groups keep fewer than 5 (4) low index bits puts two group rows of a warp on the same banks -- and
+// (b) leaves the last two passes equal, so the exchange between them stays inside one warp (ntt_kernels.cuh:
+// ExchScope).  ncu before the change (N=8192, split 5/4/4): 13.0 M bank conflicts in 38.5 M shared wavefronts.
+FHE_HD constexpr bool ntt_front_rem(int P) { return P >= 3; }
 
 template <int LOGN, int LOGE> struct NttShape {
     static_assert(LOGE >= 1 && LOGE <= LOGN, "need 1 <= LOGE <= LOGN");
@@ -29,12 +35,12 @@ template <int LOGN, int LOGE> struct NttShape {
     static constexpr int T = N / E;                         // threads per polynomial
     static constexpr int P = (LOGN + LOGE - 1) / LOGE;      // passes
     static constexpr int BASE = LOGN / P, REM = LOGN % P;
-    // The REM passes that get one extra stage: the first REM, except when that would leave the last two passes
-    // unequal (REM == P-1, P >= 3) -- then the last REM.  Equal last passes make the exchange between them a
-    // transposition inside 2^g <= 32 consecutive threads, i.e. inside one warp (ntt_kernels.cuh: exch_in_warp).
-    static constexpr bool BACK = ntt_extra_at_back(P, REM);
-    FHE_HD static constexpr int g(int p) { return BASE + ((BACK ? p >= 1 : p < REM) ? 1 : 0); }
-    FHE_HD static constexpr int s0(int p) { return p * BASE + (BACK ? (p >= 1 ? p - 1 : 0) : (p < REM ? p : REM)); }
+    static constexpr bool FRONT = ntt_front_rem(P);
+    static constexpr int G0 = LOGN - (P - 1) * LOGE;  // pass 0 of the FRONT rule
+    FHE_HD static constexpr int g(int p) { return FRONT ? (p == 0 ? G0 : LOGE) : BASE + (p < REM ? 1 : 0); }
+    FHE_HD static constexpr int s0(int p) {
+        return FRONT ? (p == 0 ? 0 : G0 + (p - 1) * LOGE) : p * BASE + (p < REM ? p : REM);
+    }
     FHE_HD static constexpr int nL(int p) { return LOGN - s0(p) - g(p); }
     // position of register slot e of thread tid in the layout of pass p
     FHE_HD static constexpr int pos(int p, int tid, int e) {
@@ -52,7 +58,7 @@ template <int LOGN, int LOGE> struct NttShape {
 inline int ntt_num_passes(int logn, int loge) { return (logn + loge - 1) / loge; }
 inline int ntt_pass_s0(int logn, int loge, int p) {
     const int P = ntt_num_passes(logn, loge), base = logn / P, rem = logn % P;
-    if (ntt_extra_at_back(P, rem)) return p * base + (p >= 1 ? p - 1 : 0);
+    if (ntt_front_rem(P)) return p == 0 ? 0 : (logn - (P - 1) * loge) + (p - 1) * loge;
     return p * base + (p < rem ? p : rem);
 }
 inline u64 tw_slot(int logn, int loge, u64 ref_index) {
@@ -68,12 +74,14 @@ inline u64 tw_slot(int logn, int loge, u64 ref_index) {
 }
 // coefficients per thread (log2): 32 for 32-bit words, 16 for 64-bit words (register budget of the
 // polymul kernel, which keeps NTT(a) in registers while transforming b)
-// Measured on B200 (q = 65537, fraction of HBM peak, 16 vs 32 coefficients per thread): N=2048 NTT 0.96 vs 0.86 and
-// polymul 0.59 vs 0.52; N=4096 polymul 0.52 vs 0.50 -- hence 16 per thread for those two degrees.
+// Measured on B200 (q = 65537, fraction of HBM peak, 16 vs 32 coefficients per thread, conflict-free pass split):
+// N=2048 NTT 0.97 vs 0.85, polymul 0.62 vs 0.61 -- hence 16 per thread there; N=4096 polymul 0.55 vs 0.60, INTT
+// 0.86 vs 0.90, NTT 0.90 vs 0.88 -- 32 per thread (with the old 4/4/4 split, two-way bank conflicts in the middle
+// pass, 16 per thread was the faster one at N=4096 too).
 template <class M> struct LogE {
     static constexpr int MAXE = sizeof(typename M::W) == 4 ? 5 : 4;
     static constexpr int of(int logn) {
-        return (sizeof(typename M::W) == 4 && (logn == 11 || logn == 12)) ? 4 : logn < MAXE ? logn : MAXE;
+        return (sizeof(typename M::W) == 4 && logn == 11) ? 4 : logn < MAXE ? logn : MAXE;
     }
 };
 

@@ -6,6 +6,7 @@
 // (mul / mul_mut: A = evals or ntt(a), B = evals or ntt(b), C = A.B pointwise, c = intt(C), the
 // result keeps C as its cached evals).
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 #include "ntt_core.cuh"
 
@@ -33,9 +34,12 @@ template <int LOGN, int LOGE> struct KernelGeom {
 #endif
     static constexpr int CT = S::T > FHE_NTT_MIN_CT ? S::T : FHE_NTT_MIN_CT;   // threads per CTA
     static constexpr int PPC = CT / S::T;                // polynomials per CTA
-    static constexpr int PADN = S::N + (S::N >> 5);      // padded words per polynomial in smem
+    template <int WB> __host__ __device__ static constexpr int padn() { return S::N + (S::N >> (WB == 4 ? 5 : 4)); }  // padded words per polynomial in smem
+    static constexpr int PADN = padn<4>();
 };
-__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }
+__host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 5); }
+// one pad word per 128 bytes: every 32 words of 4 bytes, every 16 words of 8 bytes
+template <int WB> __host__ __device__ constexpr int pad_idx_w(int i) { return i + (i >> (WB == 4 ? 5 : 4)); }
 
 template <int T> __device__ __forceinline__ void group_sync() {
     if (T <= 32) __syncwarp(); else __syncthreads();
@@ -63,15 +67,20 @@ __device__ __forceinline__ void exchange(typename M::W (&x)[1 << LOGE], typename
 #else
     if constexpr (LEAD) group_sync<S::T>();  // earlier readers of sm are done
 #endif
+    // pos(p, tid, e) = pos(p, tid, 0) | pos(p, 0, e) on disjoint bits (tid < T = 2^k and e >> g select different bits
+    // of the group index), and i + (i >> 5) is additive over disjoint bits: thread base + compile-time offset, so
+    // every STS/LDS below takes an immediate offset instead of per-element LOP3/LEA address arithmetic.
+    constexpr int WB = (int)sizeof(typename M::W);
+    const int bf = pad_idx_w<WB>(S::pos(FROM, tid, 0)), bt = pad_idx_w<WB>(S::pos(TO, tid, 0));
 #pragma unroll
-    for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(FROM, tid, e))] = x[e];
+    for (int e = 0; e < S::E; e++) sm[bf + pad_idx_w<WB>(S::pos(FROM, 0, e))] = x[e];
 #ifdef FHE_NTT_FULL_SYNC
     group_sync<S::T>();
 #else
     if constexpr (ExchScope<LOGN, LOGE, FROM, TO>::in_warp) __syncwarp(); else __syncthreads();
 #endif
 #pragma unroll
-    for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(TO, tid, e))];
+    for (int e = 0; e < S::E; e++) x[e] = sm[bt + pad_idx_w<WB>(S::pos(TO, 0, e))];
 }
 
 template <class M, int LOGN, int LOGE, int PASS = 0, bool FIRST = true>
@@ -92,24 +101,61 @@ __device__ __forceinline__ void inv_chain(typename M::W (&x)[1 << LOGE], typenam
     }
 }
 
+// Polynomial data is touched once.  STREAM reads it without allocating in L1 and stores it evict-first, so that L1
+// keeps the twiddle tables (at N >= 4096 the per-thread twiddles of the last pass are as many bytes as the
+// polynomial).  Measured (q = 65537): polymul N=4096/8192/16384 +1/+2/+3 %, but the transform-only kernels LOSE
+// 2..7 % -- hence on for the polymul at N >= 4096 only (ntt_stream()).
+#ifndef FHE_NTT_STREAM
+#define FHE_NTT_STREAM 1
+#endif
+__host__ __device__ constexpr bool ntt_stream(int logn, int mode) { return FHE_NTT_STREAM && mode == 2 /* MODE_MUL */ && logn >= 12; }
+#ifndef FHE_NTT_PREFETCH
+#define FHE_NTT_PREFETCH 0  // measured slower (N=8192 polymul 0.47 -> 0.38 of HBM peak): kept for reference only
+#endif
+__host__ __device__ constexpr bool ntt_prefetch(int logn, int mode) { return FHE_NTT_PREFETCH && mode == 2 && logn >= 11; }
+// one prefetch per 128-byte line of an N-coefficient polynomial, spread over its T threads
+template <int N, int T> __device__ __forceinline__ void prefetch_poly_l2(const u64 *g, int tid) {
+    constexpr int LINES = N / 16;
+#pragma unroll
+    for (int i = 0; i < (LINES + T - 1) / T; i++) {
+        const int line = tid + i * T;
+        if (LINES % T == 0 || line < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (size_t)line * 16));
+    }
+}
+template <bool STREAM> __device__ __forceinline__ u64 ld_poly(const u64 *p) {
+    if constexpr (STREAM) {
+        u64 v;
+        asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+        return v;
+    } else {
+        return __ldg(p);
+    }
+}
+template <bool STREAM> __device__ __forceinline__ void st_poly(u64 *p, u64 v) {
+    if constexpr (STREAM) __stcs(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+    else *p = v;
+}
+
 // global (coalesced, layout of pass 0) -> registers in the layout of pass TO
-template <class M, int LOGN, int LOGE, int TO>
+template <class M, int LOGN, int LOGE, int TO, bool STREAM = false>
 __device__ __forceinline__ void load_poly(typename M::W (&x)[1 << LOGE], const u64 *__restrict__ g, bool valid,
                                           typename M::W *sm, int tid) {
     typedef NttShape<LOGN, LOGE> S;
+    const u64 *gt = g + S::pos(0, tid, 0);
 #pragma unroll
-    for (int e = 0; e < S::E; e++) x[e] = valid ? M::load(__ldg(g + S::pos(0, tid, e))) : (typename M::W)0;
+    for (int e = 0; e < S::E; e++) x[e] = valid ? M::load(ld_poly<STREAM>(gt + S::pos(0, 0, e))) : (typename M::W)0;
     if constexpr (TO != 0) exchange<M, LOGN, LOGE, 0, TO>(x, sm, tid);
 }
 // registers in the layout of pass FROM -> global (coalesced).  LEAD as in exchange().
-template <class M, int LOGN, int LOGE, int FROM, bool LEAD = true>
+template <class M, int LOGN, int LOGE, int FROM, bool LEAD = true, bool STREAM = false>
 __device__ __forceinline__ void store_poly(typename M::W (&x)[1 << LOGE], u64 *__restrict__ g, bool valid,
                                            typename M::W *sm, int tid) {
     typedef NttShape<LOGN, LOGE> S;
     if constexpr (FROM != 0) exchange<M, LOGN, LOGE, FROM, 0, LEAD>(x, sm, tid);
     if (valid) {
+        u64 *gt = g + S::pos(0, tid, 0);
 #pragma unroll
-        for (int e = 0; e < S::E; e++) g[S::pos(0, tid, e)] = M::store(x[e]);
+        for (int e = 0; e < S::E; e++) st_poly<STREAM>(gt + S::pos(0, 0, e), M::store(x[e]));
     }
 }
 
@@ -160,13 +206,13 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 template <class M, int LOGN, int LOGE, int MODE>
 __global__ void __launch_bounds__(KernelGeom<LOGN, LOGE>::CT, ASmem<M, LOGN, LOGE, MODE>::minb)
 ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, const u64 *__restrict__ b,
-           u64 *__restrict__ c, u64 *__restrict__ c_evals, size_t batch, int flags) {
+           u64 *__restrict__ c, u64 *__restrict__ c_evals, size_t batch, int flags, int pf_dist) {
     typedef NttShape<LOGN, LOGE> S;
     typedef KernelGeom<LOGN, LOGE> G;
     typedef typename M::W W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int slot = threadIdx.x / S::T, tid = threadIdx.x % S::T;
-    W *sm = reinterpret_cast<W *>(smem_raw) + (size_t)slot * G::PADN;
+    W *sm = reinterpret_cast<W *>(smem_raw) + (size_t)slot * G::template padn<sizeof(W)>();
     const size_t poly = (size_t)blockIdx.x * G::PPC + slot;
     const bool valid = poly < batch;
     const size_t off = poly * S::N;
@@ -192,17 +238,30 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
         const TwSrc<M> twf = {P.c_fwd, P.fwd};
         const TwSrc<M> twi = {P.c_inv, P.inv};
         constexpr bool PARK = ASmem<M, LOGN, LOGE, MODE>::on;
+        constexpr bool ST = ntt_stream(LOGN, MODE);
+        if constexpr (ntt_prefetch(LOGN, MODE)) {
+            // Pull b into L2 while a is loaded and transformed, and both operands of the polynomial this SM slot
+            // will most likely process next (pf_dist = CTAs resident on the whole GPU, CTAs being dispatched in
+            // order): the few resident warps of the large degrees cannot hide an HBM round trip per operand.
+            const bool b_own = !(flags & B_BROADCAST);
+            if (valid && b_own) prefetch_poly_l2<S::N, S::T>(b + off, tid);
+            const size_t nxt = poly + (size_t)pf_dist * G::PPC;
+            if (pf_dist > 0 && nxt < batch) {
+                prefetch_poly_l2<S::N, S::T>(a + nxt * S::N, tid);
+                if (b_own) prefetch_poly_l2<S::N, S::T>(b + nxt * S::N, tid);
+            }
+        }
         W A[PARK ? 1 : S::E];
-        W *sA = reinterpret_cast<W *>(smem_raw) + (size_t)G::PPC * G::PADN + (size_t)slot * S::N;  // PARK only
+        W *sA = reinterpret_cast<W *>(smem_raw) + (size_t)G::PPC * G::template padn<sizeof(W)>() + (size_t)slot * S::N;  // PARK only
         // both operands run through ONE copy of the forward-transform code (the fully unrolled transform is
         // the bulk of the kernel's instruction footprint; see profiles/: no_instruction stalls)
 #pragma unroll 1
         for (int op = 0; op < 2; op++) {
             const u64 *src = op == 0 ? a + off : (flags & B_BROADCAST) ? b : b + off;
             if (flags & (op == 0 ? A_IS_EVALS : B_IS_EVALS)) {
-                load_poly<M, LOGN, LOGE, LAST>(x, src, valid, sm, tid);
+                load_poly<M, LOGN, LOGE, LAST, ST>(x, src, valid, sm, tid);
             } else {
-                load_poly<M, LOGN, LOGE, 0>(x, src, valid, sm, tid);
+                load_poly<M, LOGN, LOGE, 0, ST>(x, src, valid, sm, tid);
                 fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
 #pragma unroll
                 for (int e = 0; e < S::E; e++) x[e] = m.fwd_out(x[e]);
@@ -229,13 +288,13 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
 #pragma unroll
             for (int e = 0; e < S::E; e++) ev[e] = m.pw_evals(x[e]);
             // b's last smem access (end of its chain, or load_poly<LAST>) was this thread's reads in layout LAST
-            store_poly<M, LOGN, LOGE, LAST, false>(ev, c_evals + off, valid, sm, tid);
+            store_poly<M, LOGN, LOGE, LAST, false, ST>(ev, c_evals + off, valid, sm, tid);
             if constexpr (S::P > 1) group_sync<S::T>();  // the evals store read layout 0: foreign words
         }
         inv_chain<M, LOGN, LOGE, LAST, false>(x, sm, tid, m, twi, P.ninv_pw, P.s_ninv_pw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
-        store_poly<M, LOGN, LOGE, 0>(x, c + off, valid, sm, tid);
+        store_poly<M, LOGN, LOGE, 0, true, ST>(x, c + off, valid, sm, tid);
     }
 }
 
@@ -244,7 +303,7 @@ int launch_one(const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c
                cudaStream_t st) {
     typedef KernelGeom<LOGN, LOGE> G;
     auto kern = ntt_kernel<M, LOGN, LOGE, MODE>;
-    const size_t smem = (size_t)G::PPC * (G::PADN + (ASmem<M, LOGN, LOGE, MODE>::on ? G::S::N : 0)) * sizeof(typename M::W);
+    const size_t smem = (size_t)G::PPC * (G::template padn<sizeof(typename M::W)>() + (ASmem<M, LOGN, LOGE, MODE>::on ? G::S::N : 0)) * sizeof(typename M::W);
     if (smem > 48 * 1024) {  // opt in once per device (and per instantiation)
         static unsigned long long done_mask = 0;
         int dev = 0;
@@ -254,9 +313,30 @@ int launch_one(const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c
             done_mask |= 1ull << (dev & 63);
         }
     }
+    {   // tuning knob: FHE_NTT_CARVE = preferred shared-memory carve-out in percent (caps the resident CTAs, leaves
+        // the rest of the 256 KB to L1 for the twiddle tables); unset = the driver's choice
+        static int carve_done = 0;
+        if (!carve_done) {
+            if (const char *e = getenv("FHE_NTT_CARVE"))
+                FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+            carve_done = 1;
+        }
+    }
     const size_t grid = (batch + G::PPC - 1) / G::PPC;
     FHE_REQUIRE(grid <= 0x7fffffffull, "batch too large for one launch");
-    kern<<<(unsigned)grid, G::CT, smem, st>>>(P, a, b, c, c_evals, batch, flags);
+    int pf_dist = 0;
+    if constexpr (ntt_prefetch(LOGN, MODE)) {  // CTAs resident on the whole device (cached per device)
+        static int resident[64] = {0};
+        int dev = 0;
+        FHE_CUDA_OK(cudaGetDevice(&dev));
+        if (resident[dev & 63] == 0) {
+            int per_sm = 0;
+            FHE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::CT, smem));
+            resident[dev & 63] = (per_sm > 0 ? per_sm : 1) * num_sms();
+        }
+        pf_dist = resident[dev & 63];
+    }
+    kern<<<(unsigned)grid, G::CT, smem, st>>>(P, a, b, c, c_evals, batch, flags, pf_dist);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -11,8 +11,8 @@ Q = 65537
 def split(LOGN, LOGE):
     P = -(-LOGN // LOGE)
     base, rem = divmod(LOGN, P)
-    if P >= 3 and rem == P - 1:  # extras on the LAST passes, so that the last two are equal (ntt_core.cuh: BACK)
-        return [base] + [base + 1] * rem
+    if P >= 3:  # pass 0 takes the remainder, every later pass LOGE stages (ntt_core.cuh: FRONT)
+        return [LOGN - (P - 1) * LOGE] + [LOGE] * (P - 1)
     return [base + 1 if p < rem else base for p in range(P)]
 
 
