@@ -174,12 +174,13 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
     // The 32-bit polymul on 128-thread CTAs asks for five resident CTAs (<= 102 registers, no spills): measured
     // 0.775 of HBM peak at N=1024 against 0.74 with ptxas' unconstrained 139 registers (three CTAs).
     // measured (q = 65537, hbm fraction before -> after): polymul N=1024 0.74 -> 0.78 (CT=128, five CTAs); NTT N=16384
-    // 0.47 -> 0.57 (CT=512, two CTAs of 64 registers instead of one of ~100); CT=256: NTT slower when bounded
-    // (0.80 -> 0.73), polymul about even
+    // 0.47 -> 0.57 (CT=512, two CTAs of 64 registers instead of one of ~100).  CT=256 (N=8192): with immediate-offset
+    // exchanges ptxas settles for 48 registers on the forward transform and serialises its loads (0.71); a bound of
+    // three CTAs lets it spend 80 and hoist them (0.78) -- the opposite of what the bound did to the older code
     static constexpr int CT_ = KernelGeom<LOGN, LOGE>::CT;
     static constexpr bool W32 = sizeof(typename M::W) == 4;
 #ifndef FHE_NTT_MINB_256
-#define FHE_NTT_MINB_256 0
+#define FHE_NTT_MINB_256 3
 #endif
 #ifndef FHE_NTT_MINB_512
 #define FHE_NTT_MINB_512 2
