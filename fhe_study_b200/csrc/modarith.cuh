@@ -43,7 +43,10 @@ FHE_HD u64 umin(u64 a, u64 b) { return a < b ? a : b; }
 // A twiddle w with its Shoup companion wp = floor(w * 2^wordbits / q).
 // aligned to its size so that one vector load (LDG.64 / LDG.128) fetches both words; unaligned, the compiler
 // issued two scalar loads per twiddle (124 of the 188 LDG of the N=1024 polymul)
-template <typename W> struct alignas(2 * sizeof(W)) Tw { W w, wp; };
+#ifndef FHE_TW64_ALIGN
+#define FHE_TW64_ALIGN 16
+#endif
+template <typename W> struct alignas(sizeof(W) == 8 ? FHE_TW64_ALIGN : 2 * sizeof(W)) Tw { W w, wp; };
 typedef Tw<u32> Tw32;
 typedef Tw<u64> Tw64;
 
