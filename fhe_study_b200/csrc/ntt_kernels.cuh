@@ -191,6 +191,9 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 #ifndef FHE_MUL_MINB_256
 #define FHE_MUL_MINB_256 3
 #endif
+#ifndef FHE_MUL_MINB_E16   // 128-thread polymul CTAs with 16 coefficients per thread (N=2048)
+#define FHE_MUL_MINB_E16 8  // 63 registers, no spills: N=2048 polymul 0.652 (5 CTAs) -> 0.677 (6) -> 0.690 (7) -> 0.697 (8) -> 0.701 (9, spills)
+#endif
 #ifndef FHE_MUL64_MINB
 #define FHE_MUL64_MINB 0
 #endif
@@ -199,7 +202,7 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 #endif
     static constexpr int minb = on ? FHE_A_SMEM_MINB
                                 : !W32 ? (CT_ == 128 ? (MODE == MODE_MUL ? FHE_MUL64_MINB : FHE_NTT64_MINB) : 0)
-                                : MODE == MODE_MUL ? (CT_ == 128 ? FHE_MUL_MINB : CT_ == 64 ? 2 * FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0)
+                                : MODE == MODE_MUL ? (CT_ == 128 ? (LOGE == 4 ? FHE_MUL_MINB_E16 : FHE_MUL_MINB) : CT_ == 64 ? 2 * FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0)
                                 : (CT_ == 256 ? (MODE == MODE_INV ? FHE_INV_MINB_256 : FHE_NTT_MINB_256)
                                    : CT_ == 512 ? FHE_NTT_MINB_512 : 0);
 };
