@@ -228,6 +228,7 @@ struct Small32 {
     typedef Tw32 T;
     u32 q, q2;
     u32 qinv_neg;  // -q^-1 mod 2^32
+    u32 qinv;      //  q^-1 mod 2^32
     Tw32 one;      // w = 1           : mul_tw(x, one) = x mod q in [0,2q) for any 32-bit x
     Tw32 r;        // w = 2^32 mod q  : undoes the Montgomery factor
     u32 qk[16];    // 2q << K: offset of the K-th executed inverse stage (read from the constant bank by IADD3)
@@ -271,12 +272,14 @@ struct Small32 {
     FHE_HD u32 canon2(u32 x) const { return csub(x, q); }
     FHE_HD u32 fwd_out(u32 x) const { return x; }
     FHE_HD u32 fwd_canon(u32 x) const { return csub(mul_tw(x, one), q); }
-    // a*b*2^-32 mod q in [0,2q); needs a*b < q*2^32
+    // a*b*2^-32 mod q in (0,2q); needs a*b < q*2^32.  Subtractive Montgomery form: m = lo * q^-1, so m*q has the
+    // same low word as a*b and a*b - m*q = (hi - mulhi(m,q)) * 2^32 exactly; hi, mulhi(m,q) < q, and adding q makes
+    // the difference positive -- one IADD3 instead of the carry test (lo != 0) of the additive form.
     FHE_HD u32 pw_mul(u32 a, u32 b) const {
         u64 p = (u64)a * b;
         u32 lo = (u32)p, hi = (u32)(p >> 32);
-        u32 m = lo * qinv_neg;
-        return hi + mulhi_u32(m, q) + (lo != 0u ? 1u : 0u);
+        u32 m = lo * qinv;
+        return hi - mulhi_u32(m, q) + q;
     }
     FHE_HD u32 pw_evals(u32 t) const { return csub(mul_tw(t, r), q); }
     FHE_HD u32 mul(u32 a, u32 b) const { return pw_evals(pw_mul(a, b)); }  // canonical a*b (a*b < q*2^32)

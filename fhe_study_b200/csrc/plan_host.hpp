@@ -132,6 +132,7 @@ inline void init_mod(Small32 &m, u64 q) {
     m.q = (u32)q;
     m.q2 = (u32)(2 * q);
     m.qinv_neg = neg_inv32((u32)q);
+    m.qinv = (u32)0 - m.qinv_neg;
     m.one = make_tw((u32)1, (u32)q, (Tw32 *)nullptr);
     m.r = make_tw((u32)((1ull << 32) % q), (u32)q, (Tw32 *)nullptr);
     for (int k = 0; k < 16; k++) m.qk[k] = (u32)((2 * q) << k);  // wraps only where the policy is not selected
