@@ -28,8 +28,8 @@ Q = 65537
 N = 1024
 BATCH = 65536  # 3 * 65536 * 8 KiB = 1.5 GiB per step: far larger than the 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this exact workload (ncu --set full capture)
-NCU_TRAFFIC_BYTES = 1073805000 + 499717632
-NCU_TRAFFIC_SOURCE = "profiles/r1_polymul_n1024_q65537_ncu_full_d.csv"
+NCU_TRAFFIC_BYTES = 1073804000 + 499474432
+NCU_TRAFFIC_SOURCE = "profiles/r1_polymul_n1024_q65537_ncu_full_e.csv"
 
 
 def peaks():
