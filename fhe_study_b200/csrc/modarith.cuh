@@ -116,7 +116,8 @@ struct Lazy64 {
     typedef u64 W;
     typedef Tw64 T;
     u64 q, q2;
-    u64 qinv_neg;  // -q^-1 mod 2^64
+    u64 qinv_neg;  // -q^-1 mod 2^64 (kept for the plan's layout; the device uses qinv)
+    u64 qinv;      //  q^-1 mod 2^64
     u64 r2;        // 2^128 mod q
 
     FHE_HD u64 mul_tw(u64 y, T t) const { return y * t.w - mulhi_u64(y, t.wp) * q; }
@@ -145,10 +146,11 @@ struct Lazy64 {
     FHE_HD u64 canon4(u64 x) const { return csub(csub(x, q2), q); }
     FHE_HD u64 canon2(u64 x) const { return csub(x, q); }
     // Montgomery product a*b*2^-64 mod q in [0,q) (a*b < q*2^64).
+    // subtractive form: m*q has the low word of a*b, so a*b - m*q = (hi - mulhi(m,q)) * 2^64 exactly; hi, mulhi < q
     FHE_HD u64 mont(u64 a, u64 b) const {
         u64 lo = a * b, hi = mulhi_u64(a, b);
-        u64 m = lo * qinv_neg;
-        u64 t = hi + mulhi_u64(m, q) + (lo != 0ull ? 1ull : 0ull);
+        u64 m = lo * qinv;
+        u64 t = hi - mulhi_u64(m, q) + q;  // (0, 2q)
         return csub(t, q);
     }
     FHE_HD u64 mul(u64 a, u64 b) const { return mont(mont(a, b), r2); }
@@ -169,6 +171,7 @@ struct Strict64 {
     typedef Tw64 T;
     u64 q, q2;  // q2 unused
     u64 qinv_neg;
+    u64 qinv;   // q^-1 mod 2^64
     u64 r2;
 
     FHE_HD u64 mul_tw(u64 y, T t) const {  // canonical result
@@ -202,8 +205,8 @@ struct Strict64 {
     FHE_HD u64 canon2(u64 x) const { return x; }
     FHE_HD u64 mont(u64 a, u64 b) const {
         u64 lo = a * b, hi = mulhi_u64(a, b);
-        u64 m = lo * qinv_neg;
-        u64 t = hi + mulhi_u64(m, q) + (lo != 0ull ? 1ull : 0ull);  // < 2q < 2^64
+        u64 m = lo * qinv;
+        u64 t = hi - mulhi_u64(m, q) + q;  // subtractive form (see Lazy64::mont): (0, 2q), 2q < 2^64
         return t >= q ? t - q : t;
     }
     FHE_HD u64 mul(u64 a, u64 b) const { return mont(mont(a, b), r2); }

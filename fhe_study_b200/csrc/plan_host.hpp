@@ -112,6 +112,7 @@ inline void init_mod(Lazy64 &m, u64 q) {
     m.q = q;
     m.q2 = 2 * q;
     m.qinv_neg = neg_inv64(q);
+    m.qinv = (u64)0 - m.qinv_neg;
     u64 r = (u64)((((u128_t)1) << 64) % q);
     m.r2 = hp_mulmod(r, r, q);
 }
@@ -119,6 +120,7 @@ inline void init_mod(Strict64 &m, u64 q) {
     m.q = q;
     m.q2 = 0;
     m.qinv_neg = neg_inv64(q);
+    m.qinv = (u64)0 - m.qinv_neg;
     u64 r = (u64)((((u128_t)1) << 64) % q);
     m.r2 = hp_mulmod(r, r, q);
 }
