@@ -219,6 +219,9 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
     W *sm = reinterpret_cast<W *>(smem_raw) + (size_t)slot * G::template padn<sizeof(W)>();
     const size_t poly = (size_t)blockIdx.x * G::PPC + slot;
     const bool valid = poly < batch;
+    // slots past the end of a ragged batch read the last polynomial (and store nothing): unconditional loads, no
+    // zero-filled registers
+    const size_t off_ld = (valid ? poly : batch - 1) * S::N;
     const size_t off = poly * S::N;
     const M &m = P.mod;
     constexpr int LAST = S::P - 1;
@@ -226,14 +229,14 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
 
     if constexpr (MODE == MODE_FWD) {
         const TwSrc<M> tw = {P.c_fwd, P.fwd};
-        load_poly<M, LOGN, LOGE, 0>(x, a + off, valid, sm, tid);
+        load_poly<M, LOGN, LOGE, 0>(x, a + off_ld, true, sm, tid);
         fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, tw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.fwd_canon(x[e]);
         store_poly<M, LOGN, LOGE, LAST, false>(x, c + off, valid, sm, tid);  // last smem access: own reads in layout LAST
     } else if constexpr (MODE == MODE_INV) {
         const TwSrc<M> tw = {P.c_inv, P.inv};
-        load_poly<M, LOGN, LOGE, LAST>(x, a + off, valid, sm, tid);
+        load_poly<M, LOGN, LOGE, LAST>(x, a + off_ld, true, sm, tid);
         inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, tw, P.ninv, P.s_ninv);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
@@ -261,11 +264,11 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
         // the bulk of the kernel's instruction footprint; see profiles/: no_instruction stalls)
 #pragma unroll 1
         for (int op = 0; op < 2; op++) {
-            const u64 *src = op == 0 ? a + off : (flags & B_BROADCAST) ? b : b + off;
+            const u64 *src = op == 0 ? a + off_ld : (flags & B_BROADCAST) ? b : b + off_ld;
             if (flags & (op == 0 ? A_IS_EVALS : B_IS_EVALS)) {
-                load_poly<M, LOGN, LOGE, LAST, ST>(x, src, valid, sm, tid);
+                load_poly<M, LOGN, LOGE, LAST, ST>(x, src, true, sm, tid);
             } else {
-                load_poly<M, LOGN, LOGE, 0, ST>(x, src, valid, sm, tid);
+                load_poly<M, LOGN, LOGE, 0, ST>(x, src, true, sm, tid);
                 fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
 #pragma unroll
                 for (int e = 0; e < S::E; e++) x[e] = m.fwd_out(x[e]);
