@@ -117,19 +117,22 @@ def model_fwd(a, q, roots, LOGN, LOGE, inverse=False, roots_inv=None, n_inv=None
     return mem
 
 
-def conflicts(LOGN, LOGE, pad_shift=5):
+def conflicts(LOGN, LOGE, word_bytes=4):
+    """worst bank-conflict degree of each pass layout (1 = conflict-free) under the kernel's padding: one pad word
+    per 128 bytes (i + i/32 for 4-byte words, i + i/16 for 8-byte words; an 8-byte access is served per half-warp)"""
     gs = split(LOGN, LOGE)
     E, T = 1 << LOGE, 1 << (LOGN - LOGE)
+    lanes, banks_n, pad_shift = (32, 32, 5) if word_bytes == 4 else (16, 16, 4)
     worst = {}
     for p in range(len(gs)):
         w = 0
-        for warp0 in range(0, T, 32):
-            lays = [layout(LOGN, LOGE, gs, p, t) for t in range(warp0, min(warp0 + 32, T))]
+        for t0 in range(0, T, lanes):
+            lays = [layout(LOGN, LOGE, gs, p, t) for t in range(t0, min(t0 + lanes, T))]
             for e in range(E):
                 banks = Counter()
                 for lay in lays:
                     idx = lay[e][0]
-                    banks[(idx + (idx >> pad_shift)) & 31] += 1
+                    banks[(idx + (idx >> pad_shift)) % banks_n] += 1
                 w = max(w, max(banks.values()))
         worst[p] = w
     return gs, worst
