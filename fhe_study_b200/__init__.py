@@ -109,6 +109,12 @@ class NttPlan:
         except Exception:
             pass
 
+    def config(self):
+        """Diagnostics: (policy, log2 coefficients per thread, dual, gpark, staged) the plan selected."""
+        arr = (C.c_int * 5)()
+        check(lib.fhe_ntt_plan_config(self._h, arr))
+        return {"policy": arr[0], "loge": arr[1], "dual": arr[2], "gpark": arr[3], "staged": arr[4]}
+
     def info(self):
         psi, n_inv = C.c_uint64(), C.c_uint64()
         roots = np.empty(self.n, dtype=np.uint64)

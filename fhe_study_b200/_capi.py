@@ -45,6 +45,7 @@ SIGNATURES = {
     "fhe_ntt_plan_create": (I, [U64, U64, C.POINTER(P)]),
     "fhe_ntt_plan_destroy": (None, [P]),
     "fhe_ntt_plan_info": (I, [P, C.POINTER(U64), C.POINTER(U64), P, P]),
+    "fhe_ntt_plan_config": (I, [P, C.POINTER(I)]),
     "fhe_ntt_fwd": (I, [P, P, P, SZ]),
     "fhe_ntt_inv": (I, [P, P, P, SZ]),
     "fhe_rq_mul": (I, [P, P, P, P, SZ, I, P]),

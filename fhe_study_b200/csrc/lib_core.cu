@@ -23,28 +23,40 @@ cudaStream_t current_stream() { return t_stream; }
 void count_launch(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // keep stream-ordered scratch cached in the pool instead of returning it to the OS at every synchronisation
 void device_init_once() {
-    static unsigned long long done_mask = 0;
+    static std::atomic<unsigned long long> done_mask{0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return;
-    if ((done_mask >> (dev & 63)) & 1ull) return;
+    if ((done_mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     cudaGetLastError();
-    done_mask |= 1ull << (dev & 63);
+    done_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
 }
 int num_sms() {
-    static int sms[64] = {0};
+    static std::atomic<int> sms[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (sms[dev & 63] == 0) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
-        sms[dev & 63] = p.multiProcessorCount;
+    int v = sms[dev & 63].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        sms[dev & 63].store(v, std::memory_order_relaxed);
     }
-    return sms[dev & 63];
+    return v;
+}
+// A handle (plan, key, ...) belongs to the device it was created on: using it while another device is current would
+// launch kernels that read the other GPU's memory (an illegal-address fault without peer access).
+int check_device(int handle_device, const char *what) {
+    int dev = -1;
+    FHE_CUDA_OK(cudaGetDevice(&dev));
+    if (dev != handle_device) {
+        set_error(std::string(what) + ": handle was created on device " + std::to_string(handle_device) +
+                  " but device " + std::to_string(dev) + " is current (fhe_set_device)");
+        return -1;
+    }
+    return 0;
 }
 
 }  // namespace fhe
@@ -77,9 +89,15 @@ template <class M> int upload_tables(fhe_ntt_plan *p, NttParams<M> &dst) {
     return 0;
 }
 
+// polymul of two coefficient-form operands: the dual-operand kernel where the plan says so (FHE_NTT_DUAL overrides)
+inline int mul_mode_for(const fhe_ntt_plan *plan, int mode, int flags) {
+    if (mode != MODE_MUL || (flags & (A_IS_EVALS | B_IS_EVALS))) return mode;
+    return plan->gpark ? MODE_MULG : plan->staged ? MODE_MULS : plan->dual ? MODE_MUL2 : mode;
+}
 int launch_plan(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
                 int flags, cudaStream_t st) {
     int rc;
+    mode = mul_mode_for(plan, mode, flags);
     switch (plan->kind) {
         case 3: rc = ntt_launch_small32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
         case 0: rc = ntt_launch_lazy32(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
@@ -89,7 +107,20 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, 
     if (!rc) count_launch(1);
     return rc;
 }
-
+// packed 32-bit words in global memory (q <= 2^32): the same kernels instantiated with u32 loads and stores
+int launch_plan(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *b, u32 *c, u32 *c_evals, size_t batch,
+                int flags, cudaStream_t st) {
+    int rc;
+    mode = mul_mode_for(plan, mode, flags);
+    switch (plan->kind) {
+        case 3: rc = ntt_launch_small32_u32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
+        case 0: rc = ntt_launch_lazy32_u32(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
+        case 1: rc = ntt_launch_lazy64_u32(plan->logn, plan->loge, mode, plan->p64, a, b, c, c_evals, batch, flags, st); break;
+        default: set_error("the 32-bit word format needs q <= 2^32"); return -1;
+    }
+    if (!rc) count_launch(1);
+    return rc;
+}
 
 thread_local PipeStreams t_pipe;
 
@@ -104,37 +135,52 @@ size_t pipe_chunk_bytes() {
     return v;
 }
 
-int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
+// inside the chunk loops a failing CUDA call must not return: the side streams may still have work queued on the
+// staging buffers, so the loop is left and the common tail synchronises all streams before anything is freed
+#define FHE_PIPE_OK(expr)                                                               \
+    {                                                                                   \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+            rc = -2;                                                                    \
+            break;                                                                      \
+        }                                                                               \
+    }
+
+// Host-buffer batches of NTT / INTT / polymul, W = u64 or u32 words: chunked, double-buffered on the device; the H2D
+// copy of chunk i+1, the ONE kernel launch of chunk i and the D2H copy of chunk i-1 overlap on three streams.
+template <typename W>
+int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const W *a, const W *b, W *c, W *c_evals, size_t batch,
                       int flags, cudaStream_t st, size_t chunk) {
     int rc = t_pipe.init();
     if (rc) return rc;
     PipeStreams &ps = t_pipe;
-    const size_t n = plan->host.n, cbytes = chunk * n * sizeof(u64);
+    const size_t n = plan->host.n, cbytes = chunk * n * sizeof(W);
     const int nbuf = 1 + (b ? 1 : 0) + 1 + (c_evals ? 1 : 0);
     Scratch scratch;
     if ((rc = scratch.alloc(2 * nbuf * cbytes, st))) return rc;
-    u64 *dev = scratch.ptr<u64>();
+    W *dev = scratch.ptr<W>();
     FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch is used from the side streams as well
     auto buf = [&](int which, int parity) { return dev + ((size_t)parity * nbuf + which) * chunk * n; };
     const int ib = 1, ic = b ? 2 : 1, ie = ic + 1;
     size_t i = 0;
     for (size_t off = 0; off < batch; off += chunk, i++) {
-        const size_t nb = std::min(chunk, batch - off), bytes = nb * n * sizeof(u64);
+        const size_t nb = std::min(chunk, batch - off), bytes = nb * n * sizeof(W);
         const int par = (int)(i & 1);
-        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // inputs of chunk i-2 consumed
-        FHE_CUDA_OK(cudaMemcpyAsync(buf(0, par), a + off * n, bytes, cudaMemcpyHostToDevice, ps.h2d));
-        if (b) FHE_CUDA_OK(cudaMemcpyAsync(buf(ib, par), b + off * n, bytes, cudaMemcpyHostToDevice, ps.h2d));
-        FHE_CUDA_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
-        FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.h2d_done[par], 0));
-        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
-        if ((rc = launch_plan(plan, mode, buf(0, par), b ? buf(ib, par) : nullptr, buf(ic, par),
-                              c_evals ? buf(ie, par) : nullptr, nb, flags, st)))
+        if (i >= 2) FHE_PIPE_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // inputs of chunk i-2 consumed
+        FHE_PIPE_OK(cudaMemcpyAsync(buf(0, par), a + off * n, bytes, cudaMemcpyHostToDevice, ps.h2d));
+        if (b) FHE_PIPE_OK(cudaMemcpyAsync(buf(ib, par), b + off * n, bytes, cudaMemcpyHostToDevice, ps.h2d));
+        FHE_PIPE_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
+        FHE_PIPE_OK(cudaStreamWaitEvent(st, ps.h2d_done[par], 0));
+        if (i >= 2) FHE_PIPE_OK(cudaStreamWaitEvent(st, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
+        if ((rc = launch_plan(plan, mode, buf(0, par), b ? buf(ib, par) : (const W *)nullptr, buf(ic, par),
+                              c_evals ? buf(ie, par) : (W *)nullptr, nb, flags, st)))
             break;
-        FHE_CUDA_OK(cudaEventRecord(ps.comp_done[par], st));
-        FHE_CUDA_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
-        FHE_CUDA_OK(cudaMemcpyAsync(c + off * n, buf(ic, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
-        if (c_evals) FHE_CUDA_OK(cudaMemcpyAsync(c_evals + off * n, buf(ie, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
-        FHE_CUDA_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
+        FHE_PIPE_OK(cudaEventRecord(ps.comp_done[par], st));
+        FHE_PIPE_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
+        FHE_PIPE_OK(cudaMemcpyAsync(c + off * n, buf(ic, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
+        if (c_evals) FHE_PIPE_OK(cudaMemcpyAsync(c_evals + off * n, buf(ie, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
+        FHE_PIPE_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
     }
     cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st);
     if (rc) return rc;
@@ -146,114 +192,34 @@ int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const u64 *a, const u6
     return 0;
 }
 
-int run_ntt(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
-            int flags) {
+// NTT / INTT / polymul over words of type W (u64: SURVEY 8b layout; u32: packed format for q <= 2^32).  Every pointer
+// may be a host or a device pointer; all-device calls are ONE asynchronous kernel launch on the current stream.
+template <typename W>
+int run_ntt(const fhe_ntt_plan *plan, int mode, const W *a, const W *b, W *c, W *c_evals, size_t batch, int flags) {
     FHE_REQUIRE(plan != nullptr, "null plan");
     if (batch == 0) return 0;
     FHE_REQUIRE(a != nullptr && c != nullptr && (mode != MODE_MUL || b != nullptr), "null polynomial pointer");
+    if (sizeof(W) == 4) FHE_REQUIRE(plan->host.q <= (1ull << 32), "the 32-bit word format needs q <= 2^32");
+    int rc = check_device(plan->device, "NTT plan");
+    if (rc) return rc;
     cudaStream_t st = current_stream();
-    const size_t bytes = batch * plan->host.n * sizeof(u64);
+    const size_t bytes = batch * plan->host.n * sizeof(W);
     if (mode != MODE_MUL) b = nullptr;
     const bool bcast = mode == MODE_MUL && (flags & B_BROADCAST);
     if (!bcast) {   // all-host call on a batch worth pipelining (>= 4 chunks of ~32 MiB per operand)
-        const size_t chunk = std::max<size_t>(1, pipe_chunk_bytes() / (plan->host.n * sizeof(u64)));
+        const size_t chunk = std::max<size_t>(1, pipe_chunk_bytes() / (plan->host.n * sizeof(W)));
         if (batch >= 4 * chunk && is_host_ptr(a) && (!b || is_host_ptr(b)) && is_host_ptr(c) &&
             (!c_evals || is_host_ptr(c_evals)) && a != c && b != c)
-            return run_ntt_pipelined(plan, mode, a, b, c, c_evals, batch, flags, st, chunk);
+            return run_ntt_pipelined<W>(plan, mode, a, b, c, c_evals, batch, flags, st, chunk);
     }
     IoBuf ba, bb, bc, be;
-    int rc;
     if ((rc = ba.init(a, bytes, true, false, st))) return rc;
-    if ((rc = bb.init(mode == MODE_MUL ? b : nullptr, bcast ? plan->host.n * sizeof(u64) : bytes, true, false, st))) return rc;
+    if ((rc = bb.init(mode == MODE_MUL ? b : nullptr, bcast ? plan->host.n * sizeof(W) : bytes, true, false, st))) return rc;
     if ((rc = bc.init(c, bytes, false, true, st))) return rc;
     if ((rc = be.init(c_evals, bytes, false, true, st))) return rc;
-    rc = launch_plan(plan, mode, ba.ptr<u64>(), bb.ptr<u64>(), bc.ptr<u64>(), be.ptr<u64>(), batch, flags, st);
+    rc = launch_plan(plan, mode, ba.ptr<W>(), bb.ptr<W>(), bc.ptr<W>(), be.ptr<W>(), batch, flags, st);
     if (rc) return rc;
     return finish_all({&ba, &bb, &bc, &be}, st);
-}
-}  // namespace
-
-namespace {
-// ---- packed 32-bit wire format (q <= 2^32): halves the PCIe bytes of the host-buffer path ------------------------
-__global__ void widen_u32_kernel(const u32 *__restrict__ in, u64 *__restrict__ out, size_t len4) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len4; i += (size_t)gridDim.x * blockDim.x) {
-        const uint4 v = reinterpret_cast<const uint4 *>(in)[i];
-        reinterpret_cast<ulonglong2 *>(out)[2 * i] = make_ulonglong2(v.x, v.y);
-        reinterpret_cast<ulonglong2 *>(out)[2 * i + 1] = make_ulonglong2(v.z, v.w);
-    }
-}
-__global__ void narrow_u64_kernel(const u64 *__restrict__ in, u32 *__restrict__ out, size_t len4) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len4; i += (size_t)gridDim.x * blockDim.x) {
-        const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(in)[2 * i], b = reinterpret_cast<const ulonglong2 *>(in)[2 * i + 1];
-        reinterpret_cast<uint4 *>(out)[i] = make_uint4((u32)a.x, (u32)a.y, (u32)b.x, (u32)b.y);
-    }
-}
-inline unsigned grid_for_len(size_t work) {
-    size_t g = (work + 255) / 256;
-    const size_t cap = (size_t)num_sms() * 16;
-    return (unsigned)(g < 1 ? 1 : g > cap ? cap : g);
-}
-
-// Chunked, double-buffered: [copy u32 in] -> widen -> transform -> narrow -> [copy u32 out]; host or device pointers.
-int run_ntt_wire32(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *b, u32 *c, u32 *c_evals, size_t batch,
-                   int flags) {
-    FHE_REQUIRE(plan != nullptr, "null plan");
-    if (batch == 0) return 0;
-    FHE_REQUIRE(a != nullptr && c != nullptr && (mode != MODE_MUL || b != nullptr), "null polynomial pointer");
-    FHE_REQUIRE(plan->host.q <= (1ull << 32), "the 32-bit wire format needs q <= 2^32");
-    FHE_REQUIRE(plan->host.n % 4 == 0, "the 32-bit wire format needs n >= 4");
-    FHE_REQUIRE(!(flags & B_BROADCAST), "FHE_B_BROADCAST is not supported on the 32-bit wire");
-    if (mode != MODE_MUL) b = nullptr;
-    cudaStream_t st = current_stream();
-    int rc = t_pipe.init();
-    if (rc) return rc;
-    PipeStreams &ps = t_pipe;
-    const size_t n = plan->host.n;
-    const size_t chunk = std::min(batch, std::max<size_t>(1, pipe_chunk_bytes() / (n * sizeof(u32))));
-    const size_t w = chunk * n;  // words per chunk buffer
-    const bool host = is_host_ptr(a) || (b && is_host_ptr(b)) || is_host_ptr(c) || (c_evals && is_host_ptr(c_evals));
-    // per parity: u64 A, B, C, E and u32 a, b, c, e  (unused ones still reserved; at most ~0.8 GB)
-    Scratch s64, s32;
-    if ((rc = s64.alloc(2 * 4 * w * sizeof(u64), st))) return rc;
-    if ((rc = s32.alloc(2 * 4 * w * sizeof(u32), st))) return rc;
-    FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch is used from the side streams as well
-    auto b64 = [&](int which, int par) { return s64.ptr<u64>() + ((size_t)par * 4 + which) * w; };
-    auto b32 = [&](int which, int par) { return s32.ptr<u32>() + ((size_t)par * 4 + which) * w; };
-    size_t i = 0;
-    for (size_t off = 0; off < batch && !rc; off += chunk, i++) {
-        const size_t nb = std::min(chunk, batch - off), words = nb * n, bytes = words * sizeof(u32);
-        const int par = (int)(i & 1);
-        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // staging of chunk i-2 consumed
-        FHE_CUDA_OK(cudaMemcpyAsync(b32(0, par), a + off * n, bytes, cudaMemcpyDefault, ps.h2d));
-        if (b) FHE_CUDA_OK(cudaMemcpyAsync(b32(1, par), b + off * n, bytes, cudaMemcpyDefault, ps.h2d));
-        FHE_CUDA_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
-        FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.h2d_done[par], 0));
-        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(st, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
-        widen_u32_kernel<<<grid_for_len(words / 4), 256, 0, st>>>(b32(0, par), b64(0, par), words / 4);
-        if (b) widen_u32_kernel<<<grid_for_len(words / 4), 256, 0, st>>>(b32(1, par), b64(1, par), words / 4);
-        count_launch(b ? 2 : 1);
-        if ((rc = launch_plan(plan, mode, b64(0, par), b ? b64(1, par) : nullptr, b64(2, par), c_evals ? b64(3, par) : nullptr,
-                              nb, flags, st)))
-            break;
-        narrow_u64_kernel<<<grid_for_len(words / 4), 256, 0, st>>>(b64(2, par), b32(2, par), words / 4);
-        if (c_evals) narrow_u64_kernel<<<grid_for_len(words / 4), 256, 0, st>>>(b64(3, par), b32(3, par), words / 4);
-        count_launch(c_evals ? 2 : 1);
-        FHE_CUDA_OK(cudaGetLastError());
-        FHE_CUDA_OK(cudaEventRecord(ps.comp_done[par], st));
-        FHE_CUDA_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
-        FHE_CUDA_OK(cudaMemcpyAsync(c + off * n, b32(2, par), bytes, cudaMemcpyDefault, ps.d2h));
-        if (c_evals) FHE_CUDA_OK(cudaMemcpyAsync(c_evals + off * n, b32(3, par), bytes, cudaMemcpyDefault, ps.d2h));
-        FHE_CUDA_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
-    }
-    // the side streams own part of the work: the call returns with everything complete (also for device pointers)
-    cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st);
-    (void)host;
-    if (rc) return rc;
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-        set_error(std::string("32-bit wire path failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
-        return -2;
-    }
-    return 0;
 }
 }  // namespace
 
@@ -271,6 +237,8 @@ PipeStreams &thread_pipe() { return t_pipe; }
 // device-pointer transform launch for the other translation units (glwe_rq.cu)
 int plan_launch(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
                 int flags, cudaStream_t st) {
+    int rc = check_device(plan->device, "NTT plan");
+    if (rc) return rc;
     return launch_plan(plan, mode, a, b, c, c_evals, batch, flags, st);
 }
 }  // namespace fhe
@@ -329,6 +297,18 @@ int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
                         : p->kind == 1 ? ntt_loge_ok_lazy64(p->logn, v) : ntt_loge_ok_strict64(p->logn, v);
         if (ok) p->loge = v;
     }
+    // Which polymul kernel serves two coefficient-form operands (measured on B200, q = 65537, M polymul/s):
+    //   dual-operand (MODE_MUL2): N=2048 94.9 -> 99.7; slower elsewhere (N=1024 217 -> 199, N=16384 6.75 -> 5.84)
+    //   NTT(a) parked in the output row (MODE_MULG): N=16384 6.75 -> 7.76 (two 64-register CTAs per SM); N=8192 unchanged
+    //   persistent + cp.async operand staging (MODE_MULS): N=16384 6.75 -> 6.93, N=8192 18.7 -> 15.5: off
+    // FHE_NTT_DUAL / FHE_NTT_GPARK / FHE_NTT_STAGED = 0|1 override (tuning knobs and tests).
+    const bool w32 = p->kind == 0 || p->kind == 3;
+    p->dual = w32 && p->logn == 11;
+    if (const char *e = getenv("FHE_NTT_DUAL")) p->dual = atoi(e) != 0;
+    p->gpark = w32 && p->logn >= 14;
+    if (const char *e = getenv("FHE_NTT_GPARK")) p->gpark = atoi(e) != 0;
+    p->staged = 0;
+    if (const char *e = getenv("FHE_NTT_STAGED")) p->staged = atoi(e) != 0;
     int rc = p->kind == 0 ? upload_tables(p.get(), p->p32)
              : p->kind == 3 ? upload_tables(p.get(), p->psm)
              : p->kind == 1 ? upload_tables(p.get(), p->p64)
@@ -356,25 +336,34 @@ int fhe_ntt_plan_info(const fhe_ntt_plan *plan, uint64_t *psi, uint64_t *n_inv, 
     if (roots_inv) memcpy(roots_inv, plan->host.roots_inv.data(), plan->host.n * sizeof(u64));
     return 0;
 }
+int fhe_ntt_plan_config(const fhe_ntt_plan *plan, int *config) {
+    FHE_REQUIRE(plan != nullptr && config != nullptr, "null plan or config");
+    config[0] = plan->kind;
+    config[1] = plan->loge;
+    config[2] = plan->dual;
+    config[3] = plan->gpark;
+    config[4] = plan->staged;
+    return 0;
+}
 int fhe_ntt_fwd(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *out, size_t batch) {
-    return run_ntt(plan, MODE_FWD, in, nullptr, out, nullptr, batch, 0);
+    return run_ntt<u64>(plan, MODE_FWD, in, nullptr, out, nullptr, batch, 0);
 }
 int fhe_ntt_inv(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *out, size_t batch) {
-    return run_ntt(plan, MODE_INV, in, nullptr, out, nullptr, batch, 0);
+    return run_ntt<u64>(plan, MODE_INV, in, nullptr, out, nullptr, batch, 0);
 }
 int fhe_rq_mul(const fhe_ntt_plan *plan, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, int flags,
                uint64_t *c_evals) {
-    return run_ntt(plan, MODE_MUL, a, b, c, c_evals, batch, flags);
+    return run_ntt<u64>(plan, MODE_MUL, a, b, c, c_evals, batch, flags);
 }
 int fhe_ntt_fwd_u32(const fhe_ntt_plan *plan, const uint32_t *in, uint32_t *out, size_t batch) {
-    return run_ntt_wire32(plan, MODE_FWD, in, nullptr, out, nullptr, batch, 0);
+    return run_ntt<u32>(plan, MODE_FWD, in, nullptr, out, nullptr, batch, 0);
 }
 int fhe_ntt_inv_u32(const fhe_ntt_plan *plan, const uint32_t *in, uint32_t *out, size_t batch) {
-    return run_ntt_wire32(plan, MODE_INV, in, nullptr, out, nullptr, batch, 0);
+    return run_ntt<u32>(plan, MODE_INV, in, nullptr, out, nullptr, batch, 0);
 }
 int fhe_rq_mul_u32(const fhe_ntt_plan *plan, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch, int flags,
                    uint32_t *c_evals) {
-    return run_ntt_wire32(plan, MODE_MUL, a, b, c, c_evals, batch, flags);
+    return run_ntt<u32>(plan, MODE_MUL, a, b, c, c_evals, batch, flags);
 }
 
 }  // extern "C"

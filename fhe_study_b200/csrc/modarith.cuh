@@ -154,11 +154,19 @@ struct Lazy64 {
         return csub(t, q);
     }
     FHE_HD u64 mul(u64 a, u64 b) const { return mont(mont(a, b), r2); }
-    static constexpr bool PW_SCALED = false;
-    FHE_HD u64 fwd_out(u64 x) const { return canon4(x); }
+    // Pointwise product of the polymul: ONE Montgomery product; its 2^-64 is folded into the n^-1 constants of the
+    // inverse transform (ninv_pw / s_ninv_pw), as Small32 does.  Operands only need to be below 2q (4q^2 < q * 2^64
+    // for q < 2^62), so the forward output takes one conditional subtraction instead of two, and the product stays in
+    // (0, 2q), which is what the inverse butterflies accept: no final subtraction either.
+    static constexpr bool PW_SCALED = true;
+    FHE_HD u64 fwd_out(u64 x) const { return csub(x, q2); }
     FHE_HD u64 fwd_canon(u64 x) const { return canon4(x); }
-    FHE_HD u64 pw_mul(u64 a, u64 b) const { return mul(a, b); }
-    FHE_HD u64 pw_evals(u64 t) const { return t; }
+    FHE_HD u64 pw_mul(u64 a, u64 b) const {
+        u64 lo = a * b, hi = mulhi_u64(a, b);
+        u64 m = lo * qinv;
+        return hi - mulhi_u64(m, q) + q;  // (0, 2q), congruent to a*b*2^-64
+    }
+    FHE_HD u64 pw_evals(u64 t) const { return mont(t, r2); }  // canonical a*b (t < 2q, r2 < q: t*r2 < q * 2^64)
     FHE_HD static u64 load(u64 v) { return v; }
     FHE_HD static u64 store(u64 v) { return v; }
 };
@@ -210,11 +218,11 @@ struct Strict64 {
         return t >= q ? t - q : t;
     }
     FHE_HD u64 mul(u64 a, u64 b) const { return mont(mont(a, b), r2); }
-    static constexpr bool PW_SCALED = false;
-    FHE_HD u64 fwd_out(u64 x) const { return canon4(x); }
-    FHE_HD u64 fwd_canon(u64 x) const { return canon4(x); }
-    FHE_HD u64 pw_mul(u64 a, u64 b) const { return mul(a, b); }
-    FHE_HD u64 pw_evals(u64 t) const { return t; }
+    static constexpr bool PW_SCALED = true;  // one Montgomery product; 2^-64 folded into ninv_pw (see Lazy64)
+    FHE_HD u64 fwd_out(u64 x) const { return x; }
+    FHE_HD u64 fwd_canon(u64 x) const { return x; }
+    FHE_HD u64 pw_mul(u64 a, u64 b) const { return mont(a, b); }
+    FHE_HD u64 pw_evals(u64 t) const { return mont(t, r2); }
     FHE_HD static u64 load(u64 v) { return v; }
     FHE_HD static u64 store(u64 v) { return v; }
 };

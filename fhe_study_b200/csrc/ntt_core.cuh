@@ -78,10 +78,16 @@ inline u64 tw_slot(int logn, int loge, u64 ref_index) {
 // N=2048 NTT 0.97 vs 0.85, polymul 0.62 vs 0.61 -- hence 16 per thread there; N=4096 polymul 0.55 vs 0.60, INTT
 // 0.86 vs 0.90, NTT 0.90 vs 0.88 -- 32 per thread (with the old 4/4/4 split, two-way bank conflicts in the middle
 // pass, 16 per thread was the faster one at N=4096 too).
+// 64-bit words: the fully unrolled polymul at 16 coefficients per thread is 92-114 KB of SASS and 112+ registers; ncu
+// showed it bound by instruction fetch (SM instruction-cache hit rate 62 %, GPC-level instruction requests at 100 % of
+// their peak, no_instruction the top stall: profiles/r2_polymul_q62_n1024_*).  8 coefficients per thread halve code
+// and registers: N=1024 polymul 36.4 -> 43.9 M/s, N=2048 17.2 -> 19.5 M/s; from N=4096 on the extra exchange pass
+// costs more than the smaller code gives back (8.74 vs 7.83 M/s), so 16 per thread stays there.
 template <class M> struct LogE {
-    static constexpr int MAXE = sizeof(typename M::W) == 4 ? 5 : 4;
+    static constexpr bool W32 = sizeof(typename M::W) == 4;
+    static constexpr int MAXE = W32 ? 5 : 4;
     static constexpr int of(int logn) {
-        return (sizeof(typename M::W) == 4 && logn == 11) ? 4 : logn < MAXE ? logn : MAXE;
+        return (W32 && logn == 11) ? 4 : (!W32 && logn >= 3 && logn <= 11) ? 3 : logn < MAXE ? logn : MAXE;
     }
 };
 
@@ -120,6 +126,38 @@ template <class M, int LOGN, int LOGE, int PASS, int LS = 0>
 FHE_HD void fwd_pass(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw) {
     fwd_stage<M, LOGN, LOGE, PASS, LS>(x, tid, m, tw);
     if constexpr (LS + 1 < NttShape<LOGN, LOGE>::g(PASS)) fwd_pass<M, LOGN, LOGE, PASS, LS + 1>(x, tid, m, tw);
+}
+
+// Two polynomials through the same forward pass at once (the two operands of a polymul): every twiddle is fetched
+// once and applied to both register sets, and the two butterfly streams are independent of each other (twice the
+// instruction-level parallelism per warp).
+template <class M, int LOGN, int LOGE, int PASS, int LS>
+FHE_HD void fwd_stage2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LOGE], int tid, const M &m,
+                       const TwSrc<M> &tw) {
+    typedef NttShape<LOGN, LOGE> S;
+    constexpr int g = S::g(PASS), s0 = S::s0(PASS), nL = S::nL(PASS), G = 1 << g;
+    constexpr int half = 1 << (g - 1 - LS);
+#pragma unroll
+    for (int qi = 0; qi < (S::E >> g); qi++) {
+        const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
+#pragma unroll
+        for (int hi = 0; hi < (1 << LS); hi++) {
+            const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
+            const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
+#pragma unroll
+            for (int lo = 0; lo < half; lo++) {
+                const int ru = (hi << (g - LS)) | lo;
+                m.fwd(x[qi * G + ru], x[qi * G + ru + half], t);
+                m.fwd(y[qi * G + ru], y[qi * G + ru + half], t);
+            }
+        }
+    }
+}
+template <class M, int LOGN, int LOGE, int PASS, int LS = 0>
+FHE_HD void fwd_pass2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LOGE], int tid, const M &m,
+                      const TwSrc<M> &tw) {
+    fwd_stage2<M, LOGN, LOGE, PASS, LS>(x, y, tid, m, tw);
+    if constexpr (LS + 1 < NttShape<LOGN, LOGE>::g(PASS)) fwd_pass2<M, LOGN, LOGE, PASS, LS + 1>(x, y, tid, m, tw);
 }
 
 // Inverse: the same groups, local stages in descending order.  When PASS == 0 the final stage

@@ -1,10 +1,6 @@
-// ntt_inst_small32.cu -- instantiates the NTT / INTT / polymul kernels for the Small32 modular policy.
+// ntt_inst_small32.cu -- instantiates the NTT / INTT / polymul kernels for the Small32 modular policy, u64 global words.
 #include "ntt_kernels.cuh"
 
 namespace fhe {
-int ntt_launch_small32(int logn, int loge, int mode, const NttParams<Small32> &P, const u64 *a, const u64 *b, u64 *c,
-                  u64 *c_evals, size_t batch, int flags, cudaStream_t st) {
-    return launch_ntt<Small32>(logn, loge, mode, P, a, b, c, c_evals, batch, flags, st);
-}
-bool ntt_loge_ok_small32(int logn, int loge) { return ntt_loge_supported<Small32>(logn, loge); }
+FHE_NTT_INSTANTIATE(small32, Small32, u64)
 }  // namespace fhe

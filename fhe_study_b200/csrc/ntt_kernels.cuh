@@ -7,6 +7,9 @@
 // result keeps C as its cached evals).
 #pragma once
 #include <stdlib.h>
+
+#include <atomic>
+
 #include "common.cuh"
 #include "ntt_core.cuh"
 
@@ -24,7 +27,14 @@ template <class M> struct NttParams {
     typename M::T c_fwd[64], c_inv[64];
 };
 
-enum NttMode { MODE_FWD = 0, MODE_INV = 1, MODE_MUL = 2 };
+// MODE_MUL : polymul with run-time evals flags, both operands through ONE copy of the forward code (one after the other)
+// MODE_MUL2: polymul of two operands in coefficient form, transformed TOGETHER (fwd_pass2: shared twiddle fetches,
+//            two independent butterfly streams, both operands' global loads in flight at once)
+// MODE_MULG: MODE_MUL with NTT(a) parked in the product's own output row (global memory, L2-resident for the few
+//            microseconds until the pointwise product reads it back) instead of E live registers: at N = 16384 that
+//            is the difference between one 512-thread CTA of ~116 registers and two of 64 per SM
+enum NttMode { MODE_FWD = 0, MODE_INV = 1, MODE_MUL = 2, MODE_MUL2 = 3, MODE_MULS = 4, MODE_MULG = 5 };
+__host__ __device__ constexpr bool is_mul_mode(int mode) { return mode >= MODE_MUL; }
 enum MulFlags { A_IS_EVALS = 1, B_IS_EVALS = 2, B_BROADCAST = 4 };  // B_BROADCAST: b is ONE polynomial, used for every product
 
 template <int LOGN, int LOGE> struct KernelGeom {
@@ -83,6 +93,33 @@ __device__ __forceinline__ void exchange(typename M::W (&x)[1 << LOGE], typename
     for (int e = 0; e < S::E; e++) x[e] = sm[bt + pad_idx_w<WB>(S::pos(TO, 0, e))];
 }
 
+// the same for two register sets through two buffers: one barrier orders both
+template <class M, int LOGN, int LOGE, int FROM, int TO, bool LEAD = true>
+__device__ __forceinline__ void exchange2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LOGE], typename M::W *smx,
+                                          typename M::W *smy, int tid) {
+    typedef NttShape<LOGN, LOGE> S;
+    if constexpr (LEAD) group_sync<S::T>();
+    constexpr int WB = (int)sizeof(typename M::W);
+    const int bf = pad_idx_w<WB>(S::pos(FROM, tid, 0)), bt = pad_idx_w<WB>(S::pos(TO, tid, 0));
+#pragma unroll
+    for (int e = 0; e < S::E; e++) smx[bf + pad_idx_w<WB>(S::pos(FROM, 0, e))] = x[e];
+#pragma unroll
+    for (int e = 0; e < S::E; e++) smy[bf + pad_idx_w<WB>(S::pos(FROM, 0, e))] = y[e];
+    if constexpr (ExchScope<LOGN, LOGE, FROM, TO>::in_warp) __syncwarp(); else __syncthreads();
+#pragma unroll
+    for (int e = 0; e < S::E; e++) x[e] = smx[bt + pad_idx_w<WB>(S::pos(TO, 0, e))];
+#pragma unroll
+    for (int e = 0; e < S::E; e++) y[e] = smy[bt + pad_idx_w<WB>(S::pos(TO, 0, e))];
+}
+template <class M, int LOGN, int LOGE, int PASS = 0, bool FIRST = true>
+__device__ __forceinline__ void fwd_chain2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LOGE], typename M::W *smx,
+                                           typename M::W *smy, int tid, const M &m, const TwSrc<M> &tw) {
+    typedef NttShape<LOGN, LOGE> S;
+    if constexpr (PASS > 0) exchange2<M, LOGN, LOGE, PASS - 1, PASS, FIRST>(x, y, smx, smy, tid);
+    fwd_pass2<M, LOGN, LOGE, PASS>(x, y, tid, m, tw);
+    if constexpr (PASS + 1 < S::P) fwd_chain2<M, LOGN, LOGE, PASS + 1, false>(x, y, smx, smy, tid, m, tw);
+}
+
 template <class M, int LOGN, int LOGE, int PASS = 0, bool FIRST = true>
 __device__ __forceinline__ void fwd_chain(typename M::W (&x)[1 << LOGE], typename M::W *sm, int tid, const M &m,
                                           const TwSrc<M> &tw) {
@@ -108,20 +145,9 @@ __device__ __forceinline__ void inv_chain(typename M::W (&x)[1 << LOGE], typenam
 #ifndef FHE_NTT_STREAM
 #define FHE_NTT_STREAM 1
 #endif
-__host__ __device__ constexpr bool ntt_stream(int logn, int mode) { return FHE_NTT_STREAM && mode == 2 /* MODE_MUL */ && logn >= 12; }
-#ifndef FHE_NTT_PREFETCH
-#define FHE_NTT_PREFETCH 0  // measured slower (N=8192 polymul 0.47 -> 0.38 of HBM peak): kept for reference only
-#endif
-__host__ __device__ constexpr bool ntt_prefetch(int logn, int mode) { return FHE_NTT_PREFETCH && mode == 2 && logn >= 11; }
-// one prefetch per 128-byte line of an N-coefficient polynomial, spread over its T threads
-template <int N, int T> __device__ __forceinline__ void prefetch_poly_l2(const u64 *g, int tid) {
-    constexpr int LINES = N / 16;
-#pragma unroll
-    for (int i = 0; i < (LINES + T - 1) / T; i++) {
-        const int line = tid + i * T;
-        if (LINES % T == 0 || line < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (size_t)line * 16));
-    }
-}
+__host__ __device__ constexpr bool ntt_stream(int logn, int mode) { return FHE_NTT_STREAM && is_mul_mode(mode) && logn >= 12; }
+// Global I/O word: u64 (the layout of SURVEY 8b: one 8-byte word per coefficient) or u32 (packed wire / device
+// format for q <= 2^32: half the HBM and PCIe bytes).  A warp-wide access is lane-contiguous in both (128 or 256 B).
 template <bool STREAM> __device__ __forceinline__ u64 ld_poly(const u64 *p) {
     if constexpr (STREAM) {
         u64 v;
@@ -131,42 +157,66 @@ template <bool STREAM> __device__ __forceinline__ u64 ld_poly(const u64 *p) {
         return __ldg(p);
     }
 }
+template <bool STREAM> __device__ __forceinline__ u32 ld_poly(const u32 *p) {
+    if constexpr (STREAM) {
+        u32 v;
+        asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        return v;
+    } else {
+        return __ldg(p);
+    }
+}
 template <bool STREAM> __device__ __forceinline__ void st_poly(u64 *p, u64 v) {
     if constexpr (STREAM) __stcs(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
     else *p = v;
 }
+template <bool STREAM> __device__ __forceinline__ void st_poly(u32 *p, u32 v) {
+    if constexpr (STREAM) __stcs(p, v);
+    else *p = v;
+}
 
 // global (coalesced, layout of pass 0) -> registers in the layout of pass TO
-template <class M, int LOGN, int LOGE, int TO, bool STREAM = false>
-__device__ __forceinline__ void load_poly(typename M::W (&x)[1 << LOGE], const u64 *__restrict__ g, bool valid,
+template <class M, int LOGN, int LOGE, int TO, bool STREAM = false, typename IOW = u64>
+__device__ __forceinline__ void load_poly(typename M::W (&x)[1 << LOGE], const IOW *__restrict__ g, bool valid,
                                           typename M::W *sm, int tid) {
     typedef NttShape<LOGN, LOGE> S;
-    const u64 *gt = g + S::pos(0, tid, 0);
+    const IOW *gt = g + S::pos(0, tid, 0);
 #pragma unroll
-    for (int e = 0; e < S::E; e++) x[e] = valid ? M::load(ld_poly<STREAM>(gt + S::pos(0, 0, e))) : (typename M::W)0;
+    for (int e = 0; e < S::E; e++) x[e] = valid ? (typename M::W)ld_poly<STREAM>(gt + S::pos(0, 0, e)) : (typename M::W)0;
     if constexpr (TO != 0) exchange<M, LOGN, LOGE, 0, TO>(x, sm, tid);
 }
 // registers in the layout of pass FROM -> global (coalesced).  LEAD as in exchange().
-template <class M, int LOGN, int LOGE, int FROM, bool LEAD = true, bool STREAM = false>
-__device__ __forceinline__ void store_poly(typename M::W (&x)[1 << LOGE], u64 *__restrict__ g, bool valid,
+template <class M, int LOGN, int LOGE, int FROM, bool LEAD = true, bool STREAM = false, typename IOW = u64>
+__device__ __forceinline__ void store_poly(typename M::W (&x)[1 << LOGE], IOW *__restrict__ g, bool valid,
                                            typename M::W *sm, int tid) {
     typedef NttShape<LOGN, LOGE> S;
     if constexpr (FROM != 0) exchange<M, LOGN, LOGE, FROM, 0, LEAD>(x, sm, tid);
     if (valid) {
-        u64 *gt = g + S::pos(0, tid, 0);
+        IOW *gt = g + S::pos(0, tid, 0);
 #pragma unroll
-        for (int e = 0; e < S::E; e++) st_poly<STREAM>(gt + S::pos(0, 0, e), M::store(x[e]));
+        for (int e = 0; e < S::E; e++) st_poly<STREAM>(gt + S::pos(0, 0, e), (IOW)x[e]);
     }
 }
 
-// Polymul with NTT(a) parked in shared memory while b is transformed (instead of 32 more live registers): lets more
-// CTAs be resident.  Only for one-warp transforms on 32-bit words.  FHE_A_SMEM_MINB = resident CTAs asked of ptxas.
+// Polymul with NTT(a) parked in shared memory while b is transformed (instead of E more live registers): lets more
+// CTAs be resident.  A thread reads back exactly the words it wrote, so no barrier is involved.
+//   32-bit words: FHE_A_SMEM_MINB = resident CTAs asked of ptxas (N=1024 only; measured slower, off).
+//   64-bit words: FHE_A_SMEM64 (degrees up to 2^FHE_A_SMEM64_MAXLOGN): the 64-bit polymul holds 2 x 32 registers of
+//   coefficients and sits at 112-126 registers = 16 warps per SM otherwise.
 #ifndef FHE_A_SMEM_MINB
 #define FHE_A_SMEM_MINB 0
 #endif
+#ifndef FHE_A_SMEM64
+#define FHE_A_SMEM64 0
+#endif
+#ifndef FHE_A_SMEM64_MAXLOGN
+#define FHE_A_SMEM64_MAXLOGN 12
+#endif
 template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
-    static constexpr bool on = FHE_A_SMEM_MINB > 0 && MODE == MODE_MUL && sizeof(typename M::W) == 4 &&
-                               NttShape<LOGN, LOGE>::T <= 32 && LOGN == 10;
+    static constexpr bool W32 = sizeof(typename M::W) == 4;
+    static constexpr bool on = MODE == MODE_MUL &&
+                               (W32 ? (FHE_A_SMEM_MINB > 0 && NttShape<LOGN, LOGE>::T <= 32 && LOGN == 10)
+                                    : (FHE_A_SMEM64 > 0 && LOGN >= 6 && LOGN <= FHE_A_SMEM64_MAXLOGN));
 #ifndef FHE_MUL_MINB
 #define FHE_MUL_MINB 5
 #endif
@@ -178,7 +228,7 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
     // exchanges ptxas settles for 48 registers on the forward transform and serialises its loads (0.71); a bound of
     // three CTAs lets it spend 80 and hoist them (0.78) -- the opposite of what the bound did to the older code
     static constexpr int CT_ = KernelGeom<LOGN, LOGE>::CT;
-    static constexpr bool W32 = sizeof(typename M::W) == 4;
+    static constexpr bool MUL = is_mul_mode(MODE);
 #ifndef FHE_NTT_MINB_256
 #define FHE_NTT_MINB_256 3
 #endif
@@ -200,23 +250,46 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 #ifndef FHE_NTT64_MINB
 #define FHE_NTT64_MINB 0
 #endif
-    static constexpr int minb = on ? FHE_A_SMEM_MINB
-                                : !W32 ? (CT_ == 128 ? (MODE == MODE_MUL ? FHE_MUL64_MINB : FHE_NTT64_MINB) : 0)
-                                : MODE == MODE_MUL ? (CT_ == 128 ? (LOGE == 4 ? FHE_MUL_MINB_E16 : FHE_MUL_MINB) : CT_ == 64 ? 2 * FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0)
+#ifndef FHE_MUL2_MINB      // dual-operand polymul, 128-thread CTAs, 32 coefficients per thread
+#define FHE_MUL2_MINB FHE_MUL_MINB
+#endif
+#ifndef FHE_MUL2_MINB_E16
+#define FHE_MUL2_MINB_E16 FHE_MUL_MINB_E16
+#endif
+#ifndef FHE_MUL2_MINB_256
+#define FHE_MUL2_MINB_256 FHE_MUL_MINB_256
+#endif
+    static constexpr int mul_minb = MODE == MODE_MUL2
+        ? (CT_ == 128 ? (LOGE == 4 ? FHE_MUL2_MINB_E16 : FHE_MUL2_MINB) : CT_ == 64 ? 2 * FHE_MUL2_MINB : CT_ == 256 ? FHE_MUL2_MINB_256 : 0)
+        : (CT_ == 128 ? (LOGE == 4 ? FHE_MUL_MINB_E16 : FHE_MUL_MINB) : CT_ == 64 ? 2 * FHE_MUL_MINB : CT_ == 256 ? FHE_MUL_MINB_256 : 0);
+#ifndef FHE_MULG_MINB_512
+#define FHE_MULG_MINB_512 2
+#endif
+#ifndef FHE_MULG_MINB_256
+#define FHE_MULG_MINB_256 4
+#endif
+    static constexpr int minb = MODE == MODE_MULG ? (CT_ == 512 ? FHE_MULG_MINB_512 : CT_ == 256 ? FHE_MULG_MINB_256 : 0)
+                                : (on && W32) ? FHE_A_SMEM_MINB
+                                : !W32 ? (CT_ == 128 ? (MUL ? FHE_MUL64_MINB : FHE_NTT64_MINB) : 0)
+                                : MUL ? mul_minb
                                 : (CT_ == 256 ? (MODE == MODE_INV ? FHE_INV_MINB_256 : FHE_NTT_MINB_256)
                                    : CT_ == 512 ? FHE_NTT_MINB_512 : 0);
+    // dynamic shared memory of one CTA, in words of M::W
+    static constexpr size_t words = (size_t)KernelGeom<LOGN, LOGE>::PPC *
+        ((MODE == MODE_MUL2 ? 2 : 1) * KernelGeom<LOGN, LOGE>::template padn<sizeof(typename M::W)>() + (on ? NttShape<LOGN, LOGE>::N : 0));
 };
 
-template <class M, int LOGN, int LOGE, int MODE>
+template <class M, int LOGN, int LOGE, int MODE, typename IOW>
 __global__ void __launch_bounds__(KernelGeom<LOGN, LOGE>::CT, ASmem<M, LOGN, LOGE, MODE>::minb)
-ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, const u64 *__restrict__ b,
-           u64 *__restrict__ c, u64 *__restrict__ c_evals, size_t batch, int flags, int pf_dist) {
+ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, const IOW *__restrict__ b,
+           IOW *__restrict__ c, IOW *__restrict__ c_evals, size_t batch, int flags) {
     typedef NttShape<LOGN, LOGE> S;
     typedef KernelGeom<LOGN, LOGE> G;
     typedef typename M::W W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PADW = G::template padn<sizeof(W)>();
     const int slot = threadIdx.x / S::T, tid = threadIdx.x % S::T;
-    W *sm = reinterpret_cast<W *>(smem_raw) + (size_t)slot * G::template padn<sizeof(W)>();
+    W *sm = reinterpret_cast<W *>(smem_raw) + (size_t)slot * PADW;
     const size_t poly = (size_t)blockIdx.x * G::PPC + slot;
     const bool valid = poly < batch;
     // slots past the end of a ragged batch read the last polynomial (and store nothing): unconditional loads, no
@@ -229,168 +302,286 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const u64 *__restrict__ a, co
 
     if constexpr (MODE == MODE_FWD) {
         const TwSrc<M> tw = {P.c_fwd, P.fwd};
-        load_poly<M, LOGN, LOGE, 0>(x, a + off_ld, true, sm, tid);
+        load_poly<M, LOGN, LOGE, 0, false, IOW>(x, a + off_ld, true, sm, tid);
         fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, tw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.fwd_canon(x[e]);
-        store_poly<M, LOGN, LOGE, LAST, false>(x, c + off, valid, sm, tid);  // last smem access: own reads in layout LAST
+        store_poly<M, LOGN, LOGE, LAST, false, false, IOW>(x, c + off, valid, sm, tid);  // last smem access: own reads in layout LAST
     } else if constexpr (MODE == MODE_INV) {
         const TwSrc<M> tw = {P.c_inv, P.inv};
-        load_poly<M, LOGN, LOGE, LAST>(x, a + off_ld, true, sm, tid);
+        load_poly<M, LOGN, LOGE, LAST, false, IOW>(x, a + off_ld, true, sm, tid);
         inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, tw, P.ninv, P.s_ninv);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
-        store_poly<M, LOGN, LOGE, 0>(x, c + off, valid, sm, tid);
+        store_poly<M, LOGN, LOGE, 0, true, false, IOW>(x, c + off, valid, sm, tid);
     } else {
         const TwSrc<M> twf = {P.c_fwd, P.fwd};
         const TwSrc<M> twi = {P.c_inv, P.inv};
-        constexpr bool PARK = ASmem<M, LOGN, LOGE, MODE>::on;
         constexpr bool ST = ntt_stream(LOGN, MODE);
-        if constexpr (ntt_prefetch(LOGN, MODE)) {
-            // Pull b into L2 while a is loaded and transformed, and both operands of the polynomial this SM slot
-            // will most likely process next (pf_dist = CTAs resident on the whole GPU, CTAs being dispatched in
-            // order): the few resident warps of the large degrees cannot hide an HBM round trip per operand.
-            const bool b_own = !(flags & B_BROADCAST);
-            if (valid && b_own) prefetch_poly_l2<S::N, S::T>(b + off, tid);
-            const size_t nxt = poly + (size_t)pf_dist * G::PPC;
-            if (pf_dist > 0 && nxt < batch) {
-                prefetch_poly_l2<S::N, S::T>(a + nxt * S::N, tid);
-                if (b_own) prefetch_poly_l2<S::N, S::T>(b + nxt * S::N, tid);
-            }
-        }
-        W A[PARK ? 1 : S::E];
-        W *sA = reinterpret_cast<W *>(smem_raw) + (size_t)G::PPC * G::template padn<sizeof(W)>() + (size_t)slot * S::N;  // PARK only
-        // both operands run through ONE copy of the forward-transform code (the fully unrolled transform is
-        // the bulk of the kernel's instruction footprint; see profiles/: no_instruction stalls)
+        if constexpr (MODE == MODE_MUL2) {
+            W y[S::E];
+            W *smy = reinterpret_cast<W *>(smem_raw) + (size_t)(G::PPC + slot) * PADW;
+            load_poly<M, LOGN, LOGE, 0, ST, IOW>(x, a + off_ld, true, sm, tid);
+            load_poly<M, LOGN, LOGE, 0, ST, IOW>(y, (flags & B_BROADCAST) ? b : b + off_ld, true, smy, tid);
+            fwd_chain2<M, LOGN, LOGE, 0, false>(x, y, sm, smy, tid, m, twf);  // fresh shared memory: no lead barrier
+#pragma unroll
+            for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(m.fwd_out(x[e]), m.fwd_out(y[e]));
+        } else {
+            constexpr bool PARK = ASmem<M, LOGN, LOGE, MODE>::on;
+            constexpr bool GPARK = MODE == MODE_MULG;
+            W A[(PARK || GPARK) ? 1 : S::E];
+            // GPARK: this thread's E words of NTT(a) rest in the first N * sizeof(W) bytes of its own output row
+            // (the launcher rules out c aliasing an operand); lane-contiguous, read back by the thread that wrote them
+            W *gA = reinterpret_cast<W *>(c + off) + tid;
+            W *sA = reinterpret_cast<W *>(smem_raw) + (size_t)G::PPC * PADW + (size_t)slot * S::N;  // PARK only
+            // both operands run through ONE copy of the forward-transform code (the fully unrolled transform is
+            // the bulk of the kernel's instruction footprint; see profiles/: no_instruction stalls)
 #pragma unroll 1
-        for (int op = 0; op < 2; op++) {
-            const u64 *src = op == 0 ? a + off_ld : (flags & B_BROADCAST) ? b : b + off_ld;
-            if (flags & (op == 0 ? A_IS_EVALS : B_IS_EVALS)) {
-                load_poly<M, LOGN, LOGE, LAST, ST>(x, src, true, sm, tid);
-            } else {
-                load_poly<M, LOGN, LOGE, 0, ST>(x, src, true, sm, tid);
-                fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
-#pragma unroll
-                for (int e = 0; e < S::E; e++) x[e] = m.fwd_out(x[e]);
-            }
-            if (op == 0) {
-                if constexpr (PARK) {
-#pragma unroll
-                    for (int e = 0; e < S::E; e++) sA[e * S::T + tid] = x[e];
+            for (int op = 0; op < 2; op++) {
+                const IOW *src = op == 0 ? a + off_ld : (flags & B_BROADCAST) ? b : b + off_ld;
+                if (flags & (op == 0 ? A_IS_EVALS : B_IS_EVALS)) {
+                    load_poly<M, LOGN, LOGE, LAST, ST, IOW>(x, src, true, sm, tid);
                 } else {
+                    load_poly<M, LOGN, LOGE, 0, ST, IOW>(x, src, true, sm, tid);
+                    fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
 #pragma unroll
-                    for (int e = 0; e < S::E; e++) A[e] = x[e];
+                    for (int e = 0; e < S::E; e++) x[e] = m.fwd_out(x[e]);
+                }
+                if (op == 0) {
+                    if constexpr (GPARK) {
+                        if (valid) {
+#pragma unroll
+                            for (int e = 0; e < S::E; e++) gA[e * S::T] = x[e];
+                        }
+                    } else if constexpr (PARK) {
+#pragma unroll
+                        for (int e = 0; e < S::E; e++) sA[e * S::T + tid] = x[e];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < S::E; e++) A[e] = x[e];
+                    }
                 }
             }
-        }
-        if constexpr (PARK) {
+            if constexpr (GPARK) {
+                if (valid) {
 #pragma unroll
-            for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(sA[e * S::T + tid], x[e]);
-        } else {
+                    for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(__ldcg(gA + e * S::T), x[e]);
+                }
+            } else if constexpr (PARK) {
 #pragma unroll
-            for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(A[e], x[e]);
+                for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(sA[e * S::T + tid], x[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(A[e], x[e]);
+            }
         }
         if (c_evals != nullptr) {  // ring_nq.rs:606 -- the product keeps its evals
             W ev[S::E];
 #pragma unroll
             for (int e = 0; e < S::E; e++) ev[e] = m.pw_evals(x[e]);
-            // b's last smem access (end of its chain, or load_poly<LAST>) was this thread's reads in layout LAST
-            store_poly<M, LOGN, LOGE, LAST, false, ST>(ev, c_evals + off, valid, sm, tid);
+            // the last smem access (end of the forward chain, or load_poly<LAST>) was this thread's reads in layout LAST
+            store_poly<M, LOGN, LOGE, LAST, false, ST, IOW>(ev, c_evals + off, valid, sm, tid);
             if constexpr (S::P > 1) group_sync<S::T>();  // the evals store read layout 0: foreign words
         }
         inv_chain<M, LOGN, LOGE, LAST, false>(x, sm, tid, m, twi, P.ninv_pw, P.s_ninv_pw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
-        store_poly<M, LOGN, LOGE, 0, true, ST>(x, c + off, valid, sm, tid);
+        store_poly<M, LOGN, LOGE, 0, true, ST, IOW>(x, c + off, valid, sm, tid);
     }
 }
 
-template <class M, int LOGN, int LOGE, int MODE>
-int launch_one(const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch, int flags,
+// ---- large degrees: persistent CTAs with the operands staged in shared memory by asynchronous copies --------------
+// At N >= 8192 a polynomial is one CTA of 256-512 threads with ~100 registers, so one to three CTAs are resident and
+// nothing else on the SM covers the HBM round trip of an operand load.  Here a CTA loops over polynomials; every
+// thread copies ITS OWN words of the next operand into a staging buffer with cp.async (LDGSTS: no destination
+// register, no scoreboard wait) while it transforms the current one: b arrives during fwd(a), the next polynomial's a
+// during fwd(b) / pointwise / inverse / store.  A thread only ever reads the staging words it copied itself, so
+// cp.async.wait_group is the only synchronisation the staging needs.
+template <int BYTES> __device__ __forceinline__ void cp_async_word(void *smem_dst, const void *gsrc) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+#ifndef FHE_STAGED_MINB_256   // resident CTAs asked of ptxas for the 256-thread shape (N = 8192): <= 128 registers
+#define FHE_STAGED_MINB_256 2
+#endif
+template <class M, int LOGN, int LOGE, typename IOW> struct StagedGeom {
+    typedef NttShape<LOGN, LOGE> S;
+    static constexpr int PADW = KernelGeom<LOGN, LOGE>::template padn<sizeof(typename M::W)>();
+    static constexpr size_t exch_bytes = ((size_t)PADW * sizeof(typename M::W) + 15) / 16 * 16;
+    static constexpr size_t smem = exch_bytes + (size_t)S::N * sizeof(IOW);
+    static constexpr bool fits = S::T >= 128 && S::T <= 1024 && smem <= 227 * 1024;
+};
+template <class M, int LOGN, int LOGE, typename IOW>
+__global__ void __launch_bounds__(NttShape<LOGN, LOGE>::T, NttShape<LOGN, LOGE>::T <= 256 ? FHE_STAGED_MINB_256 : 1)
+ntt_mul_staged_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, const IOW *__restrict__ b,
+                      IOW *__restrict__ c, IOW *__restrict__ c_evals, size_t batch, int flags) {
+    typedef NttShape<LOGN, LOGE> S;
+    typedef typename M::W W;
+    typedef StagedGeom<M, LOGN, LOGE, IOW> SG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W *sm = reinterpret_cast<W *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int t0 = S::pos(0, tid, 0);
+    IOW *stg = reinterpret_cast<IOW *>(smem_raw + SG::exch_bytes) + t0;  // this thread's staging words: stg[pos(0,0,e)]
+    const M &m = P.mod;
+    const TwSrc<M> twf = {P.c_fwd, P.fwd};
+    const TwSrc<M> twi = {P.c_inv, P.inv};
+    constexpr int LAST = S::P - 1;
+    auto stage = [&](const IOW *src) {
+#pragma unroll
+        for (int e = 0; e < S::E; e++) cp_async_word<sizeof(IOW)>(stg + S::pos(0, 0, e), src + t0 + S::pos(0, 0, e));
+        cp_async_commit();
+    };
+    size_t poly = blockIdx.x;
+    if (poly < batch) stage(a + poly * S::N);
+    for (; poly < batch; poly += gridDim.x) {
+        const size_t off = poly * S::N;
+        W x[S::E], A[S::E];
+        cp_async_wait_all();
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = (W)stg[S::pos(0, 0, e)];
+        stage((flags & B_BROADCAST) ? b : b + off);
+        fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
+#pragma unroll
+        for (int e = 0; e < S::E; e++) A[e] = m.fwd_out(x[e]);
+        cp_async_wait_all();
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = (W)stg[S::pos(0, 0, e)];
+        if (poly + gridDim.x < batch) stage(a + (poly + gridDim.x) * S::N);
+        fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(A[e], m.fwd_out(x[e]));
+        if (c_evals != nullptr) {
+            W ev[S::E];
+#pragma unroll
+            for (int e = 0; e < S::E; e++) ev[e] = m.pw_evals(x[e]);
+            store_poly<M, LOGN, LOGE, LAST, false, true, IOW>(ev, c_evals + off, true, sm, tid);
+            if constexpr (S::P > 1) group_sync<S::T>();
+        }
+        inv_chain<M, LOGN, LOGE, LAST, false>(x, sm, tid, m, twi, P.ninv_pw, P.s_ninv_pw);
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
+        store_poly<M, LOGN, LOGE, 0, true, true, IOW>(x, c + off, true, sm, tid);
+    }
+}
+template <class M, int LOGN, int LOGE, typename IOW>
+int launch_staged(const NttParams<M> &P, const IOW *a, const IOW *b, IOW *c, IOW *c_evals, size_t batch, int flags,
+                  cudaStream_t st) {
+    typedef StagedGeom<M, LOGN, LOGE, IOW> SG;
+    auto kern = ntt_mul_staged_kernel<M, LOGN, LOGE, IOW>;
+    static std::atomic<int> resident[64];
+    int dev = 0;
+    FHE_CUDA_OK(cudaGetDevice(&dev));
+    int per_sm = resident[dev & 63].load(std::memory_order_acquire);
+    if (per_sm == 0) {
+        FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG::smem));
+        FHE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SG::S::T, SG::smem));
+        if (per_sm < 1) per_sm = 1;
+        resident[dev & 63].store(per_sm, std::memory_order_release);
+    }
+    const size_t cap = (size_t)per_sm * num_sms();
+    const unsigned grid = (unsigned)(batch < cap ? batch : cap);
+    kern<<<grid, SG::S::T, SG::smem, st>>>(P, a, b, c, c_evals, batch, flags);
+    FHE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+// MODE_MULS: polymul through ntt_mul_staged_kernel (two coefficient-form operands, degrees >= 2^13)
+constexpr bool staged_instantiated(int logn) { return logn >= 13; }
+
+template <class M, int LOGN, int LOGE, int MODE, typename IOW>
+int launch_one(const NttParams<M> &P, const IOW *a, const IOW *b, IOW *c, IOW *c_evals, size_t batch, int flags,
                cudaStream_t st) {
     typedef KernelGeom<LOGN, LOGE> G;
-    auto kern = ntt_kernel<M, LOGN, LOGE, MODE>;
-    const size_t smem = (size_t)G::PPC * (G::template padn<sizeof(typename M::W)>() + (ASmem<M, LOGN, LOGE, MODE>::on ? G::S::N : 0)) * sizeof(typename M::W);
+    auto kern = ntt_kernel<M, LOGN, LOGE, MODE, IOW>;
+    const size_t smem = ASmem<M, LOGN, LOGE, MODE>::words * sizeof(typename M::W);
     if (smem > 48 * 1024) {  // opt in once per device (and per instantiation)
-        static unsigned long long done_mask = 0;
+        static std::atomic<unsigned long long> done_mask{0};
         int dev = 0;
         FHE_CUDA_OK(cudaGetDevice(&dev));
-        if (!((done_mask >> (dev & 63)) & 1ull)) {
+        if (!((done_mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
             FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            done_mask |= 1ull << (dev & 63);
-        }
-    }
-    {   // tuning knob: FHE_NTT_CARVE = preferred shared-memory carve-out in percent (caps the resident CTAs, leaves
-        // the rest of the 256 KB to L1 for the twiddle tables); unset = the driver's choice
-        static int carve_done = 0;
-        if (!carve_done) {
-            if (const char *e = getenv("FHE_NTT_CARVE"))
-                FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-            carve_done = 1;
+            done_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
         }
     }
     const size_t grid = (batch + G::PPC - 1) / G::PPC;
     FHE_REQUIRE(grid <= 0x7fffffffull, "batch too large for one launch");
-    int pf_dist = 0;
-    if constexpr (ntt_prefetch(LOGN, MODE)) {  // CTAs resident on the whole device (cached per device)
-        static int resident[64] = {0};
-        int dev = 0;
-        FHE_CUDA_OK(cudaGetDevice(&dev));
-        if (resident[dev & 63] == 0) {
-            int per_sm = 0;
-            FHE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::CT, smem));
-            resident[dev & 63] = (per_sm > 0 ? per_sm : 1) * num_sms();
-        }
-        pf_dist = resident[dev & 63];
-    }
-    kern<<<(unsigned)grid, G::CT, smem, st>>>(P, a, b, c, c_evals, batch, flags, pf_dist);
+    kern<<<(unsigned)grid, G::CT, smem, st>>>(P, a, b, c, c_evals, batch, flags);
     FHE_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <class M, int LOGN, int LE>
-int launch_modes(int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, size_t batch,
+// does the dual-operand polymul fit one CTA's shared memory at this shape?
+template <class M, int LOGN, int LOGE> constexpr bool mul2_fits() {
+    return ASmem<M, LOGN, LOGE, MODE_MUL2>::words * sizeof(typename M::W) <= 227 * 1024;
+}
+
+template <class M, int LOGN, int LE, typename IOW>
+int launch_modes(int mode, const NttParams<M> &P, const IOW *a, const IOW *b, IOW *c, IOW *c_evals, size_t batch,
                  int flags, cudaStream_t st) {
     switch (mode) {
-        case MODE_FWD: return launch_one<M, LOGN, LE, MODE_FWD>(P, a, b, c, c_evals, batch, flags, st);
-        case MODE_INV: return launch_one<M, LOGN, LE, MODE_INV>(P, a, b, c, c_evals, batch, flags, st);
-        default: return launch_one<M, LOGN, LE, MODE_MUL>(P, a, b, c, c_evals, batch, flags, st);
+        case MODE_FWD: return launch_one<M, LOGN, LE, MODE_FWD, IOW>(P, a, b, c, c_evals, batch, flags, st);
+        case MODE_INV: return launch_one<M, LOGN, LE, MODE_INV, IOW>(P, a, b, c, c_evals, batch, flags, st);
+        case MODE_MULG:
+            if constexpr (staged_instantiated(LOGN) && sizeof(typename M::W) == 4) {
+                if (c != a && c != b && c_evals == nullptr)
+                    return launch_one<M, LOGN, LE, MODE_MULG, IOW>(P, a, b, c, c_evals, batch, flags, st);
+            }
+            return launch_one<M, LOGN, LE, MODE_MUL, IOW>(P, a, b, c, c_evals, batch, flags, st);
+        case MODE_MULS:
+            if constexpr (staged_instantiated(LOGN) && StagedGeom<M, LOGN, LE, IOW>::fits) {
+                if ((flags & (A_IS_EVALS | B_IS_EVALS)) == 0)
+                    return launch_staged<M, LOGN, LE, IOW>(P, a, b, c, c_evals, batch, flags, st);
+            }
+            return launch_one<M, LOGN, LE, MODE_MUL, IOW>(P, a, b, c, c_evals, batch, flags, st);
+        case MODE_MUL2:
+            if constexpr (mul2_fits<M, LOGN, LE>()) {
+                if ((flags & (A_IS_EVALS | B_IS_EVALS)) == 0)
+                    return launch_one<M, LOGN, LE, MODE_MUL2, IOW>(P, a, b, c, c_evals, batch, flags, st);
+            }
+            // fall through: evals flags (or a shape that does not fit) take the generic polymul
+        default: return launch_one<M, LOGN, LE, MODE_MUL, IOW>(P, a, b, c, c_evals, batch, flags, st);
     }
 }
 
 // `loge` must be a value ntt_loge_supported() accepts for (M, logn): the default LogE<M>::of(logn), or, for
-// the tunable degrees, one of the alternatives instantiated below.
-// tunable degrees of the 32-bit policies: which coefficients-per-thread settings are instantiated
-constexpr bool ntt_alt_loge(int logn, int loge, int wbytes) {
-    return wbytes == 4 && ((logn >= 10 && logn <= 12 && loge >= 3 && loge <= 5) || (logn >= 13 && logn <= 14 && loge >= 4 && loge <= 5));
+// the tunable degrees, one of the alternatives instantiated below (u64 I/O only).
+constexpr bool ntt_alt_loge(int logn, int loge, int wbytes, int iobytes) {
+    if (iobytes != 8) return false;
+    if (wbytes == 4)
+        return (logn >= 10 && logn <= 12 && loge >= 3 && loge <= 5) || (logn >= 13 && logn <= 14 && loge >= 4 && loge <= 5);
+    // 64-bit words: 8 or 16 coefficients per thread (4 was measured too: slower at every degree)
+    return logn >= 10 && logn <= 13 && loge >= 3 && loge <= 4;
 }
-template <class M, int LOGN>
-int launch_logn(int loge, int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals,
+template <class M, int LOGN, typename IOW>
+int launch_logn(int loge, int mode, const NttParams<M> &P, const IOW *a, const IOW *b, IOW *c, IOW *c_evals,
                 size_t batch, int flags, cudaStream_t st) {
     constexpr int DEF = LogE<M>::of(LOGN);
-    constexpr int WB = (int)sizeof(typename M::W);
-    if constexpr (ntt_alt_loge(LOGN, 3, WB) && DEF != 3) {
-        if (loge == 3) return launch_modes<M, LOGN, 3>(mode, P, a, b, c, c_evals, batch, flags, st);
+    constexpr int WB = (int)sizeof(typename M::W), IB = (int)sizeof(IOW);
+    if constexpr (ntt_alt_loge(LOGN, 3, WB, IB) && DEF != 3) {
+        if (loge == 3) return launch_modes<M, LOGN, 3, IOW>(mode, P, a, b, c, c_evals, batch, flags, st);
     }
-    if constexpr (ntt_alt_loge(LOGN, 4, WB) && DEF != 4) {
-        if (loge == 4) return launch_modes<M, LOGN, 4>(mode, P, a, b, c, c_evals, batch, flags, st);
+    if constexpr (ntt_alt_loge(LOGN, 4, WB, IB) && DEF != 4) {
+        if (loge == 4) return launch_modes<M, LOGN, 4, IOW>(mode, P, a, b, c, c_evals, batch, flags, st);
     }
-    if constexpr (ntt_alt_loge(LOGN, 5, WB) && DEF != 5) {
-        if (loge == 5) return launch_modes<M, LOGN, 5>(mode, P, a, b, c, c_evals, batch, flags, st);
+    if constexpr (ntt_alt_loge(LOGN, 5, WB, IB) && DEF != 5) {
+        if (loge == 5) return launch_modes<M, LOGN, 5, IOW>(mode, P, a, b, c, c_evals, batch, flags, st);
     }
     if (loge != DEF) {
         set_error("internal: unsupported coefficients-per-thread setting");
         return -1;
     }
-    return launch_modes<M, LOGN, DEF>(mode, P, a, b, c, c_evals, batch, flags, st);
+    return launch_modes<M, LOGN, DEF, IOW>(mode, P, a, b, c, c_evals, batch, flags, st);
 }
-template <class M> bool ntt_loge_supported(int logn, int loge) {
+template <class M, typename IOW> bool ntt_loge_supported(int logn, int loge) {
     if (loge == LogE<M>::of(logn)) return true;
-    return ntt_alt_loge(logn, loge, (int)sizeof(typename M::W));
+    return ntt_alt_loge(logn, loge, (int)sizeof(typename M::W), (int)sizeof(IOW));
 }
 
-template <class M>
-int launch_ntt(int logn, int loge, int mode, const NttParams<M> &P, const u64 *a, const u64 *b, u64 *c, u64 *c_evals,
+template <class M, typename IOW>
+int launch_ntt(int logn, int loge, int mode, const NttParams<M> &P, const IOW *a, const IOW *b, IOW *c, IOW *c_evals,
                size_t batch, int flags, cudaStream_t st) {
     constexpr int MAXLOGN = sizeof(typename M::W) == 4 ? 15 : 14;  // one CTA's shared memory holds the polynomial
     if (logn < 1 || logn > MAXLOGN) {
@@ -398,16 +589,24 @@ int launch_ntt(int logn, int loge, int mode, const NttParams<M> &P, const u64 *a
         return -1;
     }
     switch (logn) {
-#define FHE_CASE(L) case L: return launch_logn<M, L>(loge, mode, P, a, b, c, c_evals, batch, flags, st);
+#define FHE_CASE(L) case L: return launch_logn<M, L, IOW>(loge, mode, P, a, b, c, c_evals, batch, flags, st);
         FHE_CASE(1) FHE_CASE(2) FHE_CASE(3) FHE_CASE(4) FHE_CASE(5) FHE_CASE(6) FHE_CASE(7) FHE_CASE(8)
         FHE_CASE(9) FHE_CASE(10) FHE_CASE(11) FHE_CASE(12) FHE_CASE(13) FHE_CASE(14)
 #undef FHE_CASE
         case 15:
             if constexpr (sizeof(typename M::W) == 4)
-                return launch_logn<M, 15>(loge, mode, P, a, b, c, c_evals, batch, flags, st);
+                return launch_logn<M, 15, IOW>(loge, mode, P, a, b, c, c_evals, batch, flags, st);
     }
     set_error("unsupported ring degree");
     return -1;
 }
+
+// one launcher per (policy, I/O word), each instantiated in its own translation unit (ntt_inst_*.cu)
+#define FHE_NTT_INSTANTIATE(NAME, POLICY, IOW)                                                                        \
+    int ntt_launch_##NAME(int logn, int loge, int mode, const NttParams<POLICY> &P, const IOW *a, const IOW *b, IOW *c, \
+                          IOW *c_evals, size_t batch, int flags, cudaStream_t st) {                                    \
+        return launch_ntt<POLICY, IOW>(logn, loge, mode, P, a, b, c, c_evals, batch, flags, st);                       \
+    }                                                                                                                  \
+    bool ntt_loge_ok_##NAME(int logn, int loge) { return ntt_loge_supported<POLICY, IOW>(logn, loge); }
 
 }  // namespace fhe

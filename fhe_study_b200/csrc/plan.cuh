@@ -4,14 +4,19 @@
 #include "plan_host.hpp"
 
 namespace fhe {
-int ntt_launch_lazy32(int, int, int, const NttParams<Lazy32> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int, cudaStream_t);
-int ntt_launch_lazy64(int, int, int, const NttParams<Lazy64> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int, cudaStream_t);
-int ntt_launch_strict64(int, int, int, const NttParams<Strict64> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int, cudaStream_t);
-int ntt_launch_small32(int, int, int, const NttParams<Small32> &, const u64 *, const u64 *, u64 *, u64 *, size_t, int, cudaStream_t);
-bool ntt_loge_ok_lazy32(int, int);
-bool ntt_loge_ok_lazy64(int, int);
-bool ntt_loge_ok_strict64(int, int);
-bool ntt_loge_ok_small32(int, int);
+#define FHE_NTT_DECLARE(NAME, POLICY, IOW)                                                                           \
+    int ntt_launch_##NAME(int, int, int, const NttParams<POLICY> &, const IOW *, const IOW *, IOW *, IOW *, size_t, int, \
+                          cudaStream_t);                                                                             \
+    bool ntt_loge_ok_##NAME(int, int);
+FHE_NTT_DECLARE(lazy32, Lazy32, u64)
+FHE_NTT_DECLARE(lazy64, Lazy64, u64)
+FHE_NTT_DECLARE(strict64, Strict64, u64)
+FHE_NTT_DECLARE(small32, Small32, u64)
+// packed 32-bit words in global memory (q <= 2^32: Small32 / Lazy32, and Lazy64 for 2^30 <= q <= 2^32)
+FHE_NTT_DECLARE(lazy32_u32, Lazy32, u32)
+FHE_NTT_DECLARE(lazy64_u32, Lazy64, u32)
+FHE_NTT_DECLARE(small32_u32, Small32, u32)
+#undef FHE_NTT_DECLARE
 }  // namespace fhe
 
 // One plan per (device, q, n); owned by the cache in lib_core.cu, reference-counted by create/destroy.
@@ -21,6 +26,9 @@ struct fhe_ntt_plan {
     int logn = 0;
     int loge = 0;  // log2(coefficients per thread) the device tables were laid out for
     int refs = 0;
+    int gpark = 0;   // polymul with NTT(a) parked in the output row (MODE_MULG; 32-bit words, degrees >= 2^13)
+    int staged = 0;  // polymul through the persistent staged kernel (MODE_MULS; degrees >= 2^13)
+    int dual = 0;  // polymul of two coefficient-form operands through the dual-operand kernel (MODE_MUL2)
     fhe::HostTables host;
     void *d_fwd = nullptr, *d_inv = nullptr;
     fhe::NttParams<fhe::Lazy32> p32;

@@ -62,6 +62,10 @@ FHE_API void fhe_ntt_plan_destroy(fhe_ntt_plan *plan);
 /* psi = the primitive 2n-th root the reference's search returns (arith/src/ntt.rs:115-131), n_inv, and
  * (optionally, may be NULL) the two n-entry tables in the reference's order roots[i] = psi^bitrev(i). */
 FHE_API int fhe_ntt_plan_info(const fhe_ntt_plan *plan, uint64_t *psi, uint64_t *n_inv, uint64_t *roots, uint64_t *roots_inv);
+/* Diagnostics: which kernel shape the plan selected -- config[0] = modular policy (0 Lazy32, 1 Lazy64, 2 Strict64,
+ * 3 Small32), [1] = log2(coefficients per thread), [2] = dual-operand polymul, [3] = NTT(a) parked in the output
+ * row, [4] = persistent staged polymul.  (No reference counterpart; used by the tests and the tuning tools.) */
+FHE_API int fhe_ntt_plan_config(const fhe_ntt_plan *plan, int *config);
 
 /* NTT::ntt (arith/src/ntt.rs:44-73): natural order in, bit-reversed order out; `batch` polynomials. */
 FHE_API int fhe_ntt_fwd(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *out, size_t batch);
