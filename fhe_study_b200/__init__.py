@@ -88,6 +88,26 @@ def launch_count() -> int:
     return int(lib.fhe_launch_count())
 
 
+def pack_bits(bits: int, a: np.ndarray) -> np.ndarray:
+    """Host-side serialiser of the bit-packed format: u64 coefficients (last axis a multiple of 32) -> u32 words."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.shape[-1] % 32:
+        raise ValueError("the last axis must be a multiple of 32 coefficients")
+    out = np.empty(a.shape[:-1] + (a.shape[-1] // 32 * int(bits),), dtype=np.uint32)
+    check(lib.fhe_pack_bits(int(bits), ptr(a), ptr(out), a.size))
+    return out
+
+
+def unpack_bits(bits: int, w: np.ndarray) -> np.ndarray:
+    """Inverse of pack_bits: u32 words (last axis a multiple of `bits`) -> u64 coefficients."""
+    w = np.ascontiguousarray(w, dtype=np.uint32)
+    if w.shape[-1] % int(bits):
+        raise ValueError("the last axis must be a multiple of `bits` words")
+    out = np.empty(w.shape[:-1] + (w.shape[-1] // int(bits) * 32,), dtype=np.uint64)
+    check(lib.fhe_unpack_bits(int(bits), ptr(w), ptr(out), out.size))
+    return out
+
+
 class NttPlan:
     """(q, n) plan: mirrors the reference's global ``(q,n) -> (roots, roots_inv, n_inv)`` cache
     (arith/src/ntt.rs:18-38).  Raises FheError where the reference panics."""
@@ -171,6 +191,33 @@ class NttPlan:
         if _numel(a) != _numel(b):
             raise ValueError("operand sizes differ")
         check(lib.fhe_rq_mul_u32(self._h, ptr(a), ptr(b), ptr(out), self._batch(a), int(flags), ptr(evals_out)))
+        return out
+
+    # bit-packed wire format (q < 2^30, n >= 1024): n*bits/32 u32 words per polynomial, read and written by the kernels
+    def _batch_packed(self, a, bits) -> int:
+        row = self.n // 32 * int(bits)
+        ne = _numel(a)
+        if ne % row:
+            raise ValueError("buffer length is not a multiple of n*bits/32 words")
+        return ne // row
+
+    def ntt_packed(self, bits, a, out=None):
+        out = _empty_like(a) if out is None else out
+        _check_u32(a, out)
+        check(lib.fhe_ntt_fwd_packed(self._h, int(bits), ptr(a), ptr(out), self._batch_packed(a, bits)))
+        return out
+
+    def intt_packed(self, bits, a, out=None):
+        out = _empty_like(a) if out is None else out
+        _check_u32(a, out)
+        check(lib.fhe_ntt_inv_packed(self._h, int(bits), ptr(a), ptr(out), self._batch_packed(a, bits)))
+        return out
+
+    def mul_packed(self, bits, a, b, out=None, flags: int = 0, evals_out=None):
+        out = _empty_like(a) if out is None else out
+        _check_u32(a, b, out, evals_out)
+        check(lib.fhe_rq_mul_packed(self._h, int(bits), ptr(a), ptr(b), ptr(out), self._batch_packed(a, bits), int(flags),
+                                    ptr(evals_out)))
         return out
 
 

@@ -52,6 +52,11 @@ SIGNATURES = {
     "fhe_ntt_fwd_u32": (I, [P, P, P, SZ]),
     "fhe_ntt_inv_u32": (I, [P, P, P, SZ]),
     "fhe_rq_mul_u32": (I, [P, P, P, P, SZ, I, P]),
+    "fhe_ntt_fwd_packed": (I, [P, I, P, P, SZ]),
+    "fhe_ntt_inv_packed": (I, [P, I, P, P, SZ]),
+    "fhe_rq_mul_packed": (I, [P, I, P, P, P, SZ, I, P]),
+    "fhe_pack_bits": (I, [I, P, P, SZ]),
+    "fhe_unpack_bits": (I, [I, P, P, SZ]),
     "fhe_tn_mul": (I, [U64, P, P, P, SZ]),
     "fhe_tn_add": (I, [P, P, P, SZ]),
     "fhe_tn_sub": (I, [P, P, P, SZ]),

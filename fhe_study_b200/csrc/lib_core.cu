@@ -7,6 +7,7 @@
 #include <map>
 #include <memory>
 #include <tuple>
+#include <type_traits>
 
 #include "../../include/fhe_b200.h"
 #include "plan.cuh"
@@ -122,6 +123,21 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *b, 
     return rc;
 }
 
+// bit-packed words (q < 2^30, n >= 1024): `bits` rides in the upper bits of the kernel's flags word
+constexpr int PACKED_BITS_SHIFT = 8;
+int launch_plan(const fhe_ntt_plan *plan, int mode, const pk32 *a, const pk32 *b, pk32 *c, pk32 *c_evals, size_t batch,
+                int flags, cudaStream_t st) {
+    int rc;
+    mode = mul_mode_for(plan, mode, flags);
+    switch (plan->kind) {
+        case 3: rc = ntt_launch_small32_pk(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
+        case 0: rc = ntt_launch_lazy32_pk(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
+        default: set_error("the bit-packed format needs q < 2^30"); return -1;
+    }
+    if (!rc) count_launch(1);
+    return rc;
+}
+
 thread_local PipeStreams t_pipe;
 
 // bytes per operand and pipeline stage of the chunked host-buffer paths (FHE_PIPE_CHUNK_MB overrides; tuning knob).
@@ -147,29 +163,30 @@ size_t pipe_chunk_bytes() {
         }                                                                               \
     }
 
-// Host-buffer batches of NTT / INTT / polymul, W = u64 or u32 words: chunked, double-buffered on the device; the H2D
-// copy of chunk i+1, the ONE kernel launch of chunk i and the D2H copy of chunk i-1 overlap on three streams.
+// Host-buffer batches of NTT / INTT / polymul, W = u64, u32 or bit-packed words (`row` words per polynomial):
+// chunked, double-buffered on the device; the H2D copy of chunk i+1, the ONE kernel launch of chunk i and the D2H copy
+// of chunk i-1 overlap on three streams.
 template <typename W>
 int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const W *a, const W *b, W *c, W *c_evals, size_t batch,
-                      int flags, cudaStream_t st, size_t chunk) {
+                      int flags, cudaStream_t st, size_t chunk, size_t row) {
     int rc = t_pipe.init();
     if (rc) return rc;
     PipeStreams &ps = t_pipe;
-    const size_t n = plan->host.n, cbytes = chunk * n * sizeof(W);
+    const size_t cbytes = chunk * row * sizeof(W);
     const int nbuf = 1 + (b ? 1 : 0) + 1 + (c_evals ? 1 : 0);
     Scratch scratch;
     if ((rc = scratch.alloc(2 * nbuf * cbytes, st))) return rc;
     W *dev = scratch.ptr<W>();
     FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch is used from the side streams as well
-    auto buf = [&](int which, int parity) { return dev + ((size_t)parity * nbuf + which) * chunk * n; };
+    auto buf = [&](int which, int parity) { return dev + ((size_t)parity * nbuf + which) * chunk * row; };
     const int ib = 1, ic = b ? 2 : 1, ie = ic + 1;
     size_t i = 0;
     for (size_t off = 0; off < batch; off += chunk, i++) {
-        const size_t nb = std::min(chunk, batch - off), bytes = nb * n * sizeof(W);
+        const size_t nb = std::min(chunk, batch - off), bytes = nb * row * sizeof(W);
         const int par = (int)(i & 1);
         if (i >= 2) FHE_PIPE_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // inputs of chunk i-2 consumed
-        FHE_PIPE_OK(cudaMemcpyAsync(buf(0, par), a + off * n, bytes, cudaMemcpyHostToDevice, ps.h2d));
-        if (b) FHE_PIPE_OK(cudaMemcpyAsync(buf(ib, par), b + off * n, bytes, cudaMemcpyHostToDevice, ps.h2d));
+        FHE_PIPE_OK(cudaMemcpyAsync(buf(0, par), a + off * row, bytes, cudaMemcpyHostToDevice, ps.h2d));
+        if (b) FHE_PIPE_OK(cudaMemcpyAsync(buf(ib, par), b + off * row, bytes, cudaMemcpyHostToDevice, ps.h2d));
         FHE_PIPE_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
         FHE_PIPE_OK(cudaStreamWaitEvent(st, ps.h2d_done[par], 0));
         if (i >= 2) FHE_PIPE_OK(cudaStreamWaitEvent(st, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
@@ -178,8 +195,8 @@ int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const W *a, const W *b
             break;
         FHE_PIPE_OK(cudaEventRecord(ps.comp_done[par], st));
         FHE_PIPE_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
-        FHE_PIPE_OK(cudaMemcpyAsync(c + off * n, buf(ic, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
-        if (c_evals) FHE_PIPE_OK(cudaMemcpyAsync(c_evals + off * n, buf(ie, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
+        FHE_PIPE_OK(cudaMemcpyAsync(c + off * row, buf(ic, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
+        if (c_evals) FHE_PIPE_OK(cudaMemcpyAsync(c_evals + off * row, buf(ie, par), bytes, cudaMemcpyDeviceToHost, ps.d2h));
         FHE_PIPE_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
     }
     cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st);
@@ -192,29 +209,40 @@ int run_ntt_pipelined(const fhe_ntt_plan *plan, int mode, const W *a, const W *b
     return 0;
 }
 
-// NTT / INTT / polymul over words of type W (u64: SURVEY 8b layout; u32: packed format for q <= 2^32).  Every pointer
-// may be a host or a device pointer; all-device calls are ONE asynchronous kernel launch on the current stream.
+// NTT / INTT / polymul over words of type W (u64: SURVEY 8b layout; u32: packed words for q <= 2^32; pk32: `bits`
+// bits per coefficient).  Every pointer may be a host or a device pointer; all-device calls are ONE asynchronous
+// kernel launch on the current stream.
 template <typename W>
-int run_ntt(const fhe_ntt_plan *plan, int mode, const W *a, const W *b, W *c, W *c_evals, size_t batch, int flags) {
+int run_ntt(const fhe_ntt_plan *plan, int mode, const W *a, const W *b, W *c, W *c_evals, size_t batch, int flags,
+            int bits = 0) {
     FHE_REQUIRE(plan != nullptr, "null plan");
     if (batch == 0) return 0;
     FHE_REQUIRE(a != nullptr && c != nullptr && (mode != MODE_MUL || b != nullptr), "null polynomial pointer");
-    if (sizeof(W) == 4) FHE_REQUIRE(plan->host.q <= (1ull << 32), "the 32-bit word format needs q <= 2^32");
+    FHE_REQUIRE((flags & ~7) == 0, "unknown flag bits");
+    size_t row = plan->host.n;  // words per polynomial
+    if (std::is_same<W, u32>::value) FHE_REQUIRE(plan->host.q <= (1ull << 32), "the 32-bit word format needs q <= 2^32");
+    if (std::is_same<W, pk32>::value) {
+        FHE_REQUIRE(bits >= 16 && bits <= 31, "bit-packed format: 16 <= bits <= 31");
+        FHE_REQUIRE(plan->host.q <= (1ull << bits), "bit-packed format: q does not fit the field width");
+        FHE_REQUIRE(plan->host.n >= 1024, "the bit-packed format needs n >= 1024");
+        row = plan->host.n / 32 * (size_t)bits;
+        flags |= bits << PACKED_BITS_SHIFT;
+    }
     int rc = check_device(plan->device, "NTT plan");
     if (rc) return rc;
     cudaStream_t st = current_stream();
-    const size_t bytes = batch * plan->host.n * sizeof(W);
+    const size_t bytes = batch * row * sizeof(W);
     if (mode != MODE_MUL) b = nullptr;
     const bool bcast = mode == MODE_MUL && (flags & B_BROADCAST);
     if (!bcast) {   // all-host call on a batch worth pipelining (>= 4 chunks of ~32 MiB per operand)
-        const size_t chunk = std::max<size_t>(1, pipe_chunk_bytes() / (plan->host.n * sizeof(W)));
+        const size_t chunk = std::max<size_t>(1, pipe_chunk_bytes() / (row * sizeof(W)));
         if (batch >= 4 * chunk && is_host_ptr(a) && (!b || is_host_ptr(b)) && is_host_ptr(c) &&
             (!c_evals || is_host_ptr(c_evals)) && a != c && b != c)
-            return run_ntt_pipelined<W>(plan, mode, a, b, c, c_evals, batch, flags, st, chunk);
+            return run_ntt_pipelined<W>(plan, mode, a, b, c, c_evals, batch, flags, st, chunk, row);
     }
     IoBuf ba, bb, bc, be;
     if ((rc = ba.init(a, bytes, true, false, st))) return rc;
-    if ((rc = bb.init(mode == MODE_MUL ? b : nullptr, bcast ? plan->host.n * sizeof(W) : bytes, true, false, st))) return rc;
+    if ((rc = bb.init(mode == MODE_MUL ? b : nullptr, bcast ? row * sizeof(W) : bytes, true, false, st))) return rc;
     if ((rc = bc.init(c, bytes, false, true, st))) return rc;
     if ((rc = be.init(c_evals, bytes, false, true, st))) return rc;
     rc = launch_plan(plan, mode, ba.ptr<W>(), bb.ptr<W>(), bc.ptr<W>(), be.ptr<W>(), batch, flags, st);
@@ -354,6 +382,62 @@ int fhe_ntt_inv(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *out, siz
 int fhe_rq_mul(const fhe_ntt_plan *plan, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, int flags,
                uint64_t *c_evals) {
     return run_ntt<u64>(plan, MODE_MUL, a, b, c, c_evals, batch, flags);
+}
+int fhe_ntt_fwd_packed(const fhe_ntt_plan *plan, int bits, const uint32_t *in, uint32_t *out, size_t batch) {
+    return run_ntt<pk32>(plan, MODE_FWD, reinterpret_cast<const pk32 *>(in), nullptr, reinterpret_cast<pk32 *>(out), nullptr, batch, 0, bits);
+}
+int fhe_ntt_inv_packed(const fhe_ntt_plan *plan, int bits, const uint32_t *in, uint32_t *out, size_t batch) {
+    return run_ntt<pk32>(plan, MODE_INV, reinterpret_cast<const pk32 *>(in), nullptr, reinterpret_cast<pk32 *>(out), nullptr, batch, 0, bits);
+}
+int fhe_rq_mul_packed(const fhe_ntt_plan *plan, int bits, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch,
+                      int flags, uint32_t *c_evals) {
+    return run_ntt<pk32>(plan, MODE_MUL, reinterpret_cast<const pk32 *>(a), reinterpret_cast<const pk32 *>(b),
+                         reinterpret_cast<pk32 *>(c), reinterpret_cast<pk32 *>(c_evals), batch, flags, bits);
+}
+// host-side (de)serialisation of the bit-packed format: `len` coefficients <-> len * bits / 32 words (len % 32 == 0)
+int fhe_pack_bits(int bits, const uint64_t *in, uint32_t *out, size_t len) {
+    FHE_REQUIRE(bits >= 1 && bits <= 32 && in != nullptr && out != nullptr && len % 32 == 0, "fhe_pack_bits: bad arguments");
+    const size_t blocks = len / 32;
+    for (size_t blk = 0; blk < blocks; blk++) {
+        const uint64_t *src = in + blk * 32;
+        uint32_t *dst = out + blk * (size_t)bits;
+        uint64_t acc = 0;
+        int have = 0;
+        size_t w = 0;
+        for (int i = 0; i < 32; i++) {
+            FHE_REQUIRE(bits == 32 ? src[i] <= 0xffffffffull : (src[i] >> bits) == 0, "fhe_pack_bits: coefficient does not fit the field");
+            acc |= src[i] << have;
+            have += bits;
+            if (have >= 32) {
+                dst[w++] = (uint32_t)acc;
+                acc >>= 32;
+                have -= 32;
+            }
+        }
+    }
+    return 0;
+}
+int fhe_unpack_bits(int bits, const uint32_t *in, uint64_t *out, size_t len) {
+    FHE_REQUIRE(bits >= 1 && bits <= 32 && in != nullptr && out != nullptr && len % 32 == 0, "fhe_unpack_bits: bad arguments");
+    const uint64_t mask = bits == 32 ? 0xffffffffull : ((1ull << bits) - 1);
+    const size_t blocks = len / 32;
+    for (size_t blk = 0; blk < blocks; blk++) {
+        const uint32_t *src = in + blk * (size_t)bits;
+        uint64_t *dst = out + blk * 32;
+        uint64_t acc = 0;
+        int have = 0;
+        size_t w = 0;
+        for (int i = 0; i < 32; i++) {
+            if (have < bits) {
+                acc |= (uint64_t)src[w++] << have;
+                have += 32;
+            }
+            dst[i] = acc & mask;
+            acc >>= bits;
+            have -= bits;
+        }
+    }
+    return 0;
 }
 int fhe_ntt_fwd_u32(const fhe_ntt_plan *plan, const uint32_t *in, uint32_t *out, size_t batch) {
     return run_ntt<u32>(plan, MODE_FWD, in, nullptr, out, nullptr, batch, 0);

@@ -198,6 +198,61 @@ __device__ __forceinline__ void store_poly(typename M::W (&x)[1 << LOGE], IOW *_
     }
 }
 
+// ---- bit-packed global format (the PCIe wire of the host-buffer path) ----------------------------------------------
+// A polynomial is n * bits / 32 consecutive u32 words, coefficient i in bits [i*bits, (i+1)*bits), little endian,
+// 16 <= bits <= 31 (q = 65537: 17 bits instead of 32 or 64 per coefficient over PCIe).  Only for shapes whose
+// pass-0 layout gives the 32 lanes of a warp 32 consecutive coefficients per register slot (T a multiple of 32 and
+// nL(0) >= 5: every n >= 1024): then a warp's slot-e fields form ONE word-aligned block of `bits` words, the field
+// shift (bits * lane) & 31 is the same for all of a thread's slots, a load is two lane-contiguous LDG.32 and a funnel
+// shift, and a store is assembled from <= 3 neighbouring lanes with warp shuffles.
+struct pk32 { u32 v; };  // tag type: u32 words of the packed format
+template <typename IOW> struct IoTraits { static constexpr bool packed = false; };
+template <> struct IoTraits<pk32> { static constexpr bool packed = true; };
+// words from the start of the batch to polynomial `poly`
+template <typename IOW, int N> __device__ __forceinline__ size_t row_offset(size_t poly, int bits) {
+    if constexpr (IoTraits<IOW>::packed) return poly * (size_t)((N >> 5) * bits);
+    else return poly * (size_t)N;
+}
+template <int LOGN, int LOGE> __host__ __device__ constexpr bool packed_shape_ok() {
+    typedef NttShape<LOGN, LOGE> S;
+    return S::T % 32 == 0 && S::nL(0) >= 5;
+}
+template <class M, int LOGN, int LOGE, int TO, bool STREAM>
+__device__ __forceinline__ void load_poly_packed(typename M::W (&x)[1 << LOGE], const pk32 *__restrict__ g, int bits,
+                                                 typename M::W *sm, int tid) {
+    typedef NttShape<LOGN, LOGE> S;
+    static_assert(packed_shape_ok<LOGN, LOGE>(), "packed format: unsupported shape");
+    const u32 bo = (u32)bits * (u32)tid, sh = bo & 31u, mask = (1u << bits) - 1u;
+    const u32 *gw = reinterpret_cast<const u32 *>(g) + (bo >> 5);
+    const bool two = sh + (u32)bits > 32u;  // the field straddles a word boundary (thread constant)
+#pragma unroll
+    for (int e = 0; e < S::E; e++) {
+        const u32 w = (u32)(S::pos(0, 0, e) >> 5) * (u32)bits;  // pos(0,0,e) is a multiple of 32
+        const u32 lo = __ldg(gw + w), hi = two ? __ldg(gw + w + 1) : 0u;
+        x[e] = (typename M::W)(__funnelshift_r(lo, hi, sh) & mask);
+    }
+    if constexpr (TO != 0) exchange<M, LOGN, LOGE, 0, TO>(x, sm, tid);
+}
+template <class M, int LOGN, int LOGE, int FROM, bool LEAD, bool STREAM>
+__device__ __forceinline__ void store_poly_packed(typename M::W (&x)[1 << LOGE], pk32 *__restrict__ g, int bits, bool valid,
+                                                  typename M::W *sm, int tid) {
+    typedef NttShape<LOGN, LOGE> S;
+    static_assert(packed_shape_ok<LOGN, LOGE>(), "packed format: unsupported shape");
+    if constexpr (FROM != 0) exchange<M, LOGN, LOGE, FROM, 0, LEAD>(x, sm, tid);
+    const u32 lane = (u32)tid & 31u;
+    // word `lane` of the warp's block covers block bits [32*lane, 32*lane+32): fields f0, f0+1, f0+2
+    const u32 f0 = (32u * lane) / (u32)bits, a0 = 32u * lane - f0 * (u32)bits, a1 = (u32)bits - a0, a2 = a1 + (u32)bits;
+    u32 *gw = reinterpret_cast<u32 *>(g) + (u32)(tid >> 5) * (u32)bits + lane;
+#pragma unroll
+    for (int e = 0; e < S::E; e++) {
+        const u32 v = (u32)x[e];
+        const u32 v0 = __shfl_sync(0xffffffffu, v, f0 & 31u), v1 = __shfl_sync(0xffffffffu, v, (f0 + 1u) & 31u),
+                  v2 = __shfl_sync(0xffffffffu, v, (f0 + 2u) & 31u);
+        const u32 word = (v0 >> a0) | (a1 < 32u ? v1 << a1 : 0u) | (a2 < 32u ? v2 << a2 : 0u);
+        if (valid && lane < (u32)bits) gw[(u32)(S::pos(0, 0, e) >> 5) * (u32)bits] = word;
+    }
+}
+
 // Polymul with NTT(a) parked in shared memory while b is transformed (instead of E more live registers): lets more
 // CTAs be resident.  A thread reads back exactly the words it wrote, so no barrier is involved.
 //   32-bit words: FHE_A_SMEM_MINB = resident CTAs asked of ptxas (N=1024 only; measured slower, off).
@@ -279,6 +334,20 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
         ((MODE == MODE_MUL2 ? 2 : 1) * KernelGeom<LOGN, LOGE>::template padn<sizeof(typename M::W)>() + (on ? NttShape<LOGN, LOGE>::N : 0));
 };
 
+// I/O dispatch of the kernels below: plain words or the packed format (`bits` is only read by the latter)
+template <class M, int LOGN, int LOGE, int TO, bool STREAM, typename IOW>
+__device__ __forceinline__ void load_any(typename M::W (&x)[1 << LOGE], const IOW *__restrict__ g, int bits, typename M::W *sm,
+                                         int tid) {
+    if constexpr (IoTraits<IOW>::packed) load_poly_packed<M, LOGN, LOGE, TO, STREAM>(x, g, bits, sm, tid);
+    else load_poly<M, LOGN, LOGE, TO, STREAM, IOW>(x, g, true, sm, tid);
+}
+template <class M, int LOGN, int LOGE, int FROM, bool LEAD, bool STREAM, typename IOW>
+__device__ __forceinline__ void store_any(typename M::W (&x)[1 << LOGE], IOW *__restrict__ g, int bits, bool valid,
+                                          typename M::W *sm, int tid) {
+    if constexpr (IoTraits<IOW>::packed) store_poly_packed<M, LOGN, LOGE, FROM, LEAD, STREAM>(x, g, bits, valid, sm, tid);
+    else store_poly<M, LOGN, LOGE, FROM, LEAD, STREAM, IOW>(x, g, valid, sm, tid);
+}
+
 template <class M, int LOGN, int LOGE, int MODE, typename IOW>
 __global__ void __launch_bounds__(KernelGeom<LOGN, LOGE>::CT, ASmem<M, LOGN, LOGE, MODE>::minb)
 ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, const IOW *__restrict__ b,
@@ -294,26 +363,27 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, co
     const bool valid = poly < batch;
     // slots past the end of a ragged batch read the last polynomial (and store nothing): unconditional loads, no
     // zero-filled registers
-    const size_t off_ld = (valid ? poly : batch - 1) * S::N;
-    const size_t off = poly * S::N;
+    const int bits = flags >> 8;  // packed format only (FHE_PACKED_BITS_SHIFT)
+    const size_t off_ld = row_offset<IOW, S::N>(valid ? poly : batch - 1, bits);
+    const size_t off = row_offset<IOW, S::N>(poly, bits);
     const M &m = P.mod;
     constexpr int LAST = S::P - 1;
     W x[S::E];
 
     if constexpr (MODE == MODE_FWD) {
         const TwSrc<M> tw = {P.c_fwd, P.fwd};
-        load_poly<M, LOGN, LOGE, 0, false, IOW>(x, a + off_ld, true, sm, tid);
+        load_any<M, LOGN, LOGE, 0, false, IOW>(x, a + off_ld, bits, sm, tid);
         fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, tw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.fwd_canon(x[e]);
-        store_poly<M, LOGN, LOGE, LAST, false, false, IOW>(x, c + off, valid, sm, tid);  // last smem access: own reads in layout LAST
+        store_any<M, LOGN, LOGE, LAST, false, false, IOW>(x, c + off, bits, valid, sm, tid);  // last smem access: own reads in layout LAST
     } else if constexpr (MODE == MODE_INV) {
         const TwSrc<M> tw = {P.c_inv, P.inv};
-        load_poly<M, LOGN, LOGE, LAST, false, IOW>(x, a + off_ld, true, sm, tid);
+        load_any<M, LOGN, LOGE, LAST, false, IOW>(x, a + off_ld, bits, sm, tid);
         inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, tw, P.ninv, P.s_ninv);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
-        store_poly<M, LOGN, LOGE, 0, true, false, IOW>(x, c + off, valid, sm, tid);
+        store_any<M, LOGN, LOGE, 0, true, false, IOW>(x, c + off, bits, valid, sm, tid);
     } else {
         const TwSrc<M> twf = {P.c_fwd, P.fwd};
         const TwSrc<M> twi = {P.c_inv, P.inv};
@@ -321,8 +391,8 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, co
         if constexpr (MODE == MODE_MUL2) {
             W y[S::E];
             W *smy = reinterpret_cast<W *>(smem_raw) + (size_t)(G::PPC + slot) * PADW;
-            load_poly<M, LOGN, LOGE, 0, ST, IOW>(x, a + off_ld, true, sm, tid);
-            load_poly<M, LOGN, LOGE, 0, ST, IOW>(y, (flags & B_BROADCAST) ? b : b + off_ld, true, smy, tid);
+            load_any<M, LOGN, LOGE, 0, ST, IOW>(x, a + off_ld, bits, sm, tid);
+            load_any<M, LOGN, LOGE, 0, ST, IOW>(y, (flags & B_BROADCAST) ? b : b + off_ld, bits, smy, tid);
             fwd_chain2<M, LOGN, LOGE, 0, false>(x, y, sm, smy, tid, m, twf);  // fresh shared memory: no lead barrier
 #pragma unroll
             for (int e = 0; e < S::E; e++) x[e] = m.pw_mul(m.fwd_out(x[e]), m.fwd_out(y[e]));
@@ -340,9 +410,9 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, co
             for (int op = 0; op < 2; op++) {
                 const IOW *src = op == 0 ? a + off_ld : (flags & B_BROADCAST) ? b : b + off_ld;
                 if (flags & (op == 0 ? A_IS_EVALS : B_IS_EVALS)) {
-                    load_poly<M, LOGN, LOGE, LAST, ST, IOW>(x, src, true, sm, tid);
+                    load_any<M, LOGN, LOGE, LAST, ST, IOW>(x, src, bits, sm, tid);
                 } else {
-                    load_poly<M, LOGN, LOGE, 0, ST, IOW>(x, src, true, sm, tid);
+                    load_any<M, LOGN, LOGE, 0, ST, IOW>(x, src, bits, sm, tid);
                     fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
 #pragma unroll
                     for (int e = 0; e < S::E; e++) x[e] = m.fwd_out(x[e]);
@@ -380,13 +450,13 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, co
 #pragma unroll
             for (int e = 0; e < S::E; e++) ev[e] = m.pw_evals(x[e]);
             // the last smem access (end of the forward chain, or load_poly<LAST>) was this thread's reads in layout LAST
-            store_poly<M, LOGN, LOGE, LAST, false, ST, IOW>(ev, c_evals + off, valid, sm, tid);
+            store_any<M, LOGN, LOGE, LAST, false, ST, IOW>(ev, c_evals + off, bits, valid, sm, tid);
             if constexpr (S::P > 1) group_sync<S::T>();  // the evals store read layout 0: foreign words
         }
         inv_chain<M, LOGN, LOGE, LAST, false>(x, sm, tid, m, twi, P.ninv_pw, P.s_ninv_pw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
-        store_poly<M, LOGN, LOGE, 0, true, ST, IOW>(x, c + off, valid, sm, tid);
+        store_any<M, LOGN, LOGE, 0, true, ST, IOW>(x, c + off, bits, valid, sm, tid);
     }
 }
 
@@ -525,13 +595,13 @@ int launch_modes(int mode, const NttParams<M> &P, const IOW *a, const IOW *b, IO
         case MODE_FWD: return launch_one<M, LOGN, LE, MODE_FWD, IOW>(P, a, b, c, c_evals, batch, flags, st);
         case MODE_INV: return launch_one<M, LOGN, LE, MODE_INV, IOW>(P, a, b, c, c_evals, batch, flags, st);
         case MODE_MULG:
-            if constexpr (staged_instantiated(LOGN) && sizeof(typename M::W) == 4) {
+            if constexpr (staged_instantiated(LOGN) && sizeof(typename M::W) == 4 && !IoTraits<IOW>::packed) {
                 if (c != a && c != b && c_evals == nullptr)
                     return launch_one<M, LOGN, LE, MODE_MULG, IOW>(P, a, b, c, c_evals, batch, flags, st);
             }
             return launch_one<M, LOGN, LE, MODE_MUL, IOW>(P, a, b, c, c_evals, batch, flags, st);
         case MODE_MULS:
-            if constexpr (staged_instantiated(LOGN) && StagedGeom<M, LOGN, LE, IOW>::fits) {
+            if constexpr (staged_instantiated(LOGN) && !IoTraits<IOW>::packed && StagedGeom<M, LOGN, LE, IOW>::fits) {
                 if ((flags & (A_IS_EVALS | B_IS_EVALS)) == 0)
                     return launch_staged<M, LOGN, LE, IOW>(P, a, b, c, c_evals, batch, flags, st);
             }
@@ -573,7 +643,12 @@ int launch_logn(int loge, int mode, const NttParams<M> &P, const IOW *a, const I
         set_error("internal: unsupported coefficients-per-thread setting");
         return -1;
     }
-    return launch_modes<M, LOGN, DEF, IOW>(mode, P, a, b, c, c_evals, batch, flags, st);
+    if constexpr (IoTraits<IOW>::packed && !packed_shape_ok<LOGN, DEF>()) {
+        set_error("the bit-packed format needs n >= 1024");
+        return -1;
+    } else {
+        return launch_modes<M, LOGN, DEF, IOW>(mode, P, a, b, c, c_evals, batch, flags, st);
+    }
 }
 template <class M, typename IOW> bool ntt_loge_supported(int logn, int loge) {
     if (loge == LogE<M>::of(logn)) return true;

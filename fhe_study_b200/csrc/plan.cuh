@@ -16,6 +16,9 @@ FHE_NTT_DECLARE(small32, Small32, u64)
 FHE_NTT_DECLARE(lazy32_u32, Lazy32, u32)
 FHE_NTT_DECLARE(lazy64_u32, Lazy64, u32)
 FHE_NTT_DECLARE(small32_u32, Small32, u32)
+// bit-packed words (q < 2^30, n >= 1024): the PCIe wire of the host-buffer path
+FHE_NTT_DECLARE(small32_pk, Small32, pk32)
+FHE_NTT_DECLARE(lazy32_pk, Lazy32, pk32)
 #undef FHE_NTT_DECLARE
 }  // namespace fhe
 

@@ -89,6 +89,18 @@ FHE_API int fhe_ntt_inv_u32(const fhe_ntt_plan *plan, const uint32_t *in, uint32
 FHE_API int fhe_rq_mul_u32(const fhe_ntt_plan *plan, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch, int flags,
                            uint32_t *c_evals);
 
+/* Bit-packed wire format of the same three calls (q < 2^30, q <= 2^bits, 16 <= bits <= 31, n >= 1024): a polynomial is
+ * n*bits/32 uint32_t words, coefficient i in bits [i*bits, (i+1)*bits) little-endian -- 17 bits per coefficient for
+ * the reference's q = 65537 instead of 128 (Vec<Zq>), 64 or 32.  The kernels read and write this format directly
+ * (one launch per chunk); it exists because the host-buffer path is PCIe-bound.  fhe_pack_bits / fhe_unpack_bits are
+ * the host-side (de)serialisers (len % 32 == 0); the format is also the on-disk layout of fhe_b200_file.h. */
+FHE_API int fhe_ntt_fwd_packed(const fhe_ntt_plan *plan, int bits, const uint32_t *in, uint32_t *out, size_t batch);
+FHE_API int fhe_ntt_inv_packed(const fhe_ntt_plan *plan, int bits, const uint32_t *in, uint32_t *out, size_t batch);
+FHE_API int fhe_rq_mul_packed(const fhe_ntt_plan *plan, int bits, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch,
+                              int flags, uint32_t *c_evals);
+FHE_API int fhe_pack_bits(int bits, const uint64_t *in, uint32_t *out, size_t len);
+FHE_API int fhe_unpack_bits(int bits, const uint32_t *in, uint64_t *out, size_t len);
+
 /* ---- Tn = T_q[X]/(X^n+1), q = 2^64 (arith/src/ring_torus.rs) ------------------------------------------- */
 /* impl Mul<Tn> for Tn -> naive_poly_mul (ring_torus.rs:251-298): exact negacyclic product mod 2^64. */
 FHE_API int fhe_tn_mul(uint64_t n, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch);
