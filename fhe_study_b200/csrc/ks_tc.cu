@@ -6,99 +6,80 @@
 // engine: the legacy mma.sync path saturates its IMMA pipe at ~0.8 POPS (profiles/r1_keyswitch_imma_*),
 // tcgen05 reads both operands from shared memory through descriptors and accumulates in tensor memory.
 //
-// CTA = 256 ciphertexts x 256 columns (32 key words x 8 planes), K step 128, 3-stage ring (64 KB/stage):
+// CTA = 256 ciphertexts x 256 columns (32 key words x 8 planes), K step 128.  Two rings of different depth: the A
+// tiles (expanded mask bits, 32 KB per K step) are refilled by the CTA's own threads within a few hundred cycles of
+// their stage being freed, the key blocks (32 KB per K step) come from L2 / HBM with a round trip of about two K steps
+// of MMA time -- so A gets 3 stages and B gets 4 (224 KB of shared memory in all; r1 ran 3 + 3 and the tensor pipe
+// idled 18 % of the time waiting for key blocks):
 //   warp 0      : one lane streams the key blocks with cp.async.bulk (TMA 1-D) -> full_b[s]
 //   warp 1      : allocates TMEM (512 columns = two 128x256 s32 accumulators); one lane issues, per K step,
-//                 4 x 2 tcgen05.mma (M=128, N=256, K=32) and commits them to empty[s]
+//                 4 x 2 tcgen05.mma (M=128, N=256, K=32) and commits them to empty_a[sa] and empty_b[sb]
 //   warps 2..9  : 256 threads, one ciphertext row each: expand 2 mask words per K step into 128 bytes of the
 //                 swizzled A tiles (never materialised in HBM), fence.proxy.async, arrive on full_a[s];
 //                 at the end they are the epilogue: tcgen05.ld the accumulator rows, shift-and-add the 8 plane
 //                 sums of each key word, subtract from (0,..,0,b) (tfhe/src/tlwe.rs:111) and store.
 #include "../../include/fhe_b200.h"
 #include "runtime.cuh"
+#include <stdlib.h>
+
+#include <atomic>
+
+#include "tc_common.cuh"
 #include "tlwe.cuh"
 
 namespace fhe {
 
-constexpr int TC_BM = 256, TC_BN = 256, TC_BK = 128, TC_STAGES = 3;
+constexpr int TC_BM = 256, TC_BN = 256, TC_BK = 128;
+#ifndef FHE_KS_STAGES_A
+#define FHE_KS_STAGES_A 3
+#endif
+#ifndef FHE_KS_STAGES_B
+#define FHE_KS_STAGES_B 3
+#endif
+constexpr int TC_SA = FHE_KS_STAGES_A, TC_SB = FHE_KS_STAGES_B;
 constexpr int TC_THREADS = 320;                       // 10 warps
 constexpr int TC_A_HALF = 128 * TC_BK;                // 16 KB: one 128-row A tile
+constexpr int TC_A_BYTES = 2 * TC_A_HALF;             // 32 KB: both A tiles of a K step
 constexpr int TC_B_BYTES = TC_BN * TC_BK;             // 32 KB
-constexpr int TC_STAGE = 2 * TC_A_HALF + TC_B_BYTES;  // 64 KB
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE + 256;
+constexpr size_t TC_RING = (size_t)TC_SA * TC_A_BYTES + (size_t)TC_SB * TC_B_BYTES;
+constexpr size_t TC_SMEM = TC_RING + 256;
+static_assert(TC_SMEM <= 227 * 1024, "ks_tc: rings exceed one CTA's shared memory");
+static_assert((2 * TC_SA + 2 * TC_SB + 1) * 8 + 4 <= 256, "ks_tc: barrier block too small");
 
-__device__ __forceinline__ u32 tc_smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void tc_mbar_init(u32 bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void tc_mbar_expect_tx(u32 bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_arrive(u32 bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_wait(u32 bar, u32 parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "TC_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra TC_DONE;\n"
-        "bra TC_WAIT;\n"
-        "TC_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tc_bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows 128 B apart, 8-row groups 1024 B apart
-__device__ __forceinline__ u64 tc_smem_desc(u32 saddr) {
-    return (u64)((saddr >> 4) & 0x3FFFu) | ((u64)1 << 16) /* LBO (unused for swizzled K-major) */ |
-           ((u64)(1024 >> 4) << 32) /* SBO */ | ((u64)1 << 46) /* descriptor version (sm_100) */ |
-           ((u64)2 << 61) /* SWIZZLE_128B */;
-}
-// instruction descriptor: D = s32, A = B = u8, both K-major, M = 128, N = 256
-constexpr u32 TC_IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void tc_mma_i8(u32 tmem_d, u64 adesc, u64 bdesc, u32 accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit(u32 bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ u32 tc_spread4(u32 nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster (neighbouring blocks of 256 ciphertexts, same
+// column tile) need the same key blocks: each fetches HALF of every block and multicasts it into both shared memories,
+// so the L2 -> SM key traffic halves.  At 3 M bootstraps/s that traffic is 8.6 TB/s for CL = 1 -- the chip-wide L2
+// limit (~12 TB/s at full clock) minus what the mask words take -- which is what held the tensor pipe at 82 %.
+template <int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ks_tc_kernel(const unsigned char *__restrict__ blocks, const u64 *__restrict__ ct, u64 *__restrict__ out, size_t batch,
              u32 kn_in, u32 kn_out) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    u64 *bars = reinterpret_cast<u64 *>(smem + (size_t)TC_STAGES * TC_STAGE);
-    // bars[0..S) full_a, [S..2S) full_b, [2S..3S) empty, [3S] accumulators ready ; then the TMEM base address
-    u32 *tmem_slot = reinterpret_cast<u32 *>(bars + 3 * TC_STAGES + 1);
+    unsigned char *ringA = smem, *ringB = smem + (size_t)TC_SA * TC_A_BYTES;
+    u64 *bars = reinterpret_cast<u64 *>(smem + TC_RING);
+    // bars: [0,SA) full_a, [SA,2SA) empty_a, [2SA,2SA+SB) full_b, [2SA+SB,2SA+2SB) empty_b, then accumulators ready
+    u32 *tmem_slot = reinterpret_cast<u32 *>(bars + 2 * TC_SA + 2 * TC_SB + 1);
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u32 KT = kn_in / 2, w = kn_out + 1;
     const size_t b0 = (size_t)blockIdx.x * TC_BM;
     const u32 nt = blockIdx.y;
     const unsigned char *gB = blocks + (size_t)nt * KT * TC_B_BYTES;
     auto full_a = [&](u32 s) { return tc_smem_u32(&bars[s]); };
-    auto full_b = [&](u32 s) { return tc_smem_u32(&bars[TC_STAGES + s]); };
-    auto empty = [&](u32 s) { return tc_smem_u32(&bars[2 * TC_STAGES + s]); };
-    const u32 acc_bar = tc_smem_u32(&bars[3 * TC_STAGES]);
+    auto empty_a = [&](u32 s) { return tc_smem_u32(&bars[TC_SA + s]); };
+    auto full_b = [&](u32 s) { return tc_smem_u32(&bars[2 * TC_SA + s]); };
+    auto empty_b = [&](u32 s) { return tc_smem_u32(&bars[2 * TC_SA + TC_SB + s]); };
+    const u32 acc_bar = tc_smem_u32(&bars[2 * TC_SA + 2 * TC_SB]);
 
     if (tid == 0) {
-        for (u32 s = 0; s < TC_STAGES; s++) {
+        for (u32 s = 0; s < TC_SA; s++) {
             tc_mbar_init(full_a(s), 256);
+            tc_mbar_init(empty_a(s), 1);
+        }
+        for (u32 s = 0; s < TC_SB; s++) {
             tc_mbar_init(full_b(s), 1);
-            tc_mbar_init(empty(s), 1);
+            tc_mbar_init(empty_b(s), CL);  // the stage is rewritten for every CTA of the cluster at once
         }
         tc_mbar_init(acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -111,37 +92,45 @@ ks_tc_kernel(const unsigned char *__restrict__ blocks, const u64 *__restrict__ c
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CL > 1) tc_cluster_sync();  // the peer's barriers are initialised before anything arrives on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const u32 tmem_base = *tmem_slot;
+    constexpr unsigned short CL_MASK = (unsigned short)((1u << CL) - 1u);
 
     if (warp == 0) {
         // ===== key-block producer =====
         if (lane == 0) {
+            const u32 rank = CL > 1 ? tc_cluster_rank() : 0u;
+            constexpr u32 PART = TC_B_BYTES / CL;
             for (u32 kt = 0; kt < KT; kt++) {
-                const u32 s = kt % TC_STAGES, ph = (kt / TC_STAGES) & 1;
-                tc_mbar_wait(empty(s), ph ^ 1);
+                const u32 s = kt % TC_SB, ph = (kt / TC_SB) & 1;
+                tc_mbar_wait(empty_b(s), ph ^ 1);  // stage s is free in EVERY CTA of the cluster
                 tc_mbar_expect_tx(full_b(s), TC_B_BYTES);
-                tc_bulk_g2s(tc_smem_u32(smem + (size_t)s * TC_STAGE + 2 * TC_A_HALF), gB + (size_t)kt * TC_B_BYTES, TC_B_BYTES,
-                            full_b(s));
+                const u32 dst = tc_smem_u32(ringB + (size_t)s * TC_B_BYTES + (size_t)rank * PART);
+                const unsigned char *src = gB + (size_t)kt * TC_B_BYTES + (size_t)rank * PART;
+                if constexpr (CL > 1) tc_bulk_g2s_multicast(dst, src, PART, full_b(s), CL_MASK);
+                else tc_bulk_g2s(dst, src, PART, full_b(s));
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             for (u32 kt = 0; kt < KT; kt++) {
-                const u32 s = kt % TC_STAGES, ph = (kt / TC_STAGES) & 1;
-                tc_mbar_wait(full_a(s), ph);
-                tc_mbar_wait(full_b(s), ph);
+                const u32 sa_i = kt % TC_SA, pha = (kt / TC_SA) & 1, sb_i = kt % TC_SB, phb = (kt / TC_SB) & 1;
+                tc_mbar_wait(full_a(sa_i), pha);
+                tc_mbar_wait(full_b(sb_i), phb);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const u32 sa = tc_smem_u32(smem + (size_t)s * TC_STAGE);
+                const u32 sa = tc_smem_u32(ringA + (size_t)sa_i * TC_A_BYTES), sb = tc_smem_u32(ringB + (size_t)sb_i * TC_B_BYTES);
 #pragma unroll
                 for (u32 k = 0; k < TC_BK / 32; k++) {
-                    const u64 bd = tc_smem_desc(sa + 2 * TC_A_HALF + k * 32);
+                    const u64 bd = tc_smem_desc(sb + k * 32);
                     const u32 accum = (kt | k) != 0 ? 1u : 0u;
                     tc_mma_i8(tmem_base, tc_smem_desc(sa + k * 32), bd, accum);
                     tc_mma_i8(tmem_base + 256, tc_smem_desc(sa + TC_A_HALF + k * 32), bd, accum);
                 }
-                tc_commit(empty(s));  // arrives when the MMAs above have finished reading stage s
+                tc_commit(empty_a(sa_i));  // both arrive when the MMAs above have finished reading their stages
+                if constexpr (CL > 1) tc_commit_multicast(empty_b(sb_i), CL_MASK);
+                else tc_commit(empty_b(sb_i));
             }
             tc_commit(acc_bar);
         }
@@ -153,14 +142,14 @@ ks_tc_kernel(const unsigned char *__restrict__ blocks, const u64 *__restrict__ c
         const u64 *cp = ct + (b0 + e) * (size_t)(kn_in + 1);
         u64 w0 = row_ok ? __ldg(cp) : 0, w1 = row_ok ? __ldg(cp + 1) : 0;
         for (u32 kt = 0; kt < KT; kt++) {
-            const u32 s = kt % TC_STAGES, ph = (kt / TC_STAGES) & 1;
+            const u32 s = kt % TC_SA, ph = (kt / TC_SA) & 1;
             const u64 c0 = w0, c1 = w1;
             if (kt + 1 < KT) {
                 w0 = row_ok ? __ldg(cp + 2 * (size_t)(kt + 1)) : 0;
                 w1 = row_ok ? __ldg(cp + 2 * (size_t)(kt + 1) + 1) : 0;
             }
-            tc_mbar_wait(empty(s), ph ^ 1);
-            unsigned char *A = smem + (size_t)s * TC_STAGE + (size_t)half * TC_A_HALF + (size_t)row * 128;
+            tc_mbar_wait(empty_a(s), ph ^ 1);
+            unsigned char *A = ringA + (size_t)s * TC_A_BYTES + (size_t)half * TC_A_HALF + (size_t)row * 128;
 #pragma unroll
             for (u32 c = 0; c < 8; c++) {
                 const u64 wd = c < 4 ? c0 : c1;
@@ -213,21 +202,48 @@ ks_tc_kernel(const unsigned char *__restrict__ blocks, const u64 *__restrict__ c
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+    if constexpr (CL > 1) tc_cluster_sync();  // no CTA leaves while its peer may still write into it or arrive on its barriers
 }
 
-int key_switch_tc_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
-    static unsigned long long done_mask = 0;
+// FHE_KS_CLUSTER=1|2 overrides the cluster size (tuning knob and tests)
+static int ks_cluster_size() {
+    static const int v = [] {
+        const char *e = getenv("FHE_KS_CLUSTER");
+        const int c = e ? atoi(e) : 2;
+        return c == 1 ? 1 : 2;
+    }();
+    return v;
+}
+template <int CL>
+static int launch_ks_tc(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
+    static std::atomic<unsigned long long> done_mask{0};
     int dev = 0;
     FHE_CUDA_OK(cudaGetDevice(&dev));
-    if (!((done_mask >> (dev & 63)) & 1ull)) {
-        FHE_CUDA_OK(cudaFuncSetAttribute(ks_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        done_mask |= 1ull << (dev & 63);
+    if (!((done_mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+        FHE_CUDA_OK(cudaFuncSetAttribute(ks_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        done_mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    dim3 grid((unsigned)((batch + TC_BM - 1) / TC_BM), k.mma_n_tiles);
-    ks_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(k.mma_blocks, ct, out, batch, (u32)k.kn_in, (u32)k.kn_out);
+    unsigned gx = (unsigned)((batch + TC_BM - 1) / TC_BM);
+    gx = (gx + CL - 1) / CL * CL;  // whole clusters; a block past the end of the batch only feeds its peer
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, k.mma_n_tiles);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FHE_CUDA_OK(cudaLaunchKernelEx(&cfg, ks_tc_kernel<CL>, (const unsigned char *)k.mma_blocks, ct, out, batch, (u32)k.kn_in,
+                                   (u32)k.kn_out));
     count_launch(1);
-    FHE_CUDA_OK(cudaGetLastError());
     return 0;
+}
+int key_switch_tc_device(const Ksk &k, const u64 *ct, u64 *out, size_t batch, cudaStream_t st) {
+    return ks_cluster_size() == 2 ? launch_ks_tc<2>(k, ct, out, batch, st) : launch_ks_tc<1>(k, ct, out, batch, st);
 }
 
 }  // namespace fhe
