@@ -40,22 +40,23 @@ def ntt_sweep(fhe, dev, quick):
     for q in (Q17, Q62):
         for logn in (10, 11, 12, 13, 14):
             n = 1 << logn
-            batch = (1 << 26) // n  # 512 MiB per operand
+            batch = (1 << 26) // n  # 512 MiB per u64 operand
             plan = fhe.NttPlan(q, n)
-            a = torch.randint(0, min(q, 2**62), (batch, n), dtype=torch.int64, device=dev)
-            b = torch.randint(0, min(q, 2**62), (batch, n), dtype=torch.int64, device=dev)
-            c = torch.empty_like(a)
-            row = {"q": q, "n": n, "batch": batch}
-            for name, fn, nbuf in (
-                ("ntt", lambda: plan.ntt(a, out=c), 2),
-                ("intt", lambda: plan.intt(a, out=c), 2),
-                ("polymul", lambda: plan.mul(a, b, out=c), 3),
-            ):
-                ms = _time(fn, reps)
-                gbs = nbuf * n * 8 * batch / (ms * 1e-3) / 1e9
-                row[name] = {"per_s": batch / (ms * 1e-3), "ms": ms, "hbm_gbs": gbs, "hbm_frac": gbs / peak}
-            out.append(row)
-            del a, b, c
+            for fmt, dt, wb in (("u64", torch.int64, 8),) + ((("u32", torch.int32, 4),) if q <= 2**32 else ()):
+                a = torch.randint(0, min(q, 2**31 - 1 if wb == 4 else 2**62), (batch, n), dtype=dt, device=dev)
+                b = torch.randint(0, min(q, 2**31 - 1 if wb == 4 else 2**62), (batch, n), dtype=dt, device=dev)
+                c = torch.empty_like(a)
+                row = {"q": q, "n": n, "batch": batch, "format": fmt, "bytes_per_coeff": wb}
+                fns = (("ntt", lambda: plan.ntt(a, out=c), 2), ("intt", lambda: plan.intt(a, out=c), 2),
+                       ("polymul", lambda: plan.mul(a, b, out=c), 3)) if wb == 8 else \
+                      (("ntt", lambda: plan.ntt_u32(a, out=c), 2), ("intt", lambda: plan.intt_u32(a, out=c), 2),
+                       ("polymul", lambda: plan.mul_u32(a, b, out=c), 3))
+                for name, fn, nbuf in fns:
+                    ms = _time(fn, reps)
+                    gbs = nbuf * n * wb * batch / (ms * 1e-3) / 1e9
+                    row[name] = {"per_s": batch / (ms * 1e-3), "ms": ms, "hbm_gbs": gbs, "hbm_frac": gbs / peak}
+                out.append(row)
+                del a, b, c
     # batch sweep at N=1024 (BASELINE configs[1]: batch 1..64k), device-resident; small batches are launch-latency bound
     plan = fhe.NttPlan(Q17, 1024)
     batch_sweep = []
@@ -283,6 +284,21 @@ def gfhe_path(fhe, dev, quick, cpu=True):
     return row
 
 
+def compact_sweep(extras):
+    """The NTT sweep as short rows for the `roofline` key of the bench line: [q bits, n, format, M polymul/s,
+    fraction of HBM peak, fraction of the measured Shoup-modmul peak, fraction of the binding (slower) roofline],
+    plus the same binding fraction for the forward and inverse transforms alone."""
+    rows = []
+    for r in extras.get("ntt", {}).get("sweep", []):
+        pm = r["polymul"]
+        rows.append({"q_bits": int(r["q"]).bit_length(), "n": r["n"], "fmt": r["format"], "M_polymul_per_s": round(pm["per_s"] / 1e6, 3),
+                     "hbm": round(pm["hbm_frac"], 3), "modmul": round(pm["modmul_frac"], 3), "frac": round(pm["roofline_frac"], 3),
+                     "ntt_frac": round(r["ntt"]["roofline_frac"], 3), "intt_frac": round(r["intt"]["roofline_frac"], 3)})
+    return {"rows": rows, "frac_is": "max(hbm, modmul): achieved / the slower of the HBM and integer-modmul rooflines",
+            "min_polymul_frac": min((x["frac"] for x in rows), default=None),
+            "peaks": extras.get("ntt", {}).get("int_peaks")}
+
+
 def run(fhe, dev, quick=False, cpu=True):
     res = {}
     for name, fn in (("ntt", lambda: ntt_sweep(fhe, dev, quick)), ("tfhe", lambda: tfhe_paths(fhe, dev, quick, cpu)),
@@ -292,4 +308,17 @@ def run(fhe, dev, quick=False, cpu=True):
             res[name] = fn()
         except Exception as ex:  # one failing extra must not hide the others
             res[name] = {"error": repr(ex)}
+    compact = {}
+    try:
+        t = res["tfhe"]
+        compact["extprod"] = {k: {"extprod_per_s": t[k]["extprod_per_s"], "cmux_per_s": t[k]["cmux_per_s"], "batch": t[k]["batch"],
+                                  "int_roofline_frac": t[k]["int_roofline_frac"], "hbm_frac": t[k]["hbm_frac"],
+                                  "cpu_extprod_per_s": t[k].get("cpu_extprod_per_s")} for k in ("P4a_n64_k4", "P4b_n1024_k1")}
+    except Exception:
+        pass
+    try:
+        compact["bfv"] = res["bfv"]
+    except Exception:
+        pass
+    res["compact"] = compact
     return res

@@ -77,6 +77,14 @@ def synchronize() -> None:
     check(lib.fhe_synchronize())
 
 
+def rq_check_canonical(q: int, words) -> int | None:
+    """Validation pass for Rq buffers (precondition of every Rq entry point: 0 <= v < q): index of the first
+    word >= q, or None."""
+    bad = C.c_uint64()
+    check(lib.fhe_rq_check_canonical(int(q), ptr(words), _numel(words), C.byref(bad)))
+    return None if bad.value == 2**64 - 1 else int(bad.value)
+
+
 def int_peak(kind: int) -> float:
     """Measured integer-pipe peak (ops/s): 0 = IMAD32, 1 = Shoup modmul 32-bit, 2 = Shoup modmul 64-bit."""
     v = C.c_double()
@@ -560,6 +568,71 @@ def bfv_decrypt(plan: NttPlan, t, sk, ct, out=None):
     out = _new(ct, (batch, plan.n)) if out is None else out
     _check_u64(sk, ct, out)
     check(lib.fhe_bfv_decrypt(plan._h, plan.q, plan.n, int(t), ptr(sk), ptr(ct), ptr(out), batch))
+    return out
+
+
+def bfv_keygen(plan: NttPlan, sigma=3.2, seed=0):
+    """BFV::new_key (bfv/src/lib.rs:120-140) sampled on the device: (sk[n], pk[2n]) as numpy arrays."""
+    sk, pk = np.empty(plan.n, dtype=np.uint64), np.empty(2 * plan.n, dtype=np.uint64)
+    check(lib.fhe_bfv_keygen(plan._h, plan.q, plan.n, float(sigma), int(seed), ptr(sk), ptr(pk)))
+    return sk, pk
+
+
+def bfv_rlk_generate(q, n, p, sk, sigma=3.2, seed=0):
+    """BFV::rlk_key (bfv/src/lib.rs:202-225) on the device: rlk[2n] mod p*q."""
+    _check_u64(sk)
+    out = _new(sk, (2 * int(n),))
+    check(lib.fhe_bfv_rlk_generate(int(q), int(n), int(p), float(sigma), int(seed), ptr(sk), ptr(out)))
+    return out
+
+
+def bfv_mul_const(q, n, t, pq, rlk, c, m, out=None):
+    """BFV::mul_const (bfv/src/lib.rs:189-200) for a batch of RLWEs and plaintext polynomials mod t."""
+    out = _empty_like(c) if out is None else out
+    _check_u64(rlk, c, m, out)
+    check(lib.fhe_bfv_mul_const(int(q), int(n), int(t), int(pq), ptr(rlk), ptr(c), ptr(m), ptr(out), _numel(c) // (2 * int(n))))
+    return out
+
+
+def ckks_keygen(plan: NttPlan, sigma=3.2, seed=0):
+    """CKKS::new_key (ckks/src/lib.rs:46-63) sampled on the device: (sk[n], pk[2n])."""
+    sk, pk = np.empty(plan.n, dtype=np.uint64), np.empty(2 * plan.n, dtype=np.uint64)
+    check(lib.fhe_ckks_keygen(plan._h, plan.q, plan.n, float(sigma), int(seed), ptr(sk), ptr(pk)))
+    return sk, pk
+
+
+def ckks_encrypt(plan: NttPlan, pk, m, sigma=3.2, seed=0):
+    """CKKS::encrypt (ckks/src/lib.rs:66-84); m = batch x n int64 (elements of R); returns batch x 2n u64."""
+    m = np.ascontiguousarray(m, dtype=np.int64)
+    batch = m.size // plan.n
+    out = np.empty((batch, 2 * plan.n), dtype=np.uint64)
+    _check_u64(pk)
+    check(lib.fhe_ckks_encrypt(plan._h, plan.q, plan.n, ptr(pk), ptr(m), float(sigma), int(seed), ptr(out), batch))
+    return out
+
+
+def ckks_decrypt(plan: NttPlan, sk, ct):
+    """CKKS::decrypt (ckks/src/lib.rs:86-94): batch x n int64 (centred representatives mod q)."""
+    _check_u64(sk, ct)
+    batch = _numel(ct) // (2 * plan.n)
+    out = np.empty((batch, plan.n), dtype=np.int64)
+    check(lib.fhe_ckks_decrypt(plan._h, plan.q, plan.n, ptr(sk), ptr(ct), ptr(out), batch))
+    return out
+
+
+def ckks_add(q, n, c0, c1, sub=False):
+    """CKKS::add / CKKS::sub (ckks/src/lib.rs:113-118; sub as written adds the second components)."""
+    out = _empty_like(c0)
+    _check_u64(c0, c1, out)
+    fn = lib.fhe_ckks_sub if sub else lib.fhe_ckks_add
+    check(fn(int(q), int(n), ptr(c0), ptr(c1), ptr(out), _numel(c0) // (2 * int(n))))
+    return out
+
+
+def compute_lookup_table(n, k, t):
+    """compute_lookup_table (tfhe/src/tlwe.rs:196-214): the trivial TGLWE of the staircase table, (k+1)*n words."""
+    out = np.empty((int(k) + 1) * int(n), dtype=np.uint64)
+    check(lib.fhe_compute_lookup_table(int(n), int(k), int(t), ptr(out)))
     return out
 
 

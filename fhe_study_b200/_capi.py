@@ -38,6 +38,7 @@ SIGNATURES = {
     "fhe_last_error": (C.c_char_p, []),
     "fhe_device_count": (I, [C.POINTER(I)]),
     "fhe_set_device": (I, [I]),
+    "fhe_current_device": (I, [C.POINTER(I)]),
     "fhe_set_stream": (I, [P]),
     "fhe_synchronize": (I, []),
     "fhe_launch_count": (U64, []),
@@ -46,6 +47,7 @@ SIGNATURES = {
     "fhe_ntt_plan_destroy": (None, [P]),
     "fhe_ntt_plan_info": (I, [P, C.POINTER(U64), C.POINTER(U64), P, P]),
     "fhe_ntt_plan_config": (I, [P, C.POINTER(I)]),
+    "fhe_rq_check_canonical": (I, [U64, P, SZ, C.POINTER(U64)]),
     "fhe_ntt_fwd": (I, [P, P, P, SZ]),
     "fhe_ntt_inv": (I, [P, P, P, SZ]),
     "fhe_rq_mul": (I, [P, P, P, P, SZ, I, P]),
@@ -57,6 +59,15 @@ SIGNATURES = {
     "fhe_rq_mul_packed": (I, [P, I, P, P, P, SZ, I, P]),
     "fhe_pack_bits": (I, [I, P, P, SZ]),
     "fhe_unpack_bits": (I, [I, P, P, SZ]),
+    "fhe_bfv_keygen": (I, [P, U64, U64, C.c_double, U64, P, P]),
+    "fhe_bfv_rlk_generate": (I, [U64, U64, U64, C.c_double, U64, P, P]),
+    "fhe_bfv_mul_const": (I, [U64, U64, U64, U64, P, P, P, P, SZ]),
+    "fhe_ckks_keygen": (I, [P, U64, U64, C.c_double, U64, P, P]),
+    "fhe_ckks_encrypt": (I, [P, U64, U64, P, P, C.c_double, U64, P, SZ]),
+    "fhe_ckks_decrypt": (I, [P, U64, U64, P, P, P, SZ]),
+    "fhe_ckks_add": (I, [U64, U64, P, P, P, SZ]),
+    "fhe_ckks_sub": (I, [U64, U64, P, P, P, SZ]),
+    "fhe_compute_lookup_table": (I, [U64, U64, U64, P]),
     "fhe_tn_mul": (I, [U64, P, P, P, SZ]),
     "fhe_tn_add": (I, [P, P, P, SZ]),
     "fhe_tn_sub": (I, [P, P, P, SZ]),

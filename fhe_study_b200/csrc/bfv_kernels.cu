@@ -9,30 +9,9 @@
 
 #include "../../include/fhe_b200.h"
 #include "runtime.cuh"
+#include "scheme_common.cuh"
 
 namespace fhe {
-
-// Rust `f64 as i64`: saturating, NaN -> 0 (cvt.rzi.s64.f64 has exactly these semantics)
-__device__ __forceinline__ i64 f64_as_i64(double x) { return __double2ll_rz(x); }
-// Zq::from_f64 (zq.rs:32-40): r = round(e) as i64; out of [0, q): ((r % q) + q) % q with the signed remainder,
-// i.e. the mathematical r mod q.  Nearly every scaled coefficient takes that branch (t*v/q >> q), and two software
-// 64-bit divisions per coefficient were the bulk of the kernel: |r| mod q is one Barrett step with
-// mu = floor((2^64 - 1) / q) (quotient estimate low by at most two for any 64-bit operand), the sign is applied after.
-__device__ __forceinline__ u64 zq_from_f64(u64 q, u64 mu, double e) {
-    const i64 ei = f64_as_i64(round(e));
-    if (ei >= 0 && (u64)ei < q) return (u64)ei;
-    const u64 mag = ei < 0 ? (u64)0 - (u64)ei : (u64)ei;  // |r| (2^63 for i64::MIN)
-    u64 r = mag - __umul64hi(mag, mu) * q;                 // quotient estimate low by at most 2: r in [0, 3q)
-    if (r >= q) r -= q;
-    if (r >= q) r -= q;
-    return (ei < 0 && r != 0) ? q - r : r;
-}
-// one coefficient of ring_n::mul_div_round (ring_n.rs:130-138): round((num as f64 * v as f64) / den as f64) -> Zq
-__device__ __forceinline__ u64 scale_round(u64 q, u64 mu, i64 v, double num, double den) {
-    return zq_from_f64(q, mu, __ddiv_rn(__dmul_rn(num, __ll2double_rn(v)), den));
-}
-__device__ __forceinline__ u64 zq_sub(u64 q, u64 a, u64 b) { return a >= b ? a - b : (q + a) - b; }  // zq.rs:259-277
-__device__ __forceinline__ u64 zq_add(u64 q, u64 a, u64 b) { u64 v = a + b; return v >= q ? v - q : v; }  // zq.rs:219-231
 
 // fold of the scaled pair (ring_nq.rs:132-141): res[c] = f(conv[c]) - f(conv[c+n]); index c+n exists for c <= n-2
 __device__ __forceinline__ u64 scale_fold(u64 q, u64 mu, u32 n, u32 c, u64 lo, u64 hi, double num, double den) {
@@ -176,13 +155,6 @@ __global__ void bfv_decrypt_finish_kernel(const u64 *__restrict__ ct, const u64 
 // ---- BFV::encrypt (bfv/src/lib.rs:142-160) with a counter-based sampler (the CPU restatement orc_bfv_encrypt_ctr) -------
 // draw p of ciphertext r is SplitMix64 output r*25n + p + 1: p < n -> u_x = from_f64(-1 + 2 unit) (Uniform(-1,1), lib.rs:149);
 // n + 12x + t -> e1_x, 13n + 12x + t -> e2_x, each from_f64(sigma * (sum of 12 units - 6)) (Normal(0, sigma) stand-in)
-__device__ __forceinline__ u64 bfv_draw(u64 seed, u64 pos) {
-    u64 z = seed + (pos + 1) * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-__device__ __forceinline__ double bfv_unit(u64 v) { return __dmul_rn(__ull2double_rn(v >> 11), 1.0 / 9007199254740992.0); }
 __global__ void bfv_sample_u_kernel(u64 *__restrict__ U, size_t batch, u32 n, u64 q, u64 seed) {
     const size_t total = batch * n;
     const u64 mu = ~0ull / q;
@@ -210,6 +182,73 @@ __global__ void bfv_encrypt_finish_kernel(const u64 *__restrict__ P0, const u64 
         const u64 md = (u64)(((unsigned __int128)mv * dq) % q);                         // m * floor(q/t), ring_nq.rs:274-281
         ct[r * 2 * n + x] = zq_add(q, zq_add(q, P0[i], e1), md);                        // &pk.0 * &u + e_1 + m*delta
         ct[r * 2 * n + n + x] = zq_add(q, P1[i], e2);                                   // &pk.1 * &u + e_2
+    }
+}
+
+// ---- BFV::new_key (bfv/src/lib.rs:120-140), counter-based sampler (orc_bfv_keygen_ctr) ---------------------------------
+// draws: p < n: s_p = draw % 2 ; n + x: a_x = draw % q ; 2n + 12x + t: e_x.  Writes s, -a (for the product), a and e.
+__global__ void bfv_keygen_sample_kernel(u64 *__restrict__ sk, u64 *__restrict__ neg_a, u64 *__restrict__ a, u64 *__restrict__ e,
+                                         u32 n, u64 q, double sigma, u64 seed) {
+    const u64 mu = ~0ull / q;
+    for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+        const u64 s = bfv_draw(seed, x) % 2, av = bfv_draw(seed, (u64)n + x) % q;
+        sk[x] = s >= q ? s % q : s;  // Zq::from_u64 (zq.rs:21-31)
+        a[x] = av;
+        neg_a[x] = av == 0 ? 0 : q - av;  // Neg (zq.rs:302-314)
+        e[x] = zq_from_f64(q, mu, ctr_gauss(seed, 2 * (u64)n + 12 * (u64)x, sigma));
+    }
+}
+__global__ void rq_add_inplace_kernel(u64 *__restrict__ acc, const u64 *__restrict__ b, u32 n, u64 q) {
+    for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) acc[x] = zq_add(q, acc[x], b[x]);
+}
+
+// ---- BFV::rlk_key (bfv/src/lib.rs:202-225) in the ring mod pq, counter-based sampler (orc_bfv_rlk_key_ctr) ------------------
+// One CTA, thread c owns coefficient c: a*s and s*s through tmp_naive_mul (lib.rs:93-98) = ring_n::naive_mul (wrapping
+// 64-bit sums == `i128 as i64`), Rq::from_vec_i64 (ring_nq.rs:164-170: Zq::from_f64(c as f64) per UNFOLDED coefficient),
+// then the X^n+1 fold as a Zq subtraction; rlk.0 = -(a*s + e) + (s*s)*p, rlk.1 = a.
+__global__ void bfv_rlk_kernel(const u64 *__restrict__ sk, u64 *__restrict__ rlk, u32 n, u64 q, u64 p, double sigma, u64 seed) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    u64 *s = reinterpret_cast<u64 *>(sm_raw), *a = s + n;
+    const u64 pq = p * q, mu = ~0ull / pq;
+    const u32 c = threadIdx.x;
+    s[c] = sk[c] >= pq ? sk[c] % pq : sk[c];  // s.0.remodule(pq)
+    a[c] = bfv_draw(seed, c) % pq;
+    __syncthreads();
+    u64 las = 0, has = 0, lss = 0, hss = 0;
+    u32 j = c;
+    for (u32 i = 0; i < n; i++) {
+        const u64 as = a[i] * s[j], ss = s[i] * s[j];
+        if (i <= c) { las += as; lss += ss; } else { has += as; hss += ss; }
+        j = j == 0 ? n - 1 : j - 1;
+    }
+    auto from_i64 = [&](u64 v) { return zq_from_f64(pq, mu, __ll2double_rn((i64)v)); };
+    u64 as = from_i64(las), ss = from_i64(lss);
+    if (c + 1 < n) {
+        as = zq_sub(pq, as, from_i64(has));
+        ss = zq_sub(pq, ss, from_i64(hss));
+    }
+    const u64 e = zq_from_f64(pq, mu, ctr_gauss(seed, (u64)n + 12 * (u64)c, sigma));
+    const u64 t0 = zq_add(pq, as, e);
+    const u64 neg = t0 == 0 ? 0 : pq - t0;
+    const u64 pm = p >= pq ? p % pq : p;                                              // Zq::from_u64(pq, p), ring_nq.rs:274-281
+    const u64 ssp = (u64)(((unsigned __int128)ss * pm) % pq);
+    rlk[c] = zq_add(pq, neg, ssp);
+    rlk[n + c] = a[c];
+}
+
+// md rows of BFV::mul_const (lib.rs:189-200): (m.remodule(q) * floor(q/t), 0)
+__global__ void bfv_mul_const_md_kernel(const u64 *__restrict__ m, u64 *__restrict__ md, size_t batch, u32 n, u64 q, u64 t) {
+    const size_t total = batch * 2 * n;
+    const u64 delta = q / t, dq = delta >= q ? delta % q : delta;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (2 * n);
+        const u32 x = (u32)(i % (2 * n));
+        u64 v = 0;
+        if (x < n) {
+            const u64 mv = m[r * n + x] >= q ? m[r * n + x] % q : m[r * n + x];
+            v = (u64)(((unsigned __int128)mv * dq) % q);
+        }
+        md[i] = v;
     }
 }
 
@@ -276,6 +315,60 @@ int fhe_bfv_decrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, uint64_t t
     count_launch(1);
     FHE_CUDA_OK(cudaGetLastError());
     return finish_all({&bs, &bc, &bm}, st);
+}
+int fhe_bfv_keygen(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, double sigma, uint64_t seed, uint64_t *sk, uint64_t *pk) {
+    FHE_REQUIRE(plan != nullptr, "null plan");
+    FHE_REQUIRE(sk && pk, "fhe_bfv_keygen: null pointer");
+    FHE_REQUIRE(q >= 2 && n >= 1, "fhe_bfv_keygen: bad parameters");
+    cudaStream_t st = current_stream();
+    IoBuf bs, bp;
+    Scratch tmp;  // -a | e
+    int rc;
+    if ((rc = bs.init(sk, n * 8, false, true, st))) return rc;
+    if ((rc = bp.init(pk, 2 * n * 8, false, true, st))) return rc;
+    if ((rc = tmp.alloc(2 * n * 8, st))) return rc;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    bfv_keygen_sample_kernel<<<grid, 256, 0, st>>>(bs.ptr<u64>(), tmp.ptr<u64>(), bp.ptr<u64>() + n, tmp.ptr<u64>() + n, (u32)n, q,
+                                                 sigma, seed);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    if ((rc = plan_launch(plan, 2, tmp.ptr<u64>(), bs.ptr<u64>(), bp.ptr<u64>(), nullptr, 1, 0, st))) return rc;  // &(-a) * &s
+    rq_add_inplace_kernel<<<grid, 256, 0, st>>>(bp.ptr<u64>(), tmp.ptr<u64>() + n, (u32)n, q);                     // + e
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return finish_all({&bs, &bp}, st);
+}
+int fhe_bfv_rlk_generate(uint64_t q, uint64_t n, uint64_t p, double sigma, uint64_t seed, const uint64_t *sk, uint64_t *rlk) {
+    FHE_REQUIRE(sk && rlk, "fhe_bfv_rlk_generate: null pointer");
+    FHE_REQUIRE(n >= 1 && n <= 1024, "fhe_bfv_rlk_generate: n must be in 1..1024 (one thread per coefficient)");
+    FHE_REQUIRE(q >= 2 && p >= 1 && (unsigned __int128)p * q < ((unsigned __int128)1 << 63),
+                "fhe_bfv_rlk_generate: p*q must be < 2^63 (Zq arithmetic mod p*q, zq.rs:225)");
+    cudaStream_t st = current_stream();
+    IoBuf bs, bk;
+    int rc;
+    if ((rc = bs.init(sk, n * 8, true, false, st))) return rc;
+    if ((rc = bk.init(rlk, 2 * n * 8, false, true, st))) return rc;
+    bfv_rlk_kernel<<<1, (unsigned)n, 2 * n * sizeof(u64), st>>>(bs.ptr<u64>(), bk.ptr<u64>(), (u32)n, q, p, sigma, seed);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return finish_all({&bs, &bk}, st);
+}
+int fhe_bfv_mul_const(uint64_t q, uint64_t n, uint64_t t, uint64_t pq, const uint64_t *rlk, const uint64_t *c, const uint64_t *m,
+                      uint64_t *out, size_t batch) {
+    if (batch == 0) return 0;
+    FHE_REQUIRE(rlk && c && m && out, "fhe_bfv_mul_const: null pointer");
+    FHE_REQUIRE(t >= 1 && q >= 2 && n >= 1, "fhe_bfv_mul_const: bad parameters");
+    cudaStream_t st = current_stream();
+    IoBuf bm;
+    Scratch md;
+    int rc;
+    if ((rc = bm.init(m, batch * n * 8, true, false, st))) return rc;
+    if ((rc = md.alloc(batch * 2 * n * 8, st))) return rc;
+    const unsigned grid = (unsigned)std::min<size_t>((batch * 2 * n + 255) / 256, (size_t)num_sms() * 16);
+    bfv_mul_const_md_kernel<<<grid, 256, 0, st>>>(bm.ptr<u64>(), md.ptr<u64>(), batch, (u32)n, q, t);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return bfv_launch(1, q, n, t, pq, rlk, c, md.ptr<u64>(), out, batch);  // RLWE::mul(t, rlk, c, md)
 }
 int fhe_bfv_tensor(uint64_t q, uint64_t n, uint64_t t, const uint64_t *a, const uint64_t *b, uint64_t *c012, size_t batch) {
     return bfv_launch(0, q, n, t, 0, nullptr, a, b, c012, batch);

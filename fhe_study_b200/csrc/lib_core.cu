@@ -251,6 +251,15 @@ int run_ntt(const fhe_ntt_plan *plan, int mode, const W *a, const W *b, W *c, W 
 }
 }  // namespace
 
+namespace {
+__global__ void first_noncanonical_kernel(const u64 *__restrict__ w, size_t len, u64 q, unsigned long long *first) {
+    unsigned long long best = ~0ull;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x)
+        if (w[i] >= q && i < best) best = i;
+    if (best != ~0ull) atomicMin(first, best);
+}
+}  // namespace
+
 namespace fhe {
 bool is_host_ptr(const void *p) {
     if (p == nullptr) return false;
@@ -281,6 +290,11 @@ int fhe_device_count(int *count) {
 }
 int fhe_set_device(int device) {
     FHE_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+int fhe_current_device(int *device) {
+    FHE_REQUIRE(device != nullptr, "null device out-pointer");
+    FHE_CUDA_OK(cudaGetDevice(device));
     return 0;
 }
 int fhe_set_stream(void *cuda_stream) {
@@ -362,6 +376,25 @@ int fhe_ntt_plan_info(const fhe_ntt_plan *plan, uint64_t *psi, uint64_t *n_inv, 
     if (n_inv) *n_inv = plan->host.n_inv;
     if (roots) memcpy(roots, plan->host.roots.data(), plan->host.n * sizeof(u64));
     if (roots_inv) memcpy(roots_inv, plan->host.roots_inv.data(), plan->host.n * sizeof(u64));
+    return 0;
+}
+int fhe_rq_check_canonical(uint64_t q, const uint64_t *words, size_t len, uint64_t *first_bad) {
+    FHE_REQUIRE(first_bad != nullptr && (words != nullptr || len == 0), "fhe_rq_check_canonical: null pointer");
+    *first_bad = ~0ull;
+    if (len == 0) return 0;
+    cudaStream_t st = current_stream();
+    IoBuf bw;
+    int rc = bw.init(words, len * sizeof(u64), true, false, st);
+    if (rc) return rc;
+    Scratch res;
+    if ((rc = res.alloc(sizeof(unsigned long long), st))) return rc;
+    FHE_CUDA_OK(cudaMemsetAsync(res.ptr<void>(), 0xff, sizeof(unsigned long long), st));
+    const size_t g = (len + 255) / 256, cap = (size_t)num_sms() * 16;
+    first_noncanonical_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, st>>>(bw.ptr<u64>(), len, q, res.ptr<unsigned long long>());
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    FHE_CUDA_OK(cudaMemcpyAsync(first_bad, res.ptr<void>(), sizeof(u64), cudaMemcpyDeviceToHost, st));
+    FHE_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }
 int fhe_ntt_plan_config(const fhe_ntt_plan *plan, int *config) {

@@ -177,6 +177,34 @@ int fhe_sample_extract(uint64_t n, uint64_t k, const uint64_t *ct, uint64_t h, u
     return finish_all({&bi, &bo}, st);
 }
 
+// compute_lookup_table (tlwe.rs:196-214): coefficients [0 x delta, 1 x delta, ..., (t-1) x delta] (delta = n/t) as an Rq
+// mod t, encoded by TGLWE::encode (tglwe.rs:49-58: c * floor(u64::MAX / t), wrapping), mask = 0.
+namespace {
+__global__ void lookup_table_kernel(u64 *__restrict__ out, u64 n, u64 k, u64 t, u64 delta_n) {
+    const u64 total = (k + 1) * n, delta = ~0ull / t;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        u64 v = 0;
+        if (i >= k * n) {
+            const u64 c = i - k * n;
+            if (c < t * delta_n) v = (c / delta_n) * delta;  // Zq::from_u64(t, v) = v for v < t
+        }
+        out[i] = v;
+    }
+}
+}  // namespace
+int fhe_compute_lookup_table(uint64_t n, uint64_t k, uint64_t t, uint64_t *table) {
+    FHE_REQUIRE(table != nullptr, "fhe_compute_lookup_table: null pointer");
+    FHE_REQUIRE(n >= 1 && k >= 1 && t >= 1 && t <= n, "fhe_compute_lookup_table: need 1 <= t <= n (delta = n/t >= 1)");
+    cudaStream_t st = current_stream();
+    IoBuf bo;
+    int rc;
+    if ((rc = bo.init(table, (k + 1) * n * 8, false, true, st))) return rc;
+    lookup_table_kernel<<<(unsigned)(((k + 1) * n + 255) / 256), 256, 0, st>>>(bo.ptr<u64>(), n, k, t, n / t);
+    count_launch(1);
+    FHE_CUDA_OK(cudaGetLastError());
+    return finish_all({&bo}, st);
+}
+
 // blind_rotation (tlwe.rs:121-148).  bsk == NULL or as_written == 0: AS EXECUTED by the reference (the CMux
 // closure is a lazy iterator that is dropped): acc = table.left_rotate(mod_switch(c).b).
 // as_written != 0: additionally runs the loop the source spells out, for j in 1..k:
@@ -186,6 +214,8 @@ int fhe_blind_rotate(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, int as
     if (batch == 0) return 0;
     FHE_REQUIRE(table && ct && acc_out, "null pointer");
     FHE_REQUIRE(n >= 1 && k >= 1 && (n & (n - 1)) == 0, "fhe_blind_rotate: n must be a power of two");
+    // T64::mod_switch asserts q2.is_power_of_two() (torus.rs:58-66); blind_rotation switches to q2 = k*n (tlwe.rs:125)
+    FHE_REQUIRE(((k * n) & (k * n - 1)) == 0, "fhe_blind_rotate: k*n must be a power of two (T64::mod_switch, torus.rs:58-66)");
     FHE_REQUIRE(!as_written || k == 1 || bsk != nullptr, "fhe_blind_rotate: as_written needs the k TGGSW handles");
     cudaStream_t st = current_stream();
     const size_t glwe = (k + 1) * n;
@@ -230,6 +260,7 @@ int fhe_bootstrap(uint64_t n, uint64_t k, const fhe_ksk *ksk, const uint64_t *ta
     if (batch == 0) return 0;
     FHE_REQUIRE(table && ct && out, "null pointer");
     FHE_REQUIRE(n >= 1 && k >= 1 && (n & (n - 1)) == 0, "fhe_bootstrap: n must be a power of two");
+    FHE_REQUIRE(((k * n) & (k * n - 1)) == 0, "fhe_bootstrap: k*n must be a power of two (T64::mod_switch, torus.rs:58-66)");
     FHE_REQUIRE(ksk->k.kn_in == k * n, "fhe_bootstrap: KSK input dimension must be k*n");
     cudaStream_t st = current_stream();
     IoBuf bt, bc, bo;
@@ -266,6 +297,8 @@ int fhe_bootstrap_chain(uint64_t n, uint64_t k, const fhe_tggsw *const *bsk, uin
     if (batch == 0) return 0;
     FHE_REQUIRE(table && ct && out && (steps == 0 || bsk), "fhe_bootstrap_chain: null pointer");
     FHE_REQUIRE(n >= 2 && k >= 1 && (n & (n - 1)) == 0, "fhe_bootstrap_chain: n must be a power of two");
+    FHE_REQUIRE(mode != 0 || ((k * n) & (k * n - 1)) == 0,
+                "fhe_bootstrap_chain: k*n must be a power of two in the as-written mode (T64::mod_switch, torus.rs:58-66)");
     FHE_REQUIRE(steps <= c_kn, "fhe_bootstrap_chain: more TGGSWs than mask elements");
     FHE_REQUIRE(ksk == nullptr || ksk->k.kn_in == k * n, "fhe_bootstrap_chain: KSK input dimension must be k*n");
     std::vector<const Tggsw *> gs(steps);

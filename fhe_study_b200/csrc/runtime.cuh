@@ -87,6 +87,16 @@ struct PipeStreams {
         int dev = 0;
         FHE_CUDA_OK(cudaGetDevice(&dev));
         if (device == dev) return 0;
+        if (device >= 0) {  // the thread moved to another device: the old streams and events belong to the old one
+            int cur = dev;
+            if (cudaSetDevice(device) == cudaSuccess) {
+                cudaStreamDestroy(h2d); cudaStreamDestroy(d2h); cudaStreamDestroy(comp2);
+                for (int i = 0; i < 2; i++) { cudaEventDestroy(h2d_done[i]); cudaEventDestroy(comp_done[i]); cudaEventDestroy(d2h_done[i]); }
+            }
+            cudaSetDevice(cur);
+            cudaGetLastError();
+            device = -1;
+        }
         FHE_CUDA_OK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
         FHE_CUDA_OK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
         FHE_CUDA_OK(cudaStreamCreateWithFlags(&comp2, cudaStreamNonBlocking));
@@ -115,23 +125,35 @@ int run_host_pipelined(const void *in, size_t in_unit, void *out, size_t out_uni
     if ((rc = sin.alloc(2 * chunk * in_unit, st))) return rc;
     if ((rc = sout.alloc(2 * chunk * out_unit, st))) return rc;
     FHE_CUDA_OK(cudaStreamSynchronize(st));  // the scratch (and the caller's) is used from the side streams as well
+    // a failing CUDA call inside the loop must not return: the side streams may still have work queued on the staging
+    // buffers (freed by the Scratch destructors), so the loop is left and the common tail synchronises every stream first
+#define FHE_PIPE_TRY(expr)                                                              \
+    {                                                                                   \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+            rc = -2;                                                                    \
+            break;                                                                      \
+        }                                                                               \
+    }
     size_t i = 0;
     for (size_t off = 0; off < batch && !rc; off += chunk, i++) {
         const size_t nb = batch - off < chunk ? batch - off : chunk;
         const int par = (int)(i & 1);
         cudaStream_t cs = par ? ps.comp2 : st;
         char *din = sin.ptr<char>() + (size_t)par * chunk * in_unit, *dout = sout.ptr<char>() + (size_t)par * chunk * out_unit;
-        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // staging of chunk i-2 consumed
-        FHE_CUDA_OK(cudaMemcpyAsync(din, (const char *)in + off * in_unit, nb * in_unit, cudaMemcpyHostToDevice, ps.h2d));
-        FHE_CUDA_OK(cudaEventRecord(ps.h2d_done[par], ps.h2d));
-        FHE_CUDA_OK(cudaStreamWaitEvent(cs, ps.h2d_done[par], 0));
-        if (i >= 2) FHE_CUDA_OK(cudaStreamWaitEvent(cs, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
+        if (i >= 2) FHE_PIPE_TRY(cudaStreamWaitEvent(ps.h2d, ps.comp_done[par], 0));  // staging of chunk i-2 consumed
+        FHE_PIPE_TRY(cudaMemcpyAsync(din, (const char *)in + off * in_unit, nb * in_unit, cudaMemcpyHostToDevice, ps.h2d));
+        FHE_PIPE_TRY(cudaEventRecord(ps.h2d_done[par], ps.h2d));
+        FHE_PIPE_TRY(cudaStreamWaitEvent(cs, ps.h2d_done[par], 0));
+        if (i >= 2) FHE_PIPE_TRY(cudaStreamWaitEvent(cs, ps.d2h_done[par], 0));       // outputs of chunk i-2 drained
         if ((rc = fn(din, dout, nb, cs, par))) break;
-        FHE_CUDA_OK(cudaEventRecord(ps.comp_done[par], cs));
-        FHE_CUDA_OK(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
-        FHE_CUDA_OK(cudaMemcpyAsync((char *)out + off * out_unit, dout, nb * out_unit, cudaMemcpyDeviceToHost, ps.d2h));
-        FHE_CUDA_OK(cudaEventRecord(ps.d2h_done[par], ps.d2h));
+        FHE_PIPE_TRY(cudaEventRecord(ps.comp_done[par], cs));
+        FHE_PIPE_TRY(cudaStreamWaitEvent(ps.d2h, ps.comp_done[par], 0));
+        FHE_PIPE_TRY(cudaMemcpyAsync((char *)out + off * out_unit, dout, nb * out_unit, cudaMemcpyDeviceToHost, ps.d2h));
+        FHE_PIPE_TRY(cudaEventRecord(ps.d2h_done[par], ps.d2h));
     }
+#undef FHE_PIPE_TRY
     cudaError_t e1 = cudaStreamSynchronize(ps.d2h), e2 = cudaStreamSynchronize(ps.h2d), e3 = cudaStreamSynchronize(st),
                 e4 = cudaStreamSynchronize(ps.comp2);
     if (rc) return rc;

@@ -4,7 +4,7 @@
 // The reference multiplies torus polynomials with an O(N^2) u128 schoolbook, negacyclic fold by
 // wrapping_sub and truncation to u64 (ring_torus.rs:266-298): that IS the exact negacyclic convolution
 // in Z_{2^64}[X]/(X^N+1), so any exact algorithm is bit-identical.  Here the convolution is
-// computed over the integers with two 30-bit NTT primes (P = p1*p2 ~ 2^60) on small limbs, lifted to the
+// computed over the integers with two 27-bit NTT primes (P = p1*p2 ~ 2^54, torus.cuh) on small limbs, lifted to the
 // centred representative by CRT, and recombined mod 2^64:
 //   * Tn*Tn     : both operands in four 16-bit limbs; plane products are bounded by N*2^32, the four
 //                 weight classes 2^(16w), w = 0..3, by 4*N*2^32 < P/2 (N <= 2^15);

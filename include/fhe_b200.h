@@ -43,6 +43,8 @@ extern "C" {
 FHE_API const char *fhe_last_error(void);            /* per-thread message of the last failing call */
 FHE_API int fhe_device_count(int *count);
 FHE_API int fhe_set_device(int device);              /* cudaSetDevice for the calling thread */
+FHE_API int fhe_current_device(int *device);         /* the calling thread's current device; every handle (plan, key) must
+                                                        be used on the device it was created on, else the call fails */
 FHE_API int fhe_set_stream(void *cuda_stream);       /* cudaStream_t used by this thread's calls (NULL = default) */
 FHE_API int fhe_synchronize(void);                   /* wait for this thread's stream */
 /* number of kernels this library has launched from this process (bench.py's gpu_launches) */
@@ -69,6 +71,12 @@ FHE_API int fhe_ntt_plan_info(const fhe_ntt_plan *plan, uint64_t *psi, uint64_t 
  * 3 Small32), [1] = log2(coefficients per thread), [2] = dual-operand polymul, [3] = NTT(a) parked in the output
  * row, [4] = persistent staged polymul.  (No reference counterpart; used by the tests and the tuning tools.) */
 FHE_API int fhe_ntt_plan_config(const fhe_ntt_plan *plan, int *config);
+
+/* PRECONDITION of every Rq entry point below: coefficients are canonical, 0 <= v < q, as the reference's Zq type
+ * guarantees (arith/src/zq.rs:21-31).  The kernels do not reduce on load (the 32-bit policies read the low word
+ * only), so unreduced words give wrong results silently; fhe_rq_check_canonical is the validation pass for callers
+ * that cannot vouch for their buffers: *first_bad = index of the first word >= q, or UINT64_MAX if there is none. */
+FHE_API int fhe_rq_check_canonical(uint64_t q, const uint64_t *words, size_t len, uint64_t *first_bad);
 
 /* NTT::ntt (arith/src/ntt.rs:44-73): natural order in, bit-reversed order out; `batch` polynomials. */
 FHE_API int fhe_ntt_fwd(const fhe_ntt_plan *plan, const uint64_t *in, uint64_t *out, size_t batch);
@@ -180,6 +188,10 @@ FHE_API int fhe_tglwe_encrypt(uint64_t n, uint64_t k, const uint64_t *sk, const 
 FHE_API int fhe_tglwe_decrypt(uint64_t n, uint64_t k, const uint64_t *sk, const uint64_t *ct, uint64_t *p, size_t batch);
 /* TLWE::mod_switch(q2) (tlwe.rs:114-118, torus.rs:58-66): every word >> (64 - log2 q2); q2 a power of two. */
 FHE_API int fhe_tlwe_mod_switch(const uint64_t *ct, uint64_t q2, uint64_t *out, size_t len);
+/* compute_lookup_table (tfhe/src/tlwe.rs:196-214 with TGLWE::encode, tglwe.rs:49-58): the trivial TGLWE (k zero mask
+ * polynomials, then v) with v_c = floor(c / (n/t)) * floor(u64::MAX / t); (k+1)*n words.  n/t >= 1 and t * (n/t) <= n
+ * as in the reference's parameters (a longer coefficient list would be folded by Rq::from_vec: not supported here). */
+FHE_API int fhe_compute_lookup_table(uint64_t n, uint64_t k, uint64_t t, uint64_t *table);
 /* TGLWE::sample_extraction(h) (tglwe.rs:89-115): `batch` TGLWEs ((k+1)*n) -> TLWEs (k*n+1). */
 FHE_API int fhe_sample_extract(uint64_t n, uint64_t k, const uint64_t *ct, uint64_t h, uint64_t *out, size_t batch);
 /* blind_rotation (tlwe.rs:121-148).  as_written == 0: AS THE REFERENCE EXECUTES IT (its CMux loop is a lazy
@@ -238,6 +250,31 @@ FHE_API int fhe_bfv_encrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, ui
  * reference; here they are passed so that the map kernels need no plan internals).  m: batch * n words. */
 FHE_API int fhe_bfv_decrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, uint64_t t, const uint64_t *sk, const uint64_t *ct,
                             uint64_t *m, size_t batch);
+
+/* BFV::new_key (lib.rs:120-140): s <- Uniform(0,2), a <- Uniform(0,q), e <- Normal(0, sigma); pk = (-a*s + e, a) with the
+ * product through the (q, n) plan.  The reference samples from an unseeded thread_rng; the device uses the counter-based
+ * sampler specified in oracle/fhe_oracle.c (orc_bfv_keygen_ctr), bit-exact against it.  sk: n words, pk: 2n words. */
+FHE_API int fhe_bfv_keygen(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, double sigma, uint64_t seed, uint64_t *sk, uint64_t *pk);
+/* BFV::rlk_key (lib.rs:202-225) in the ring mod p*q, products through tmp_naive_mul (lib.rs:93-98):
+ * rlk = (-(a*s + e) + (s*s)*p, a), 2n words mod p*q (p*q < 2^63).  Sampler: orc_bfv_rlk_key_ctr.  n <= 1024. */
+FHE_API int fhe_bfv_rlk_generate(uint64_t q, uint64_t n, uint64_t p, double sigma, uint64_t seed, const uint64_t *sk, uint64_t *rlk);
+/* BFV::mul_const (lib.rs:189-200): out_b = RLWE::mul(t, rlk, c_b, (m_b.remodule(q) * floor(q/t), 0)); m: batch * n words mod t. */
+FHE_API int fhe_bfv_mul_const(uint64_t q, uint64_t n, uint64_t t, uint64_t pq, const uint64_t *rlk, const uint64_t *c,
+                              const uint64_t *m, uint64_t *out, size_t batch);
+
+/* ---- CKKS over Rq (ckks/src/lib.rs:46-119; the encoder of ckks/src/encoder.rs is out of scope: plaintexts are
+ * elements of R = Z[X]/(X^n+1), int64 coefficients, as CKKS::encrypt / decrypt take and return them) ------------------ */
+/* CKKS::new_key (lib.rs:46-63): s, a <- Uniform(-1,1) through Zq::from_f64, e <- Normal; pk = (-a*s + e, a). */
+FHE_API int fhe_ckks_keygen(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, double sigma, uint64_t seed, uint64_t *sk, uint64_t *pk);
+/* CKKS::encrypt (lib.rs:66-84): ct_b = (m_b.to_rq(q) + e_0 + v*pk.0, v*pk.1 + e_1); m: batch * n int64, ct: batch * 2n words. */
+FHE_API int fhe_ckks_encrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, const uint64_t *pk, const int64_t *m, double sigma,
+                             uint64_t seed, uint64_t *ct, size_t batch);
+/* CKKS::decrypt (lib.rs:86-94): m_b = (c.0 + c.1*s).mod_centered_q() (ring_n.rs:113-127), batch * n int64. */
+FHE_API int fhe_ckks_decrypt(const fhe_ntt_plan *plan, uint64_t q, uint64_t n, const uint64_t *sk, const uint64_t *ct, int64_t *m,
+                             size_t batch);
+/* CKKS::add (lib.rs:113-115) and CKKS::sub (lib.rs:116-118; as written it ADDS the second components). */
+FHE_API int fhe_ckks_add(uint64_t q, uint64_t n, const uint64_t *c0, const uint64_t *c1, uint64_t *out, size_t batch);
+FHE_API int fhe_ckks_sub(uint64_t q, uint64_t n, const uint64_t *c0, const uint64_t *c1, uint64_t *out, size_t batch);
 
 /* ---- coefficient-wise Rq / Tn operations (arith/src/ring_nq.rs, ring_torus.rs, zq.rs, torus.rs) ------------- */
 /* Add / Sub / Neg / mul_by_u64 (ring_nq.rs:267-281,406-561) on `len` coefficients mod q (any q < 2^63). */

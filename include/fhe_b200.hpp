@@ -12,10 +12,13 @@
 // Header-only; link with -lfhe_b200.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -36,10 +39,24 @@ struct RingParam {
 
 namespace detail {
 struct PlanDeleter { void operator()(fhe_ntt_plan *p) const { fhe_ntt_plan_destroy(p); } };
+// The reference's (q, n) -> tables CACHE is permanent (arith/src/ntt.rs:18-38).  The library's own cache is
+// reference-counted, so this mirror keeps one reference per (device, q, n) for the life of the process: otherwise every
+// operator*, ntt and intt would drop the last reference and redo the root search, the table build, two cudaMalloc
+// and two blocking uploads.
 inline std::shared_ptr<fhe_ntt_plan> plan(const RingParam &p) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, uint64_t, uint64_t>, std::shared_ptr<fhe_ntt_plan>> cache;
+    int dev = 0;
+    check(fhe_current_device(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple(dev, p.q, (uint64_t)p.n);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
     fhe_ntt_plan *h = nullptr;
-    check(fhe_ntt_plan_create(p.q, p.n, &h));  // cached per (device, q, n) inside the library (ntt.rs:18-38)
-    return std::shared_ptr<fhe_ntt_plan>(h, PlanDeleter());
+    check(fhe_ntt_plan_create(p.q, p.n, &h));
+    std::shared_ptr<fhe_ntt_plan> sp(h, PlanDeleter());
+    cache.emplace(key, sp);
+    return sp;
 }
 inline void same(const RingParam &a, const RingParam &b) {
     if (a != b) throw std::runtime_error("fhe_b200: ring parameter mismatch (the reference's assert_eq!(param))");

@@ -145,6 +145,13 @@ def _declare(L):
     d("orc_bfv_encrypt", None, U64, U64, U64, U64, P, P, P)
     d("orc_bfv_decrypt", None, U64, U64, U64, P, P, P)
     d("orc_bfv_rlk_key", None, U64, U64, U64, U64, P, P)
+    d("orc_bfv_keygen_ctr", None, U64, U64, U64, D, P, P)
+    d("orc_bfv_rlk_key_ctr", None, U64, U64, U64, U64, D, P, P)
+    d("orc_bfv_mul_const", None, U64, U64, U64, U64, P, P, P, P)
+    d("orc_ckks_keygen_ctr", None, U64, U64, U64, D, P, P)
+    d("orc_ckks_encrypt_ctr", None, U64, U64, U64, D, P, P, U64, P)
+    d("orc_ckks_decrypt", None, U64, U64, P, P, U64, P)
+    d("orc_ckks_addsub", None, U64, U64, P, P, U64, I, P)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -338,4 +345,61 @@ def bfv_mul(q: int, n: int, t: int, pq: int, rlk, a, b, threads: int = 1) -> np.
     rlk, a, b = u64(rlk), u64(a), u64(b)
     out = np.empty_like(a)
     lib().orc_bfv_mul_batch(q, n, t, pq, ptr(rlk), ptr(a), ptr(b), ptr(out), a.size // (2 * n), threads)
+    return out
+
+
+def bfv_keygen_ctr(seed: int, q: int, n: int, sigma: float):
+    """BFV::new_key (bfv/src/lib.rs:120-140) with the counter-based sampler the device reproduces: (sk, pk[2n])."""
+    sk, pk = np.empty(n, dtype=np.uint64), np.empty(2 * n, dtype=np.uint64)
+    lib().orc_bfv_keygen_ctr(seed, q, n, float(sigma), ptr(sk), ptr(pk))
+    return sk, pk
+
+
+def bfv_rlk_key_ctr(seed: int, q: int, n: int, p: int, sigma: float, sk) -> np.ndarray:
+    """BFV::rlk_key (bfv/src/lib.rs:202-225) with the counter-based sampler: rlk[2n] mod p*q."""
+    sk = u64(sk)
+    out = np.empty(2 * n, dtype=np.uint64)
+    lib().orc_bfv_rlk_key_ctr(seed, q, n, p, float(sigma), ptr(sk), ptr(out))
+    return out
+
+
+def bfv_mul_const(q: int, n: int, t: int, pq: int, rlk, c, m) -> np.ndarray:
+    """BFV::mul_const (bfv/src/lib.rs:189-200) for a batch: c = batch x 2n, m = batch x n (mod t)."""
+    rlk, c, m = u64(rlk), u64(c), u64(m)
+    out = np.empty_like(c)
+    for i in range(c.size // (2 * n)):
+        lib().orc_bfv_mul_const(q, n, t, pq, ptr(rlk), ptr(c.reshape(-1)[i * 2 * n:]), ptr(m.reshape(-1)[i * n:]),
+                                ptr(out.reshape(-1)[i * 2 * n:]))
+    return out
+
+
+def ckks_keygen_ctr(seed: int, q: int, n: int, sigma: float):
+    sk, pk = np.empty(n, dtype=np.uint64), np.empty(2 * n, dtype=np.uint64)
+    lib().orc_ckks_keygen_ctr(seed, q, n, float(sigma), ptr(sk), ptr(pk))
+    return sk, pk
+
+
+def ckks_encrypt_ctr(seed: int, q: int, n: int, sigma: float, pk, msgs) -> np.ndarray:
+    """CKKS::encrypt (ckks/src/lib.rs:66-84); msgs = batch x n int64 (elements of R)."""
+    pk = u64(pk)
+    msgs = np.ascontiguousarray(msgs, dtype=np.int64)
+    batch = msgs.size // n
+    out = np.empty((batch, 2 * n), dtype=np.uint64)
+    lib().orc_ckks_encrypt_ctr(seed, q, n, float(sigma), ptr(pk), ptr(msgs), batch, ptr(out))
+    return out
+
+
+def ckks_decrypt(q: int, n: int, sk, ct) -> np.ndarray:
+    """CKKS::decrypt (ckks/src/lib.rs:86-94): batch x n int64 (centred representatives)."""
+    sk, ct = u64(sk), u64(ct)
+    batch = ct.size // (2 * n)
+    out = np.empty((batch, n), dtype=np.int64)
+    lib().orc_ckks_decrypt(q, n, ptr(sk), ptr(ct), batch, ptr(out))
+    return out
+
+
+def ckks_addsub(q: int, n: int, c0, c1, sub: bool) -> np.ndarray:
+    c0, c1 = u64(c0), u64(c1)
+    out = np.empty_like(c0)
+    lib().orc_ckks_addsub(q, n, ptr(c0), ptr(c1), c0.size // (2 * n), int(sub), ptr(out))
     return out

@@ -1134,3 +1134,112 @@ API void orc_bfv_rlk_key(u64 seed, u64 q, u64 n, u64 p, const u64 *sk, u64 *rlk 
     orc_rq_addsub(pq, n, as, ss, rlk, 0);
     free(s);
 }
+
+/* ---- device-reproducible (counter-based) key generation for BFV, and the CKKS Rq paths ----------
+ * Same sampler as orc_bfv_encrypt_ctr: draw p = SplitMix64 output p + 1 (ctr_draw), units = top 53 bits (ctr_unit),
+ * Normal(0, sigma) stand-in = sigma * (sum of 12 units - 6). */
+static double ctr_gauss(u64 seed, u64 pos0, double sigma) {
+    double acc = 0.0;
+    for (u64 k = 0; k < 12; k++) acc += ctr_unit(ctr_draw(seed, pos0 + k));
+    return sigma * (acc - 6.0);
+}
+/* BFV::new_key (bfv/src/lib.rs:120-140): s <- Uniform(0,2) (u64), a <- Uniform(0,q) (u64), e <- Normal; pk = (-a*s + e, a).
+ * draws: p < n: s_p = draw % 2 ; n + x: a_x = draw % q ; 2n + 12x + t: e_x. */
+API void orc_bfv_keygen_ctr(u64 seed, u64 q, u64 n, double sigma, u64 *sk, u64 *pk /* 2n */) {
+    u64 *a = pk + n, *e = (u64 *)malloc(sizeof(u64) * 2 * n), *na = e + n;
+    for (u64 x = 0; x < n; x++) {
+        sk[x] = orc_zq_from_u64(q, ctr_draw(seed, x) % 2);
+        a[x] = orc_zq_from_u64(q, ctr_draw(seed, n + x) % q);
+        e[x] = orc_zq_from_f64(q, ctr_gauss(seed, 2 * n + 12 * x, sigma));
+    }
+    orc_rq_addsub(q, n, a, NULL, na, 2);
+    orc_rq_mul(q, n, na, sk, pk, 0, 0, NULL); /* &(-a) * &s */
+    orc_rq_addsub(q, n, pk, e, pk, 0);
+    free(e);
+}
+/* BFV::rlk_key (bfv/src/lib.rs:202-225) in the ring mod pq = p*q, products through tmp_naive_mul (lib.rs:93-98):
+ * rlk = ( -(a*s + e) + (s*s)*p , a ).  draws: p < n: a_x = draw % pq ; n + 12x + t: e_x. */
+API void orc_bfv_rlk_key_ctr(u64 seed, u64 q, u64 n, u64 p, double sigma, const u64 *sk, u64 *rlk /* 2n */) {
+    u64 pq = p * q;
+    u64 *s = (u64 *)malloc(sizeof(u64) * 4 * n), *e = s + n, *as = e + n, *ss = as + n;
+    u64 *a = rlk + n;
+    orc_rq_remodule(n, sk, pq, s);
+    for (u64 x = 0; x < n; x++) {
+        a[x] = orc_zq_from_u64(pq, ctr_draw(seed, x) % pq);
+        e[x] = orc_zq_from_f64(pq, ctr_gauss(seed, n + 12 * x, sigma));
+    }
+    tmp_naive_mul(pq, n, a, s, as);
+    orc_rq_addsub(pq, n, as, e, as, 0);
+    orc_rq_addsub(pq, n, as, NULL, as, 2);
+    tmp_naive_mul(pq, n, s, s, ss);
+    orc_rq_mul_u64(pq, n, ss, p, ss);
+    orc_rq_addsub(pq, n, as, ss, rlk, 0);
+    free(s);
+}
+/* BFV::mul_const (bfv/src/lib.rs:189-200): md = (m.remodule(q) * floor(q/t), 0); RLWE::mul(t, rlk, c, md) */
+API void orc_bfv_mul_const(u64 q, u64 n, u64 t, u64 pq, const u64 *rlk, const u64 *c, const u64 *m, u64 *out) {
+    u64 *md = (u64 *)calloc(2 * n, sizeof(u64));
+    orc_rq_remodule(n, m, q, md);
+    orc_rq_mul_u64(q, n, md, q / t, md);
+    orc_bfv_mul(q, n, t, pq, rlk, c, md, out);
+    free(md);
+}
+
+/* CKKS over Rq (ckks/src/lib.rs:46-119).  new_key (:46-63): e <- Normal, s <- Uniform(-1,1) (f64 -> Zq::from_f64),
+ * a <- Uniform(-1,1); pk = (-a*s + e, a).  draws: p < n: s_p = from_f64(-1 + 2u) ; n + x: a_x ; 2n + 12x + t: e_x. */
+API void orc_ckks_keygen_ctr(u64 seed, u64 q, u64 n, double sigma, u64 *sk, u64 *pk /* 2n */) {
+    u64 *a = pk + n, *e = (u64 *)malloc(sizeof(u64) * 2 * n), *na = e + n;
+    for (u64 x = 0; x < n; x++) {
+        sk[x] = orc_zq_from_f64(q, -1.0 + 2.0 * ctr_unit(ctr_draw(seed, x)));
+        a[x] = orc_zq_from_f64(q, -1.0 + 2.0 * ctr_unit(ctr_draw(seed, n + x)));
+        e[x] = orc_zq_from_f64(q, ctr_gauss(seed, 2 * n + 12 * x, sigma));
+    }
+    orc_rq_addsub(q, n, a, NULL, na, 2);
+    orc_rq_mul(q, n, na, sk, pk, 0, 0, NULL);
+    orc_rq_addsub(q, n, pk, e, pk, 0);
+    free(e);
+}
+/* CKKS::encrypt (:66-84): m in R (i64 coefficients) -> m.to_rq(q) (ring_nq.rs:116-129: Zq::from_f64(c as f64));
+ * ct = (m + e_0 + v*pk.0, v*pk.1 + e_1).  draws of ciphertext r (base r*25n): p < n: v_p ; n + 12x + t: e0_x ; 13n + 12x + t: e1_x. */
+API void orc_ckks_encrypt_ctr(u64 seed, u64 q, u64 n, double sigma, const u64 *pk, const i64 *msgs, u64 batch, u64 *ct) {
+    u64 *v = (u64 *)malloc(sizeof(u64) * 4 * n), *e0 = v + n, *e1 = e0 + n, *mq = e1 + n;
+    for (u64 r = 0; r < batch; r++) {
+        u64 base = r * 25 * n, *c = ct + r * 2 * n;
+        for (u64 x = 0; x < n; x++) {
+            v[x] = orc_zq_from_f64(q, -1.0 + 2.0 * ctr_unit(ctr_draw(seed, base + x)));
+            e0[x] = orc_zq_from_f64(q, ctr_gauss(seed, base + n + 12 * x, sigma));
+            e1[x] = orc_zq_from_f64(q, ctr_gauss(seed, base + 13 * n + 12 * x, sigma));
+            mq[x] = orc_zq_from_f64(q, (double)msgs[r * n + x]);
+        }
+        orc_rq_mul(q, n, v, pk, c, 0, 0, NULL);
+        orc_rq_addsub(q, n, c, e0, c, 0);
+        orc_rq_addsub(q, n, c, mq, c, 0);
+        orc_rq_mul(q, n, v, pk + n, c + n, 0, 0, NULL);
+        orc_rq_addsub(q, n, c + n, e1, c + n, 0);
+    }
+    free(v);
+}
+/* CKKS::decrypt (:86-94): m = c.0 + c.1*s, then Rq::mod_centered_q (ring_nq.rs:359-361 -> ring_n.rs:113-127):
+ * res = v % q; if res > q/2 { res - q } on i64 */
+API void orc_ckks_decrypt(u64 q, u64 n, const u64 *sk, const u64 *ct, u64 batch, i64 *m) {
+    u64 *cs = (u64 *)malloc(sizeof(u64) * n);
+    for (u64 r = 0; r < batch; r++) {
+        const u64 *c = ct + r * 2 * n;
+        orc_rq_mul(q, n, c + n, sk, cs, 0, 0, NULL);
+        orc_rq_addsub(q, n, c, cs, cs, 0);
+        for (u64 x = 0; x < n; x++) {
+            i64 res = (i64)cs[x] % (i64)q;
+            if (res > (i64)q / 2) res -= (i64)q;
+            m[r * n + x] = res;
+        }
+    }
+    free(cs);
+}
+/* CKKS::add (:113-115) and CKKS::sub (:116-118).  As written, sub subtracts the first components and ADDS the
+ * second ones ((&c0.0 - &c1.0, &c0.1 + &c1.1)); reproduced as is. */
+API void orc_ckks_addsub(u64 q, u64 n, const u64 *c0, const u64 *c1, u64 batch, int sub, u64 *out) {
+    for (u64 r = 0; r < batch; r++) {
+        orc_rq_addsub(q, n, c0 + r * 2 * n, c1 + r * 2 * n, out + r * 2 * n, sub ? 1 : 0);
+        orc_rq_addsub(q, n, c0 + r * 2 * n + n, c1 + r * 2 * n + n, out + r * 2 * n + n, 0);
+    }
+}
