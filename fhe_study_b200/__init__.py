@@ -711,3 +711,49 @@ def tn_mul_u64(a, s):
 
 def tn_mul_div_round(a, num, den):
     return _map1(lib.fhe_tn_mul_div_round, a, int(num), int(den))
+
+
+# ---- flat on-disk / wire container (include/fhe_b200_file.h) -------------------------------------
+FILE_KINDS = {"rq": 1, "tn": 2, "tlwe": 3, "tglwe": 4, "tggsw": 5, "ksk": 6, "rlwe": 7, "rlk": 8, "secret": 9, "glev_rq": 10}
+ENC_U64, ENC_U32, ENC_PACKED = 0, 1, 2
+
+
+def save(path: str, kind: str, words: np.ndarray, words_per_object: int, q: int = 0, n: int = 0, k: int = 0, l: int = 0,
+         encoding: int = ENC_U64, bits: int = 0) -> dict:
+    """Write `words` (u64 values, count x words_per_object) as one container file.  encoding = ENC_U32 / ENC_PACKED store
+    Rq data (q <= 2^32 / q <= 2^bits) in the narrower wire formats of the host-buffer path."""
+    from ._capi import FileInfo
+
+    words = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1)
+    if words.size % int(words_per_object):
+        raise ValueError("payload is not a whole number of objects")
+    info = FileInfo(kind=FILE_KINDS[kind], encoding=int(encoding), bits=int(bits), q=int(q), n=int(n), k=int(k), l=int(l),
+                    count=words.size // int(words_per_object), words_per_object=int(words_per_object))
+    if encoding == ENC_U32:
+        payload = words.astype(np.uint32)
+        if (payload.astype(np.uint64) != words).any():
+            raise ValueError("coefficients do not fit 32 bits")
+    elif encoding == ENC_PACKED:
+        payload = pack_bits(bits, words.reshape(-1, int(words_per_object))).reshape(-1)
+    else:
+        payload = words
+    check(lib.fhe_file_write(path.encode(), C.byref(info), ptr(payload)))
+    return {f[0]: getattr(info, f[0]) for f in FileInfo._fields_}
+
+
+def load(path: str):
+    """Read a container file: (info dict, u64 words shaped count x words_per_object)."""
+    from ._capi import FileInfo
+
+    info = FileInfo()
+    check(lib.fhe_file_read_info(path.encode(), C.byref(info)))
+    raw = np.empty(int(info.payload_bytes), dtype=np.uint8)
+    check(lib.fhe_file_read_payload(path.encode(), ptr(raw), raw.size))
+    shape = (int(info.count), int(info.words_per_object))
+    if info.encoding == ENC_U32:
+        words = raw.view(np.uint32).astype(np.uint64).reshape(shape)
+    elif info.encoding == ENC_PACKED:
+        words = unpack_bits(int(info.bits), raw.view(np.uint32).reshape(shape[0], -1))
+    else:
+        words = raw.view(np.uint64).reshape(shape).copy()
+    return {f[0]: getattr(info, f[0]) for f in FileInfo._fields_}, words

@@ -32,6 +32,14 @@ def _load():
 
 lib = _load()
 
+class FileInfo(C.Structure):
+    """fhe_file_info of include/fhe_b200_file.h"""
+
+    _fields_ = [("version", C.c_uint32), ("kind", C.c_uint32), ("encoding", C.c_uint32), ("bits", C.c_uint32),
+                ("q", U64), ("n", U64), ("k", U64), ("l", U64), ("count", U64), ("words_per_object", U64),
+                ("payload_bytes", U64), ("checksum", U64)]
+
+
 # name -> (restype, argtypes); mirrors include/fhe_b200.h one to one (tests/test_capi_symbols.py checks
 # that the header, this table and the .so agree).
 SIGNATURES = {
@@ -68,6 +76,10 @@ SIGNATURES = {
     "fhe_ckks_add": (I, [U64, U64, P, P, P, SZ]),
     "fhe_ckks_sub": (I, [U64, U64, P, P, P, SZ]),
     "fhe_compute_lookup_table": (I, [U64, U64, U64, P]),
+    "fhe_file_payload_bytes": (U64, [C.POINTER(FileInfo)]),
+    "fhe_file_write": (I, [C.c_char_p, C.POINTER(FileInfo), P]),
+    "fhe_file_read_info": (I, [C.c_char_p, C.POINTER(FileInfo)]),
+    "fhe_file_read_payload": (I, [C.c_char_p, P, SZ]),
     "fhe_tn_mul": (I, [U64, P, P, P, SZ]),
     "fhe_tn_add": (I, [P, P, P, SZ]),
     "fhe_tn_sub": (I, [P, P, P, SZ]),

@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_functions():
-    src = open(os.path.join(ROOT, "include", "fhe_b200.h")).read()
+    src = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("fhe_b200.h", "fhe_b200_file.h"))
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(fhe_[a-z0-9_]+)\s*\(", src)))
 

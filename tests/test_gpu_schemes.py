@@ -125,3 +125,30 @@ def test_bootstrap_requires_power_of_two_kn(fhe):
     ct = np.zeros((1, k * n + 1), dtype=np.uint64)
     with pytest.raises(fhe.FheError):
         fhe.blind_rotate(n, k, table, ct, k * n)
+
+
+def test_container_files_feed_the_device_paths(fhe, orc, tmp_path):
+    # a key-switching key, a TGGSW and packed Rq operands written to the flat container, read back and
+    # handed to the C ABI without conversion give the same results as the originals
+    kn, l = 64, 64
+    ksk = orc.uniform(31, kn * l * (kn + 1))
+    fhe.save(str(tmp_path / "ksk.fheb"), "ksk", ksk, kn + 1, q=0, n=kn, k=kn, l=l)
+    info, back = fhe.load(str(tmp_path / "ksk.fheb"))
+    cts = orc.uniform(32, (9, kn + 1))
+    K1, K2 = fhe.Ksk(kn, kn, l, ksk), fhe.Ksk(int(info["k"]), int(info["n"]), int(info["l"]), back.reshape(-1))
+    assert (K1.key_switch(cts) == K2.key_switch(cts)).all()
+    n, k = 64, 2
+    glwe = (k + 1) * n
+    tggsw = orc.uniform(33, (k + 1) * 64 * glwe)
+    fhe.save(str(tmp_path / "g.fheb"), "tggsw", tggsw, glwe, q=0, n=n, k=k, l=64)
+    _, gb = fhe.load(str(tmp_path / "g.fheb"))
+    ct = orc.uniform(34, (5, glwe))
+    assert (fhe.Tggsw(n, k, gb.reshape(-1)).extprod(ct) == fhe.Tggsw(n, k, tggsw).extprod(ct)).all()
+    q, nn = Q17, 1024
+    a, b = orc.uniform(35, (6, nn), q), orc.uniform(36, (6, nn), q)
+    fhe.save(str(tmp_path / "a.fheb"), "rq", a, nn, q=q, n=nn, encoding=fhe.ENC_PACKED, bits=17)
+    ia, pa = fhe.load(str(tmp_path / "a.fheb"))
+    assert (pa == a).all()
+    plan = fhe.NttPlan(q, nn)
+    got = plan.mul_packed(17, fhe.pack_bits(17, pa), fhe.pack_bits(17, b))
+    assert (fhe.unpack_bits(17, got) == orc.rq_mul_batch(q, nn, a, b)).all()
