@@ -11,6 +11,7 @@
 //   gfhe::GLWE<Rq> / GLev<Rq> / KSK<Rq>   gfhe/src/glwe.rs:57-66,126-137,197-204,263-280 ; gfhe/src/glev.rs:14,67-80
 // Header-only; link with -lfhe_b200.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -389,6 +390,93 @@ struct RLWE {  // bfv/src/lib.rs:35-47
         k.insert(k.end(), rlk.second.begin(), rlk.second.end());
         check(fhe_bfv_mul_relin(p.q, p.n, t, pq, k.data(), fa.data(), fb.data(), out.data(), 1));
         return RLWE{Rq(p, std::vector<uint64_t>(out.begin(), out.begin() + p.n)), Rq(p, std::vector<uint64_t>(out.begin() + p.n, out.end()))};
+    }
+    // RLWE::tensor (lib.rs:59-85): (c0, c1, c2)
+    static std::array<Rq, 3> tensor(uint64_t t, const RLWE &a, const RLWE &b) {
+        detail::same(a.c0.param, b.c0.param);
+        const RingParam p = a.c0.param;
+        std::vector<uint64_t> fa = a.flat(), fb = b.flat(), out(3 * p.n);
+        check(fhe_bfv_tensor(p.q, p.n, t, fa.data(), fb.data(), out.data(), 1));
+        auto part = [&](size_t i) { return Rq(p, std::vector<uint64_t>(out.begin() + i * p.n, out.begin() + (i + 1) * p.n)); };
+        return {part(0), part(1), part(2)};
+    }
+    // BFV::relinearize_204 (lib.rs:251-271)
+    static RLWE relinearize_204(uint64_t pq, const std::vector<uint64_t> &rlk, const Rq &c0, const Rq &c1, const Rq &c2) {
+        const RingParam p = c0.param;
+        std::vector<uint64_t> c(c0.coeffs), out(2 * p.n);
+        c.insert(c.end(), c1.coeffs.begin(), c1.coeffs.end());
+        c.insert(c.end(), c2.coeffs.begin(), c2.coeffs.end());
+        check(fhe_bfv_relinearize(p.q, p.n, pq, rlk.data(), c.data(), out.data(), 1));
+        return from_flat(p, out);
+    }
+    // BFV::mul_const (lib.rs:189-200): m is a plaintext polynomial mod t
+    static RLWE mul_const(uint64_t pq, const std::vector<uint64_t> &rlk, const RLWE &c, const Rq &m) {
+        const RingParam p = c.c0.param;
+        std::vector<uint64_t> fc = c.flat(), out(2 * p.n);
+        check(fhe_bfv_mul_const(p.q, p.n, m.param.q, pq, rlk.data(), fc.data(), m.coeffs.data(), out.data(), 1));
+        return from_flat(p, out);
+    }
+    // BFV::new_key / rlk_key / encrypt (lib.rs:120-160,202-225) with the device sampler (seeded twins of the rng-taking functions)
+    static std::pair<Rq, std::vector<uint64_t>> new_key(const RingParam &p, double sigma, uint64_t seed) {
+        Rq sk = Rq::zero(p);
+        std::vector<uint64_t> pk(2 * p.n);
+        check(fhe_bfv_keygen(detail::plan(p).get(), p.q, p.n, sigma, seed, sk.coeffs.data(), pk.data()));
+        return {sk, pk};
+    }
+    static std::vector<uint64_t> rlk_key(const RingParam &p, uint64_t pmul, const Rq &sk, double sigma, uint64_t seed) {
+        std::vector<uint64_t> rlk(2 * p.n);
+        check(fhe_bfv_rlk_generate(p.q, p.n, pmul, sigma, seed, sk.coeffs.data(), rlk.data()));
+        return rlk;
+    }
+    static RLWE encrypt(uint64_t t, const std::vector<uint64_t> &pk, const Rq &m, const RingParam &p, double sigma, uint64_t seed) {
+        std::vector<uint64_t> out(2 * p.n);
+        check(fhe_bfv_encrypt(detail::plan(p).get(), p.q, p.n, t, pk.data(), m.coeffs.data(), sigma, seed, out.data(), 1));
+        return from_flat(p, out);
+    }
+    std::vector<uint64_t> flat() const {
+        std::vector<uint64_t> v(c0.coeffs);
+        v.insert(v.end(), c1.coeffs.begin(), c1.coeffs.end());
+        return v;
+    }
+    static RLWE from_flat(const RingParam &p, const std::vector<uint64_t> &w) {
+        return RLWE{Rq(p, std::vector<uint64_t>(w.begin(), w.begin() + p.n)), Rq(p, std::vector<uint64_t>(w.begin() + p.n, w.end()))};
+    }
+};
+
+// compute_lookup_table (tfhe/src/tlwe.rs:196-214)
+inline TGLWE compute_lookup_table(size_t n, size_t k, uint64_t t) {
+    TGLWE table(n, k);
+    check(fhe_compute_lookup_table(n, k, t, table.data.data()));
+    return table;
+}
+
+// ---- CKKS over Rq (ckks/src/lib.rs:46-119); plaintexts are elements of R (int64 coefficients) ------------------------
+struct CKKS {
+    RingParam ring;
+    std::pair<Rq, std::vector<uint64_t>> new_key(double sigma, uint64_t seed) const {  // lib.rs:46-63
+        Rq sk = Rq::zero(ring);
+        std::vector<uint64_t> pk(2 * ring.n);
+        check(fhe_ckks_keygen(detail::plan(ring).get(), ring.q, ring.n, sigma, seed, sk.coeffs.data(), pk.data()));
+        return {sk, pk};
+    }
+    RLWE encrypt(const std::vector<uint64_t> &pk, const std::vector<int64_t> &m, double sigma, uint64_t seed) const {  // lib.rs:66-84
+        std::vector<uint64_t> out(2 * ring.n);
+        check(fhe_ckks_encrypt(detail::plan(ring).get(), ring.q, ring.n, pk.data(), m.data(), sigma, seed, out.data(), 1));
+        return RLWE::from_flat(ring, out);
+    }
+    std::vector<int64_t> decrypt(const Rq &sk, const RLWE &c) const {  // lib.rs:86-94
+        std::vector<uint64_t> fc = c.flat();
+        std::vector<int64_t> m(ring.n);
+        check(fhe_ckks_decrypt(detail::plan(ring).get(), ring.q, ring.n, sk.coeffs.data(), fc.data(), m.data(), 1));
+        return m;
+    }
+    RLWE add(const RLWE &a, const RLWE &b) const { return addsub(a, b, false); }  // lib.rs:113-115
+    RLWE sub(const RLWE &a, const RLWE &b) const { return addsub(a, b, true); }   // lib.rs:116-118 (adds the second components, as written)
+  private:
+    RLWE addsub(const RLWE &a, const RLWE &b, bool sub) const {
+        std::vector<uint64_t> fa = a.flat(), fb = b.flat(), out(2 * ring.n);
+        check((sub ? fhe_ckks_sub : fhe_ckks_add)(ring.q, ring.n, fa.data(), fb.data(), out.data(), 1));
+        return RLWE::from_flat(ring, out);
     }
 };
 

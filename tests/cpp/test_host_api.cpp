@@ -141,6 +141,51 @@ int main() {
         RLWE ct{Rq(p, c0), Rq::zero(p)};
         EXPECT(RLWE::decrypt(8, Rq(p, std::vector<uint64_t>(16, 1)), ct).coeffs == m);
     }
+    {   // test_mul_relin / test_tensor (bfv/src/lib.rs:504-601) with keys and ciphertexts generated on the device:
+        // decrypt(mul(enc(m1), enc(m2))) == m1 * m2 in Z_t[X]/(X^n+1); mul == relinearize_204(tensor(..))
+        RingParam p{Q, 16};
+        const uint64_t t = 2, pmul = Q * Q, pq = pmul * Q;
+        auto [sk, pk] = RLWE::new_key(p, 3.2, 11);
+        std::vector<uint64_t> rlk = RLWE::rlk_key(p, pmul, sk, 3.2, 12);
+        std::mt19937_64 rng(5);
+        for (int it = 0; it < 20; it++) {
+            std::vector<uint64_t> m1(16), m2(16), want(16, 0);
+            for (auto &x : m1) x = rng() % t;
+            for (auto &x : m2) x = rng() % t;
+            for (size_t i = 0; i < 16; i++)
+                for (size_t j = 0; j < 16; j++) {
+                    const size_t d = (i + j) % 16;
+                    const uint64_t v = m1[i] * m2[j] % t;
+                    want[d] = (i + j >= 16) ? (want[d] + t - v) % t : (want[d] + v) % t;
+                }
+            RLWE c1 = RLWE::encrypt(t, pk, Rq(RingParam{t, 16}, m1), p, 3.2, 100 + it);
+            RLWE c2 = RLWE::encrypt(t, pk, Rq(RingParam{t, 16}, m2), p, 3.2, 200 + it);
+            std::vector<uint64_t> k0(rlk.begin(), rlk.begin() + 16), k1(rlk.begin() + 16, rlk.end());
+            RLWE c3 = RLWE::mul(t, pq, {k0, k1}, c1, c2);
+            auto tns = RLWE::tensor(t, c1, c2);
+            RLWE c3b = RLWE::relinearize_204(pq, rlk, tns[0], tns[1], tns[2]);
+            EXPECT(c3.flat() == c3b.flat());
+            EXPECT(RLWE::decrypt(t, sk, c3).coeffs == want);
+        }
+    }
+    {   // compute_lookup_table (tlwe.rs:196-214) at the bootstrapping test's parameters: a staircase of t plateaus
+        TGLWE table = compute_lookup_table(1024, 1, 128);
+        const uint64_t delta = ~0ull / 128;
+        bool ok = true;
+        for (size_t c = 0; c < 1024; c++) ok = ok && table.data[c] == 0 && table.data[1024 + c] == (c / 8) * delta;
+        EXPECT(ok);
+    }
+    {   // CKKS Rq paths (ckks/src/lib.rs:46-119): decrypt(encrypt(m)) = m up to the noise, add is homomorphic
+        CKKS ckks{RingParam{Q, 32}};
+        auto [sk, pk] = ckks.new_key(3.2, 3);
+        std::vector<int64_t> m0(32), m1(32);
+        for (size_t i = 0; i < 32; i++) { m0[i] = (int64_t)(100 * i) - 1500; m1[i] = 7 - (int64_t)i * 13; }
+        RLWE c0 = ckks.encrypt(pk, m0, 3.2, 5), c1 = ckks.encrypt(pk, m1, 3.2, 6);
+        std::vector<int64_t> d0 = ckks.decrypt(sk, c0), ds = ckks.decrypt(sk, ckks.add(c0, c1));
+        bool ok = true;
+        for (size_t i = 0; i < 32; i++) ok = ok && std::llabs(d0[i] - m0[i]) < 200 && std::llabs(ds[i] - (m0[i] + m1[i])) < 400;
+        EXPECT(ok);
+    }
     std::printf(failures ? "%d FAILURES\n" : "ALL OK\n", failures);
     return failures ? 1 : 0;
 }
