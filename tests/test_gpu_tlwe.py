@@ -119,8 +119,9 @@ def test_blind_rotation_as_executed_and_as_written(fhe, orc):
         want = np.empty((k + 1) * n, dtype=np.uint64)
         L.orc_blind_rotation_as_executed(n, k, orc.ptr(np.ascontiguousarray(cts[b])), n * k, orc.ptr(table), orc.ptr(want))
         assert (got[b] == want).all()
-    # as written (extension): k=3 so the loop body runs for j=1,2
-    n, k, batch = 64, 3, 3
+    # as written (extension): k=4 so the loop body runs for j=1,2,3 (k*n must be a power of two: T64::mod_switch
+    # asserts it, torus.rs:58-66, so the reference panics for k=3)
+    n, k, batch = 64, 4, 3
     glwe = (k + 1) * n
     bsk = orc.uniform(8, (k, (k + 1) * 64 * glwe))
     table = orc.uniform(9, glwe)
