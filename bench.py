@@ -36,8 +36,8 @@ N = 1024
 BATCH = 65536  # 3 * 65536 * 8 KiB = 1.5 GiB per step: far larger than the 126 MB L2
 WIRE_BITS = 17  # ceil(log2 q): the bit-packed wire of the end-to-end leg
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this exact workload (ncu --set full capture)
-NCU_TRAFFIC_BYTES = 1073804000 + 499474432
-NCU_TRAFFIC_SOURCE = "profiles/r1_polymul_n1024_q65537_ncu_full_e.csv (kernel unchanged in r2; re-captured: profiles/r2_polymul_n1024_*)"
+NCU_TRAFFIC_BYTES = 1073805000 + 501989376
+NCU_TRAFFIC_SOURCE = "profiles/r2_polymul_n1024_q65537_u64_ncu_full_a.csv (ncu --set full of tools/prof.py polymul 10 65537 65536)"
 
 
 def peaks():
@@ -575,7 +575,7 @@ def main():
             "bound": "int32 Shoup modmul (3 IMAD on the fmaheavy pipe)", "achieved": modmul_rate / 1e12, "peak": modmul_peak / 1e12,
             "unit": "T modmul/s", "frac": modmul_rate / modmul_peak, "modmul_per_polymul": modmul_per_polymul,
             "peak_source": "fhe_int_peak(1) microbenchmark, this run",
-            "note": "ncu: fmaheavy (IMAD) pipe 81 % active, issue slots 62 %: the kernel is co-limited by the integer pipe and HBM",
+            "note": "ncu (profiles/r2_polymul_n1024_q65537_u64_ncu_full_a.csv): fmaheavy (IMAD) pipe 81 % active, issue slots 61 %, GPC instruction-cache requests 87 % of peak: co-limited by the integer pipe, instruction fetch and HBM",
         },
         "u32_device_format": {
             "value": value_u32, "unit": "polymul/s", "algorithmic_bytes_per_polymul": 3 * N * 4,

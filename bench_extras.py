@@ -124,7 +124,13 @@ def tfhe_paths(fhe, dev, quick, cpu=True):
         logn = n.bit_length() - 1
         modmul = 2 * ((k + 1) * 64 * (n // 2) * logn + 2 * (k + 1) * ((n // 2) * logn + n)) + 2 * (k + 1) * 64 * 2 * (k + 1) * n
         row["modmul_per_unit"] = modmul
-        row["int_roofline_frac"] = row["extprod_per_s"] * modmul / fhe.int_peak(1)
+        pk = fhe.int_peak(1)
+        row["int_roofline_frac"] = row["extprod_per_s"] * modmul / pk
+        # the same against SURVEY 8d's count (ONE transform set: (k+1)*64 forward + 2(k+1) inverse + 2(k+1)^2*64*n MACs);
+        # the kernel runs the set under two CRT primes, which is what `modmul` above counts
+        survey = (k + 1) * 64 * (n // 2) * logn + 2 * (k + 1) * ((n // 2) * logn + n) + 2 * (k + 1) * (k + 1) * 64 * n
+        row["modmul_per_unit_survey_8d"] = survey
+        row["int_roofline_frac_survey_8d_count"] = row["extprod_per_s"] * survey / pk
         row["hbm_frac"] = row["extprod_per_s"] * 2 * (k + 1) * n * 8 / (_hbm_peak() * 1e9)
         if cpu:
             sample = max(1, min(batch, cores * (4 if n <= 64 else 1)))
@@ -224,6 +230,27 @@ def bfv_path(fhe, dev, quick, cpu=True):
         ms = _time(lambda: fhe.bfv_mul_relin(q, n, t, pq, rlk, a, b, out=out), 5 if quick else 20)
         row = {"q": q, "n": n, "t": t, "batch": batch, "mul_relin_per_s": batch / (ms * 1e-3), "ms": ms,
                "hbm_gbs": 48 * n * batch / (ms * 1e-3) / 1e9}
+        if batch == 4096:
+            # one call of 4096 ciphertexts is a single ~6 us kernel behind ~10 us of host call path: replaying 16 such
+            # calls from one CUDA graph shows the rate the device sustains at this batch size
+            try:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fhe.use_torch_stream()
+                    fhe.bfv_mul_relin(q, n, t, pq, rlk, a, b, out=out)
+                    with torch.cuda.graph(g, stream=side):
+                        fhe.use_torch_stream()
+                        for _ in range(16):
+                            fhe.bfv_mul_relin(q, n, t, pq, rlk, a, b, out=out)
+                torch.cuda.current_stream().wait_stream(side)
+                fhe.use_torch_stream()
+                gms = _time(g.replay, 20)
+                row["graph_replay_16_calls"] = {"mul_relin_per_s": 16 * batch / (gms * 1e-3), "us_per_call": gms * 1e3 / 16}
+            except Exception as ex:
+                fhe.use_torch_stream()
+                row["graph_replay_16_calls"] = {"error": repr(ex)[:200]}
         if cpu and batch == 4096:
             ha, hb, hr = (x.cpu().numpy().view(np.uint64) for x in (a, b, rlk))
             reps = 50

@@ -28,6 +28,19 @@ if op == "tn":
     torch.cuda.synchronize()
     print("done tn", n, batch)
     sys.exit(0)
+if op == "bfv":
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
+    q, n, t = 65537, 16, 2
+    pq = q * q * q
+    a = torch.randint(0, q, (batch, 2 * n), dtype=torch.int64, device="cuda")
+    b = torch.randint(0, q, (batch, 2 * n), dtype=torch.int64, device="cuda")
+    rlk = torch.randint(0, pq, (2 * n,), dtype=torch.int64, device="cuda")
+    out = torch.empty_like(a)
+    for _ in range(3):
+        fhe.bfv_mul_relin(q, n, t, pq, rlk, a, b, out=out)
+    torch.cuda.synchronize()
+    print("done bfv", batch)
+    sys.exit(0)
 if op in ("bootstrap", "extprod"):
     g = torch.Generator(device="cuda").manual_seed(1)
     r = lambda *shape: torch.randint(-(2**63), 2**63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
@@ -52,6 +65,15 @@ if op in ("bootstrap", "extprod"):
     print("done", op)
     sys.exit(0)
 plan = fhe.NttPlan(q, n)
+if op == "polymul32":  # the packed 32-bit device format
+    a = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda")
+    b = torch.randint(0, q, (batch, n), dtype=torch.int32, device="cuda")
+    c = torch.empty_like(a)
+    for _ in range(reps):
+        plan.mul_u32(a, b, out=c)
+    torch.cuda.synchronize()
+    print("done", op, n, q, batch, reps)
+    sys.exit(0)
 a = torch.randint(0, min(q, 2**62), (batch, n), dtype=torch.int64, device="cuda")
 b = torch.randint(0, min(q, 2**62), (batch, n), dtype=torch.int64, device="cuda")
 c = torch.empty_like(a)
