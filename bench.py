@@ -178,8 +178,10 @@ def run_reference(args, emit):
     emit(line)
 
 
-def measure_pcie(torch, dev, mib=256, reps=5):
-    """Pinned-memory copy rates of this rank: H2D alone, D2H alone, both at once (GB/s)."""
+def measure_pcie(torch, dev, mib=256, reps=8, sync=None):
+    """Pinned-memory copy rates of this rank: H2D alone, D2H alone, both at once (GB/s).  `sync` (a barrier) is called in
+    front of every phase so that all ranks copy at the same time: the per-rank numbers then show what the host gives
+    each GPU when N of them transfer concurrently."""
     n = mib << 20
     h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
     h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -190,6 +192,8 @@ def measure_pcie(torch, dev, mib=256, reps=5):
     def timed(fn):
         fn()
         torch.cuda.synchronize()
+        if sync is not None:
+            sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
@@ -524,7 +528,7 @@ def main():
             t.copy_(src)
         return t
 
-    pcie = measure_pcie(torch, dev)
+    pcie = measure_pcie(torch, dev, sync=barrier)
     pw = N // 32 * WIRE_BITS
     # pack the operands on the device (one launch of the library's own kernel is not available for a bare repack, so
     # the host-side serialiser of the ABI does it; outside the timed region -- it is the shim's gather step)
@@ -600,7 +604,10 @@ def main():
                     "chunked H2D / one kernel launch per chunk / D2H on three streams",
             "h2d_gbs_achieved": h2d_p * e2e_value / world / batch / 1e9,
             "pcie_microbench_gbs_per_rank": pcie_all,
-            "pcie_bound_polymul_per_s": world * min(pcie_all["bidir_each_gbs"]) * 1e9 / (2 * pw * 4),
+            # what the measured copy rates allow (2 packed operands in, 1 out per polymul): from the H2D-only rates (an upper
+            # bound: the D2H stream shares the link) and from the rates with both directions busy
+            "pcie_bound_polymul_per_s": {"h2d_alone": sum(pcie_all["h2d_gbs"]) * 1e9 / (2 * pw * 4),
+                                         "both_directions_busy": sum(pcie_all["bidir_each_gbs"]) * 1e9 / (2 * pw * 4)},
             "u32_wire": {"value": e2e32_value, "h2d_bytes_per_step": 2 * N * 4 * batch, "d2h_bytes_per_step": N * 4 * batch,
                          "matches_device_result": same32, "call": "fhe_rq_mul_u32"},
             "u64_wire": {"value": e2e64_value, "h2d_bytes_per_step": 2 * N * 8 * batch, "d2h_bytes_per_step": N * 8 * batch,

@@ -46,3 +46,11 @@ def test_our_arm_line():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["gpu_matches_on_sample"]
     assert d["gpu_launches"] == 3 and d["clocks"]["sm_mhz"] > 0
     assert d["bootstrap"]["value"] > 0 and d["bootstrap"]["e2e"]["matches_device_result"]
+    # round 2: the keys the driver keeps carry the other formats and the measured peaks
+    assert "17 bits" in e["call"] and e["u32_wire"]["matches_device_result"] and e["u64_wire"]["matches_device_result"]
+    assert e["value"] > e["u32_wire"]["value"] > e["u64_wire"]["value"]  # PCIe-bound: fewer wire bytes, more polymul/s
+    assert e["pcie_microbench_gbs_per_rank"]["h2d_gbs"][0] > 1
+    assert r["u32_device_format"]["matches_u64_result"] and r["u32_device_format"]["value"] > 0
+    assert 0.3 < r["int"]["frac"] < 1.2
+    b = d["bootstrap"]["roofline"]
+    assert b["peak_source"].startswith("measured") and 0.3 < b["frac"] < 1.05
