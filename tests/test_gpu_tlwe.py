@@ -181,6 +181,44 @@ def test_bootstrap_at_baseline_batch_spot_checked(fhe, orc, p5):
     assert np.array_equal(got_p, got[perm])
 
 
+def test_bootstrap_at_64k_batch_both_cluster_modes(fhe, orc, p5, monkeypatch):
+    # upper end of BASELINE configs[4] (8k-64k TLWE inputs): 65536 ciphertexts on one GPU, device-resident; rows spread
+    # over the batch against the oracle, and the whole result equal to eight 8192-row calls (independent units).
+    # The cluster size of the tensor-core kernel is read once per process, so the single-CTA variant is checked in a
+    # child process on a smaller batch.
+    import torch
+
+    n, k, kn = p5["n"], p5["k"], p5["kn"]
+    batch = 65536
+    K = fhe.Ksk(kn, kn, 64, p5["ksk"])
+    table = orc.uniform(601, (k + 1) * n)
+    g = torch.Generator(device="cuda").manual_seed(602)
+    cts = torch.randint(-(2**63), 2**63 - 1, (batch, kn + 1), dtype=torch.int64, device="cuda", generator=g)
+    dt = torch.from_numpy(table.view(np.int64)).cuda()
+    fhe.use_torch_stream()
+    got = fhe.bootstrap(n, k, K, dt, cts, kn)
+    rows = np.unique(np.concatenate([np.arange(4), batch - 1 - np.arange(4), orc.uniform(603, 24, batch).astype(np.int64)]))
+    sel = cts[torch.from_numpy(rows).cuda()].cpu().numpy().view(np.uint64)
+    want = orc.bootstrapping(n, k, p5["ksk"], table, np.ascontiguousarray(sel).reshape(-1), kn, threads=8)
+    assert np.array_equal(got[torch.from_numpy(rows).cuda()].cpu().numpy().view(np.uint64).reshape(-1), want)
+    for i in range(0, batch, 8192):
+        assert torch.equal(fhe.bootstrap(n, k, K, dt, cts[i:i + 8192].contiguous(), kn), got[i:i + 8192])
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests'); import numpy as np, oracle, fhe_study_b200 as fhe\n"
+            "kn, l = 1024, 64\nksk = oracle.uniform(4, kn * l * (kn + 1)); K = fhe.Ksk(kn, kn, l, ksk)\n"
+            "ct = oracle.uniform(6, (700, kn + 1)); got = K.key_switch(ct); rows = [0, 255, 256, 511, 699]\n"
+            "want = oracle.key_switch(kn, kn, l, ksk, ct[rows].copy(), threads=8).reshape(len(rows), kn + 1)\n"
+            "assert (got[rows] == want).all(); print('single-CTA ok')")
+    import os
+
+    env = dict(os.environ, FHE_KS_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "single-CTA ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("kn_in,kn_out,l,uniform", [(16, 16, 64, True), (5, 33, 7, False), (64, 64, 64, False), (3, 1, 1, True)])
 def test_ksk_generated_on_device_equals_cpu_restatement(fhe, orc, kn_in, kn_out, l, uniform):
     # TLWE::new_ksk (tlwe.rs:84-100) on the device, counter-based sampler: bit-exact against the
