@@ -5,9 +5,11 @@
 //
 // Per CTA (256 threads), for each prime r in {p1, p2}:
 //   rounds of SLOTS = 256/T concurrent digit NTTs (T = N/32 threads, 32 coefficients per thread in registers):
-//     - slot s builds the bit polynomial of digit d = (i, j): bit 63-j of x_i (Tn::decompose, torus.rs:43-52),
-//       runs the register-blocked forward NTT (csub-free butterflies: primes < 2^27 leave the headroom) and
-//       leaves NTT(digit) in its shared-memory slot, reduced to [0, 2p);
+//     - slot s takes the bit polynomial of digit d = (i, j): bit 63-j of x_i (Tn::decompose, torus.rs:43-52) -- ONE
+//       32-bit word per thread, the inputs being kept as bit planes -- looks the first three butterfly stages up in
+//       a 256-entry table per byte (the stages are linear and their twiddles the same for every thread), runs the rest
+//       of the register-blocked forward NTT (csub-free butterflies: primes < 2^27 leave the headroom) and leaves
+//       NTT(digit) in its shared-memory slot, reduced to [0, 2p);
 //     - all threads then MAC the round's digits against the resident TGGSW: thread t owns the items
 //       I = t + 256 m of the (component, limb, position) space; 64-bit accumulators in registers
 //       (products < 2^55, at most (k+1)*64 <= 512 of them), one IMAD.WIDE per MAC, 128-bit key loads;
@@ -37,6 +39,19 @@ template <int LOGN, int K1> struct XpGeom {
     static constexpr int SLOTS = CT / S::T;             // concurrent NTTs
     static constexpr int ND = K1 * 64;                  // digit polynomials per accumulator
     static constexpr int PADN = N + (N >> 5);
+    static_assert(LOGN >= 6, "the table-driven first stages need a first pass of at least three stages on 32 coefficients");
+    // The decomposed inputs are kept as BIT PLANES: row (accumulator, component, thread tn of a digit transform) holds
+    // 64 words, word j = the 32 coefficients that thread owns in digit (component, j), bit 8*o + jj = register slot
+    // oct_slot(o, jj).  One pad word per row: rows are written along j and read along tn.
+    static constexpr int PLANE_ROW = 65;
+    // First three stages of a digit transform by table.  Stage LS of pass 0 pairs the slots ru, ru + (G >> (LS+1)) of
+    // a G = 2^g(0) group with twiddle roots[2^LS + (ru >> (g-LS))]: on the 8 slots  base + jj * (G/8)  of an OCTET the
+    // three stages are a fixed linear map of the 8 input BITS, the same for every octet, thread and digit.  The table
+    // holds its 256 images (built at kernel start by running the butterfly code itself on the 256 bit patterns, so the
+    // lazy representatives are the ones the stages would produce): two 128-bit loads replace 12 butterflies.
+    static constexpr int OCT_G = 1 << S::g(0), OCT_STRIDE = OCT_G >> 3;
+    __host__ __device__ static constexpr int oct_slot(int o, int jj) { return (o / OCT_STRIDE) * OCT_G + jj * OCT_STRIDE + (o % OCT_STRIDE); }
+    static constexpr size_t TAB_BYTES = (size_t)2 * 2 * 256 * 16;   // [prime][outputs 0-3 | 4-7][byte] uint4
     static constexpr int UNITS = K1 * 2;                // (component, limb)
     static constexpr int ITEMS = UNITS * N;
     static constexpr int IPT = (ITEMS + CT - 1) / CT;   // MAC items per thread (per accumulator)
@@ -61,11 +76,15 @@ template <int LOGN, int K1> struct XpGeom {
     static constexpr int LIVE_SLOTS = S::T >= 32 ? A * UNITS : ((A * UNITS * S::T + 31) / 32) * (32 / S::T);
     // the second prime's residues live in the free exchange slots when there are enough of them
     static constexpr bool RES2_IN_XCH = (SLOTS - LIVE_SLOTS) * PADN >= A * UNITS * N;
-    static constexpr size_t SMEM = (size_t)A * K1 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)(RES2_IN_XCH ? 1 : 2) * A * UNITS * N * 4;
+    static constexpr size_t PLANES_BYTES = ((size_t)A * K1 * S::T * PLANE_ROW * 4 + 15) / 16 * 16;
+    static constexpr size_t XCH_BYTES = (size_t)SLOTS * PADN * 4, RES_BYTES = (size_t)(RES2_IN_XCH ? 1 : 2) * A * UNITS * N * 4;
+    static constexpr size_t SMEM = PLANES_BYTES + XCH_BYTES + RES_BYTES + TAB_BYTES;
+    static_assert(XCH_BYTES % 16 == 0 && RES_BYTES % 16 == 0, "the tables behind them hold uint4 words");
     static constexpr size_t SMEM_CHAIN = SMEM;
     static_assert(SLOTS % A == 0 && A * UNITS <= SLOTS, "need a slot per inverse transform");
     static_assert(ND % DPR == 0, "every round must be full: the digit transforms synchronise whole warps");
     static_assert(S::T <= 32, "one digit NTT must fit a warp (N <= 1024) in this kernel");
+    static_assert(S::E == 32 && CT >= 256, "bit planes: 32 coefficients per thread; table build: one entry per thread");
 };
 
 struct XpParams {
@@ -93,37 +112,59 @@ __device__ __forceinline__ u32 reduce64(u64 acc, u32 p, u64 mu) {
     return (u32)(r >= p ? r - p : r);
 }
 
-// NTT of digit polynomial d = (i, j) of the decomposed input under prime r, left in `sm` (padded position
-// order, values < 2^28): bit 63-j of x_i (Tn::decompose, torus.rs:43-52) -> register-blocked forward NTT.
-//  * stage 0 works on bits: V = b*S is a select (mask & S), no multiplication;
+// 32 x 32 bit-matrix transpose across a warp: lane L gives row L, lane j returns column j (bit L = bit j of lane L's
+// word).  Five block-swap steps (distance 16 ... 1), one shuffle each.
+__device__ __forceinline__ u32 warp_transpose32(u32 a, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const u32 m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const u32 o = __shfl_xor_sync(0xffffffffu, a, s);
+        a = (lane & s) ? ((a & ~m) | ((o >> s) & m)) : ((a & m) | ((o << s) & ~m));
+    }
+    return a;
+}
+
+// Table entry b of one prime: stages 0-2 on the bit pattern b.  Stage 0 works on bits (ntt.rs:56-60 with U, V in {0,1}:
+// V = b*S is a select, not a multiplication); stages 1, 2 are the butterflies of the 8-point shape, whose twiddle
+// indices 2 + hi and 4 + hi are those of every octet (XpGeom).
+__device__ __forceinline__ void octet_table_entry(const Small32 &ms, const TwSrc<Small32> &twf, int b, uint4 *tab_lo, uint4 *tab_hi) {
+    u32 y[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) y[j] = ((u32)b >> j) & 1u;
+    const u32 S1 = twf.c0[1].w;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const u32 U = y[j], V = (0u - y[j + 4]) & S1;
+        y[j] = U + V;
+        y[j + 4] = U + ms.q2 - V;
+    }
+    fwd_pass<Small32, 3, 3, 0, 1>(y, 0, ms, twf);
+    tab_lo[b] = make_uint4(y[0], y[1], y[2], y[3]);
+    tab_hi[b] = make_uint4(y[4], y[5], y[6], y[7]);
+}
+
+// NTT of a digit polynomial under one prime, left in `sm` (padded position order, values < 2^28).  `w` holds the
+// thread's 32 coefficients (bits).
+//  * stages 0-2 come out of the octet table (tab_lo / tab_hi of this prime);
 //  * the csub-free butterflies leave values < (2*LOGN+1)*p < 2^32; the final partial reduction
 //    x - (x >> 27)*p = (x mod 2^27) + (x >> 27)*(2^27 - p) < 2^27 + 21*2^21 < 2^28 costs one shift and one IMAD
 //    (the MAC then adds at most (k+1)*64 <= 320 products < 2^28 * 2^27: below 2^64).
-template <int LOGN>
-__device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32> &twf, int d, const u64 *xin, u32 *sm,
-                                          int tid) {
-    constexpr int LOGE = LOGN < 5 ? LOGN : 5;
+template <int LOGN, int K1>
+__device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32> &twf, u32 w, const uint4 *tab_lo,
+                                          const uint4 *tab_hi, u32 *sm, int tid) {
+    typedef XpGeom<LOGN, K1> G;
+    constexpr int LOGE = G::LOGE;
     typedef NttShape<LOGN, LOGE> S;
     constexpr int LAST = S::P - 1;
-    constexpr int G0 = 1 << S::g(0), H0 = G0 >> 1;
-    static_assert(S::g(0) >= 2, "digit_ntt: pass 0 needs at least two stages");
-    const u64 *xi = xin + (size_t)(d >> 6) * S::N;
-    const int sh = 63 - (d & 63);
     u32 x[S::E];
 #pragma unroll
-    for (int e = 0; e < S::E; e++) x[e] = (u32)(xi[S::pos(0, tid, e)] >> sh) & 1u;
-    {   // stage 0 (ntt.rs:56-60 with U, V in {0,1}): x = U + V*S, y = U - V*S (+2p), S = roots[1]
-        const u32 S1 = twf.c0[1].w;
-#pragma unroll
-        for (int qi = 0; qi < (S::E >> S::g(0)); qi++)
-#pragma unroll
-            for (int lo = 0; lo < H0; lo++) {
-                const u32 U = x[qi * G0 + lo], V = (0u - x[qi * G0 + lo + H0]) & S1;
-                x[qi * G0 + lo] = U + V;
-                x[qi * G0 + lo + H0] = U + ms.q2 - V;
-            }
+    for (int o = 0; o < 4; o++) {
+        const u32 b = (w >> (8 * o)) & 255u;
+        const uint4 lo4 = tab_lo[b], hi4 = tab_hi[b];
+        x[G::oct_slot(o, 0)] = lo4.x; x[G::oct_slot(o, 1)] = lo4.y; x[G::oct_slot(o, 2)] = lo4.z; x[G::oct_slot(o, 3)] = lo4.w;
+        x[G::oct_slot(o, 4)] = hi4.x; x[G::oct_slot(o, 5)] = hi4.y; x[G::oct_slot(o, 6)] = hi4.z; x[G::oct_slot(o, 7)] = hi4.w;
     }
-    fwd_pass<Small32, LOGN, LOGE, 0, 1>(x, tid, ms, twf);
+    if constexpr (S::g(0) > 3) fwd_pass<Small32, LOGN, LOGE, 0, 3>(x, tid, ms, twf);
     if constexpr (S::P > 1) fwd_chain<Small32, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
 #pragma unroll
     for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = x[e] - (x[e] >> 27) * ms.q;
@@ -137,8 +178,8 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     typedef typename G::S S;
     constexpr int LOGE = G::LOGE, N = G::N, LAST = S::P - 1, A = G::A, GLWE = K1 * N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *xin = reinterpret_cast<u64 *>(smem_raw);                         // [A][K1][N] decomposed inputs
-    u32 *xch = reinterpret_cast<u32 *>(xin + (size_t)A * GLWE);           // [SLOTS][PADN] exchange / NTT(digit)
+    u32 *planes = reinterpret_cast<u32 *>(smem_raw);                      // [A][K1][T][PLANE_ROW] bit planes of the inputs
+    u32 *xch = reinterpret_cast<u32 *>(smem_raw + G::PLANES_BYTES);       // [SLOTS][PADN] exchange / NTT(digit)
     u32 *res1 = xch + (size_t)G::SLOTS * G::PADN;                         // [A][UNITS][N] residues mod p1
     u32 *res2 = G::RES2_IN_XCH ? xch + (size_t)G::LIVE_SLOTS * G::PADN    // [A][UNITS][N] residues mod p2 (free slots of xch)
                                : res1 + (size_t)A * G::UNITS * N;
@@ -149,6 +190,16 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     const size_t acc0 = (size_t)blockIdx.x * A;     // first accumulator of this CTA
     const int na = (int)(batch - acc0 < (size_t)A ? batch - acc0 : (size_t)A);
     const size_t base = acc0 * GLWE;
+    uint4 *tab = reinterpret_cast<uint4 *>(smem_raw + G::PLANES_BYTES + G::XCH_BYTES + G::RES_BYTES);   // [2][2][256]
+    if (t < 256) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
+            octet_table_entry(X.ms[r], twf, t, tab + r * 512, tab + r * 512 + 256);
+        }
+    }   // ordered before the first digit transform by the barrier behind the bit planes
+    const int lane = t & 31;
+    const int my_slot = G::oct_slot(lane >> 3, lane & 7);   // register slot of plane bit `lane`
 
     const int steps = CHAIN ? ch.steps : 1;
 #pragma unroll 1
@@ -156,8 +207,12 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     // input of the external product: ct (extprod), ct2 - ct1 (TGGSW::cmux, tggsw.rs:39-41), or for the chain
     // X^{-h} acc - acc (the CMux of tlwe.rs:140-146 with ct2 = acc.left_rotate(h)).  The chain's accumulator
     // lives in this CTA's own output rows between steps (L2-resident; every HBM line is written once).
-    for (int i = t; i < A * GLWE; i += G::CT) {
-        const int aa = i / GLWE, rem = i % GLWE;
+    // Bit planes: a warp takes one (accumulator, component, transform thread tn) row at a time; lane L loads the
+    // coefficient of register slot my_slot, two warp transposes turn the 32 values into 64 plane words.
+    for (int grp = t >> 5; grp < A * K1 * S::T; grp += G::CT / 32) {
+        const int tn = grp % S::T, c = (grp / S::T) % K1, aa = grp / (S::T * K1);
+        const int p = S::pos(0, tn, my_slot), rem = (c << LOGN) + p;
+        const size_t i = (size_t)aa * GLWE + rem;
         u64 v = 0;
         if (aa < na) {
             if (CHAIN) {
@@ -165,7 +220,6 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
                 const u64 hraw = ch.h[(acc0 + aa) * steps + step];
                 const u32 h = (u32)(hraw & (N - 1));
                 const bool flip = ch.negacyclic && ((hraw >> LOGN) & 1);
-                const int c = rem >> LOGN, p = rem & (N - 1);
                 const u32 src = (u32)p + h;
                 v = src < (u32)N ? acc_g[(c << LOGN) + src] : (u64)0 - acc_g[(c << LOGN) + src - N];
                 if (flip) v = (u64)0 - v;
@@ -174,7 +228,10 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
                 v = cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
             }
         }
-        xin[i] = v;
+        const u32 whi = warp_transpose32((u32)(v >> 32), lane), wlo = warp_transpose32((u32)v, lane);
+        u32 *row = planes + (size_t)grp * G::PLANE_ROW;
+        row[31 - lane] = whi;   // digit j reads bit 63 - j (Tn::decompose, torus.rs:43-52): bit 32 + lane is digit 31 - lane
+        row[63 - lane] = wlo;
     }
     __syncthreads();
 
@@ -192,10 +249,12 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
             const int d = round * G::DPR + s_dig;
             if (d < G::ND) {
                 const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
-                digit_ntt<LOGN>(X.ms[r], twf, d, xin + (size_t)s_acc * GLWE, sm, tid);
+                const u32 w = planes[((size_t)(s_acc * K1 + (d >> 6)) * S::T + tid) * G::PLANE_ROW + (d & 63)];
+                digit_ntt<LOGN, K1>(X.ms[r], twf, w, tab + r * 512, tab + r * 512 + 256, sm, tid);
             }
             __syncthreads();
-            const int nd = min(G::DPR, G::ND - round * G::DPR);
+            constexpr int nd = G::DPR;   // ND % DPR == 0: every round is full (a compile-time trip count also keeps
+                                         // ptxas from rotating the accumulator pairs through MOVs: 98 -> 66 instructions per two digits)
             const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr) + (size_t)round * G::DPR * (G::IPT4 / 4) * G::CT + t;
 #pragma unroll 2
             for (int dd = 0; dd < nd; dd++) {
