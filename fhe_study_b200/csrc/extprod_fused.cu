@@ -87,6 +87,20 @@ template <int LOGN, int K1> struct XpGeom {
     static_assert(S::E == 32 && CT >= 256, "bit planes: 32 coefficients per thread; table build: one entry per thread");
 };
 
+// items m and m' of a thread sit on the same coefficient position when CT * (m - m') is a multiple of N: with
+// CT * 4 >= N (every instantiated shape) there are at most 4 distinct positions, selected by m mod (N / CT)
+template <int LOGN, int CT> __host__ __device__ constexpr int dv_slot(int m) {
+    return (1 << LOGN) >= CT ? m % ((1 << LOGN) / CT) : 0;
+}
+
+// 128-bit read-only key load that stays where the source puts it: as a plain __ldg ptxas sank the loads issued in
+// front of the barrier back behind it
+__device__ __forceinline__ uint4 ldg_key(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 struct XpParams {
     NttParams<Lazy32> P[2];   // plans of p1, p2 (device-order tables, n^-1 constants)
     Small32 ms[2];            // same moduli, csub-free forward butterflies
@@ -207,31 +221,45 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     // input of the external product: ct (extprod), ct2 - ct1 (TGGSW::cmux, tggsw.rs:39-41), or for the chain
     // X^{-h} acc - acc (the CMux of tlwe.rs:140-146 with ct2 = acc.left_rotate(h)).  The chain's accumulator
     // lives in this CTA's own output rows between steps (L2-resident; every HBM line is written once).
-    // Bit planes: a warp takes one (accumulator, component, transform thread tn) row at a time; lane L loads the
-    // coefficient of register slot my_slot, two warp transposes turn the 32 values into 64 plane words.
-    for (int grp = t >> 5; grp < A * K1 * S::T; grp += G::CT / 32) {
+    // Bit planes: a warp takes (accumulator, component, transform thread tn) rows, lane L loads the coefficient of
+    // register slot my_slot, two warp transposes turn the 32 values of a row into its 64 plane words.  The scattered
+    // loads of up to PB rows are issued together (one row at a time the phase was 4.6 % of the stall samples).
+    constexpr int NGRP = A * K1 * S::T, NW = G::CT / 32, GPW = (NGRP + NW - 1) / NW, PB = GPW < 8 ? GPW : 8;
+    auto plane_input = [&](int grp) -> u64 {
         const int tn = grp % S::T, c = (grp / S::T) % K1, aa = grp / (S::T * K1);
         const int p = S::pos(0, tn, my_slot), rem = (c << LOGN) + p;
         const size_t i = (size_t)aa * GLWE + rem;
-        u64 v = 0;
-        if (aa < na) {
-            if (CHAIN) {
-                const u64 *acc_g = (step == 0 ? ct1 : out) + base + (size_t)aa * GLWE;
-                const u64 hraw = ch.h[(acc0 + aa) * steps + step];
-                const u32 h = (u32)(hraw & (N - 1));
-                const bool flip = ch.negacyclic && ((hraw >> LOGN) & 1);
-                const u32 src = (u32)p + h;
-                v = src < (u32)N ? acc_g[(c << LOGN) + src] : (u64)0 - acc_g[(c << LOGN) + src - N];
-                if (flip) v = (u64)0 - v;
-                v -= acc_g[rem];
-            } else {
-                v = cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
+        if (aa >= na) return 0;
+        if (CHAIN) {
+            const u64 *acc_g = (step == 0 ? ct1 : out) + base + (size_t)aa * GLWE;
+            const u64 hraw = ch.h[(acc0 + aa) * steps + step];
+            const u32 h = (u32)(hraw & (N - 1));
+            const bool flip = ch.negacyclic && ((hraw >> LOGN) & 1);
+            const u32 src = (u32)p + h;
+            u64 v = src < (u32)N ? acc_g[(c << LOGN) + src] : (u64)0 - acc_g[(c << LOGN) + src - N];
+            if (flip) v = (u64)0 - v;
+            return v - acc_g[rem];
+        }
+        return cmux ? ct2[base + i] - ct1[base + i] : ct1[base + i];
+    };
+#pragma unroll 1
+    for (int g0 = 0; g0 < GPW; g0 += PB) {
+        u64 v[PB];
+#pragma unroll
+        for (int u = 0; u < PB; u++) {
+            const int grp = (t >> 5) + (g0 + u) * NW;
+            v[u] = (g0 + u < GPW && grp < NGRP) ? plane_input(grp) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < PB; u++) {
+            const int grp = (t >> 5) + (g0 + u) * NW;
+            if (g0 + u < GPW && grp < NGRP) {   // warp-uniform
+                const u32 whi = warp_transpose32((u32)(v[u] >> 32), lane), wlo = warp_transpose32((u32)v[u], lane);
+                u32 *row = planes + (size_t)grp * G::PLANE_ROW;
+                row[31 - lane] = whi;   // digit j reads bit 63 - j (Tn::decompose, torus.rs:43-52): bit 32 + lane is digit 31 - lane
+                row[63 - lane] = wlo;
             }
         }
-        const u32 whi = warp_transpose32((u32)(v >> 32), lane), wlo = warp_transpose32((u32)v, lane);
-        u32 *row = planes + (size_t)grp * G::PLANE_ROW;
-        row[31 - lane] = whi;   // digit j reads bit 63 - j (Tn::decompose, torus.rs:43-52): bit 32 + lane is digit 31 - lane
-        row[63 - lane] = wlo;
     }
     __syncthreads();
 
@@ -252,26 +280,45 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
                 const u32 w = planes[((size_t)(s_acc * K1 + (d >> 6)) * S::T + tid) * G::PLANE_ROW + (d & 63)];
                 digit_ntt<LOGN, K1>(X.ms[r], twf, w, tab + r * 512, tab + r * 512 + 256, sm, tid);
             }
+            // MAC of the round's digits against the resident TGGSW, two digits per iteration.  The 128-bit key loads are
+            // software-pipelined through the registers themselves: the loads of the first pair are issued BEFORE the
+            // barrier that ends the transforms (the transform registers are dead by then), and every key quad is
+            // re-loaded for the next pair right behind the four MACs that consumed it.  Before, an iteration issued
+            // its loads and sat on their L2 latency: 17 % of all stall samples on the first IMAD.WIDE of the loop
+            // (profiles/r2_extprod_fused_n1024_k1_ncu_full_b.csv).
+            constexpr int nd = G::DPR, Q = G::IPT4 / 4;   // ND % DPR == 0: every round is full
+            static_assert(nd % 2 == 0, "the MAC takes the digits in pairs");
+            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr) + (size_t)round * G::DPR * Q * G::CT + t;
+            uint4 kq[2][Q];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++)
+#pragma unroll
+                for (int v = 0; v < Q; v++) kq[h2][v] = ldg_key(Rt + (size_t)(h2 * Q + v) * G::CT);
             __syncthreads();
-            constexpr int nd = G::DPR;   // ND % DPR == 0: every round is full (a compile-time trip count also keeps
-                                         // ptxas from rotating the accumulator pairs through MOVs: 98 -> 66 instructions per two digits)
-            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr) + (size_t)round * G::DPR * (G::IPT4 / 4) * G::CT + t;
-#pragma unroll 2
-            for (int dd = 0; dd < nd; dd++) {
-                u32 rv[G::IPT4];
+#pragma unroll(nd <= 8 ? nd / 2 : 1)
+            for (int it = 0; it < nd / 2; it++) {
+                const bool more = it + 1 < nd / 2;
 #pragma unroll
-                for (int v = 0; v < G::IPT4 / 4; v++) {
-                    const uint4 q4 = __ldg(Rt + (size_t)(dd * (G::IPT4 / 4) + v) * G::CT);
-                    rv[4 * v] = q4.x; rv[4 * v + 1] = q4.y; rv[4 * v + 2] = q4.z; rv[4 * v + 3] = q4.w;
-                }
+                for (int h2 = 0; h2 < 2; h2++) {
+                    const int dd = 2 * it + h2;
+                    u32 dv[A][G::IPT < 4 ? G::IPT : 4];   // items m, m + 4, .. of a thread share the position
 #pragma unroll
-                for (int aa = 0; aa < A; aa++) {
-                    const u32 *D = xch + (size_t)(dd * A + aa) * G::PADN;
+                    for (int aa = 0; aa < A; aa++)
 #pragma unroll
-                    for (int m = 0; m < G::IPT; m++) {
-                        const int item = t + G::CT * m;
-                        const u32 dv = D[pad_idx(item & (N - 1))];
-                        acc[aa][m] += (u64)dv * rv[m];  // item >= ITEMS only when ITEMS % 256 != 0: key padding is zero
+                        for (int m = 0; m < (G::IPT < 4 ? G::IPT : 4); m++)
+                            dv[aa][m] = xch[(size_t)(dd * A + aa) * G::PADN + pad_idx((t + G::CT * m) & (N - 1))];
+#pragma unroll
+                    for (int v = 0; v < Q; v++) {
+                        const u32 k4[4] = {kq[h2][v].x, kq[h2][v].y, kq[h2][v].z, kq[h2][v].w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int m = 4 * v + j;
+                            if (m < G::IPT) {   // item >= ITEMS only when ITEMS % CT != 0: key padding is zero
+#pragma unroll
+                                for (int aa = 0; aa < A; aa++) acc[aa][m] += (u64)dv[aa][dv_slot<LOGN, G::CT>(m)] * k4[j];
+                            }
+                        }
+                        if (more) kq[h2][v] = ldg_key(Rt + (size_t)((dd + 2) * Q + v) * G::CT);
                     }
                 }
             }
