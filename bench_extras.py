@@ -131,6 +131,11 @@ def tfhe_paths(fhe, dev, quick, cpu=True):
         survey = (k + 1) * 64 * (n // 2) * logn + 2 * (k + 1) * ((n // 2) * logn + n) + 2 * (k + 1) * (k + 1) * 64 * n
         row["modmul_per_unit_survey_8d"] = survey
         row["int_roofline_frac_survey_8d_count"] = row["extprod_per_s"] * survey / pk
+        # what the fused kernel EXECUTES since r2: stages 0-2 of every forward digit transform are table lookups
+        # (extprod_fused.cu), so a forward transform multiplies in logn - 3 stages only
+        executed = 2 * ((k + 1) * 64 * (n // 2) * (logn - 3) + 2 * (k + 1) * ((n // 2) * logn + n)) + 2 * (k + 1) * 64 * 2 * (k + 1) * n
+        row["modmul_executed_per_unit"] = executed
+        row["int_roofline_frac_executed"] = row["extprod_per_s"] * executed / pk
         row["hbm_frac"] = row["extprod_per_s"] * 2 * (k + 1) * n * 8 / (_hbm_peak() * 1e9)
         if cpu:
             sample = max(1, min(batch, cores * (4 if n <= 64 else 1)))
@@ -339,8 +344,13 @@ def run(fhe, dev, quick=False, cpu=True):
     try:
         t = res["tfhe"]
         compact["extprod"] = {k: {"extprod_per_s": t[k]["extprod_per_s"], "cmux_per_s": t[k]["cmux_per_s"], "batch": t[k]["batch"],
-                                  "int_roofline_frac": t[k]["int_roofline_frac"], "hbm_frac": t[k]["hbm_frac"],
+                                  "int_roofline_frac": t[k]["int_roofline_frac"], "int_roofline_frac_executed": t[k]["int_roofline_frac_executed"],
+                                  "int_roofline_frac_survey_8d_count": t[k]["int_roofline_frac_survey_8d_count"], "hbm_frac": t[k]["hbm_frac"],
                                   "cpu_extprod_per_s": t[k].get("cpu_extprod_per_s")} for k in ("P4a_n64_k4", "P4b_n1024_k1")}
+    except Exception:
+        pass
+    try:
+        compact["extprod"]["cmux_chain_n1024_k1"] = {kk: t["P6_bootstrap_cmux_chain_extension"][kk] for kk in ("steps", "batch", "cmux_per_s")}
     except Exception:
         pass
     try:
