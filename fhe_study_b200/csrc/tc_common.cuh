@@ -79,4 +79,48 @@ __device__ __forceinline__ void tc_commit_multicast(u32 bar, unsigned short mask
                  : "memory");
 }
 
+
+// --- CTA pairs (cta_group::2): one MMA of M = 256 spans the tensor cores of both CTAs of a cluster of two.  CTA r
+// supplies rows [128 r, 128 r + 128) of A and rows [128 r, 128 r + 128) of B (N-major) from the SAME shared-memory
+// offsets; its tensor memory receives its 128 rows of D.  Only the leader (rank 0) issues.
+constexpr u32 TC_IDESC_PAIR = (2u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+__device__ __forceinline__ void tc_mma_i8_pair(u32 tmem_d, u64 adesc, u64 bdesc, u32 accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC_PAIR), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier at this offset in both CTAs of the pair when the pair MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(u32 bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void tc_mbar_arrive_remote(u32 bar, u32 rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(bar), "r"(rank)
+        : "memory");
+}
+// wait with acquire at cluster scope (the arrival came from the peer CTA)
+__device__ __forceinline__ void tc_mbar_wait_cluster(u32 bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAITC:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONEC;\n"
+        "bra TC_WAITC;\n"
+        "TC_DONEC:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+
 }  // namespace fhe

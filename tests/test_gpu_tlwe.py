@@ -213,10 +213,12 @@ def test_bootstrap_at_64k_batch_both_cluster_modes(fhe, orc, p5, monkeypatch):
             "assert (got[rows] == want).all(); print('single-CTA ok')")
     import os
 
-    env = dict(os.environ, FHE_KS_CLUSTER="1")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0 and "single-CTA ok" in r.stdout, r.stdout + r.stderr
+    # FHE_KS_CLUSTER=1: single CTAs; =3: CTA pairs (tcgen05.mma.cta_group::2, each CTA holding half of every key block)
+    for mode in ("1", "3"):
+        env = dict(os.environ, FHE_KS_CLUSTER=mode)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0 and "single-CTA ok" in r.stdout, mode + r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("kn_in,kn_out,l,uniform", [(16, 16, 64, True), (5, 33, 7, False), (64, 64, 64, False), (3, 1, 1, True)])
