@@ -19,6 +19,7 @@
 #include "ntt_kernels.cuh"
 #include "runtime.cuh"
 #include "torus.cuh"
+#include "xp_octet.cuh"
 
 #include <stdlib.h>
 
@@ -39,18 +40,12 @@ template <int LOGN, int K1> struct XpGeom {
     static constexpr int SLOTS = CT / S::T;             // concurrent NTTs
     static constexpr int ND = K1 * 64;                  // digit polynomials per accumulator
     static constexpr int PADN = N + (N >> 5);
-    static_assert(LOGN >= 6, "the table-driven first stages need a first pass of at least three stages on 32 coefficients");
     // The decomposed inputs are kept as BIT PLANES: row (accumulator, component, thread tn of a digit transform) holds
     // 64 words, word j = the 32 coefficients that thread owns in digit (component, j), bit 8*o + jj = register slot
-    // oct_slot(o, jj).  One pad word per row: rows are written along j and read along tn.
+    // oct_slot(o, jj) (xp_octet.cuh).  One pad word per row: rows are written along j and read along tn.
     static constexpr int PLANE_ROW = 65;
-    // First three stages of a digit transform by table.  Stage LS of pass 0 pairs the slots ru, ru + (G >> (LS+1)) of
-    // a G = 2^g(0) group with twiddle roots[2^LS + (ru >> (g-LS))]: on the 8 slots  base + jj * (G/8)  of an OCTET the
-    // three stages are a fixed linear map of the 8 input BITS, the same for every octet, thread and digit.  The table
-    // holds its 256 images (built at kernel start by running the butterfly code itself on the 256 bit patterns, so the
-    // lazy representatives are the ones the stages would produce): two 128-bit loads replace 12 butterflies.
-    static constexpr int OCT_G = 1 << S::g(0), OCT_STRIDE = OCT_G >> 3;
-    __host__ __device__ static constexpr int oct_slot(int o, int jj) { return (o / OCT_STRIDE) * OCT_G + jj * OCT_STRIDE + (o % OCT_STRIDE); }
+    __host__ __device__ static constexpr int oct_slot(int o, int jj) { return XpOct<LOGN>::slot(o, jj); }
+    // first three stages of a digit transform by table (xp_octet.cuh)
     static constexpr size_t TAB_BYTES = (size_t)2 * 2 * 256 * 16;   // [prime][outputs 0-3 | 4-7][byte] uint4
     static constexpr int UNITS = K1 * 2;                // (component, limb)
     static constexpr int ITEMS = UNITS * N;
@@ -138,25 +133,6 @@ __device__ __forceinline__ u32 warp_transpose32(u32 a, int lane) {
     return a;
 }
 
-// Table entry b of one prime: stages 0-2 on the bit pattern b.  Stage 0 works on bits (ntt.rs:56-60 with U, V in {0,1}:
-// V = b*S is a select, not a multiplication); stages 1, 2 are the butterflies of the 8-point shape, whose twiddle
-// indices 2 + hi and 4 + hi are those of every octet (XpGeom).
-__device__ __forceinline__ void octet_table_entry(const Small32 &ms, const TwSrc<Small32> &twf, int b, uint4 *tab_lo, uint4 *tab_hi) {
-    u32 y[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) y[j] = ((u32)b >> j) & 1u;
-    const u32 S1 = twf.c0[1].w;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const u32 U = y[j], V = (0u - y[j + 4]) & S1;
-        y[j] = U + V;
-        y[j + 4] = U + ms.q2 - V;
-    }
-    fwd_pass<Small32, 3, 3, 0, 1>(y, 0, ms, twf);
-    tab_lo[b] = make_uint4(y[0], y[1], y[2], y[3]);
-    tab_hi[b] = make_uint4(y[4], y[5], y[6], y[7]);
-}
-
 // NTT of a digit polynomial under one prime, left in `sm` (padded position order, values < 2^28).  `w` holds the
 // thread's 32 coefficients (bits).
 //  * stages 0-2 come out of the octet table (tab_lo / tab_hi of this prime);
@@ -171,14 +147,7 @@ __device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32
     typedef NttShape<LOGN, LOGE> S;
     constexpr int LAST = S::P - 1;
     u32 x[S::E];
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-        const u32 b = (w >> (8 * o)) & 255u;
-        const uint4 lo4 = tab_lo[b], hi4 = tab_hi[b];
-        x[G::oct_slot(o, 0)] = lo4.x; x[G::oct_slot(o, 1)] = lo4.y; x[G::oct_slot(o, 2)] = lo4.z; x[G::oct_slot(o, 3)] = lo4.w;
-        x[G::oct_slot(o, 4)] = hi4.x; x[G::oct_slot(o, 5)] = hi4.y; x[G::oct_slot(o, 6)] = hi4.z; x[G::oct_slot(o, 7)] = hi4.w;
-    }
-    if constexpr (S::g(0) > 3) fwd_pass<Small32, LOGN, LOGE, 0, 3>(x, tid, ms, twf);
+    digit_pass0<LOGN>(x, w, tab_lo, tab_hi, tid, ms, twf);
     if constexpr (S::P > 1) fwd_chain<Small32, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
 #pragma unroll
     for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = x[e] - (x[e] >> 27) * ms.q;
@@ -209,7 +178,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
-            octet_table_entry(X.ms[r], twf, t, tab + r * 512, tab + r * 512 + 256);
+            octet_table_entry(X.ms[r], twf, t, tab[r * 512 + t], tab[r * 512 + 256 + t]);
         }
     }   // ordered before the first digit transform by the barrier behind the bit planes
     const int lane = t & 31;

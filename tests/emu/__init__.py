@@ -29,6 +29,8 @@ def lib():
         U, P, I = C.c_uint64, C.c_void_p, C.c_int
         L.emu_ntt.argtypes = [I, U, U, I, I, P, P, P, P, I]
         L.emu_ntt.restype = I
+        L.emu_xp_digit.argtypes = [U, U, P, P]
+        L.emu_xp_digit.restype = I
         L.emu_plan.argtypes = [U, U, P, P, P, P]
         L.emu_plan.restype = I
         L.emu_modmul.argtypes = [I, U, U, U]

@@ -10,6 +10,7 @@
 
 #include "../../fhe_study_b200/csrc/ntt_core.cuh"
 #include "../../fhe_study_b200/csrc/plan_host.hpp"
+#include "../../fhe_study_b200/csrc/xp_octet.cuh"
 
 using namespace fhe;
 
@@ -116,7 +117,43 @@ static int emu_any(u64 q, u64 n, int loge, int mode, const u64 *a, const u64 *b,
     return -1;
 }
 
+// One digit transform of the external product (extprod_fused.cu: digit_ntt): a polynomial of BITS, pass 0 from the
+// octet table (xp_octet.cuh), later passes the ordinary csub-free butterflies, final fold below 2^28.
+template <int LOGN> static void run_digit(const ExpandedTables<Small32> &x, const u64 *bits, u64 *out) {
+    typedef XpOct<LOGN> O;
+    typedef typename O::S S;
+    const TwSrc<Small32> twf = {x.fwd.data(), x.fwd.data()};
+    std::vector<XpQuad> lo(256), hi(256);
+    for (int b = 0; b < 256; b++) octet_table_entry(x.mod, twf, b, lo[b], hi[b]);
+    Emu<Small32, LOGN, O::LOGE> A;
+    for (int t = 0; t < S::T; t++) {
+        u32 w = 0;
+        for (int o = 0; o < 4; o++)
+            for (int jj = 0; jj < 8; jj++) w |= (u32)(bits[S::pos(0, t, O::slot(o, jj))] & 1) << (8 * o + jj);
+        digit_pass0<LOGN>(A.r(t), w, lo.data(), hi.data(), t, x.mod, twf);
+    }
+    if constexpr (S::P > 1) A.template fwd_from<1>(x.mod, twf);
+    for (int t = 0; t < S::T; t++)
+        for (int e = 0; e < S::E; e++) {
+            const u32 v = A.regs[(size_t)t * S::E + e];
+            out[S::pos(S::P - 1, t, e)] = v - (v >> 27) * x.mod.q;   // the kernel's fold: < 2^28, congruent mod q
+        }
+}
+
 extern "C" {
+// digit transform of the external product under a 27-bit CRT prime; out = lazy representatives (< 2^28) in NTT order
+int emu_xp_digit(uint64_t q, uint64_t n, const uint64_t *bits, uint64_t *out) {
+    HostTables t;
+    if (!build_host_tables(q, n, t).empty()) return -1;
+    ExpandedTables<Small32> x;
+    expand_tables(t, x, 5);
+    switch (hp_ilog2(n)) {
+#define C(L) case L: run_digit<L>(x, bits, out); return 0;
+        C(6) C(7) C(8) C(9) C(10) C(13)
+#undef C
+    }
+    return -2;
+}
 // kind: -1 auto (as the library picks), 0 Lazy32, 1 Lazy64, 2 Strict64, 3 Small32 ; mode 0 fwd, 1 inv, 2 mul
 int emu_ntt(int kind, uint64_t q, uint64_t n, int loge, int mode, const uint64_t *a, const uint64_t *b, uint64_t *c,
             uint64_t *c_evals, int flags) {

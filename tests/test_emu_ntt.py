@@ -105,3 +105,21 @@ def test_small32_inverse_worst_case_growth(emu, orc, q, logn):
         assert np.array_equal(out, orc.ntt(q, n, a, inverse=True))
         assert emu.emu_ntt(3, q, n, 0, 2, orc.ptr(a), orc.ptr(a), orc.ptr(out), None, 0) == 0
         assert np.array_equal(out, orc.rq_mul_batch(q, n, a, a))
+
+
+@pytest.mark.parametrize("logn", [6, 7, 8, 9, 10, 13])  # pass 0 of the 32-per-thread shape holds >= 3 stages
+def test_extprod_digit_transform_from_octet_table(emu, orc, logn):
+    """xp_octet.cuh: the first three stages of a bit polynomial's transform read from the 256-entry table, then the
+    ordinary passes -- against the oracle's NTT under both CRT primes of the torus path (torus.cuh)."""
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    cases = [rng.integers(0, 2, n, dtype=np.uint64), np.ones(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)]
+    one_hot = np.zeros(n, dtype=np.uint64)
+    one_hot[n - 1] = 1
+    cases.append(one_hot)
+    for q in (0x7E90001, 0x7E00001):
+        for bits in cases:
+            out = np.zeros(n, dtype=np.uint64)
+            assert emu.emu_xp_digit(q, n, orc.ptr(bits), orc.ptr(out)) == 0
+            assert (out < 2**28).all()
+            assert (out % np.uint64(q) == orc.ntt(q, n, bits)).all()
