@@ -108,7 +108,7 @@ def tfhe_paths(fhe, dev, quick, cpu=True):
     res = {}
     reps = 2 if quick else 5
     # --- config 3/4: TGGSW x TGLWE external product and CMux, reference parameter sets -----------------
-    for name, n, k, batch in (("P4a_n64_k4", 64, 4, 4096), ("P4b_n1024_k1", 1024, 1, 1024)):
+    for name, n, k, batch in (("P4a_n64_k4", 64, 4, 4096), ("P4b_n1024_k1", 1024, 1, 1024 if quick else 4096)):
         glwe = (k + 1) * n
         tggsw = _u64_rand(torch, ((k + 1) * 64 * glwe,), dev, 1)
         g = fhe.Tggsw(n, k, tggsw)
@@ -137,6 +137,11 @@ def tfhe_paths(fhe, dev, quick, cpu=True):
         row["modmul_executed_per_unit"] = executed
         row["int_roofline_frac_executed"] = row["extprod_per_s"] * executed / pk
         row["hbm_frac"] = row["extprod_per_s"] * 2 * (k + 1) * n * 8 / (_hbm_peak() * 1e9)
+        if n == 1024 and batch > 1024:
+            # a batch that does not fill whole waves of accumulator pairs: the library falls back to one accumulator per
+            # 256-thread CTA there (extprod_fused.cu: xp_use_pair)
+            ms_s = _time(lambda: g.extprod(ct1[:1024], out=out[:1024]), reps, warm=1)
+            row["batch_1024"] = {"extprod_per_s": 1024 / (ms_s * 1e-3), "extprod_ms": ms_s}
         if cpu:
             sample = max(1, min(batch, cores * (4 if n <= 64 else 1)))
             hg = tggsw.cpu().numpy().view(np.uint64)

@@ -25,18 +25,20 @@
 
 namespace fhe {
 
-// threads per CTA: 256, or (tuning experiment FHE_XP_CT512) 512 at n = 1024, k = 1 with two accumulators per CTA that
-// share every key load at unchanged occupancy (16 warps, 128 registers, 132 KB shared memory per SM)
-#ifndef FHE_XP_CT512
-#define FHE_XP_CT512 0
-#endif
-__host__ __device__ constexpr int xp_ct(int logn, int k1) { return (logn == 10 && k1 == 2 && FHE_XP_CT512) ? 512 : 256; }
+// Threads per CTA: 256 with one accumulator, or -- n = 1024, k = 1 only -- 512 with TWO accumulators that share every key
+// load (same occupancy: 16 warps, 128 registers, one 512-thread CTA per SM instead of two of 256).  The pair halves the
+// key bytes through the L1 data pipe (ncu: 69 % busy, the busiest unit of the 256-thread kernel): extprod 1.83 -> 1.86 M/s,
+// CMux chain 1.72 -> 1.82 M CMux/s.  A batch too small to give every SM a pair keeps the 256-thread kernel (xp_use_pair).
+// Both read ONE fused key layout, the one written for xp_layout_ct() threads.
+__host__ __device__ constexpr int xp_layout_ct(int logn, int k1) { return (logn == 10 && k1 == 2) ? 512 : 256; }
+__host__ __device__ constexpr bool xp_has_pair(int logn, int k1) { return logn == 10 && k1 == 2; }
 
-template <int LOGN, int K1> struct XpGeom {
+template <int LOGN, int K1, int CT_ = 256> struct XpGeom {
     static constexpr int N = 1 << LOGN;
     static constexpr int LOGE = LOGN < 5 ? LOGN : 5;
     typedef NttShape<LOGN, LOGE> S;
-    static constexpr int CT = xp_ct(LOGN, K1);
+    static constexpr int CT = CT_, LCT = xp_layout_ct(LOGN, K1);
+    static_assert(CT == 256 || (CT == 512 && xp_has_pair(LOGN, K1)), "512 threads: n = 1024, k = 1 only");
     static constexpr int SLOTS = CT / S::T;             // concurrent NTTs
     static constexpr int ND = K1 * 64;                  // digit polynomials per accumulator
     static constexpr int PADN = N + (N >> 5);
@@ -51,6 +53,24 @@ template <int LOGN, int K1> struct XpGeom {
     static constexpr int ITEMS = UNITS * N;
     static constexpr int IPT = (ITEMS + CT - 1) / CT;   // MAC items per thread (per accumulator)
     static constexpr int IPT4 = (IPT + 3) / 4 * 4;      // padded to whole uint4 loads
+    static constexpr int Q = IPT4 / 4;                  // key quads per thread and digit
+    // MAC item m of thread t.  With the layout's own thread count: t + CT * m.  A 256-thread CTA on the 512-thread
+    // layout plays the layout's threads t and t + 256: m < IPT/2 are the items of the first, the rest of the second.
+    __host__ __device__ static constexpr int item(int t, int m) {
+        return CT == LCT ? t + CT * m : t + CT * (m / (IPT / 2)) + LCT * (m % (IPT / 2));
+    }
+    // uint4 index of key quad v of thread t inside a digit's Q * CT quads ([v][thread] in the layout's geometry)
+    __host__ __device__ static constexpr int quad(int t, int v) {
+        return CT == LCT ? v * CT + t : (v % (Q / 2)) * LCT + t + CT * (v / (Q / 2));
+    }
+    // the items of a thread sit on NPOS distinct coefficient positions (CT * 4 >= N in every instantiated shape)
+    static constexpr int NPOS = IPT < 4 ? IPT : (N >= CT ? (N / CT < 4 ? N / CT : 4) : 1);
+    __host__ __device__ static constexpr int pos_slot(int m) {
+        return CT == LCT ? (N >= CT ? m % (N / CT) : 0) : 2 * (m / (IPT / 2)) + (m & 1);
+    }
+    __host__ __device__ static constexpr int slot_pos(int t, int sl) {
+        return CT == LCT ? (t + CT * sl) & (N - 1) : t + CT * (sl >> 1) + LCT * (sl & 1);
+    }
     // Accumulators per CTA.  The MAC streams the whole transformed TGGSW (2 * ND * ITEMS * 4 B) from L2 once per
     // CTA; small rings leave registers and shared memory for several accumulators, which then share every key load
     // (n = 64, k = 4: 1.6 MB of key per 2.5 KB accumulator -- L2 bandwidth, not arithmetic, was the limit).
@@ -65,6 +85,11 @@ template <int LOGN, int K1> struct XpGeom {
     // n=1024 two 128-register CTAs are faster (1.44 vs 1.27 M/s; the chain even 1.28 vs 0.91 M CMux/s)
     static constexpr int MINB = CT == 512 ? 1 : LOGN <= 7 ? (FHE_XP_A_SMALL > 4 ? 2 : 3) : (LOGN == 10 && A > 1) ? 1 : 2;
     static constexpr int DPR = SLOTS / A;               // digits per round (each for all A accumulators)
+    // digits whose key quads are in flight in the MAC (registers: KDEPTH * IPT4 words)
+#ifndef FHE_XP_KDEPTH10
+#define FHE_XP_KDEPTH10 2
+#endif
+    static constexpr int KDEPTH = (LOGN == 10 && K1 == 2) ? FHE_XP_KDEPTH10 : 2;
     static constexpr int ROUNDS = (ND + DPR - 1) / DPR;
     // slots whose threads run an inverse transform (whole warps do): the slots behind them are free for the
     // residues of the second prime
@@ -82,12 +107,6 @@ template <int LOGN, int K1> struct XpGeom {
     static_assert(S::E == 32 && CT >= 256, "bit planes: 32 coefficients per thread; table build: one entry per thread");
 };
 
-// items m and m' of a thread sit on the same coefficient position when CT * (m - m') is a multiple of N: with
-// CT * 4 >= N (every instantiated shape) there are at most 4 distinct positions, selected by m mod (N / CT)
-template <int LOGN, int CT> __host__ __device__ constexpr int dv_slot(int m) {
-    return (1 << LOGN) >= CT ? m % ((1 << LOGN) / CT) : 0;
-}
-
 // 128-bit read-only key load that stays where the source puts it: as a plain __ldg ptxas sank the loads issued in
 // front of the barrier back behind it
 __device__ __forceinline__ uint4 ldg_key(const uint4 *p) {
@@ -96,11 +115,17 @@ __device__ __forceinline__ uint4 ldg_key(const uint4 *p) {
     return v;
 }
 
+static void init_xp_mod(XpSmall &m, u64 p) {
+    init_mod(static_cast<Small32 &>(m), p);
+    m.zero = 0;
+    m.negq = (u32)0 - (u32)p;
+}
+
 struct XpParams {
     NttParams<Lazy32> P[2];   // plans of p1, p2 (device-order tables, n^-1 constants)
-    Small32 ms[2];            // same moduli, csub-free forward butterflies
+    XpSmall ms[2];            // same moduli, csub-free forward butterflies (xp_octet.cuh)
     u64 mu[2];                // floor(2^64 / p_r): Barrett constant for the 64-bit accumulators
-    const u32 *R[2];          // fused key layout: R[r][d][v][t][j] = NTT value of item t + 256 (4v + j) of digit d
+    const u32 *R[2];          // fused key layout: R[r][d][v][t][j] = NTT value of item t + LCT (4v + j) of digit d, t < LCT = xp_layout_ct()
                               // (one uint4 per thread and v: every warp load is 512 contiguous bytes)
     CrtParams cp;
 };
@@ -139,25 +164,25 @@ __device__ __forceinline__ u32 warp_transpose32(u32 a, int lane) {
 //  * the csub-free butterflies leave values < (2*LOGN+1)*p < 2^32; the final partial reduction
 //    x - (x >> 27)*p = (x mod 2^27) + (x >> 27)*(2^27 - p) < 2^27 + 21*2^21 < 2^28 costs one shift and one IMAD
 //    (the MAC then adds at most (k+1)*64 <= 320 products < 2^28 * 2^27: below 2^64).
-template <int LOGN, int K1>
-__device__ __forceinline__ void digit_ntt(const Small32 &ms, const TwSrc<Small32> &twf, u32 w, const uint4 *tab_lo,
+template <int LOGN, int K1, int CT>
+__device__ __forceinline__ void digit_ntt(const XpSmall &ms, const TwSrc<XpSmall> &twf, u32 w, const uint4 *tab_lo,
                                           const uint4 *tab_hi, u32 *sm, int tid) {
-    typedef XpGeom<LOGN, K1> G;
+    typedef XpGeom<LOGN, K1, CT> G;
     constexpr int LOGE = G::LOGE;
     typedef NttShape<LOGN, LOGE> S;
     constexpr int LAST = S::P - 1;
     u32 x[S::E];
     digit_pass0<LOGN>(x, w, tab_lo, tab_hi, tid, ms, twf);
-    if constexpr (S::P > 1) fwd_chain<Small32, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
+    if constexpr (S::P > 1) fwd_chain<XpSmall, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
 #pragma unroll
-    for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = x[e] - (x[e] >> 27) * ms.q;
+    for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = ms.fold27(x[e]);
 }
 
-template <int LOGN, int K1, bool CHAIN>
-__global__ void __launch_bounds__(XpGeom<LOGN, K1>::CT, XpGeom<LOGN, K1>::MINB)
+template <int LOGN, int K1, bool CHAIN, int CT>
+__global__ void __launch_bounds__(CT, XpGeom<LOGN, K1, CT>::MINB)
 extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__ ct1, const u64 *__restrict__ ct2,
                      u64 *out, int cmux, const XpChain ch, size_t batch) {
-    typedef XpGeom<LOGN, K1> G;
+    typedef XpGeom<LOGN, K1, CT> G;
     typedef typename G::S S;
     constexpr int LOGE = G::LOGE, N = G::N, LAST = S::P - 1, A = G::A, GLWE = K1 * N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -177,7 +202,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     if (t < 256) {
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
+            const TwSrc<XpSmall> twf = {X.P[r].c_fwd, X.P[r].fwd};
             octet_table_entry(X.ms[r], twf, t, tab[r * 512 + t], tab[r * 512 + 256 + t]);
         }
     }   // ordered before the first digit transform by the barrier behind the bit planes
@@ -245,9 +270,9 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
         for (int round = 0; round < G::ROUNDS; round++) {
             const int d = round * G::DPR + s_dig;
             if (d < G::ND) {
-                const TwSrc<Small32> twf = {X.P[r].c_fwd, X.P[r].fwd};
+                const TwSrc<XpSmall> twf = {X.P[r].c_fwd, X.P[r].fwd};
                 const u32 w = planes[((size_t)(s_acc * K1 + (d >> 6)) * S::T + tid) * G::PLANE_ROW + (d & 63)];
-                digit_ntt<LOGN, K1>(X.ms[r], twf, w, tab + r * 512, tab + r * 512 + 256, sm, tid);
+                digit_ntt<LOGN, K1, CT>(X.ms[r], twf, w, tab + r * 512, tab + r * 512 + 256, sm, tid);
             }
             // MAC of the round's digits against the resident TGGSW, two digits per iteration.  The 128-bit key loads are
             // software-pipelined through the registers themselves: the loads of the first pair are issued BEFORE the
@@ -255,27 +280,28 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
             // re-loaded for the next pair right behind the four MACs that consumed it.  Before, an iteration issued
             // its loads and sat on their L2 latency: 17 % of all stall samples on the first IMAD.WIDE of the loop
             // (profiles/r2_extprod_fused_n1024_k1_ncu_full_b.csv).
-            constexpr int nd = G::DPR, Q = G::IPT4 / 4;   // ND % DPR == 0: every round is full
-            static_assert(nd % 2 == 0, "the MAC takes the digits in pairs");
-            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr) + (size_t)round * G::DPR * Q * G::CT + t;
-            uint4 kq[2][Q];
+            constexpr int nd = G::DPR, Q = G::Q;   // ND % DPR == 0: every round is full
+            constexpr int KD = G::KDEPTH;                 // digits whose key quads are in flight
+            static_assert(nd % KD == 0, "the MAC takes the digits KD at a time");
+            const uint4 *Rt = reinterpret_cast<const uint4 *>(Rr) + (size_t)round * G::DPR * Q * G::CT;
+            uint4 kq[KD][Q];
 #pragma unroll
-            for (int h2 = 0; h2 < 2; h2++)
+            for (int h2 = 0; h2 < KD; h2++)
 #pragma unroll
-                for (int v = 0; v < Q; v++) kq[h2][v] = ldg_key(Rt + (size_t)(h2 * Q + v) * G::CT);
+                for (int v = 0; v < Q; v++) kq[h2][v] = ldg_key(Rt + (size_t)h2 * Q * G::CT + G::quad(t, v));
             __syncthreads();
-#pragma unroll(nd <= 8 ? nd / 2 : 1)
-            for (int it = 0; it < nd / 2; it++) {
-                const bool more = it + 1 < nd / 2;
+#pragma unroll(nd <= 8 ? nd / KD : 1)
+            for (int it = 0; it < nd / KD; it++) {
+                const bool more = it + 1 < nd / KD;
 #pragma unroll
-                for (int h2 = 0; h2 < 2; h2++) {
-                    const int dd = 2 * it + h2;
-                    u32 dv[A][G::IPT < 4 ? G::IPT : 4];   // items m, m + 4, .. of a thread share the position
+                for (int h2 = 0; h2 < KD; h2++) {
+                    const int dd = KD * it + h2;
+                    u32 dv[A][G::NPOS];   // the items of a thread share NPOS coefficient positions
 #pragma unroll
                     for (int aa = 0; aa < A; aa++)
 #pragma unroll
-                        for (int m = 0; m < (G::IPT < 4 ? G::IPT : 4); m++)
-                            dv[aa][m] = xch[(size_t)(dd * A + aa) * G::PADN + pad_idx((t + G::CT * m) & (N - 1))];
+                        for (int sl = 0; sl < G::NPOS; sl++)
+                            dv[aa][sl] = xch[(size_t)(dd * A + aa) * G::PADN + pad_idx(G::slot_pos(t, sl))];
 #pragma unroll
                     for (int v = 0; v < Q; v++) {
                         const u32 k4[4] = {kq[h2][v].x, kq[h2][v].y, kq[h2][v].z, kq[h2][v].w};
@@ -284,10 +310,10 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
                             const int m = 4 * v + j;
                             if (m < G::IPT) {   // item >= ITEMS only when ITEMS % CT != 0: key padding is zero
 #pragma unroll
-                                for (int aa = 0; aa < A; aa++) acc[aa][m] += (u64)dv[aa][dv_slot<LOGN, G::CT>(m)] * k4[j];
+                                for (int aa = 0; aa < A; aa++) acc[aa][m] += (u64)dv[aa][G::pos_slot(m)] * k4[j];
                             }
                         }
-                        if (more) kq[h2][v] = ldg_key(Rt + (size_t)((dd + 2) * Q + v) * G::CT);
+                        if (more) kq[h2][v] = ldg_key(Rt + (size_t)(dd + KD) * Q * G::CT + G::quad(t, v));
                     }
                 }
             }
@@ -300,7 +326,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
         for (int aa = 0; aa < A; aa++)
 #pragma unroll
             for (int m = 0; m < G::IPT; m++) {
-                const int item = t + G::CT * m;
+                const int item = G::item(t, m);
                 if (item < G::ITEMS)
                     xch[(size_t)(aa * G::UNITS + (item >> LOGN)) * G::PADN + pad_idx(item & (N - 1))] = reduce64(acc[aa][m], ml.q, X.mu[r]);
             }
@@ -336,7 +362,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     }  // step
 }
 
-// unfused key layout (u64, [d][u][x]) -> fused layout (u32, [d][v][t][j], item = t + 256 (4v + j)), zero padded
+// unfused key layout (u64, [d][u][x]) -> fused layout (u32, [d][v][t][j], item = t + ct (4v + j), ct = xp_layout_ct()), zero padded
 __global__ void tggsw_fused_layout_kernel(const u64 *__restrict__ R, u32 *__restrict__ Rf, int nd, int items, int ipt4, int ct) {
     const size_t total = (size_t)nd * ct * ipt4;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -348,15 +374,31 @@ __global__ void tggsw_fused_layout_kernel(const u64 *__restrict__ R, u32 *__rest
     }
 }
 
-template <int LOGN, int K1>
-static int launch_fused(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, int cmux, cudaStream_t st) {
-    typedef XpGeom<LOGN, K1> G;
+// Which kernel for a batch (FHE_XP_CT=256|512 forces one: tests, A/B runs).  Pair CTAs run one per SM and a wave of
+// them takes as long as a wave of two 256-thread CTAs per SM minus ~2 %, but their last wave is all-or-nothing, while
+// a last wave of at most one 256-thread CTA per SM finishes in ~0.6 of a wave (the CTA has the SM to itself).  Measured
+// on 148 SMs, M extprod/s (256 | 512): batch 148: 1.50 | 0.90, 296: 1.71 | 1.79, 1024: 1.75 | 1.60, 1184: 1.80 | 1.85,
+// 4144: 1.83 | 1.86.  The estimate below reproduces those orderings.
+static bool xp_use_pair(size_t batch) {
+    const char *e = getenv("FHE_XP_CT");
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 256 || forced == 512) return forced == 512;
+    const size_t S = (size_t)num_sms(), pairs = (batch + 1) / 2;
+    const double t_pair = (double)((pairs + S - 1) / S);
+    const size_t r = batch % (2 * S);
+    const double t_single = (double)(batch / (2 * S)) * 1.016 + (r == 0 ? 0.0 : r <= S ? 0.62 : 1.04);
+    return t_pair <= t_single;
+}
+
+template <int LOGN, int K1, int CT>
+static int launch_fused_ct(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, int cmux, cudaStream_t st) {
+    typedef XpGeom<LOGN, K1, CT> G;
     const TorusCtx &tc = *g.tc;
     XpParams X;
     X.P[0] = tc.plan1->p32;
     X.P[1] = tc.plan2->p32;
-    init_mod(X.ms[0], TORUS_P1);
-    init_mod(X.ms[1], TORUS_P2);
+    init_xp_mod(X.ms[0], TORUS_P1);
+    init_xp_mod(X.ms[1], TORUS_P2);
     X.mu[0] = ~0ull / TORUS_P1;
     X.mu[1] = ~0ull / TORUS_P2;
     X.R[0] = g.R1f;
@@ -366,7 +408,7 @@ static int launch_fused(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out
     static unsigned long long done_mask = 0;
     int dev = 0;
     FHE_CUDA_OK(cudaGetDevice(&dev));
-    auto kern = extprod_fused_kernel<LOGN, K1, false>;
+    auto kern = extprod_fused_kernel<LOGN, K1, false, CT>;
     const int threads = G::CT;
     const size_t smem = G::SMEM;
     if (!((done_mask >> (dev & 63)) & 1ull)) {
@@ -380,14 +422,22 @@ static int launch_fused(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out
 }
 
 template <int LOGN, int K1>
-static int launch_chain(const TorusCtx &tc, const u32 *const *keys_dev, const u64 *h_dev, int steps, int negacyclic,
-                        const u64 *acc_in, u64 *acc_out, size_t batch, cudaStream_t st) {
-    typedef XpGeom<LOGN, K1> G;
+static int launch_fused(const Tggsw &g, const u64 *ct1, const u64 *ct2, u64 *out, size_t batch, int cmux, cudaStream_t st) {
+    if constexpr (xp_has_pair(LOGN, K1)) {
+        if (xp_use_pair(batch)) return launch_fused_ct<LOGN, K1, 512>(g, ct1, ct2, out, batch, cmux, st);
+    }
+    return launch_fused_ct<LOGN, K1, 256>(g, ct1, ct2, out, batch, cmux, st);
+}
+
+template <int LOGN, int K1, int CT>
+static int launch_chain_ct(const TorusCtx &tc, const u32 *const *keys_dev, const u64 *h_dev, int steps, int negacyclic,
+                           const u64 *acc_in, u64 *acc_out, size_t batch, cudaStream_t st) {
+    typedef XpGeom<LOGN, K1, CT> G;
     XpParams X;
     X.P[0] = tc.plan1->p32;
     X.P[1] = tc.plan2->p32;
-    init_mod(X.ms[0], TORUS_P1);
-    init_mod(X.ms[1], TORUS_P2);
+    init_xp_mod(X.ms[0], TORUS_P1);
+    init_xp_mod(X.ms[1], TORUS_P2);
     X.mu[0] = ~0ull / TORUS_P1;
     X.mu[1] = ~0ull / TORUS_P2;
     X.R[0] = X.R[1] = nullptr;
@@ -396,7 +446,7 @@ static int launch_chain(const TorusCtx &tc, const u32 *const *keys_dev, const u6
     static unsigned long long done_mask = 0;
     int dev = 0;
     FHE_CUDA_OK(cudaGetDevice(&dev));
-    auto kern = extprod_fused_kernel<LOGN, K1, true>;
+    auto kern = extprod_fused_kernel<LOGN, K1, true, CT>;
     if (!((done_mask >> (dev & 63)) & 1ull)) {
         FHE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_CHAIN));
         done_mask |= 1ull << (dev & 63);
@@ -408,6 +458,15 @@ static int launch_chain(const TorusCtx &tc, const u32 *const *keys_dev, const u6
     return 0;
 }
 
+template <int LOGN, int K1>
+static int launch_chain(const TorusCtx &tc, const u32 *const *keys_dev, const u64 *h_dev, int steps, int negacyclic,
+                        const u64 *acc_in, u64 *acc_out, size_t batch, cudaStream_t st) {
+    if constexpr (xp_has_pair(LOGN, K1)) {
+        if (xp_use_pair(batch)) return launch_chain_ct<LOGN, K1, 512>(tc, keys_dev, h_dev, steps, negacyclic, acc_in, acc_out, batch, st);
+    }
+    return launch_chain_ct<LOGN, K1, 256>(tc, keys_dev, h_dev, steps, negacyclic, acc_in, acc_out, batch, st);
+}
+
 #define FHE_XP_SHAPES(F) F(10, 2) F(9, 2) F(8, 2) F(6, 5) F(6, 2) F(7, 2) F(8, 3) F(9, 3)
 
 bool extprod_fused_supported(int logn, int k1) {
@@ -417,7 +476,7 @@ bool extprod_fused_supported(int logn, int k1) {
     return false;
 }
 static int fused_ipt4(int logn, int k1) {
-    const int items = k1 * 2 * (1 << logn), ct = xp_ct(logn, k1), ipt = (items + ct - 1) / ct;
+    const int items = k1 * 2 * (1 << logn), ct = xp_layout_ct(logn, k1), ipt = (items + ct - 1) / ct;
     return (ipt + 3) / 4 * 4;
 }
 
@@ -428,7 +487,7 @@ int tggsw_build_fused_layout(Tggsw &g, cudaStream_t st) {
     // the fused kernels read the plans' twiddle tables in the device order of 32 coefficients per thread
     if (g.tc->plan1->loge != (logn < 5 ? logn : 5) || g.tc->plan2->loge != g.tc->plan1->loge) return 0;
     const int nd = k1 * 64, items = k1 * 2 * (1 << logn), ipt4 = fused_ipt4(logn, k1);
-    const int ct = xp_ct(logn, k1);
+    const int ct = xp_layout_ct(logn, k1);
     const size_t words = (size_t)nd * ct * ipt4;
     FHE_CUDA_OK(cudaMalloc((void **)&g.R1f, words * sizeof(u32)));
     FHE_CUDA_OK(cudaMalloc((void **)&g.R2f, words * sizeof(u32)));

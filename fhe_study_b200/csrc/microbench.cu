@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(u64 *sink, u32 iters, u64
     const u64 seed = blockIdx.x * 256ull + threadIdx.x + 1;
     if (KIND == 2) {
         Lazy64 m;
-        m.q = q; m.q2 = 2 * q; m.qinv_neg = 0; m.qinv = 0; m.r2 = 0;
+        m.q = q; m.q2 = 2 * q; m.qinv_neg = 0; m.qinv = 0; m.r2 = 0; m.nq = (u64)0 - q;
         const Tw64 t = {w, wp};
         u64 x[CH];
 #pragma unroll

@@ -37,6 +37,32 @@ FHE_HD u64 mulhi_u64(u64 a, u64 b) {
     return (u64)(((unsigned __int128)a * b) >> 64);
 #endif
 }
+// Low 64 bits of y*w + h*nq, the tail of a 64-bit Shoup product (nq = 2^64 - q: the quotient estimate's multiple of q
+// is ADDED).  Written out as two 32x32->64 multiply-adds and four 32-bit ones that chain through the accumulator: left
+// to the compiler, y*w - h*q became two separate 64-bit products plus a negation and the additions that join their
+// partial sums -- IMAD.IADD / IMAD.X, which execute on the same fmaheavy pipe as the multiplies (ncu, 62-bit polymul:
+// fmaheavy 80 % active, the binding unit; 335 of its 2035 slots per thread were such additions and moves).
+FHE_HD u64 shoup_tail64(u64 y, u64 w, u64 h, u64 nq) {
+#if defined(__CUDA_ARCH__)
+    u32 lo, hi;
+    asm("{\n\t"
+        ".reg .u64 t;\n\t"
+        "mul.wide.u32 t, %2, %4;\n\t"
+        "mad.wide.u32 t, %6, %8, t;\n\t"
+        "mov.b64 {%0, %1}, t;\n\t"
+        "mad.lo.u32 %1, %2, %5, %1;\n\t"
+        "mad.lo.u32 %1, %3, %4, %1;\n\t"
+        "mad.lo.u32 %1, %6, %9, %1;\n\t"
+        "mad.lo.u32 %1, %7, %8, %1;\n\t"
+        "}"
+        : "=&r"(lo), "=&r"(hi)
+        : "r"((u32)y), "r"((u32)(y >> 32)), "r"((u32)w), "r"((u32)(w >> 32)), "r"((u32)h), "r"((u32)(h >> 32)),
+          "r"((u32)nq), "r"((u32)(nq >> 32)));
+    return ((u64)hi << 32) | lo;
+#else
+    return y * w + h * nq;
+#endif
+}
 FHE_HD u32 umin(u32 a, u32 b) { return a < b ? a : b; }
 FHE_HD u64 umin(u64 a, u64 b) { return a < b ? a : b; }
 
@@ -119,8 +145,9 @@ struct Lazy64 {
     u64 qinv_neg;  // -q^-1 mod 2^64 (kept for the plan's layout; the device uses qinv)
     u64 qinv;      //  q^-1 mod 2^64
     u64 r2;        // 2^128 mod q
+    u64 nq;        // 2^64 - q
 
-    FHE_HD u64 mul_tw(u64 y, T t) const { return y * t.w - mulhi_u64(y, t.wp) * q; }
+    FHE_HD u64 mul_tw(u64 y, T t) const { return shoup_tail64(y, t.w, mulhi_u64(y, t.wp), nq); }
     FHE_HD u64 csub(u64 x, u64 m) const { return umin(x, x - m); }
     FHE_HD void fwd(u64 &x, u64 &y, T t) const {
         u64 X = csub(x, q2);
@@ -181,9 +208,10 @@ struct Strict64 {
     u64 qinv_neg;
     u64 qinv;   // q^-1 mod 2^64
     u64 r2;
+    u64 nq;     // 2^64 - q
 
     FHE_HD u64 mul_tw(u64 y, T t) const {  // canonical result
-        u64 r = y * t.w - mulhi_u64(y, t.wp) * q;  // [0,2q), 2q < 2^64
+        u64 r = shoup_tail64(y, t.w, mulhi_u64(y, t.wp), nq);  // [0,2q), 2q < 2^64
         return r >= q ? r - q : r;
     }
     FHE_HD u64 add(u64 a, u64 b) const { u64 s = a + b; return s >= q ? s - q : s; }

@@ -115,6 +115,7 @@ inline void init_mod(Lazy64 &m, u64 q) {
     m.qinv = (u64)0 - m.qinv_neg;
     u64 r = (u64)((((u128_t)1) << 64) % q);
     m.r2 = hp_mulmod(r, r, q);
+    m.nq = (u64)0 - q;
 }
 inline void init_mod(Strict64 &m, u64 q) {
     m.q = q;
@@ -123,6 +124,7 @@ inline void init_mod(Strict64 &m, u64 q) {
     m.qinv = (u64)0 - m.qinv_neg;
     u64 r = (u64)((((u128_t)1) << 64) % q);
     m.r2 = hp_mulmod(r, r, q);
+    m.nq = (u64)0 - q;
 }
 
 inline u32 neg_inv32(u32 q) {

@@ -19,6 +19,22 @@ typedef uint4 XpQuad;
 struct XpQuad { u32 x, y, z, w; };
 #endif
 
+// Small32 with its forward butterfly spelled so that every addition is a THREE-input one (`zero` is a kernel-parameter
+// word holding 0, opaque to ptxas): a two-input add may be emitted as IMAD.IADD on the fmaheavy pipe, the pipe the
+// butterflies' multiplies already saturate (ncu, n = 1024, k = 1: fmaheavy 68 % active against ALU 24 %, 72 of the 442
+// fmaheavy instructions of a digit transform being IMAD.IADD / IMAD.MOV); IADD3 only exists on the ALU pipe.  Same
+// for the final fold, whose negation (IMAD.MOV) moves into the constant negq = -q.
+struct XpSmall : Small32 {
+    u32 zero, negq;
+    FHE_HD void fwd(u32 &x, u32 &y, Tw32 t) const {
+        const u32 V = mul_tw(y, t);
+        y = x - V + q2;
+        x = x + V + zero;
+    }
+    // x mod 2^27 + (x >> 27) * (2^27 - q) < 2^28 for q < 2^27 close to it, congruent to x
+    FHE_HD u32 fold27(u32 x) const { return (x >> 27) * negq + x; }
+};
+
 template <int LOGN> struct XpOct {
     static_assert(LOGN >= 6, "the table-driven first stages need a first pass of at least three stages on 32 coefficients");
     static constexpr int LOGE = 5;
@@ -32,7 +48,7 @@ template <int LOGN> struct XpOct {
 // Table entry b of one prime: stages 0-2 on the bit pattern b.  Stage 0 works on bits (U, V in {0,1}: V = b*S is a
 // select, not a multiplication); stages 1, 2 are the butterflies of the 8-point shape, whose twiddle indices 2 + hi and
 // 4 + hi are those of every octet.
-FHE_HD void octet_table_entry(const Small32 &ms, const TwSrc<Small32> &twf, int b, XpQuad &lo, XpQuad &hi) {
+template <class M> FHE_HD void octet_table_entry(const M &ms, const TwSrc<M> &twf, int b, XpQuad &lo, XpQuad &hi) {
     u32 y[8];
     for (int j = 0; j < 8; j++) y[j] = ((u32)b >> j) & 1u;
     const u32 S1 = twf.c0[1].w;
@@ -41,15 +57,15 @@ FHE_HD void octet_table_entry(const Small32 &ms, const TwSrc<Small32> &twf, int 
         y[j] = U + V;
         y[j + 4] = U + ms.q2 - V;
     }
-    fwd_pass<Small32, 3, 3, 0, 1>(y, 0, ms, twf);
+    fwd_pass<M, 3, 3, 0, 1>(y, 0, ms, twf);
     lo.x = y[0]; lo.y = y[1]; lo.z = y[2]; lo.w = y[3];
     hi.x = y[4]; hi.y = y[5]; hi.z = y[6]; hi.w = y[7];
 }
 
 // Pass 0 of a digit transform: the thread's 32 coefficients are the bits of w (bit 8*o + jj = slot(o, jj)).
-template <int LOGN>
-FHE_HD void digit_pass0(u32 (&x)[32], u32 w, const XpQuad *tab_lo, const XpQuad *tab_hi, int tid, const Small32 &ms,
-                        const TwSrc<Small32> &twf) {
+template <int LOGN, class M>
+FHE_HD void digit_pass0(u32 (&x)[32], u32 w, const XpQuad *tab_lo, const XpQuad *tab_hi, int tid, const M &ms,
+                        const TwSrc<M> &twf) {
     typedef XpOct<LOGN> O;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -60,7 +76,7 @@ FHE_HD void digit_pass0(u32 (&x)[32], u32 w, const XpQuad *tab_lo, const XpQuad 
         x[O::slot(o, 0)] = lo4.x; x[O::slot(o, 1)] = lo4.y; x[O::slot(o, 2)] = lo4.z; x[O::slot(o, 3)] = lo4.w;
         x[O::slot(o, 4)] = hi4.x; x[O::slot(o, 5)] = hi4.y; x[O::slot(o, 6)] = hi4.z; x[O::slot(o, 7)] = hi4.w;
     }
-    if constexpr (O::S::g(0) > 3) fwd_pass<Small32, LOGN, O::LOGE, 0, 3>(x, tid, ms, twf);
+    if constexpr (O::S::g(0) > 3) fwd_pass<M, LOGN, O::LOGE, 0, 3>(x, tid, ms, twf);
 }
 
 }  // namespace fhe

@@ -131,6 +131,55 @@ def test_external_product_and_cmux_dense_inputs(fhe, orc, n, k, batch, monkeypat
     monkeypatch.delenv("FHE_EXTPROD_PATH")
 
 
+@pytest.mark.parametrize("ct,batch", [("512", 5), ("512", 2), ("512", 1), ("256", 3)])
+def test_external_product_n1024_both_cta_shapes(fhe, orc, ct, batch, monkeypatch):
+    # n = 1024, k = 1 has two fused kernels reading ONE key layout: 256 threads / one accumulator, and 512 threads / a
+    # PAIR of accumulators sharing every key load (picked when batch > SM count).  FHE_XP_CT forces either; an odd
+    # batch leaves the last pair half empty.
+    n, k = 1024, 1
+    glwe = (k + 1) * n
+    tggsw = orc.uniform(91, (k + 1) * 64 * glwe)
+    ct1 = orc.uniform(92, (batch, glwe))
+    ct2 = orc.uniform(93, (batch, glwe))
+    ct1[batch - 1, :] = M64 - 1
+    g = fhe.Tggsw(n, k, tggsw)
+    monkeypatch.setenv("FHE_XP_CT", ct)
+    assert (g.extprod(ct1).reshape(-1) == orc.extprod(n, k, tggsw, ct1.reshape(-1))).all()
+    assert (g.cmux(ct1, ct2).reshape(-1) == orc.cmux(n, k, tggsw, ct1.reshape(-1), ct2.reshape(-1))).all()
+    steps = 2
+    size = (k + 1) * 64 * glwe
+    bsk = orc.uniform(94, steps * size)
+    h = orc.uniform(95, (batch, steps)) % np.uint64(2 * n)
+    handles = [fhe.Tggsw(n, k, bsk[j * size:(j + 1) * size]) for j in range(steps)]
+    assert np.array_equal(fhe.cmux_chain(n, k, handles, ct1, h, negacyclic=True), orc.cmux_chain(n, k, bsk, ct1, h, negacyclic=True))
+    monkeypatch.delenv("FHE_XP_CT")
+
+
+def test_external_product_n1024_kernels_agree_at_batch(fhe, orc, monkeypatch):
+    # a batch on both sides of the switch (SM count): the two kernels and the automatic choice give identical rows
+    import torch
+
+    n, k, batch = 1024, 1, 301
+    glwe = (k + 1) * n
+    tggsw = orc.uniform(96, (k + 1) * 64 * glwe)
+    g = fhe.Tggsw(n, k, tggsw)
+    gen = torch.Generator(device="cuda").manual_seed(97)
+    ct1 = torch.randint(-(2**63), 2**63 - 1, (batch, glwe), dtype=torch.int64, device="cuda", generator=gen)
+    ct2 = torch.randint(-(2**63), 2**63 - 1, (batch, glwe), dtype=torch.int64, device="cuda", generator=gen)
+    fhe.use_torch_stream()
+    auto = g.cmux(ct1, ct2).clone()
+    for ct in ("256", "512"):
+        monkeypatch.setenv("FHE_XP_CT", ct)
+        assert torch.equal(g.cmux(ct1, ct2), auto), ct
+    monkeypatch.delenv("FHE_XP_CT")
+    rows = [0, 1, 150, 299, 300]
+    sel = torch.tensor(rows, device="cuda")
+    a1 = np.ascontiguousarray(ct1[sel].cpu().numpy().view(np.uint64))
+    a2 = np.ascontiguousarray(ct2[sel].cpu().numpy().view(np.uint64))
+    want = orc.cmux(n, k, tggsw, a1.reshape(-1), a2.reshape(-1))
+    assert np.array_equal(auto[sel].cpu().numpy().view(np.uint64).reshape(-1), want)
+
+
 def test_extprod_worst_case_bound(fhe, orc, monkeypatch):
     # all-ones rows and accumulators maximise the integer magnitude the two-prime lift has to carry
     for n, k in ((1024, 1), (64, 4), (2048, 1)):
