@@ -38,6 +38,9 @@ template <int LOGN, int K1, int CT_ = 256> struct XpGeom {
     static constexpr int LOGE = LOGN < 5 ? LOGN : 5;
     typedef NttShape<LOGN, LOGE> S;
     static constexpr int CT = CT_, LCT = xp_layout_ct(LOGN, K1);
+    // forward-butterfly policy: three-input adds (xp_octet.cuh) except at n = 64, k = 4, the one shape they slow down
+    // (6.99 -> 6.34 M/s; n = 128, k = 1: 15.2 -> 16.0 with them, n = 1024, k = 1: +1 %, the others unchanged)
+    typedef XpSmallT<!(LOGN <= 6 && K1 > 2)> Mod;
     static_assert(CT == 256 || (CT == 512 && xp_has_pair(LOGN, K1)), "512 threads: n = 1024, k = 1 only");
     static constexpr int SLOTS = CT / S::T;             // concurrent NTTs
     static constexpr int ND = K1 * 64;                  // digit polynomials per accumulator
@@ -165,7 +168,7 @@ __device__ __forceinline__ u32 warp_transpose32(u32 a, int lane) {
 //    x - (x >> 27)*p = (x mod 2^27) + (x >> 27)*(2^27 - p) < 2^27 + 21*2^21 < 2^28 costs one shift and one IMAD
 //    (the MAC then adds at most (k+1)*64 <= 320 products < 2^28 * 2^27: below 2^64).
 template <int LOGN, int K1, int CT>
-__device__ __forceinline__ void digit_ntt(const XpSmall &ms, const TwSrc<XpSmall> &twf, u32 w, const uint4 *tab_lo,
+__device__ __forceinline__ void digit_ntt(const typename XpGeom<LOGN, K1, CT>::Mod &ms, const TwSrc<typename XpGeom<LOGN, K1, CT>::Mod> &twf, u32 w, const uint4 *tab_lo,
                                           const uint4 *tab_hi, u32 *sm, int tid) {
     typedef XpGeom<LOGN, K1, CT> G;
     constexpr int LOGE = G::LOGE;
@@ -173,7 +176,7 @@ __device__ __forceinline__ void digit_ntt(const XpSmall &ms, const TwSrc<XpSmall
     constexpr int LAST = S::P - 1;
     u32 x[S::E];
     digit_pass0<LOGN>(x, w, tab_lo, tab_hi, tid, ms, twf);
-    if constexpr (S::P > 1) fwd_chain<XpSmall, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
+    if constexpr (S::P > 1) fwd_chain<typename G::Mod, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
 #pragma unroll
     for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = ms.fold27(x[e]);
 }
@@ -202,8 +205,8 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
     if (t < 256) {
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            const TwSrc<XpSmall> twf = {X.P[r].c_fwd, X.P[r].fwd};
-            octet_table_entry(X.ms[r], twf, t, tab[r * 512 + t], tab[r * 512 + 256 + t]);
+            const TwSrc<typename G::Mod> twf = {X.P[r].c_fwd, X.P[r].fwd};
+            octet_table_entry(reinterpret_cast<const typename G::Mod &>(X.ms[r]), twf, t, tab[r * 512 + t], tab[r * 512 + 256 + t]);
         }
     }   // ordered before the first digit transform by the barrier behind the bit planes
     const int lane = t & 31;
@@ -270,9 +273,9 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
         for (int round = 0; round < G::ROUNDS; round++) {
             const int d = round * G::DPR + s_dig;
             if (d < G::ND) {
-                const TwSrc<XpSmall> twf = {X.P[r].c_fwd, X.P[r].fwd};
+                const TwSrc<typename G::Mod> twf = {X.P[r].c_fwd, X.P[r].fwd};
                 const u32 w = planes[((size_t)(s_acc * K1 + (d >> 6)) * S::T + tid) * G::PLANE_ROW + (d & 63)];
-                digit_ntt<LOGN, K1, CT>(X.ms[r], twf, w, tab + r * 512, tab + r * 512 + 256, sm, tid);
+                digit_ntt<LOGN, K1, CT>(reinterpret_cast<const typename G::Mod &>(X.ms[r]), twf, w, tab + r * 512, tab + r * 512 + 256, sm, tid);
             }
             // MAC of the round's digits against the resident TGGSW, two digits per iteration.  The 128-bit key loads are
             // software-pipelined through the registers themselves: the loads of the first pair are issued BEFORE the

@@ -2,7 +2,9 @@
 // fraction of the slower of the integer-mulmod and HBM rooflines").  Register-only kernels, no memory traffic:
 //   kind 0: 32-bit IMAD (mad.lo.u32) lane-ops/s
 //   kind 1: 32-bit Shoup modmul/s (the 3-multiply twiddle product of Lazy32/Small32 butterflies)
-//   kind 2: 64-bit Shoup modmul/s (Lazy64: one 64x64 high product + two low products)
+//   kind 2: 64-bit Shoup modmul/s (Lazy64: one 64x64 high product + two low products) -- the better of the library's
+//           chained form (shoup_tail64) and the plain  y*w - mulhi(y,w')*q  the compiler schedules itself, so that a change
+//           of the library's own formulation cannot lower the denominator its kernels are quoted against
 //   kind 3: int8 tensor-core ops/s (2 per MAC): back-to-back tcgen05.mma.kind::i8 (M=128, N=256, K=32) on operands
 //           resident in shared memory, no loads, no epilogue -- the measured peak the key-switch GEMM is quoted against
 #include "../../include/fhe_b200.h"
@@ -17,7 +19,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256) int_peak_kernel(u64 *sink, u32 iters, u64 q, u64 w, u64 wp) {
     constexpr int CH = 8;  // independent dependency chains per thread
     const u64 seed = blockIdx.x * 256ull + threadIdx.x + 1;
-    if (KIND == 2) {
+    if (KIND == 2 || KIND == 5) {
         Lazy64 m;
         m.q = q; m.q2 = 2 * q; m.qinv_neg = 0; m.qinv = 0; m.r2 = 0; m.nq = (u64)0 - q;
         const Tw64 t = {w, wp};
@@ -26,7 +28,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(u64 *sink, u32 iters, u64
         for (int c = 0; c < CH; c++) x[c] = seed * (c + 3);
         for (u32 i = 0; i < iters; i++) {
 #pragma unroll
-            for (int c = 0; c < CH; c++) x[c] = m.mul_tw(x[c], t);
+            for (int c = 0; c < CH; c++) x[c] = KIND == 2 ? m.mul_tw(x[c], t) : x[c] * t.w - mulhi_u64(x[c], t.wp) * q;
         }
         u64 s = 0;
 #pragma unroll
@@ -167,17 +169,19 @@ extern "C" int fhe_int_peak(int kind, double *ops_per_s) {
     FHE_CUDA_OK(cudaEventCreate(&e0));
     FHE_CUDA_OK(cudaEventCreate(&e1));
     float best = 1e30f;
-    for (int rep = 0; rep < 4; rep++) {
+    const u64 wp64 = (u64)(((unsigned __int128)12345 << 64) / q64);
+    for (int rep = 0; rep < (kind == 2 ? 8 : 4); rep++) {
         FHE_CUDA_OK(cudaEventRecord(e0, st));
         if (kind == 0) int_peak_kernel<0><<<grid, 256, 0, st>>>(sink, iters, q32, 12345, 6789);
         else if (kind == 1) int_peak_kernel<1><<<grid, 256, 0, st>>>(sink, iters, q32, 12345, (u64)((12345ull << 32) / q32));
-        else int_peak_kernel<2><<<grid, 256, 0, st>>>(sink, iters, q64, 12345, (u64)(((unsigned __int128)12345 << 64) / q64));
+        else if (rep < 4) int_peak_kernel<2><<<grid, 256, 0, st>>>(sink, iters, q64, 12345, wp64);
+        else int_peak_kernel<5><<<grid, 256, 0, st>>>(sink, iters, q64, 12345, wp64);
         count_launch(1);
         FHE_CUDA_OK(cudaEventRecord(e1, st));
         FHE_CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0;
         FHE_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-        if (rep > 0 && ms < best) best = ms;
+        if ((rep & 3) > 0 && ms < best) best = ms;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

@@ -24,16 +24,19 @@ struct XpQuad { u32 x, y, z, w; };
 // butterflies' multiplies already saturate (ncu, n = 1024, k = 1: fmaheavy 68 % active against ALU 24 %, 72 of the 442
 // fmaheavy instructions of a digit transform being IMAD.IADD / IMAD.MOV); IADD3 only exists on the ALU pipe.  Same
 // for the final fold, whose negation (IMAD.MOV) moves into the constant negq = -q.
-struct XpSmall : Small32 {
+// Z = false keeps the two-input add (the small rings, whose kernels are ALU- rather than fmaheavy-heavy).
+template <bool Z> struct XpSmallT : Small32 {
     u32 zero, negq;
     FHE_HD void fwd(u32 &x, u32 &y, Tw32 t) const {
         const u32 V = mul_tw(y, t);
         y = x - V + q2;
-        x = x + V + zero;
+        if constexpr (Z) x = x + V + zero;
+        else x = x + V;
     }
     // x mod 2^27 + (x >> 27) * (2^27 - q) < 2^28 for q < 2^27 close to it, congruent to x
     FHE_HD u32 fold27(u32 x) const { return (x >> 27) * negq + x; }
 };
+typedef XpSmallT<true> XpSmall;
 
 template <int LOGN> struct XpOct {
     static_assert(LOGN >= 6, "the table-driven first stages need a first pass of at least three stages on 32 coefficients");

@@ -15,7 +15,7 @@ fhe.use_torch_stream()
 dev = torch.device("cuda", 0)
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-n, k = 1024, 1
+n, k = int(os.environ.get("XP_N", 1024)), int(os.environ.get("XP_K", 1))
 glwe = (k + 1) * n
 g = torch.Generator(device="cuda").manual_seed(7)
 r = lambda *shape: torch.randint(-(2**63), 2**63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
@@ -29,7 +29,7 @@ sum_c = int(out.sum().item())
 print("lib %s  extprod %.3f M/s  cmux %.3f M/s  checksums %d %d" % (os.environ.get("FHE_B200_LIB", "default"), batch / ms_x / 1e3,
                                                                   batch / ms_c / 1e3, sum_x, sum_c), flush=True)
 if steps:
-    cb = 592
+    cb = 592 if n == 1024 else 4096
     gs = [fhe.Tggsw(n, k, r((k + 1) * 64 * glwe)) for _ in range(steps)]
     acc = r(cb, glwe)
     h = torch.randint(0, 2 * n, (cb, steps), dtype=torch.int64, device="cuda", generator=g)
