@@ -5,6 +5,8 @@
 //   kind 2: 64-bit Shoup modmul/s (Lazy64: one 64x64 high product + two low products) -- the better of the library's
 //           chained form (shoup_tail64) and the plain  y*w - mulhi(y,w')*q  the compiler schedules itself, so that a change
 //           of the library's own formulation cannot lower the denominator its kernels are quoted against
+//   kind 6: the same 32-bit product in the Fermat form available for q = 2^16 + 1 (IMAD.WIDE + shift + IMAD + add): an
+//           experiment's evidence, not a roofline denominator
 //   kind 3: int8 tensor-core ops/s (2 per MAC): back-to-back tcgen05.mma.kind::i8 (M=128, N=256, K=32) on operands
 //           resident in shared memory, no loads, no epilogue -- the measured peak the key-switch GEMM is quoted against
 #include "../../include/fhe_b200.h"
@@ -43,7 +45,15 @@ __global__ void __launch_bounds__(256) int_peak_kernel(u64 *sink, u32 iters, u64
         for (int c = 0; c < CH; c++) x[c] = (u32)seed * (c + 3);
         for (u32 i = 0; i < iters; i++) {
 #pragma unroll
-            for (int c = 0; c < CH; c++) x[c] = KIND == 0 ? x[c] * t.w + t.wp : m.mul_tw(x[c], t);
+            for (int c = 0; c < CH; c++) {
+                if (KIND == 6) {   // Fermat-prime product (q = 2^16 + 1): y*w = hi*2^32 + lo == lo - (lo >> 16)*q + hi
+                    const u64 T = (u64)x[c] * t.w;
+                    const u32 lo = (u32)T, hi = (u32)(T >> 32);
+                    x[c] = (lo >> 16) * t.wp + lo + (hi + m.q2);   // t.wp = 2^32 - q
+                } else {
+                    x[c] = KIND == 0 ? x[c] * t.w + t.wp : m.mul_tw(x[c], t);
+                }
+            }
         }
         u32 s = 0;
 #pragma unroll
@@ -155,8 +165,8 @@ static int int8_tensor_peak(double *ops_per_s, double seconds) {
 }
 // kind 3 = burst, kind 4 = sustained over ~2 s (the clock settles under the power cap)
 extern "C" int fhe_int_peak(int kind, double *ops_per_s) {
-    FHE_REQUIRE(ops_per_s != nullptr && kind >= 0 && kind <= 4, "fhe_int_peak: kind must be 0..4");
-    if (kind >= 3) return int8_tensor_peak(ops_per_s, kind == 4 ? 2.0 : 0.0);
+    FHE_REQUIRE(ops_per_s != nullptr && kind >= 0 && kind <= 6 && kind != 5, "fhe_int_peak: kind must be 0..4 or 6");
+    if (kind == 3 || kind == 4) return int8_tensor_peak(ops_per_s, kind == 4 ? 2.0 : 0.0);
     cudaStream_t st = current_stream();
     Scratch s_sink;
     int rc0 = s_sink.alloc(8, st);
@@ -174,6 +184,7 @@ extern "C" int fhe_int_peak(int kind, double *ops_per_s) {
         FHE_CUDA_OK(cudaEventRecord(e0, st));
         if (kind == 0) int_peak_kernel<0><<<grid, 256, 0, st>>>(sink, iters, q32, 12345, 6789);
         else if (kind == 1) int_peak_kernel<1><<<grid, 256, 0, st>>>(sink, iters, q32, 12345, (u64)((12345ull << 32) / q32));
+        else if (kind == 6) int_peak_kernel<6><<<grid, 256, 0, st>>>(sink, iters, 65537, 12345, (u64)(0u - 65537u));
         else if (rep < 4) int_peak_kernel<2><<<grid, 256, 0, st>>>(sink, iters, q64, 12345, wp64);
         else int_peak_kernel<5><<<grid, 256, 0, st>>>(sink, iters, q64, 12345, wp64);
         count_launch(1);

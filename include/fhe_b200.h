@@ -51,7 +51,8 @@ FHE_API int fhe_synchronize(void);                   /* wait for this thread's s
 FHE_API uint64_t fhe_launch_count(void);
 
 /* Register-only microbenchmarks of the integer pipes (the denominators of the integer rooflines):
- * kind 0 = 32-bit IMAD lane-ops/s, 1 = 32-bit Shoup modmul/s, 2 = 64-bit Shoup modmul/s;
+ * kind 0 = 32-bit IMAD lane-ops/s, 1 = 32-bit Shoup modmul/s, 2 = 64-bit Shoup modmul/s (the better of the library's
+ * chained form and the compiler's), 6 = 32-bit product in the Fermat form of q = 2^16 + 1 (an experiment);
  * kind 3 = int8 tensor-core ops/s (tcgen05.mma.kind::i8, M=128 N=256 K=32 issued back to back from shared-memory
  * operands, no loads) as a burst, 4 = the same sustained over ~2 s: the measured peaks the key-switch GEMM is quoted
  * against. */
