@@ -68,17 +68,19 @@ namespace {
 std::mutex g_plan_mu;
 std::map<std::tuple<int, u64, u64>, fhe_ntt_plan *> g_plans;
 
-template <class M> int upload_tables(fhe_ntt_plan *p, NttParams<M> &dst) {
+template <class M> int upload_tables(fhe_ntt_plan *p, NttParams<M> &dst, void **d_fwd = nullptr, void **d_inv = nullptr) {
+    if (d_fwd == nullptr) d_fwd = &p->d_fwd;
+    if (d_inv == nullptr) d_inv = &p->d_inv;
     ExpandedTables<M> x;
     expand_tables(p->host, x, p->loge);
     const size_t bytes = sizeof(typename M::T) * p->host.n;
-    FHE_CUDA_OK(cudaMalloc(&p->d_fwd, bytes));
-    FHE_CUDA_OK(cudaMalloc(&p->d_inv, bytes));
-    FHE_CUDA_OK(cudaMemcpy(p->d_fwd, x.fwd.data(), bytes, cudaMemcpyHostToDevice));
-    FHE_CUDA_OK(cudaMemcpy(p->d_inv, x.inv.data(), bytes, cudaMemcpyHostToDevice));
+    FHE_CUDA_OK(cudaMalloc(d_fwd, bytes));
+    FHE_CUDA_OK(cudaMalloc(d_inv, bytes));
+    FHE_CUDA_OK(cudaMemcpy(*d_fwd, x.fwd.data(), bytes, cudaMemcpyHostToDevice));
+    FHE_CUDA_OK(cudaMemcpy(*d_inv, x.inv.data(), bytes, cudaMemcpyHostToDevice));
     dst.mod = x.mod;
-    dst.fwd = reinterpret_cast<const typename M::T *>(p->d_fwd);
-    dst.inv = reinterpret_cast<const typename M::T *>(p->d_inv);
+    dst.fwd = reinterpret_cast<const typename M::T *>(*d_fwd);
+    dst.inv = reinterpret_cast<const typename M::T *>(*d_inv);
     dst.ninv = x.ninv;
     dst.s_ninv = x.s_ninv;
     dst.ninv_pw = x.ninv_pw;
@@ -100,7 +102,10 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, 
     int rc;
     mode = mul_mode_for(plan, mode, flags);
     switch (plan->kind) {
-        case 3: rc = ntt_launch_small32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
+        case 3:
+            rc = plan->fermat ? ntt_launch_fermat32(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st)
+                              : ntt_launch_small32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st);
+            break;
         case 0: rc = ntt_launch_lazy32(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
         case 1: rc = ntt_launch_lazy64(plan->logn, plan->loge, mode, plan->p64, a, b, c, c_evals, batch, flags, st); break;
         default: rc = ntt_launch_strict64(plan->logn, plan->loge, mode, plan->ps64, a, b, c, c_evals, batch, flags, st);
@@ -114,7 +119,10 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *b, 
     int rc;
     mode = mul_mode_for(plan, mode, flags);
     switch (plan->kind) {
-        case 3: rc = ntt_launch_small32_u32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
+        case 3:
+            rc = plan->fermat ? ntt_launch_fermat32_u32(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st)
+                              : ntt_launch_small32_u32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st);
+            break;
         case 0: rc = ntt_launch_lazy32_u32(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
         case 1: rc = ntt_launch_lazy64_u32(plan->logn, plan->loge, mode, plan->p64, a, b, c, c_evals, batch, flags, st); break;
         default: set_error("the 32-bit word format needs q <= 2^32"); return -1;
@@ -130,7 +138,10 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const pk32 *a, const pk32 *b
     int rc;
     mode = mul_mode_for(plan, mode, flags);
     switch (plan->kind) {
-        case 3: rc = ntt_launch_small32_pk(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
+        case 3:
+            rc = plan->fermat ? ntt_launch_fermat32_pk(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st)
+                              : ntt_launch_small32_pk(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st);
+            break;
         case 0: rc = ntt_launch_lazy32_pk(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
         default: set_error("the bit-packed format needs q < 2^30"); return -1;
     }
@@ -356,6 +367,11 @@ int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
              : p->kind == 1 ? upload_tables(p.get(), p->p64)
                             : upload_tables(p.get(), p->ps64);
     if (rc) return rc;
+    // q = 65537 (the reference's modulus): radix-4 butterflies, three twiddle products and a shift per four butterflies
+    // (Fermat32).  FHE_NTT_FERMAT=0 keeps the radix-2 Small32 kernels (A/B measurements and tests).
+    p->fermat = p->kind == 3 && fermat_ok(p->host);
+    if (const char *e = getenv("FHE_NTT_FERMAT")) p->fermat = p->fermat && atoi(e) != 0;
+    if (p->fermat && (rc = upload_tables(p.get(), p->pfm, &p->d_fwd4, &p->d_inv4))) return rc;
     p->refs = 1;
     *out = p.get();
     g_plans[key] = p.release();
@@ -368,6 +384,8 @@ void fhe_ntt_plan_destroy(fhe_ntt_plan *plan) {
     g_plans.erase(std::make_tuple(plan->device, plan->host.q, plan->host.n));
     cudaFree(plan->d_fwd);
     cudaFree(plan->d_inv);
+    cudaFree(plan->d_fwd4);
+    cudaFree(plan->d_inv4);
     delete plan;
 }
 int fhe_ntt_plan_info(const fhe_ntt_plan *plan, uint64_t *psi, uint64_t *n_inv, uint64_t *roots, uint64_t *roots_inv) {
@@ -399,7 +417,7 @@ int fhe_rq_check_canonical(uint64_t q, const uint64_t *words, size_t len, uint64
 }
 int fhe_ntt_plan_config(const fhe_ntt_plan *plan, int *config) {
     FHE_REQUIRE(plan != nullptr && config != nullptr, "null plan or config");
-    config[0] = plan->kind;
+    config[0] = plan->fermat ? 4 : plan->kind;
     config[1] = plan->loge;
     config[2] = plan->dual;
     config[3] = plan->gpark;

@@ -82,6 +82,7 @@ typedef Tw<u64> Tw64;
 struct Lazy32 {
     typedef u32 W;
     typedef Tw32 T;
+    static constexpr bool RADIX4 = false;  // see Fermat32
     u32 q, q2;       // q, 2q
     u32 bk_shift;    // k-1, with 2^(k-1) <= q < 2^k
     u32 bk_mu;       // floor(2^(2k) / q)  (< 2^(k+1))
@@ -141,6 +142,7 @@ struct Lazy32 {
 struct Lazy64 {
     typedef u64 W;
     typedef Tw64 T;
+    static constexpr bool RADIX4 = false;
     u64 q, q2;
     u64 qinv_neg;  // -q^-1 mod 2^64 (kept for the plan's layout; the device uses qinv)
     u64 qinv;      //  q^-1 mod 2^64
@@ -204,6 +206,7 @@ struct Lazy64 {
 struct Strict64 {
     typedef u64 W;
     typedef Tw64 T;
+    static constexpr bool RADIX4 = false;
     u64 q, q2;  // q2 unused
     u64 qinv_neg;
     u64 qinv;   // q^-1 mod 2^64
@@ -265,6 +268,7 @@ struct Strict64 {
 struct Small32 {
     typedef u32 W;
     typedef Tw32 T;
+    static constexpr bool RADIX4 = false;
     u32 q, q2;
     u32 qinv_neg;  // -q^-1 mod 2^32
     u32 qinv;      //  q^-1 mod 2^32
@@ -324,6 +328,69 @@ struct Small32 {
     FHE_HD u32 mul(u32 a, u32 b) const { return pw_evals(pw_mul(a, b)); }  // canonical a*b (a*b < q*2^32)
     FHE_HD static u32 load(u64 v) { return (u32)v; }
     FHE_HD static u64 store(u32 v) { return (u64)v; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Fermat32: q = 2^16 + 1 = 65537, the reference's only NTT modulus (every parameter set of SURVEY appendix B).
+// Small32 with RADIX-4 butterflies.  The twiddle tables satisfy roots[2i+1] = roots[2i] * I with
+// I = psi^(n/2), I^2 = -1 (bit reversal: brev(2i+1) = brev(2i) | n/2), and the reference's root search gives
+// psi = 3^(32768/n) for this modulus, hence I = 3^16384 = -2^8 for every n.  Two consecutive Cooley-Tukey stages on the
+// four positions (e0, e1 = e0+h, e2 = e0+2h, e3 = e0+3h) -- parent twiddle S1 = roots[i], children S2a = roots[2i],
+// S2b = roots[2i+1] = I*S2a -- are, in the reference's order of operations,
+//      a0 = x0 + S1 x2, a2 = x0 - S1 x2, a1 = x1 + S1 x3, a3 = x1 - S1 x3,
+//      y0 = a0 + S2a a1, y1 = a0 - S2a a1, y2 = a2 + S2b a3, y3 = a2 - S2b a3.
+// With p1 = S2a x1, p2 = S1 x2, p3 = (S1 S2a) x3:  S2a a1 = p1 + p3 and S2b a3 = I (p1 - p3) = (p3 - p1) << 8:
+// THREE twiddle products instead of four, the fourth being a shift.  All of it is exact arithmetic in Z_q, so the
+// canonical results are those of the reference's loop (arith/src/ntt.rs:44-110) bit for bit; what changes is the number of
+// multiplier-pipe (fmaheavy) slots: 9 instead of 12 per four butterflies (ncu: that pipe is the kernel's binding unit at
+// 81 % active), for 9 instead of 8 additions on the half-idle ALU pipe.  The device tables keep S1*S2a in the slot of the
+// now unused roots[2i+1] (plan_host.hpp: radix4_patch).
+//
+// Ranges.  Forward: the shifted term is below 4q * 256 = 1024q, so the never-multiplied x path grows by at most 1026q per
+// radix-4 layer: < 2^29 after the 7 layers of n = 2^15; every product takes any 32-bit word.  The pointwise product folds
+// ONE operand below 2q first (fold: v = lo16 - hi16 + q, three ALU instructions), the other stays lazy: 2^17 * 2^29 < q * 2^32.
+// Inverse: inputs below 2q * 2^KB; the shifted difference is below q << (KB + 10), which needs KB <= 4 to stay inside a
+// word; the only output that grows is the plain sum y0 (below 2q * 2^(KB+2)), and InvSched (ntt_core.cuh) folds it where
+// the next radix-4 layer would otherwise be entered with KB > 4.
+// ---------------------------------------------------------------------------------------------------
+struct Fermat32 : Small32 {
+    static constexpr bool RADIX4 = true;
+    static constexpr int INV_KB_MAX = 4;
+    u32 q4;      // 4q
+    u32 c10;     // 1024q = (4q) << 8
+    u32 okb[8];  // q << (KB + 10): offset of the shifted difference of an inverse radix-4 block entered at KB
+
+    FHE_HD u32 fold(u32 v) const { return (v & 0xffffu) - (v >> 16) + q; }  // any 32-bit word -> [2, 2^17], same residue
+    FHE_HD void fwd4(u32 &x0, u32 &x1, u32 &x2, u32 &x3, T s1, T s2a, T s12) const {
+        const u32 p2 = mul_tw(x2, s1), p1 = mul_tw(x1, s2a), p3 = mul_tw(x3, s12);  // each in [0, 2q)
+        const u32 t0 = x0 + p2, t2 = x0 - p2 + q2;
+        const u32 s = p1 + p3;        // S2a*a1            in [0, 4q)
+        const u32 dn = p3 - p1 + q2;  // -(S2a*a3) + 2q    in (0, 4q)
+        const u32 D = dn << 8;        // I*S2a*a3 = -256 (p1 - p3) = 256 dn (mod q), below 1024q
+        x0 = t0 + s;
+        x1 = t0 - s + q4;
+        x2 = t2 + D;
+        x3 = t2 - D + c10;
+    }
+    // Two Gentleman-Sande stages (children first: Sa = roots_inv[2i], Sb = roots_inv[2i+1] = Sa / I = 256 Sa; then the
+    // parent S1 = roots_inv[i]):  y0 = x0+x1+x2+x3, y1 = Sa (d01 + 256 d23), y2 = S1 (x0+x1-x2-x3), y3 = S1 Sa (d01 - 256 d23).
+    // Inputs below 2q << KB (qk[KB]).
+    template <int KB, bool FOLD> FHE_HD void inv4(u32 &x0, u32 &x1, u32 &x2, u32 &x3, T sa, T s1sa, T s1) const {
+        static_assert(KB >= 0 && KB <= INV_KB_MAX, "Fermat32::inv4: the shifted difference would leave the word");
+        const u32 s01 = x0 + x1, s23 = x2 + x3;
+        const u32 d01 = x0 - x1 + qk[KB], d23 = x2 - x3 + qk[KB];  // (0, 2 * 2q << KB)
+        const u32 E = d23 << 8;                                    // below q << (KB + 10)
+        const u32 u = d01 + E, v = d01 - E + okb[KB];
+        const u32 w = s01 - s23 + qk[KB + 1];
+        const u32 y0 = s01 + s23;
+        x0 = FOLD ? fold(y0) : y0;
+        x1 = mul_tw(u, sa);
+        x2 = mul_tw(w, s1);
+        x3 = mul_tw(v, s1sa);
+    }
+    FHE_HD u32 fwd_canon(u32 x) const { return csub(fold(x), q); }
+    FHE_HD u32 pw_mul(u32 a, u32 b) const { return Small32::pw_mul(fold(a), b); }
+    FHE_HD u32 mul(u32 a, u32 b) const { return pw_evals(Small32::pw_mul(a, b)); }  // canonical operands
 };
 
 }  // namespace fhe

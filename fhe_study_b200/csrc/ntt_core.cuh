@@ -122,10 +122,46 @@ FHE_HD void fwd_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
         }
     }
 }
+// Radix-4 policies (M::RADIX4, modarith.cuh: Fermat32): local stages LS and LS+1 of the pass in one sweep over blocks
+// of four registers.  Parent twiddle roots[i] (stage LS), even child roots[2i] (stage LS+1), and -- in the device slot of
+// the odd child roots[2i+1], which the radix-4 form does not use -- the product roots[i]*roots[2i] (radix4_patch).
+template <class M, int LOGN, int LOGE, int PASS, int LS, bool DUAL>
+FHE_HD void fwd_stage4(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LOGE], int tid, const M &m,
+                       const TwSrc<M> &tw) {
+    typedef NttShape<LOGN, LOGE> S;
+    constexpr int g = S::g(PASS), s0 = S::s0(PASS), nL = S::nL(PASS), G = 1 << g;
+    static_assert(LS + 1 < g, "radix-4 needs two stages of the same pass");
+    constexpr int h = 1 << (g - 2 - LS);
+#pragma unroll
+    for (int qi = 0; qi < (S::E >> g); qi++) {
+        const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
+#pragma unroll
+        for (int hi = 0; hi < (1 << LS); hi++) {
+            const int i1 = (1 << (s0 + LS)) + (hi << s0) + H;
+            const int i2 = (1 << (s0 + LS + 1)) + ((2 * hi) << s0) + H, i3 = i2 + (1 << s0);
+            const typename M::T t1 = (PASS == 0) ? tw.c0[i1] : tw.tab[i1];
+            const typename M::T t2 = (PASS == 0) ? tw.c0[i2] : tw.tab[i2];
+            const typename M::T t3 = (PASS == 0) ? tw.c0[i3] : tw.tab[i3];
+#pragma unroll
+            for (int lo = 0; lo < h; lo++) {
+                const int b = qi * G + (hi << (g - LS)) + lo;
+                m.fwd4(x[b], x[b + h], x[b + 2 * h], x[b + 3 * h], t1, t2, t3);
+                if constexpr (DUAL) m.fwd4(y[b], y[b + h], y[b + 2 * h], y[b + 3 * h], t1, t2, t3);
+            }
+        }
+    }
+}
+// forward pairing: local stages (0,1), (2,3), ... ; an odd stage count leaves the last one radix-2
 template <class M, int LOGN, int LOGE, int PASS, int LS = 0>
 FHE_HD void fwd_pass(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw) {
-    fwd_stage<M, LOGN, LOGE, PASS, LS>(x, tid, m, tw);
-    if constexpr (LS + 1 < NttShape<LOGN, LOGE>::g(PASS)) fwd_pass<M, LOGN, LOGE, PASS, LS + 1>(x, tid, m, tw);
+    constexpr int g = NttShape<LOGN, LOGE>::g(PASS);
+    if constexpr (M::RADIX4 && LS + 1 < g) {
+        fwd_stage4<M, LOGN, LOGE, PASS, LS, false>(x, x, tid, m, tw);
+        if constexpr (LS + 2 < g) fwd_pass<M, LOGN, LOGE, PASS, LS + 2>(x, tid, m, tw);
+    } else {
+        fwd_stage<M, LOGN, LOGE, PASS, LS>(x, tid, m, tw);
+        if constexpr (LS + 1 < g) fwd_pass<M, LOGN, LOGE, PASS, LS + 1>(x, tid, m, tw);
+    }
 }
 
 // Two polynomials through the same forward pass at once (the two operands of a polymul): every twiddle is fetched
@@ -156,19 +192,27 @@ FHE_HD void fwd_stage2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LO
 template <class M, int LOGN, int LOGE, int PASS, int LS = 0>
 FHE_HD void fwd_pass2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LOGE], int tid, const M &m,
                       const TwSrc<M> &tw) {
-    fwd_stage2<M, LOGN, LOGE, PASS, LS>(x, y, tid, m, tw);
-    if constexpr (LS + 1 < NttShape<LOGN, LOGE>::g(PASS)) fwd_pass2<M, LOGN, LOGE, PASS, LS + 1>(x, y, tid, m, tw);
+    constexpr int g = NttShape<LOGN, LOGE>::g(PASS);
+    if constexpr (M::RADIX4 && LS + 1 < g) {
+        fwd_stage4<M, LOGN, LOGE, PASS, LS, true>(x, y, tid, m, tw);
+        if constexpr (LS + 2 < g) fwd_pass2<M, LOGN, LOGE, PASS, LS + 2>(x, y, tid, m, tw);
+    } else {
+        fwd_stage2<M, LOGN, LOGE, PASS, LS>(x, y, tid, m, tw);
+        if constexpr (LS + 1 < g) fwd_pass2<M, LOGN, LOGE, PASS, LS + 1>(x, y, tid, m, tw);
+    }
 }
 
 // Inverse: the same groups, local stages in descending order.  When PASS == 0 the final stage
 // (s = 0, the single twiddle roots_inv[1]) also applies n^-1 (M::inv_last).
-template <class M, int LOGN, int LOGE, int PASS, int LS>
+// KOVR >= 0 replaces K (radix-4 policies track the bound themselves, see InvSched)
+template <class M, int LOGN, int LOGE, int PASS, int LS, int KOVR = -1>
 FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw,
                       typename M::T ninv, typename M::T s_ninv) {
     typedef NttShape<LOGN, LOGE> S;
     constexpr int g = S::g(PASS), s0 = S::s0(PASS), nL = S::nL(PASS), G = 1 << g;
     constexpr int half = 1 << (g - 1 - LS);
-    constexpr int K = LOGN - 1 - (s0 + LS);  // inverse stages already executed (stages run from LOGN-1 down to 0)
+    // inverse stages already executed (stages run from LOGN-1 down to 0): inputs are below 2q * 2^K
+    constexpr int K = KOVR >= 0 ? KOVR : LOGN - 1 - (s0 + LS);
 #pragma unroll
     for (int qi = 0; qi < (S::E >> g); qi++) {
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
@@ -190,12 +234,103 @@ FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
         }
     }
 }
+
+// Inverse schedule of a radix-4 policy.  Stages run from LOGN-1 down to 0, pass by pass; inside a pass the local stages
+// are paired from the top -- (g-1, g-2), (g-3, g-4), ... -- the last stage of the whole transform (pass 0, local stage
+// 0: the n^-1 stage) always stays on its own, and a stage left over is radix-2.  KB = log2(bound of the inputs / 2q):
+// +1 per radix-2 stage, +2 per radix-4 layer; a radix-4 layer must be entered with KB <= M::INV_KB_MAX, so the layer in
+// front of one that would not be folds its sum output (KB back to 0: every other output is a twiddle product, below 2q).
+struct InvStep {
+    int kind;  // 0 = lower stage of a pair (nothing to do), 1 = radix-2, 2 = upper stage of a pair, 3 = last stage
+    int kb;    // KB of the inputs
+    bool fold;
+};
+template <int LOGN, int LOGE, int KBMAX> struct InvSched {
+    typedef NttShape<LOGN, LOGE> S;
+    FHE_HD static constexpr int lo_of(int p) { return p == 0 ? 1 : 0; }
+    // KB at which the next radix-4 layer after (p, ls) [exclusive] would be entered if the current KB is kb; -1 if none
+    FHE_HD static constexpr int next_r4_kb(int p, int ls, int kb) {
+        for (;;) {
+            if (ls < lo_of(p)) {
+                if (p == 0) return -1;
+                p--;
+                ls = S::g(p) - 1;
+                continue;
+            }
+            if (ls - 1 >= lo_of(p)) return kb;
+            kb++;  // a single radix-2 stage
+            ls--;
+        }
+    }
+    FHE_HD static constexpr InvStep at(int PASS, int LS) {
+        int kb = 0;
+        for (int p = S::P - 1; p >= 0; p--) {
+            int ls = S::g(p) - 1;
+            while (ls >= lo_of(p)) {
+                if (ls - 1 >= lo_of(p)) {
+                    const int nxt = next_r4_kb(p, ls - 2, kb + 2);
+                    const bool fold = nxt > KBMAX;
+                    if (p == PASS && ls == LS) return InvStep{2, kb, fold};
+                    if (p == PASS && ls - 1 == LS) return InvStep{0, kb, fold};
+                    kb = fold ? 0 : kb + 2;
+                    ls -= 2;
+                } else {
+                    if (p == PASS && ls == LS) return InvStep{1, kb, false};
+                    kb++;
+                    ls--;
+                }
+            }
+            if (p == 0 && PASS == 0 && LS == 0) return InvStep{3, kb, false};
+        }
+        return InvStep{-1, 0, false};
+    }
+};
+
+// local stages LS (children, executed first) and LS-1 (parent) of the pass in one sweep; table slots as in fwd_stage4
+template <class M, int LOGN, int LOGE, int PASS, int LS, int KB, bool FOLD>
+FHE_HD void inv_stage4(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw) {
+    typedef NttShape<LOGN, LOGE> S;
+    constexpr int g = S::g(PASS), s0 = S::s0(PASS), nL = S::nL(PASS), G = 1 << g;
+    constexpr int LP = LS - 1;
+    static_assert(LP >= 0 && LS < g, "radix-4 needs two stages of the same pass");
+    constexpr int h = 1 << (g - 1 - LS);
+#pragma unroll
+    for (int qi = 0; qi < (S::E >> g); qi++) {
+        const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
+#pragma unroll
+        for (int hi = 0; hi < (1 << LP); hi++) {
+            const int i1 = (1 << (s0 + LP)) + (hi << s0) + H;
+            const int i2 = (1 << (s0 + LS)) + ((2 * hi) << s0) + H, i3 = i2 + (1 << s0);
+            const typename M::T t1 = (PASS == 0) ? tw.c0[i1] : tw.tab[i1];
+            const typename M::T t2 = (PASS == 0) ? tw.c0[i2] : tw.tab[i2];
+            const typename M::T t3 = (PASS == 0) ? tw.c0[i3] : tw.tab[i3];
+#pragma unroll
+            for (int lo = 0; lo < h; lo++) {
+                const int b = qi * G + (hi << (g - LP)) + lo;
+                m.template inv4<KB, FOLD>(x[b], x[b + h], x[b + 2 * h], x[b + 3 * h], t2, t3, t1);
+            }
+        }
+    }
+}
+
 template <class M, int LOGN, int LOGE, int PASS, int LS = -1>
 FHE_HD void inv_pass(typename M::W (&x)[1 << LOGE], int tid, const M &m, const TwSrc<M> &tw,
                      typename M::T ninv, typename M::T s_ninv) {
     constexpr int ls = LS < 0 ? NttShape<LOGN, LOGE>::g(PASS) - 1 : LS;
-    inv_stage<M, LOGN, LOGE, PASS, ls>(x, tid, m, tw, ninv, s_ninv);
-    if constexpr (ls > 0) inv_pass<M, LOGN, LOGE, PASS, ls - 1>(x, tid, m, tw, ninv, s_ninv);
+    if constexpr (M::RADIX4) {
+        constexpr InvStep st = InvSched<LOGN, LOGE, M::INV_KB_MAX>::at(PASS, ls);
+        static_assert(st.kind >= 1, "inverse schedule: entered at the lower stage of a pair");
+        if constexpr (st.kind == 2) {
+            inv_stage4<M, LOGN, LOGE, PASS, ls, st.kb, st.fold>(x, tid, m, tw);
+            if constexpr (ls >= 2) inv_pass<M, LOGN, LOGE, PASS, ls - 2>(x, tid, m, tw, ninv, s_ninv);
+        } else {
+            inv_stage<M, LOGN, LOGE, PASS, ls, st.kb>(x, tid, m, tw, ninv, s_ninv);
+            if constexpr (ls > 0) inv_pass<M, LOGN, LOGE, PASS, ls - 1>(x, tid, m, tw, ninv, s_ninv);
+        }
+    } else {
+        inv_stage<M, LOGN, LOGE, PASS, ls>(x, tid, m, tw, ninv, s_ninv);
+        if constexpr (ls > 0) inv_pass<M, LOGN, LOGE, PASS, ls - 1>(x, tid, m, tw, ninv, s_ninv);
+    }
 }
 
 }  // namespace fhe

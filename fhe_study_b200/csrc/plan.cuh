@@ -19,6 +19,10 @@ FHE_NTT_DECLARE(small32_u32, Small32, u32)
 // bit-packed words (q < 2^30, n >= 1024): the PCIe wire of the host-buffer path
 FHE_NTT_DECLARE(small32_pk, Small32, pk32)
 FHE_NTT_DECLARE(lazy32_pk, Lazy32, pk32)
+// q = 65537: radix-4 butterflies (modarith.cuh: Fermat32), all three word formats
+FHE_NTT_DECLARE(fermat32, Fermat32, u64)
+FHE_NTT_DECLARE(fermat32_u32, Fermat32, u32)
+FHE_NTT_DECLARE(fermat32_pk, Fermat32, pk32)
 #undef FHE_NTT_DECLARE
 }  // namespace fhe
 
@@ -31,11 +35,14 @@ struct fhe_ntt_plan {
     int refs = 0;
     int gpark = 0;   // polymul with NTT(a) parked in the output row (MODE_MULG; 32-bit words, degrees >= 2^13)
     int staged = 0;  // polymul through the persistent staged kernel (MODE_MULS; degrees >= 2^13)
+    int fermat = 0;  // kind 3 and q = 65537: the transforms run under the Fermat32 policy (pfm, radix-4 tables d_fwd4 / d_inv4);
+                     // psm and d_fwd / d_inv stay valid for the fused consumers that bring their own Small32 code
     int dual = 0;  // polymul of two coefficient-form operands through the dual-operand kernel (MODE_MUL2)
     fhe::HostTables host;
-    void *d_fwd = nullptr, *d_inv = nullptr;
+    void *d_fwd = nullptr, *d_inv = nullptr, *d_fwd4 = nullptr, *d_inv4 = nullptr;
     fhe::NttParams<fhe::Lazy32> p32;
     fhe::NttParams<fhe::Lazy64> p64;
     fhe::NttParams<fhe::Strict64> ps64;
     fhe::NttParams<fhe::Small32> psm;
+    fhe::NttParams<fhe::Fermat32> pfm;
 };

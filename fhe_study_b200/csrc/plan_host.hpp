@@ -142,6 +142,19 @@ inline void init_mod(Small32 &m, u64 q) {
     for (int k = 0; k < 16; k++) m.qk[k] = (u32)((2 * q) << k);  // wraps only where the policy is not selected
 }
 
+inline void init_mod(Fermat32 &m, u64 q) {
+    init_mod(static_cast<Small32 &>(m), q);
+    m.q4 = (u32)(4 * q);
+    m.c10 = (u32)(1024 * q);
+    for (int k = 0; k < 8; k++) m.okb[k] = (u32)(q << (k + 10));  // used for k <= Fermat32::INV_KB_MAX only
+}
+// Fermat32 (radix-4 butterflies with a shift for the fourth twiddle product) is selected on top of kind 3 when the
+// modulus is 2^16 + 1 and the square root of -1 in the table is the one the policy was written for: roots[1] =
+// psi^(n/2) = -2^8.  The reference's root search gives that for every n (psi = 3^(32768/n)).
+inline bool fermat_ok(const HostTables &t) {
+    return t.q == 65537 && t.n >= 2 && t.n <= (1u << 15) && t.roots[1] == t.q - 256 && t.roots_inv[1] == 256;
+}
+
 // 3: Small32 (q < 2^22 and 2q*n <= 2^32: both transforms free of conditional subtractions), 0: Lazy32 (q < 2^30),
 // 1: Lazy64 (q < 2^62), 2: Strict64 (q < 2^63)
 inline int modulus_kind(u64 q, int logn) {
@@ -156,6 +169,29 @@ template <class M> struct ExpandedTables {
     typename M::T ninv_pw, s_ninv_pw;  // inverse transform after M::pw_mul (absorbs its 2^-wordbits factor)
     M mod;
 };
+// Radix-4 policies: the slot of the odd child roots[2i+1] of every paired stage holds roots[i] * roots[2i] instead
+// (tab in REFERENCE order; forward pairs are the local stages (0,1), (2,3), ... of each pass, inverse pairs run from the
+// top of each pass with the transform's last stage left alone -- the same rules as fwd_pass / InvSched in ntt_core.cuh).
+inline void radix4_patch(std::vector<u64> &tab, u64 q, int logn, int loge, bool inverse) {
+    const int P = ntt_num_passes(logn, loge);
+    const std::vector<u64> ref = tab;
+    for (int p = 0; p < P; p++) {
+        const int s0 = ntt_pass_s0(logn, loge, p), g = (p + 1 < P ? ntt_pass_s0(logn, loge, p + 1) : logn) - s0;
+        std::vector<int> parents;  // local stage of the parent of each pair
+        if (!inverse) {
+            for (int ls = 0; ls + 1 < g; ls += 2) parents.push_back(ls);
+        } else {
+            const int lo = p == 0 ? 1 : 0;
+            for (int ls = g - 1; ls - 1 >= lo; ls -= 2) parents.push_back(ls - 1);
+        }
+        for (int lp : parents) {
+            const int s = s0 + lp;
+            for (u64 j = 0; j < (1ull << s); j++)
+                tab[(2ull << s) + 2 * j + 1] = hp_mulmod(ref[(1ull << s) + j], ref[(2ull << s) + 2 * j], q);
+        }
+    }
+}
+
 // loge <= 0 selects the library's policy LogE<M>; tables are stored in device order (ntt_core.cuh: tw_slot).
 template <class M> void expand_tables(const HostTables &t, ExpandedTables<M> &x, int loge = 0) {
     typedef typename M::W W;
@@ -166,10 +202,15 @@ template <class M> void expand_tables(const HostTables &t, ExpandedTables<M> &x,
     const int logn = hp_ilog2(t.n);
     if (loge <= 0) loge = LogE<M>::of(logn);
     if (loge > logn) loge = logn;
+    std::vector<u64> rf = t.roots, ri = t.roots_inv;
+    if (M::RADIX4) {
+        radix4_patch(rf, t.q, logn, loge, false);
+        radix4_patch(ri, t.q, logn, loge, true);
+    }
     for (u64 i = 0; i < t.n; i++) {
         const u64 slot = tw_slot(logn, loge, i);
-        x.fwd[slot] = make_tw((W)t.roots[i], (W)t.q, (T *)nullptr);
-        x.inv[slot] = make_tw((W)t.roots_inv[i], (W)t.q, (T *)nullptr);
+        x.fwd[slot] = make_tw((W)rf[i], (W)t.q, (T *)nullptr);
+        x.inv[slot] = make_tw((W)ri[i], (W)t.q, (T *)nullptr);
     }
     x.ninv = make_tw((W)t.n_inv, (W)t.q, (T *)nullptr);
     x.s_ninv = make_tw((W)hp_mulmod(t.roots_inv[1], t.n_inv, t.q), (W)t.q, (T *)nullptr);

@@ -69,7 +69,7 @@ FHE_API void fhe_ntt_plan_destroy(fhe_ntt_plan *plan);
  * (optionally, may be NULL) the two n-entry tables in the reference's order roots[i] = psi^bitrev(i). */
 FHE_API int fhe_ntt_plan_info(const fhe_ntt_plan *plan, uint64_t *psi, uint64_t *n_inv, uint64_t *roots, uint64_t *roots_inv);
 /* Diagnostics: which kernel shape the plan selected -- config[0] = modular policy (0 Lazy32, 1 Lazy64, 2 Strict64,
- * 3 Small32), [1] = log2(coefficients per thread), [2] = dual-operand polymul, [3] = NTT(a) parked in the output
+ * 3 Small32, 4 Fermat32 = Small32 with radix-4 butterflies, q = 65537 only), [1] = log2(coefficients per thread), [2] = dual-operand polymul, [3] = NTT(a) parked in the output
  * row, [4] = persistent staged polymul.  (No reference counterpart; used by the tests and the tuning tools.) */
 FHE_API int fhe_ntt_plan_config(const fhe_ntt_plan *plan, int *config);
 

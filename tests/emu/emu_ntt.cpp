@@ -154,12 +154,21 @@ int emu_xp_digit(uint64_t q, uint64_t n, const uint64_t *bits, uint64_t *out) {
     }
     return -2;
 }
-// kind: -1 auto (as the library picks), 0 Lazy32, 1 Lazy64, 2 Strict64, 3 Small32 ; mode 0 fwd, 1 inv, 2 mul
+// kind: -1 auto (as the library picks), 0 Lazy32, 1 Lazy64, 2 Strict64, 3 Small32, 4 Fermat32 ; mode 0 fwd, 1 inv, 2 mul
 int emu_ntt(int kind, uint64_t q, uint64_t n, int loge, int mode, const uint64_t *a, const uint64_t *b, uint64_t *c,
             uint64_t *c_evals, int flags) {
     int logn = 0;
     while ((1ull << logn) < n) logn++;
-    if (kind < 0) kind = modulus_kind(q, logn);
+    if (kind < 0) {
+        kind = modulus_kind(q, logn);
+        HostTables t;
+        if (kind == 3 && build_host_tables(q, n, t).empty() && fermat_ok(t)) kind = 4;
+    }
+    if (kind == 4) {
+        HostTables t;
+        if (!build_host_tables(q, n, t).empty() || !fermat_ok(t)) return -2;
+        return emu_any<Fermat32>(q, n, loge, mode, a, b, c, c_evals, flags);
+    }
     if (kind == 0) return q < (1ull << 30) ? emu_any<Lazy32>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
     if (kind == 1) return q < (1ull << 62) ? emu_any<Lazy64>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;
     if (kind == 3) return modulus_kind(q, logn) == 3 ? emu_any<Small32>(q, n, loge, mode, a, b, c, c_evals, flags) : -2;

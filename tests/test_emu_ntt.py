@@ -123,3 +123,62 @@ def test_extprod_digit_transform_from_octet_table(emu, orc, logn):
             assert emu.emu_xp_digit(q, n, orc.ptr(bits), orc.ptr(out)) == 0
             assert (out < 2**28).all()
             assert (out % np.uint64(q) == orc.ntt(q, n, bits)).all()
+
+
+# ---- Fermat32: radix-4 butterflies for q = 65537 (modarith.cuh) ------------------------------------------------------
+@pytest.mark.parametrize("logn", range(1, 16))
+def test_fermat32_all_sizes(emu, orc, logn):
+    # every degree, every coefficients-per-thread setting that changes the pass split (and with it which stages pair
+    # up and which table slots hold parent * child products), against the oracle's radix-2 loop
+    n = 1 << logn
+    for loge in (0, 2, 3, 4, 5, 6):
+        _check(emu, orc, 4, Q17, n, loge)
+    # the policy is for the reference's modulus only
+    a = orc.uniform(1, n, Q22 if (Q22 - 1) % (2 * n) == 0 else Q30)
+    q_other = Q22 if (Q22 - 1) % (2 * n) == 0 else Q30
+    assert emu.emu_ntt(4, q_other, n, 0, 0, orc.ptr(a), None, orc.ptr(a.copy()), None, 0) == -2
+
+
+@pytest.mark.parametrize("logn", [2, 5, 9, 10, 11, 12, 13, 14, 15])
+def test_fermat32_worst_case_ranges(emu, orc, logn):
+    """The radix-4 forward lets the never-multiplied path grow by up to 1026q per layer and shifts differences by 8
+    bits; the inverse shifts differences of sums that double every stage.  Extreme and structured inputs (all q-1,
+    one-hot, alternating 0 / q-1, q-1 on one residue class of every power-of-two stride) drive those paths to their
+    bounds; results must still equal the oracle."""
+    n = 1 << logn
+    q = Q17
+    cases = [np.full(n, q - 1, dtype=np.uint64), np.zeros(n, dtype=np.uint64), np.ones(n, dtype=np.uint64)]
+    alt = np.zeros(n, dtype=np.uint64)
+    alt[::2] = q - 1
+    cases.append(alt)
+    cases.append((q - 1) - alt)
+    stride = 1
+    while stride < n:
+        v = np.zeros(n, dtype=np.uint64)
+        v[(np.arange(n) // stride) % 2 == 0] = q - 1
+        cases.append(v)
+        stride *= 4
+    hot = np.zeros(n, dtype=np.uint64)
+    hot[n - 1] = q - 1
+    cases.append(hot)
+    rng = np.random.default_rng(logn)
+    cases.append(rng.integers(q - 4, q, n, dtype=np.uint64))
+    out = np.empty(n, dtype=np.uint64)
+    for loge in (0, 3):
+        for a in cases:
+            fa = orc.ntt(q, n, a)
+            assert emu.emu_ntt(4, q, n, loge, 0, orc.ptr(a), None, orc.ptr(out), None, 0) == 0
+            assert np.array_equal(out, fa)
+            assert emu.emu_ntt(4, q, n, loge, 1, orc.ptr(a), None, orc.ptr(out), None, 0) == 0
+            assert np.array_equal(out, orc.ntt(q, n, a, inverse=True))
+            for b in (a, cases[0], cases[-1]):
+                assert emu.emu_ntt(4, q, n, loge, 2, orc.ptr(a), orc.ptr(b), orc.ptr(out), None, 0) == 0
+                assert np.array_equal(out, orc.rq_mul_batch(q, n, a, b))
+                # evals given for either operand (canonical NTT values straight into the lazy pointwise product)
+                assert emu.emu_ntt(4, q, n, loge, 2, orc.ptr(fa), orc.ptr(b), orc.ptr(out), None, 1) == 0
+                assert np.array_equal(out, orc.rq_mul_batch(q, n, a, b))
+
+
+def test_fermat32_is_what_the_library_picks(emu, orc):
+    for n in (2, 4, 1024, 16384):
+        _check(emu, orc, -1, Q17, n, 0)
