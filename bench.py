@@ -36,8 +36,12 @@ N = 1024
 BATCH = 65536  # 3 * 65536 * 8 KiB = 1.5 GiB per step: far larger than the 126 MB L2
 WIRE_BITS = 17  # ceil(log2 q): the bit-packed wire of the end-to-end leg
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this exact workload (ncu --set full capture)
-NCU_TRAFFIC_BYTES = 1073805000 + 501989376
-NCU_TRAFFIC_SOURCE = "profiles/r2_polymul_n1024_q65537_u64_ncu_full_a.csv (ncu --set full of tools/prof.py polymul 10 65537 65536)"
+# Twiddle products the Fermat32 kernel executes per N=1024 polymul (radix-4: three products and a shift per four
+# butterflies): forward 4 radix-4 layers x 256 blocks x 3 + 2 radix-2 stages x 512 = 4096, twice; inverse 4 x 256 x 3 +
+# 512 + the n^-1 stage's 1024 = 4608; pointwise 1024.  SURVEY 8d's algorithmic count for the same polymul is 17408.
+MODMUL_EXECUTED = 2 * 4096 + 4608 + 1024
+NCU_TRAFFIC_BYTES = 1073804000 + 500058368
+NCU_TRAFFIC_SOURCE = "profiles/r2_polymul_n1024_q65537_u64_fermat32_ncu_full_a.csv (ncu --set full of tools/prof.py polymul 10 65537 65536)"
 
 
 def peaks():
@@ -573,19 +577,21 @@ def main():
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "traffic": NCU_TRAFFIC_BYTES if batch == BATCH else None, "traffic_source": NCU_TRAFFIC_SOURCE,
-        "peak_source": peak_kind, "kernel": "ntt_kernel<Small32,10,5,MUL,u64>",
+        "peak_source": peak_kind, "kernel": "ntt_kernel<Fermat32,10,5,MUL,u64>",
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
         "int": {
             "bound": "int32 Shoup modmul (3 IMAD on the fmaheavy pipe)", "achieved": modmul_rate / 1e12, "peak": modmul_peak / 1e12,
             "unit": "T modmul/s", "frac": modmul_rate / modmul_peak, "modmul_per_polymul": modmul_per_polymul,
+            "modmul_executed_per_polymul": MODMUL_EXECUTED if N == 1024 else None,
+            "executed_frac": (MODMUL_EXECUTED * batch / (kern_ms * 1e-3)) / modmul_peak if N == 1024 else None,
             "peak_source": "fhe_int_peak(1) microbenchmark, this run",
-            "note": "ncu (profiles/r2_polymul_n1024_q65537_u64_ncu_full_a.csv): fmaheavy (IMAD) pipe 81 % active, issue slots 61 %, GPC instruction-cache requests 87 % of peak: co-limited by the integer pipe, instruction fetch and HBM",
+            "note": "frac counts SURVEY 8d's algorithmic modmuls (17408 per polymul) against the Shoup-modmul peak; the radix-4 Fermat32 kernel executes 13824 twiddle products (executed_frac).  ncu (profiles/r2_polymul_n1024_q65537_u64_fermat32_ncu_full_a.csv): fmaheavy (IMAD) pipe 73 % active (radix-2 Small32 kernel: 81 %), ALU pipe 55 %, issue slots 65 %, DRAM 1.574 GB per launch for 1.611 GB algorithmic: co-limited by the integer pipe, issue and HBM",
         },
         "u32_device_format": {
             "value": value_u32, "unit": "polymul/s", "algorithmic_bytes_per_polymul": 3 * N * 4,
             "hbm_frac": (3 * N * 4 * value_u32 / world / 1e9) / hbm_peak,
             "modmul_frac": value_u32 / world * modmul_per_polymul / modmul_peak, "binding": "int32 Shoup modmul",
-            "matches_u64_result": u32_same, "kernel": "ntt_kernel<Small32,10,5,MUL,u32>",
+            "matches_u64_result": u32_same, "kernel": "ntt_kernel<Fermat32,10,5,MUL,u32>",
         },
         "sustained": sustained,
         "bootstrap": boot.get("roofline"),
