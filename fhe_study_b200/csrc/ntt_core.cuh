@@ -132,6 +132,18 @@ FHE_HD void fwd_stage4(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LO
     constexpr int g = S::g(PASS), s0 = S::s0(PASS), nL = S::nL(PASS), G = 1 << g;
     static_assert(LS + 1 < g, "radix-4 needs two stages of the same pass");
     constexpr int h = 1 << (g - 2 - LS);
+    if constexpr (PASS == 0 && LS == 0 && M::FIRST_SHIFT) {  // stages 1 and 2 of the transform: twiddles known, inputs canonical
+#pragma unroll
+        for (int qi = 0; qi < (S::E >> g); qi++) {
+#pragma unroll
+            for (int lo = 0; lo < h; lo++) {
+                const int b = qi * G + lo;
+                m.fwd4_first(x[b], x[b + h], x[b + 2 * h], x[b + 3 * h]);
+                if constexpr (DUAL) m.fwd4_first(y[b], y[b + h], y[b + 2 * h], y[b + 3 * h]);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int qi = 0; qi < (S::E >> g); qi++) {
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);

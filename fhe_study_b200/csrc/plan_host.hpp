@@ -147,12 +147,15 @@ inline void init_mod(Fermat32 &m, u64 q) {
     m.q4 = (u32)(4 * q);
     m.c10 = (u32)(1024 * q);
     for (int k = 0; k < 8; k++) m.okb[k] = (u32)(q << (k + 10));  // used for k <= Fermat32::INV_KB_MAX only
+    m.c8 = (u32)(256 * q);
+    m.c13 = (u32)(8192 * q);
 }
 // Fermat32 (radix-4 butterflies with a shift for the fourth twiddle product) is selected on top of kind 3 when the
 // modulus is 2^16 + 1 and the square root of -1 in the table is the one the policy was written for: roots[1] =
 // psi^(n/2) = -2^8.  The reference's root search gives that for every n (psi = 3^(32768/n)).
 inline bool fermat_ok(const HostTables &t) {
-    return t.q == 65537 && t.n >= 2 && t.n <= (1u << 15) && t.roots[1] == t.q - 256 && t.roots_inv[1] == 256;
+    if (!(t.q == 65537 && t.n >= 2 && t.n <= (1u << 15) && t.roots[1] == t.q - 256 && t.roots_inv[1] == 256)) return false;
+    return t.n < 4 || (t.roots[2] == 4096 && t.roots[3] == 16);  // the shift-only first layer (Fermat32::fwd4_first)
 }
 
 // 3: Small32 (q < 2^22 and 2q*n <= 2^32: both transforms free of conditional subtractions), 0: Lazy32 (q < 2^30),
