@@ -32,7 +32,7 @@ def child(qname, logn, u32):
     ok = ok and bool((plan.intt(plan.ntt(a)) == a).all())
     ev = np.empty_like(a)
     ok = ok and bool((plan.mul(a, b, evals_out=ev) == want).all()) and bool((plan.mul(plan.ntt(a), b, flags=1) == want).all())
-    if q <= 2**32:
+    if q <= 2**32 and not os.environ.get("FHE_NTT_LOGE"):  # the alternative shapes exist for u64 words only
         a32, b32 = a.astype(np.uint32), b.astype(np.uint32)
         ok32 = bool((plan.mul_u32(a32, b32).astype(np.uint64) == want).all())
         ok32 = ok32 and bool((plan.ntt_u32(a32).astype(np.uint64) == oracle.ntt(q, n, a)).all())
