@@ -359,7 +359,7 @@ struct Fermat32 : Small32 {
     u32 q4;      // 4q
     u32 c10;     // 1024q = (4q) << 8
     u32 okb[8];  // q << (KB + 10): offset of the shifted difference of an inverse radix-4 block entered at KB
-    u32 c8, c13; // 256q, 8192q: offsets of the shift-only first layer (fwd4_first)
+    u32 c8, c14; // 512q, 16384q: offsets of the shift-only first layer (fwd4_first)
 #ifndef FHE_FERMAT_FIRST_SHIFT
 #define FHE_FERMAT_FIRST_SHIFT 1
 #endif
@@ -408,21 +408,23 @@ struct Fermat32 : Small32 {
     // The FIRST radix-4 layer of a forward transform (stages 1 and 2 of arith/src/ntt.rs:44-73, one block: H = hi = 0).
     // Its twiddles are the same powers of two for every n -- roots[1] = I = -2^8, roots[2] = 2^12, roots[3] = I*roots[2] =
     // 2^4 (psi^(n/4) = 3^8192; plan_host.hpp: fermat_ok checks all three) -- and its inputs are canonical (<= 2^16, the
-    // precondition of every Rq entry point), so the three products are shifts that need no reduction:
+    // precondition of every Rq entry point; the offsets below are sized for any 17-bit word, so that an unreduced
+    // 65537..131071 still gives the right residue), so the three products are shifts that need no reduction:
     //      y0 = x0 - (x2<<8) + (x1<<12) + (x3<<4)        y2 = x0 + (x2<<8) + (x1<<4) + (x3<<12)
     //      y1 = x0 - (x2<<8) - (x1<<12) - (x3<<4)        y3 = x0 + (x2<<8) - (x1<<4) - (x3<<12)
     // (I*(p1 - p3) = -2^8 (x1<<12 - x3<<4) = x1<<4 + x3<<12 because 2^20 = -2^4.)  Eleven ALU instructions and no
-    // multiplier-pipe slot instead of nine of each.  Outputs stay below 2^16 + 2^24 + c13 < 2^29.1; the later layers add
-    // at most 1026q each to the never-multiplied path, the pointwise product takes fold(a) <= 2^17 times b < 2^30.
+    // multiplier-pipe slot instead of nine of each.  Outputs stay below 2^17 + 2^25 + c14 < 2^30.1; the later layers add
+    // at most 1026q each to the never-multiplied path (< 2^30.6 after the 6 of n = 2^15), and the pointwise product takes
+    // fold(a) <= 2^17 times that: below q * 2^32.
     FHE_HD void fwd4_first(u32 &x0, u32 &x1, u32 &x2, u32 &x3) const {
         const u32 a = x2 << 8;
-        const u32 t0 = x0 - a + c8, t2 = x0 + a;  // c8 = 256q >= 2^24
+        const u32 t0 = x0 - a + c8, t2 = x0 + a;  // c8 = 512q >= 2^25
         const u32 s = (x1 << 12) + (x3 << 4);
         const u32 r = (x3 << 12) + (x1 << 4);
         x0 = t0 + s;
-        x1 = t0 - s + c13;  // c13 = 8192q >= 2^28 + 2^20
+        x1 = t0 - s + c14;  // c14 = 16384q >= 2^29 + 2^21
         x2 = t2 + r;
-        x3 = t2 - r + c13;
+        x3 = t2 - r + c14;
     }
     // Two Gentleman-Sande stages (children first: Sa = roots_inv[2i], Sb = roots_inv[2i+1] = Sa / I = 256 Sa; then the
     // parent S1 = roots_inv[i]):  y0 = x0+x1+x2+x3, y1 = Sa (d01 + 256 d23), y2 = S1 (x0+x1-x2-x3), y3 = S1 Sa (d01 - 256 d23).

@@ -147,8 +147,8 @@ inline void init_mod(Fermat32 &m, u64 q) {
     m.q4 = (u32)(4 * q);
     m.c10 = (u32)(1024 * q);
     for (int k = 0; k < 8; k++) m.okb[k] = (u32)(q << (k + 10));  // used for k <= Fermat32::INV_KB_MAX only
-    m.c8 = (u32)(256 * q);
-    m.c13 = (u32)(8192 * q);
+    m.c8 = (u32)(512 * q);
+    m.c14 = (u32)(16384 * q);
 }
 // Fermat32 (radix-4 butterflies with a shift for the fourth twiddle product) is selected on top of kind 3 when the
 // modulus is 2^16 + 1 and the square root of -1 in the table is the one the policy was written for: roots[1] =

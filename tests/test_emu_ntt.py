@@ -182,3 +182,21 @@ def test_fermat32_worst_case_ranges(emu, orc, logn):
 def test_fermat32_is_what_the_library_picks(emu, orc):
     for n in (2, 4, 1024, 16384):
         _check(emu, orc, -1, Q17, n, 0)
+
+
+def test_fermat32_unreduced_17_bit_inputs(emu, orc):
+    """The shift-only first layer is sized for any 17-bit input word: coefficients in [q, 2^17) are outside the
+    documented precondition (canonical input) but still give the residue's transform and product."""
+    q = Q17
+    rng = np.random.default_rng(17)
+    for logn in (2, 6, 10, 12, 15):
+        n = 1 << logn
+        a = rng.integers(0, 1 << 17, n, dtype=np.uint64)
+        a[0], a[-1] = (1 << 17) - 1, q
+        b = np.full(n, (1 << 17) - 1, dtype=np.uint64)
+        ar, br = a % np.uint64(q), b % np.uint64(q)
+        out = np.empty(n, dtype=np.uint64)
+        assert emu.emu_ntt(4, q, n, 0, 0, orc.ptr(a), None, orc.ptr(out), None, 0) == 0
+        assert np.array_equal(out, orc.ntt(q, n, ar))
+        assert emu.emu_ntt(4, q, n, 0, 2, orc.ptr(a), orc.ptr(b), orc.ptr(out), None, 0) == 0
+        assert np.array_equal(out, orc.rq_mul_batch(q, n, ar, br))
