@@ -326,7 +326,10 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 #ifndef FHE_MULG_MINB_256
 #define FHE_MULG_MINB_256 4
 #endif
-    static constexpr int minb = MODE == MODE_MULG ? (CT_ == 512 ? FHE_MULG_MINB_512 : CT_ == 256 ? FHE_MULG_MINB_256 : 0)
+#ifndef FHE_MULG_MINB_128
+#define FHE_MULG_MINB_128 8
+#endif
+    static constexpr int minb = MODE == MODE_MULG ? (CT_ == 512 ? FHE_MULG_MINB_512 : CT_ == 256 ? FHE_MULG_MINB_256 : CT_ == 128 ? FHE_MULG_MINB_128 : 0)
                                 : (on && W32) ? FHE_A_SMEM_MINB
                                 : !W32 ? (CT_ == 128 ? (MUL ? FHE_MUL64_MINB : FHE_NTT64_MINB)
                                           : (CT_ == 512 && !MUL) ? FHE_NTT64_MINB_512 : 0)
@@ -564,6 +567,10 @@ int launch_staged(const NttParams<M> &P, const IOW *a, const IOW *b, IOW *c, IOW
 }
 // MODE_MULS: polymul through ntt_mul_staged_kernel (two coefficient-form operands, degrees >= 2^13)
 constexpr bool staged_instantiated(int logn) { return logn >= 13; }
+#ifndef FHE_MULG_SMALL   // experiment: the output-row park at N = 1024 .. 4096 as well (FHE_NTT_GPARK=1 selects it)
+#define FHE_MULG_SMALL 0
+#endif
+constexpr bool mulg_instantiated(int logn) { return logn >= 13 || (FHE_MULG_SMALL && logn >= 10); }
 
 template <class M, int LOGN, int LOGE, int MODE, typename IOW>
 int launch_one(const NttParams<M> &P, const IOW *a, const IOW *b, IOW *c, IOW *c_evals, size_t batch, int flags,
@@ -599,7 +606,7 @@ int launch_modes(int mode, const NttParams<M> &P, const IOW *a, const IOW *b, IO
         case MODE_FWD: return launch_one<M, LOGN, LE, MODE_FWD, IOW>(P, a, b, c, c_evals, batch, flags, st);
         case MODE_INV: return launch_one<M, LOGN, LE, MODE_INV, IOW>(P, a, b, c, c_evals, batch, flags, st);
         case MODE_MULG:
-            if constexpr (staged_instantiated(LOGN) && sizeof(typename M::W) <= sizeof(IOW) && !IoTraits<IOW>::packed) {
+            if constexpr (mulg_instantiated(LOGN) && sizeof(typename M::W) <= sizeof(IOW) && !IoTraits<IOW>::packed) {
                 if (c != a && c != b && c_evals == nullptr)
                     return launch_one<M, LOGN, LE, MODE_MULG, IOW>(P, a, b, c, c_evals, batch, flags, st);
             }
