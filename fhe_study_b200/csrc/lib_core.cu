@@ -101,11 +101,13 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, 
                 int flags, cudaStream_t st) {
     int rc;
     mode = mul_mode_for(plan, mode, flags);
+    if (plan->fermat) {  // q = 65537: radix-4 butterflies (kind 3, and kind 0 at n = 2^15)
+        rc = ntt_launch_fermat32(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st);
+        if (!rc) count_launch(1);
+        return rc;
+    }
     switch (plan->kind) {
-        case 3:
-            rc = plan->fermat ? ntt_launch_fermat32(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st)
-                              : ntt_launch_small32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st);
-            break;
+        case 3: rc = ntt_launch_small32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
         case 0: rc = ntt_launch_lazy32(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
         case 1: rc = ntt_launch_lazy64(plan->logn, plan->loge, mode, plan->p64, a, b, c, c_evals, batch, flags, st); break;
         default: rc = ntt_launch_strict64(plan->logn, plan->loge, mode, plan->ps64, a, b, c, c_evals, batch, flags, st);
@@ -118,11 +120,13 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *b, 
                 int flags, cudaStream_t st) {
     int rc;
     mode = mul_mode_for(plan, mode, flags);
+    if (plan->fermat) {  // q = 65537: radix-4 butterflies (kind 3, and kind 0 at n = 2^15)
+        rc = ntt_launch_fermat32_u32(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st);
+        if (!rc) count_launch(1);
+        return rc;
+    }
     switch (plan->kind) {
-        case 3:
-            rc = plan->fermat ? ntt_launch_fermat32_u32(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st)
-                              : ntt_launch_small32_u32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st);
-            break;
+        case 3: rc = ntt_launch_small32_u32(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
         case 0: rc = ntt_launch_lazy32_u32(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
         case 1: rc = ntt_launch_lazy64_u32(plan->logn, plan->loge, mode, plan->p64, a, b, c, c_evals, batch, flags, st); break;
         default: set_error("the 32-bit word format needs q <= 2^32"); return -1;
@@ -137,11 +141,13 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const pk32 *a, const pk32 *b
                 int flags, cudaStream_t st) {
     int rc;
     mode = mul_mode_for(plan, mode, flags);
+    if (plan->fermat) {  // q = 65537: radix-4 butterflies (kind 3, and kind 0 at n = 2^15)
+        rc = ntt_launch_fermat32_pk(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st);
+        if (!rc) count_launch(1);
+        return rc;
+    }
     switch (plan->kind) {
-        case 3:
-            rc = plan->fermat ? ntt_launch_fermat32_pk(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st)
-                              : ntt_launch_small32_pk(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st);
-            break;
+        case 3: rc = ntt_launch_small32_pk(plan->logn, plan->loge, mode, plan->psm, a, b, c, c_evals, batch, flags, st); break;
         case 0: rc = ntt_launch_lazy32_pk(plan->logn, plan->loge, mode, plan->p32, a, b, c, c_evals, batch, flags, st); break;
         default: set_error("the bit-packed format needs q < 2^30"); return -1;
     }
@@ -369,7 +375,7 @@ int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
     if (rc) return rc;
     // q = 65537 (the reference's modulus): radix-4 butterflies, three twiddle products and a shift per four butterflies
     // (Fermat32).  FHE_NTT_FERMAT=0 keeps the radix-2 Small32 kernels (A/B measurements and tests).
-    p->fermat = p->kind == 3 && fermat_ok(p->host);
+    p->fermat = (p->kind == 3 || p->kind == 0) && fermat_ok(p->host);  // kind 0: n = 2^15, where 2q * n > 2^32 rules Small32 out
     if (const char *e = getenv("FHE_NTT_FERMAT")) p->fermat = p->fermat && atoi(e) != 0;
     if (p->fermat && (rc = upload_tables(p.get(), p->pfm, &p->d_fwd4, &p->d_inv4))) return rc;
     p->refs = 1;

@@ -413,6 +413,17 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, co
             W *sA = reinterpret_cast<W *>(smem_raw) + (size_t)G::PPC * PADW + (size_t)slot * S::N;  // PARK only
             // both operands run through ONE copy of the forward-transform code (the fully unrolled transform is
             // the bulk of the kernel's instruction footprint; see profiles/: no_instruction stalls)
+#ifndef FHE_NTT_PREFETCH_B   // experiment: pull b's lines into L2 while a is being transformed
+#define FHE_NTT_PREFETCH_B 0
+#endif
+            if constexpr (FHE_NTT_PREFETCH_B != 0 && !IoTraits<IOW>::packed) {
+                if (!(flags & B_BROADCAST)) {
+                    const char *pb = reinterpret_cast<const char *>(b + off_ld);
+                    constexpr int LINES = (int)(S::N * sizeof(IOW) / 128);
+#pragma unroll
+                    for (int l = tid; l < LINES; l += S::T) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)l * 128));
+                }
+            }
 #pragma unroll 1
             for (int op = 0; op < 2; op++) {
                 const IOW *src = op == 0 ? a + off_ld : (flags & B_BROADCAST) ? b : b + off_ld;

@@ -35,7 +35,7 @@ struct fhe_ntt_plan {
     int refs = 0;
     int gpark = 0;   // polymul with NTT(a) parked in the output row (MODE_MULG; 32-bit words, degrees >= 2^13)
     int staged = 0;  // polymul through the persistent staged kernel (MODE_MULS; degrees >= 2^13)
-    int fermat = 0;  // kind 3 and q = 65537: the transforms run under the Fermat32 policy (pfm, radix-4 tables d_fwd4 / d_inv4);
+    int fermat = 0;  // q = 65537 (kind 3; kind 0 at n = 2^15): the transforms run under the Fermat32 policy (pfm, radix-4 tables d_fwd4 / d_inv4);
                      // psm and d_fwd / d_inv stay valid for the fused consumers that bring their own Small32 code
     int dual = 0;  // polymul of two coefficient-form operands through the dual-operand kernel (MODE_MUL2)
     fhe::HostTables host;
