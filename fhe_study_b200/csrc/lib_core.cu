@@ -89,6 +89,16 @@ template <class M> int upload_tables(fhe_ntt_plan *p, NttParams<M> &dst, void **
         dst.c_fwd[i] = x.fwd[i < p->host.n ? i : 0];
         dst.c_inv[i] = x.inv[i < p->host.n ? i : 0];
     }
+    dst.fwdw = dst.invw = nullptr;
+    if (!x.fwdw.empty()) {  // radix-4 policies: the 4-byte twiddle tables
+        const size_t wb = sizeof(u32) * p->host.n;
+        FHE_CUDA_OK(cudaMalloc(&p->d_fwd4w, wb));
+        FHE_CUDA_OK(cudaMalloc(&p->d_inv4w, wb));
+        FHE_CUDA_OK(cudaMemcpy(p->d_fwd4w, x.fwdw.data(), wb, cudaMemcpyHostToDevice));
+        FHE_CUDA_OK(cudaMemcpy(p->d_inv4w, x.invw.data(), wb, cudaMemcpyHostToDevice));
+        dst.fwdw = reinterpret_cast<const u32 *>(p->d_fwd4w);
+        dst.invw = reinterpret_cast<const u32 *>(p->d_inv4w);
+    }
     return 0;
 }
 
@@ -392,6 +402,8 @@ void fhe_ntt_plan_destroy(fhe_ntt_plan *plan) {
     cudaFree(plan->d_inv);
     cudaFree(plan->d_fwd4);
     cudaFree(plan->d_inv4);
+    cudaFree(plan->d_fwd4w);
+    cudaFree(plan->d_inv4w);
     delete plan;
 }
 int fhe_ntt_plan_info(const fhe_ntt_plan *plan, uint64_t *psi, uint64_t *n_inv, uint64_t *roots, uint64_t *roots_inv) {

@@ -364,6 +364,10 @@ struct Fermat32 : Small32 {
 #define FHE_FERMAT_FIRST_SHIFT 1
 #endif
     static constexpr bool FIRST_SHIFT = FHE_FERMAT_FIRST_SHIFT != 0;
+#ifndef FHE_FERMAT_COMPACT_MIN   // smallest log2 n whose later passes read 4-byte twiddles (ntt_core.cuh: tw_load)
+#define FHE_FERMAT_COMPACT_MIN 13
+#endif
+    FHE_HD static constexpr bool compact(int logn) { return logn >= FHE_FERMAT_COMPACT_MIN; }
 
     FHE_HD u32 fold(u32 v) const { return (v & 0xffffu) - (v >> 16) + q; }  // any 32-bit word -> [2, 2^17], same residue
 #ifndef FHE_FERMAT_SHIFTQ

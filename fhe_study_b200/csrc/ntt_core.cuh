@@ -97,7 +97,22 @@ template <class M> struct LogE {
 template <class M> struct TwSrc {
     const typename M::T *c0;    // first 2^g(0) entries (constant bank / host array)
     const typename M::T *tab;   // full table, n entries, reference order roots[m+i]
+    const u32 *tabw;            // radix-4 policies, large degrees: the twiddles alone (4 bytes each), see tw_load
 };
+// Twiddle of a later pass (table slot i).  Fermat32 at the degrees whose tables outgrow L1 (M::compact) reads the 4-byte
+// twiddle and computes its Shoup companion: 2^32 = q (2^16 - 1) + 1, so floor(w 2^32 / q) = w (2^16 - 1) for w < q.
+template <class M, int LOGN> FHE_HD typename M::T tw_load(const TwSrc<M> &tw, int i) {
+    if constexpr (M::RADIX4) {
+        if constexpr (M::compact(LOGN)) {
+            const u32 w = tw.tabw[i];
+            return typename M::T{w, (w << 16) - w};
+        } else {
+            return tw.tab[i];
+        }
+    } else {
+        return tw.tab[i];
+    }
+}
 
 // One butterfly stage (local stage LS of pass PASS) over the thread's registers.  All trip counts are
 // compile-time constants so the register array never gets dynamically indexed.
@@ -113,7 +128,7 @@ FHE_HD void fwd_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
         for (int hi = 0; hi < (1 << LS); hi++) {
             // reference index (1<<s) + (H<<LS) + hi, stored at the lane-contiguous slot (see tw_slot)
             const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
-            const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
+            const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw_load<M, LOGN>(tw, twi);
 #pragma unroll
             for (int lo = 0; lo < half; lo++) {
                 const int ru = (hi << (g - LS)) | lo;
@@ -151,9 +166,9 @@ FHE_HD void fwd_stage4(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LO
         for (int hi = 0; hi < (1 << LS); hi++) {
             const int i1 = (1 << (s0 + LS)) + (hi << s0) + H;
             const int i2 = (1 << (s0 + LS + 1)) + ((2 * hi) << s0) + H, i3 = i2 + (1 << s0);
-            const typename M::T t1 = (PASS == 0) ? tw.c0[i1] : tw.tab[i1];
-            const typename M::T t2 = (PASS == 0) ? tw.c0[i2] : tw.tab[i2];
-            const typename M::T t3 = (PASS == 0) ? tw.c0[i3] : tw.tab[i3];
+            const typename M::T t1 = (PASS == 0) ? tw.c0[i1] : tw_load<M, LOGN>(tw, i1);
+            const typename M::T t2 = (PASS == 0) ? tw.c0[i2] : tw_load<M, LOGN>(tw, i2);
+            const typename M::T t3 = (PASS == 0) ? tw.c0[i3] : tw_load<M, LOGN>(tw, i3);
 #pragma unroll
             for (int lo = 0; lo < h; lo++) {
                 const int b = qi * G + (hi << (g - LS)) + lo;
@@ -191,7 +206,7 @@ FHE_HD void fwd_stage2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LO
 #pragma unroll
         for (int hi = 0; hi < (1 << LS); hi++) {
             const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
-            const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
+            const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw_load<M, LOGN>(tw, twi);
 #pragma unroll
             for (int lo = 0; lo < half; lo++) {
                 const int ru = (hi << (g - LS)) | lo;
@@ -236,7 +251,7 @@ FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
                     m.template inv_last_k<K>(x[qi * G + lo], x[qi * G + lo + half], ninv, s_ninv);
             } else {
                 const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
-                const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw.tab[twi];
+                const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw_load<M, LOGN>(tw, twi);
 #pragma unroll
                 for (int lo = 0; lo < half; lo++) {
                     const int ru = (hi << (g - LS)) | lo;
@@ -313,9 +328,9 @@ FHE_HD void inv_stage4(typename M::W (&x)[1 << LOGE], int tid, const M &m, const
         for (int hi = 0; hi < (1 << LP); hi++) {
             const int i1 = (1 << (s0 + LP)) + (hi << s0) + H;
             const int i2 = (1 << (s0 + LS)) + ((2 * hi) << s0) + H, i3 = i2 + (1 << s0);
-            const typename M::T t1 = (PASS == 0) ? tw.c0[i1] : tw.tab[i1];
-            const typename M::T t2 = (PASS == 0) ? tw.c0[i2] : tw.tab[i2];
-            const typename M::T t3 = (PASS == 0) ? tw.c0[i3] : tw.tab[i3];
+            const typename M::T t1 = (PASS == 0) ? tw.c0[i1] : tw_load<M, LOGN>(tw, i1);
+            const typename M::T t2 = (PASS == 0) ? tw.c0[i2] : tw_load<M, LOGN>(tw, i2);
+            const typename M::T t3 = (PASS == 0) ? tw.c0[i3] : tw_load<M, LOGN>(tw, i3);
 #pragma unroll
             for (int lo = 0; lo < h; lo++) {
                 const int b = qi * G + (hi << (g - LP)) + lo;

@@ -25,6 +25,7 @@ template <class M> struct NttParams {
     typename M::T s_ninv;       // roots_inv[1] * n^-1
     typename M::T ninv_pw, s_ninv_pw;  // same, times the scale factor M::pw_mul leaves behind (polymul only)
     typename M::T c_fwd[64], c_inv[64];
+    const u32 *fwdw, *invw;     // radix-4 policies: 4-byte twiddle tables of the large degrees (ntt_core.cuh: tw_load), else null
 };
 
 // MODE_MUL : polymul with run-time evals flags, both operands through ONE copy of the forward code (one after the other)
@@ -378,22 +379,22 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, co
     W x[S::E];
 
     if constexpr (MODE == MODE_FWD) {
-        const TwSrc<M> tw = {P.c_fwd, P.fwd};
+        const TwSrc<M> tw = {P.c_fwd, P.fwd, P.fwdw};
         load_any<M, LOGN, LOGE, 0, false, IOW>(x, a + off_ld, bits, sm, tid);
         fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, tw);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.fwd_canon(x[e]);
         store_any<M, LOGN, LOGE, LAST, false, false, IOW>(x, c + off, bits, valid, sm, tid);  // last smem access: own reads in layout LAST
     } else if constexpr (MODE == MODE_INV) {
-        const TwSrc<M> tw = {P.c_inv, P.inv};
+        const TwSrc<M> tw = {P.c_inv, P.inv, P.invw};
         load_any<M, LOGN, LOGE, LAST, false, IOW>(x, a + off_ld, bits, sm, tid);
         inv_chain<M, LOGN, LOGE, LAST>(x, sm, tid, m, tw, P.ninv, P.s_ninv);
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = m.canon2(x[e]);
         store_any<M, LOGN, LOGE, 0, true, false, IOW>(x, c + off, bits, valid, sm, tid);
     } else {
-        const TwSrc<M> twf = {P.c_fwd, P.fwd};
-        const TwSrc<M> twi = {P.c_inv, P.inv};
+        const TwSrc<M> twf = {P.c_fwd, P.fwd, P.fwdw};
+        const TwSrc<M> twi = {P.c_inv, P.inv, P.invw};
         constexpr bool ST = ntt_stream(LOGN, MODE);
         if constexpr (MODE == MODE_MUL2) {
             W y[S::E];
@@ -515,8 +516,8 @@ ntt_mul_staged_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restr
     const int t0 = S::pos(0, tid, 0);
     IOW *stg = reinterpret_cast<IOW *>(smem_raw + SG::exch_bytes) + t0;  // this thread's staging words: stg[pos(0,0,e)]
     const M &m = P.mod;
-    const TwSrc<M> twf = {P.c_fwd, P.fwd};
-    const TwSrc<M> twi = {P.c_inv, P.inv};
+    const TwSrc<M> twf = {P.c_fwd, P.fwd, P.fwdw};
+    const TwSrc<M> twi = {P.c_inv, P.inv, P.invw};
     constexpr int LAST = S::P - 1;
     auto stage = [&](const IOW *src) {
 #pragma unroll

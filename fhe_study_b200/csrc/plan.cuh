@@ -39,7 +39,7 @@ struct fhe_ntt_plan {
                      // psm and d_fwd / d_inv stay valid for the fused consumers that bring their own Small32 code
     int dual = 0;  // polymul of two coefficient-form operands through the dual-operand kernel (MODE_MUL2)
     fhe::HostTables host;
-    void *d_fwd = nullptr, *d_inv = nullptr, *d_fwd4 = nullptr, *d_inv4 = nullptr;
+    void *d_fwd = nullptr, *d_inv = nullptr, *d_fwd4 = nullptr, *d_inv4 = nullptr, *d_fwd4w = nullptr, *d_inv4w = nullptr;
     fhe::NttParams<fhe::Lazy32> p32;
     fhe::NttParams<fhe::Lazy64> p64;
     fhe::NttParams<fhe::Strict64> ps64;

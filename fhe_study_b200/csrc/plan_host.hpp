@@ -168,6 +168,7 @@ inline int modulus_kind(u64 q, int logn) {
 // Shoup-expanded tables for policy M.
 template <class M> struct ExpandedTables {
     std::vector<typename M::T> fwd, inv;
+    std::vector<u32> fwdw, invw;       // radix-4 policies: the twiddles alone, same (device) order
     typename M::T ninv, s_ninv;        // standalone inverse transform
     typename M::T ninv_pw, s_ninv_pw;  // inverse transform after M::pw_mul (absorbs its 2^-wordbits factor)
     M mod;
@@ -214,6 +215,14 @@ template <class M> void expand_tables(const HostTables &t, ExpandedTables<M> &x,
         const u64 slot = tw_slot(logn, loge, i);
         x.fwd[slot] = make_tw((W)rf[i], (W)t.q, (T *)nullptr);
         x.inv[slot] = make_tw((W)ri[i], (W)t.q, (T *)nullptr);
+    }
+    if (M::RADIX4) {
+        x.fwdw.resize(t.n);
+        x.invw.resize(t.n);
+        for (u64 i = 0; i < t.n; i++) {
+            x.fwdw[i] = (u32)x.fwd[i].w;
+            x.invw[i] = (u32)x.inv[i].w;
+        }
     }
     x.ninv = make_tw((W)t.n_inv, (W)t.q, (T *)nullptr);
     x.s_ninv = make_tw((W)hp_mulmod(t.roots_inv[1], t.n_inv, t.q), (W)t.q, (T *)nullptr);

@@ -60,8 +60,8 @@ template <class M, int LOGN, int LOGE>
 static void run(int mode, const ExpandedTables<M> &x, const u64 *a, const u64 *b, u64 *c, u64 *c_evals, int flags) {
     typedef NttShape<LOGN, LOGE> S;
     constexpr int LAST = S::P - 1;
-    const TwSrc<M> twf = {x.fwd.data(), x.fwd.data()};
-    const TwSrc<M> twi = {x.inv.data(), x.inv.data()};
+    const TwSrc<M> twf = {x.fwd.data(), x.fwd.data(), x.fwdw.data()};
+    const TwSrc<M> twi = {x.inv.data(), x.inv.data(), x.invw.data()};
     Emu<M, LOGN, LOGE> A;
     if (mode == 0) {
         A.load(a, 0);
