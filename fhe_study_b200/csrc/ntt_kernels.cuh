@@ -52,6 +52,26 @@ __host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 5); }
 // one pad word per 128 bytes: every 32 words of 4 bytes, every 16 words of 8 bytes
 template <int WB> __host__ __device__ constexpr int pad_idx_w(int i) { return i + (i >> (WB == 4 ? 5 : 4)); }
 
+// Shared-memory padding of the exchanges.  Default: one pad word per 128 bytes (pad_idx_w).  Fermat32 with 32 coefficients
+// per thread pads FOUR words per 32 instead: in the layout of the last pass (nL = 0) a thread then owns 32 consecutive words
+// starting at a multiple of 36 -- 16-byte aligned, and eight such rows land on 32 distinct banks (36 t mod 32 = 4 t) -- so
+// that side of an exchange is eight 128-bit accesses instead of thirty-two 32-bit ones.  The other layouts keep their 32
+// lanes inside one 32-word row (nL >= 5), where any per-row constant pad is conflict-free.
+#ifndef FHE_NTT_VEC_EXCH
+#define FHE_NTT_VEC_EXCH 1
+#endif
+template <class M, int LOGN, int LOGE> struct PadRule {
+    typedef NttShape<LOGN, LOGE> S;
+    static constexpr int WB = (int)sizeof(typename M::W), SH = WB == 4 ? 5 : 4;
+    static constexpr bool VEC = FHE_NTT_VEC_EXCH != 0 && M::RADIX4 && WB == 4 && LOGE == 5 && S::P >= 2 && S::g(S::P - 1) == LOGE &&
+                                S::nL(S::P - 2) >= 5;
+    static constexpr int K = VEC ? 4 : 1;
+    __host__ __device__ static constexpr int idx(int i) { return i + K * (i >> SH); }
+    static constexpr int padn = S::N + K * (S::N >> SH);
+    // pass whose layout gives every thread E consecutive words
+    __host__ __device__ static constexpr bool row_layout(int p) { return VEC && S::nL(p) == 0 && S::g(p) == LOGE; }
+};
+
 template <int T> __device__ __forceinline__ void group_sync() {
     if (T <= 32) __syncwarp(); else __syncthreads();
 }
@@ -65,6 +85,37 @@ template <int LOGN, int LOGE, int FROM, int TO> struct ExchScope {
     static constexpr int A = FROM < TO ? FROM : TO, B = FROM < TO ? TO : FROM;
     static constexpr bool in_warp = S::T <= 32 || (B == A + 1 && S::g(A) == S::g(B) && S::nL(A) <= 5 && S::T % 32 == 0);
 };
+
+// one side of an exchange: the thread's E registers <-> its words of layout P (base = the thread's first word)
+template <class M, int LOGN, int LOGE, int P>
+__device__ __forceinline__ void exch_put(const typename M::W (&x)[1 << LOGE], typename M::W *base) {
+    typedef NttShape<LOGN, LOGE> S;
+    typedef PadRule<M, LOGN, LOGE> PR;
+    if constexpr (PR::row_layout(P)) {
+        uint4 *v = reinterpret_cast<uint4 *>(base);
+#pragma unroll
+        for (int e = 0; e < S::E; e += 4) v[e >> 2] = make_uint4(x[e], x[e + 1], x[e + 2], x[e + 3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < S::E; e++) base[PR::idx(S::pos(P, 0, e))] = x[e];
+    }
+}
+template <class M, int LOGN, int LOGE, int P>
+__device__ __forceinline__ void exch_get(typename M::W (&x)[1 << LOGE], const typename M::W *base) {
+    typedef NttShape<LOGN, LOGE> S;
+    typedef PadRule<M, LOGN, LOGE> PR;
+    if constexpr (PR::row_layout(P)) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(base);
+#pragma unroll
+        for (int e = 0; e < S::E; e += 4) {
+            const uint4 q = v[e >> 2];
+            x[e] = q.x; x[e + 1] = q.y; x[e + 2] = q.z; x[e + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < S::E; e++) x[e] = base[PR::idx(S::pos(P, 0, e))];
+    }
+}
 
 // registers (layout of pass FROM) -> shared -> registers (layout of pass TO).
 // LEAD = false drops the barrier in front of the writes: allowed when this thread's previous access to `sm` was
@@ -81,17 +132,15 @@ __device__ __forceinline__ void exchange(typename M::W (&x)[1 << LOGE], typename
     // pos(p, tid, e) = pos(p, tid, 0) | pos(p, 0, e) on disjoint bits (tid < T = 2^k and e >> g select different bits
     // of the group index), and i + (i >> 5) is additive over disjoint bits: thread base + compile-time offset, so
     // every STS/LDS below takes an immediate offset instead of per-element LOP3/LEA address arithmetic.
-    constexpr int WB = (int)sizeof(typename M::W);
-    const int bf = pad_idx_w<WB>(S::pos(FROM, tid, 0)), bt = pad_idx_w<WB>(S::pos(TO, tid, 0));
-#pragma unroll
-    for (int e = 0; e < S::E; e++) sm[bf + pad_idx_w<WB>(S::pos(FROM, 0, e))] = x[e];
+    typedef PadRule<M, LOGN, LOGE> PR;
+    const int bf = PR::idx(S::pos(FROM, tid, 0)), bt = PR::idx(S::pos(TO, tid, 0));
+    exch_put<M, LOGN, LOGE, FROM>(x, sm + bf);
 #ifdef FHE_NTT_FULL_SYNC
     group_sync<S::T>();
 #else
     if constexpr (ExchScope<LOGN, LOGE, FROM, TO>::in_warp) __syncwarp(); else __syncthreads();
 #endif
-#pragma unroll
-    for (int e = 0; e < S::E; e++) x[e] = sm[bt + pad_idx_w<WB>(S::pos(TO, 0, e))];
+    exch_get<M, LOGN, LOGE, TO>(x, sm + bt);
 }
 
 // the same for two register sets through two buffers: one barrier orders both
@@ -100,17 +149,13 @@ __device__ __forceinline__ void exchange2(typename M::W (&x)[1 << LOGE], typenam
                                           typename M::W *smy, int tid) {
     typedef NttShape<LOGN, LOGE> S;
     if constexpr (LEAD) group_sync<S::T>();
-    constexpr int WB = (int)sizeof(typename M::W);
-    const int bf = pad_idx_w<WB>(S::pos(FROM, tid, 0)), bt = pad_idx_w<WB>(S::pos(TO, tid, 0));
-#pragma unroll
-    for (int e = 0; e < S::E; e++) smx[bf + pad_idx_w<WB>(S::pos(FROM, 0, e))] = x[e];
-#pragma unroll
-    for (int e = 0; e < S::E; e++) smy[bf + pad_idx_w<WB>(S::pos(FROM, 0, e))] = y[e];
+    typedef PadRule<M, LOGN, LOGE> PR;
+    const int bf = PR::idx(S::pos(FROM, tid, 0)), bt = PR::idx(S::pos(TO, tid, 0));
+    exch_put<M, LOGN, LOGE, FROM>(x, smx + bf);
+    exch_put<M, LOGN, LOGE, FROM>(y, smy + bf);
     if constexpr (ExchScope<LOGN, LOGE, FROM, TO>::in_warp) __syncwarp(); else __syncthreads();
-#pragma unroll
-    for (int e = 0; e < S::E; e++) x[e] = smx[bt + pad_idx_w<WB>(S::pos(TO, 0, e))];
-#pragma unroll
-    for (int e = 0; e < S::E; e++) y[e] = smy[bt + pad_idx_w<WB>(S::pos(TO, 0, e))];
+    exch_get<M, LOGN, LOGE, TO>(x, smx + bt);
+    exch_get<M, LOGN, LOGE, TO>(y, smy + bt);
 }
 template <class M, int LOGN, int LOGE, int PASS = 0, bool FIRST = true>
 __device__ __forceinline__ void fwd_chain2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LOGE], typename M::W *smx,
@@ -339,7 +384,7 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
                                    : CT_ == 512 ? FHE_NTT_MINB_512 : 0);
     // dynamic shared memory of one CTA, in words of M::W
     static constexpr size_t words = (size_t)KernelGeom<LOGN, LOGE>::PPC *
-        ((MODE == MODE_MUL2 ? 2 : 1) * KernelGeom<LOGN, LOGE>::template padn<sizeof(typename M::W)>() + (on ? NttShape<LOGN, LOGE>::N : 0));
+        ((MODE == MODE_MUL2 ? 2 : 1) * PadRule<M, LOGN, LOGE>::padn + (on ? NttShape<LOGN, LOGE>::N : 0));
 };
 
 // I/O dispatch of the kernels below: plain words or the packed format (`bits` is only read by the latter)
@@ -364,7 +409,7 @@ ntt_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, co
     typedef KernelGeom<LOGN, LOGE> G;
     typedef typename M::W W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int PADW = G::template padn<sizeof(W)>();
+    constexpr int PADW = PadRule<M, LOGN, LOGE>::padn;
     const int slot = threadIdx.x / S::T, tid = threadIdx.x % S::T;
     W *sm = reinterpret_cast<W *>(smem_raw) + (size_t)slot * PADW;
     const size_t poly = (size_t)blockIdx.x * G::PPC + slot;
@@ -498,7 +543,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #endif
 template <class M, int LOGN, int LOGE, typename IOW> struct StagedGeom {
     typedef NttShape<LOGN, LOGE> S;
-    static constexpr int PADW = KernelGeom<LOGN, LOGE>::template padn<sizeof(typename M::W)>();
+    static constexpr int PADW = PadRule<M, LOGN, LOGE>::padn;
     static constexpr size_t exch_bytes = ((size_t)PADW * sizeof(typename M::W) + 15) / 16 * 16;
     static constexpr size_t smem = exch_bytes + (size_t)S::N * sizeof(IOW);
     static constexpr bool fits = S::T >= 128 && S::T <= 1024 && smem <= 227 * 1024;
