@@ -44,7 +44,7 @@ template <int LOGN, int K1, int CT_ = 256> struct XpGeom {
     static_assert(CT == 256 || (CT == 512 && xp_has_pair(LOGN, K1)), "512 threads: n = 1024, k = 1 only");
     static constexpr int SLOTS = CT / S::T;             // concurrent NTTs
     static constexpr int ND = K1 * 64;                  // digit polynomials per accumulator
-    static constexpr int PADN = N + (N >> 5);
+    static constexpr int PADN = Pad32<LOGN, LOGE>::padn;   // ntt_kernels.cuh: PadRule
     // The decomposed inputs are kept as BIT PLANES: row (accumulator, component, thread tn of a digit transform) holds
     // 64 words, word j = the 32 coefficients that thread owns in digit (component, j), bit 8*o + jj = register slot
     // oct_slot(o, jj) (xp_octet.cuh).  One pad word per row: rows are written along j and read along tn.
@@ -178,7 +178,8 @@ __device__ __forceinline__ void digit_ntt(const typename XpGeom<LOGN, K1, CT>::M
     digit_pass0<LOGN>(x, w, tab_lo, tab_hi, tid, ms, twf);
     if constexpr (S::P > 1) fwd_chain<typename G::Mod, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
 #pragma unroll
-    for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = ms.fold27(x[e]);
+    for (int e = 0; e < S::E; e++) x[e] = ms.fold27(x[e]);
+    exch_put<Lazy32, LOGN, LOGE, LAST>(x, sm + Pad32<LOGN, LOGE>::idx(S::pos(LAST, tid, 0)));
 }
 
 template <int LOGN, int K1, bool CHAIN, int CT>
@@ -304,7 +305,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
                     for (int aa = 0; aa < A; aa++)
 #pragma unroll
                         for (int sl = 0; sl < G::NPOS; sl++)
-                            dv[aa][sl] = xch[(size_t)(dd * A + aa) * G::PADN + pad_idx(G::slot_pos(t, sl))];
+                            dv[aa][sl] = xch[(size_t)(dd * A + aa) * G::PADN + Pad32<LOGN, LOGE>::idx(G::slot_pos(t, sl))];
 #pragma unroll
                     for (int v = 0; v < Q; v++) {
                         const u32 k4[4] = {kq[h2][v].x, kq[h2][v].y, kq[h2][v].z, kq[h2][v].w};
@@ -331,7 +332,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
             for (int m = 0; m < G::IPT; m++) {
                 const int item = G::item(t, m);
                 if (item < G::ITEMS)
-                    xch[(size_t)(aa * G::UNITS + (item >> LOGN)) * G::PADN + pad_idx(item & (N - 1))] = reduce64(acc[aa][m], ml.q, X.mu[r]);
+                    xch[(size_t)(aa * G::UNITS + (item >> LOGN)) * G::PADN + Pad32<LOGN, LOGE>::idx(item & (N - 1))] = reduce64(acc[aa][m], ml.q, X.mu[r]);
             }
         __syncthreads();
         // warp-uniform condition: every lane of a warp that owns at least one live slot runs the transform
@@ -339,8 +340,7 @@ extprod_fused_kernel(const __grid_constant__ XpParams X, const u64 *__restrict__
         if ((t & ~31) / S::T < A * G::UNITS) {
             const TwSrc<Lazy32> twi = {X.P[r].c_inv, X.P[r].inv};
             u32 x[S::E];
-#pragma unroll
-            for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(LAST, tid, e))];
+            exch_get<Lazy32, LOGN, LOGE, LAST>(x, sm + Pad32<LOGN, LOGE>::idx(S::pos(LAST, tid, 0)));
             inv_chain<Lazy32, LOGN, LOGE, LAST>(x, sm, tid, ml, twi, X.P[r].ninv, X.P[r].s_ninv);
             if (slot < A * G::UNITS) {
                 u32 *R = (r == 0 ? res1 : res2) + (size_t)slot * N;

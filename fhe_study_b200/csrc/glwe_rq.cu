@@ -118,7 +118,7 @@ template <int LOGN, int K1> struct KsGeom {
     typedef NttShape<LOGN, LOGE> S;
     static constexpr int CT = 256;
     static constexpr int SLOTS = CT / S::T;
-    static constexpr int PADN = N + (N >> 5);
+    static constexpr int PADN = Pad32<LOGN, LOGE>::padn;   // ntt_kernels.cuh: PadRule
     static constexpr int ITEMS = K1 * N;                 // (component, position)
     static constexpr int IPT = (ITEMS + CT - 1) / CT;
     static constexpr int IPT4 = (IPT + 3) / 4 * 4;
@@ -197,8 +197,7 @@ glwe_ks_fused_kernel(const __grid_constant__ KsParams X, const u64 *__restrict__
             }
             fwd_pass<Small32, LOGN, LOGE, 0, 1>(x, tid, ms, twf);
             if constexpr (S::P > 1) fwd_chain<Small32, LOGN, LOGE, 1>(x, sm, tid, ms, twf);
-#pragma unroll
-            for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = x[e];  // < (2 LOGN + 1) q: no reduction needed
+            exch_put<Lazy32, LOGN, LOGE, LAST>(x, sm + Pad32<LOGN, LOGE>::idx(S::pos(LAST, tid, 0)));  // < (2 LOGN + 1) q: no reduction needed
         }
         __syncthreads();
         const int nd = min(G::DPR, (int)X.nd - round * G::DPR);
@@ -217,7 +216,7 @@ glwe_ks_fused_kernel(const __grid_constant__ KsParams X, const u64 *__restrict__
 #pragma unroll
                 for (int m = 0; m < G::IPT; m++) {
                     const int item = t + G::CT * m;
-                    acc[aa][m] += (u64)D[pad_idx(item & (N - 1))] * rv[m];  // key padding beyond ITEMS is zero
+                    acc[aa][m] += (u64)D[Pad32<LOGN, LOGE>::idx(item & (N - 1))] * rv[m];  // key padding beyond ITEMS is zero
                 }
             }
         }
@@ -233,15 +232,14 @@ glwe_ks_fused_kernel(const __grid_constant__ KsParams X, const u64 *__restrict__
                 const u64 a = acc[aa][m];
                 u64 r = a - __umul64hi(a, X.mu) * ms.q;
                 if (r >= ms.q) r -= ms.q;
-                xch[(size_t)(aa * K1 + (item >> LOGN)) * G::PADN + pad_idx(item & (N - 1))] = (u32)r;
+                xch[(size_t)(aa * K1 + (item >> LOGN)) * G::PADN + Pad32<LOGN, LOGE>::idx(item & (N - 1))] = (u32)r;
             }
         }
     __syncthreads();
     if ((t & ~31) / S::T < A * K1) {  // whole warps run the transform (see extprod_fused.cu)
         const TwSrc<Small32> twi = {X.P.c_inv, X.P.inv};
         u32 x[S::E];
-#pragma unroll
-        for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(LAST, tid, e))];
+        exch_get<Lazy32, LOGN, LOGE, LAST>(x, sm + Pad32<LOGN, LOGE>::idx(S::pos(LAST, tid, 0)));
         inv_chain<Small32, LOGN, LOGE, LAST>(x, sm, tid, ms, twi, X.P.ninv, X.P.s_ninv);
         const int aa = slot / K1, c = slot % K1;
         if (slot < A * K1 && aa < na) {

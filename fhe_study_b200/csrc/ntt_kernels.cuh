@@ -45,15 +45,10 @@ template <int LOGN, int LOGE> struct KernelGeom {
 #endif
     static constexpr int CT = S::T > FHE_NTT_MIN_CT ? S::T : FHE_NTT_MIN_CT;   // threads per CTA
     static constexpr int PPC = CT / S::T;                // polynomials per CTA
-    template <int WB> __host__ __device__ static constexpr int padn() { return S::N + (S::N >> (WB == 4 ? 5 : 4)); }  // padded words per polynomial in smem
-    static constexpr int PADN = padn<4>();
 };
-__host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 5); }
-// one pad word per 128 bytes: every 32 words of 4 bytes, every 16 words of 8 bytes
-template <int WB> __host__ __device__ constexpr int pad_idx_w(int i) { return i + (i >> (WB == 4 ? 5 : 4)); }
 
-// Shared-memory padding of the exchanges.  Default: one pad word per 128 bytes (pad_idx_w).  Fermat32 with 32 coefficients
-// per thread pads FOUR words per 32 instead: in the layout of the last pass (nL = 0) a thread then owns 32 consecutive words
+// Shared-memory padding of the exchanges.  Default: one pad word per 128 bytes.  32-bit words with 32 coefficients per
+// thread (and a last pass of five stages) pad FOUR words per 32 instead: in the layout of the last pass (nL = 0) a thread then owns 32 consecutive words
 // starting at a multiple of 36 -- 16-byte aligned, and eight such rows land on 32 distinct banks (36 t mod 32 = 4 t) -- so
 // that side of an exchange is eight 128-bit accesses instead of thirty-two 32-bit ones.  The other layouts keep their 32
 // lanes inside one 32-word row (nL >= 5), where any per-row constant pad is conflict-free.
@@ -63,7 +58,7 @@ template <int WB> __host__ __device__ constexpr int pad_idx_w(int i) { return i 
 template <class M, int LOGN, int LOGE> struct PadRule {
     typedef NttShape<LOGN, LOGE> S;
     static constexpr int WB = (int)sizeof(typename M::W), SH = WB == 4 ? 5 : 4;
-    static constexpr bool VEC = FHE_NTT_VEC_EXCH != 0 && M::RADIX4 && WB == 4 && LOGE == 5 && S::P >= 2 && S::g(S::P - 1) == LOGE &&
+    static constexpr bool VEC = FHE_NTT_VEC_EXCH != 0 && WB == 4 && LOGE == 5 && S::P >= 2 && S::g(S::P - 1) == LOGE &&
                                 S::nL(S::P - 2) >= 5;
     static constexpr int K = VEC ? 4 : 1;
     __host__ __device__ static constexpr int idx(int i) { return i + K * (i >> SH); }
@@ -71,6 +66,10 @@ template <class M, int LOGN, int LOGE> struct PadRule {
     // pass whose layout gives every thread E consecutive words
     __host__ __device__ static constexpr bool row_layout(int p) { return VEC && S::nL(p) == 0 && S::g(p) == LOGE; }
 };
+
+// the rule for 4-byte words, for the fused kernels that keep transform outputs in the exchange slots (extprod_fused.cu,
+// tn_fused.cu, glwe_rq.cu): the policy only contributes its word size
+template <int LOGN, int LOGE> using Pad32 = PadRule<Lazy32, LOGN, LOGE>;
 
 template <int T> __device__ __forceinline__ void group_sync() {
     if (T <= 32) __syncwarp(); else __syncthreads();

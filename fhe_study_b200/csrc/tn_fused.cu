@@ -23,7 +23,7 @@ template <int LOGN> struct TnGeom {
     static constexpr int CT = 256;
     static constexpr int SLOTS = CT / S::T;
     static constexpr int G = SLOTS / 8;                  // products per CTA
-    static constexpr int PADN = N + (N >> 5);
+    static constexpr int PADN = Pad32<LOGN, LOGE>::padn;   // ntt_kernels.cuh: PadRule
     static constexpr int IPT = G * N / CT;               // positions per thread in the pointwise step
     static constexpr size_t SMEM = (size_t)G * 2 * N * 8 + (size_t)SLOTS * PADN * 4 + (size_t)G * 4 * N * 4;
     static_assert(S::T <= 32 && SLOTS % 8 == 0 && (G * N) % CT == 0, "unsupported ring degree for the fused Tn product");
@@ -83,13 +83,14 @@ tn_mul_fused_kernel(const __grid_constant__ TnParams X, const u64 *__restrict__ 
             fwd_chain<Small32, LOGN, LOGE>(x, sm, tid, ms, twf);
             // csub-free butterflies: x < 2^16 + 2*LOGN*p < 2^32; partial reduction below 2^28 (see extprod_fused.cu)
 #pragma unroll
-            for (int e = 0; e < S::E; e++) sm[pad_idx(S::pos(LAST, tid, e))] = x[e] - (x[e] >> 27) * ms.q;
+            for (int e = 0; e < S::E; e++) x[e] = x[e] - (x[e] >> 27) * ms.q;
+            exch_put<Lazy32, LOGN, LOGE, LAST>(x, sm + Pad32<LOGN, LOGE>::idx(S::pos(LAST, tid, 0)));
         }
         __syncthreads();
         // limb convolution: class w = sum_{u+v=w} A_u * B_v (only w <= 3 reaches the low 64 bits of the product)
 #pragma unroll
         for (int m = 0; m < G::IPT; m++) {
-            const int item = t + G::CT * m, g = item >> LOGN, p = pad_idx(item & (N - 1));
+            const int item = t + G::CT * m, g = item >> LOGN, p = Pad32<LOGN, LOGE>::idx(item & (N - 1));
             u32 *base = xch + (size_t)g * 8 * G::PADN + p;
             u32 A[4], B[4];
 #pragma unroll
@@ -116,8 +117,7 @@ tn_mul_fused_kernel(const __grid_constant__ TnParams X, const u64 *__restrict__ 
         if (S::T < 8 || (slot & 7) < 4) {
             const TwSrc<Lazy32> twi = {X.P[r].c_inv, X.P[r].inv};
             u32 x[S::E];
-#pragma unroll
-            for (int e = 0; e < S::E; e++) x[e] = sm[pad_idx(S::pos(LAST, tid, e))];
+            exch_get<Lazy32, LOGN, LOGE, LAST>(x, sm + Pad32<LOGN, LOGE>::idx(S::pos(LAST, tid, 0)));
             inv_chain<Lazy32, LOGN, LOGE, LAST>(x, sm, tid, ml, twi, X.P[r].ninv, X.P[r].s_ninv);
             if ((slot & 7) < 4) {
                 // residues mod p1 go to res1, mod p2 to the (now dead) B-limb slot of the same product and limb
