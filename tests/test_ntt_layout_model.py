@@ -33,6 +33,9 @@ def test_split_rule():
 @pytest.mark.parametrize("logn", [10, 12, 13, 14, 15])
 def test_default_32bit_shapes_are_conflict_free(logn):
     # 32 coefficients per thread (the default of every 32-bit degree but N=2048)
+    # ... under PadRule (csrc/ntt_kernels.cuh): four pad words per 32, the last pass read and written as aligned
+    # 128-bit rows of a thread's 32 consecutive words
+    assert M.pad_rule(logn, 5, 4) == (4, True)
     gs, worst = M.conflicts(logn, 5, word_bytes=4)
     assert max(worst.values()) == 1, (gs, worst)
 

@@ -117,22 +117,42 @@ def model_fwd(a, q, roots, LOGN, LOGE, inverse=False, roots_inv=None, n_inv=None
     return mem
 
 
+def pad_rule(LOGN, LOGE, word_bytes=4):
+    """(pad words per row, vectorised) as PadRule in csrc/ntt_kernels.cuh: 4-byte words with 32 coefficients per thread
+    and a five-stage last pass pad FOUR words per 32 and access the last-pass layout (a thread's 32 consecutive words)
+    with 128-bit instructions; everything else pads one word per 128 bytes."""
+    gs = split(LOGN, LOGE)
+    P = len(gs)
+    nL = [LOGN - sum(gs[: p + 1]) for p in range(P)]
+    vec = word_bytes == 4 and LOGE == 5 and P >= 2 and gs[-1] == LOGE and nL[P - 2] >= 5
+    return (4 if vec else 1), vec
+
+
 def conflicts(LOGN, LOGE, word_bytes=4):
-    """worst bank-conflict degree of each pass layout (1 = conflict-free) under the kernel's padding: one pad word
-    per 128 bytes (i + i/32 for 4-byte words, i + i/16 for 8-byte words; an 8-byte access is served per half-warp)"""
+    """worst bank-conflict degree of each pass layout (1 = conflict-free) under the kernels' padding (pad_rule; an
+    8-byte access is served per half-warp, a 16-byte access per quarter-warp)"""
     gs = split(LOGN, LOGE)
     E, T = 1 << LOGE, 1 << (LOGN - LOGE)
     lanes, banks_n, pad_shift = (32, 32, 5) if word_bytes == 4 else (16, 16, 4)
+    K, vec = pad_rule(LOGN, LOGE, word_bytes)
+    pad = lambda i: i + K * (i >> pad_shift)
     worst = {}
     for p in range(len(gs)):
         w = 0
-        for t0 in range(0, T, lanes):
-            lays = [layout(LOGN, LOGE, gs, p, t) for t in range(t0, min(t0 + lanes, T))]
-            for e in range(E):
+        row = vec and p == len(gs) - 1   # 128-bit accesses: 8 threads per phase, 4 consecutive words each
+        step = 8 if row else lanes
+        for t0 in range(0, T, step):
+            lays = [layout(LOGN, LOGE, gs, p, t) for t in range(t0, min(t0 + step, T))]
+            for e in range(0, E, 4 if row else 1):
                 banks = Counter()
                 for lay in lays:
-                    idx = lay[e][0]
-                    banks[(idx + (idx >> pad_shift)) % banks_n] += 1
+                    if row:
+                        base = pad(lay[e][0])
+                        assert base % 4 == 0 and [pad(lay[e + j][0]) for j in range(4)] == [base + j for j in range(4)]
+                        for j in range(4):
+                            banks[(base + j) % banks_n] += 1
+                    else:
+                        banks[pad(lay[e][0]) % banks_n] += 1
                 w = max(w, max(banks.values()))
         worst[p] = w
     return gs, worst
