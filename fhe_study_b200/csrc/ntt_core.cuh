@@ -52,16 +52,23 @@ template <int LOGN, int LOGE> struct NttShape {
 // Device twiddle-table order.  The reference stores stage s (m = 2^s) at roots[2^s + j], j = (H << ls) + hi
 // for the butterfly block H of pass p (ls = s - s0(p)).  Threads of a warp differ in H, so reading that
 // order would touch a different cache line per lane.  The device tables therefore keep stage s at
-//   2^s + (hi << s0(p)) + H
-// (a rotation of the index bits inside each stage block, identity for pass 0), which makes every warp
-// load lane-contiguous.  tw_slot() is the host-side map reference index -> device slot.
+//   2^s + (hi << s0(p)) + H                                  (pass 0, the first stage of every pass, 64-bit policies)
+//   2^s + ((hi >> 1) << (s0(p) + 1)) + (H << 1) + (hi & 1)   (later stages of later passes, 32-bit policies)
+// (a rotation of the index bits inside each stage block, identity for pass 0), which makes every warp load
+// lane-contiguous AND puts the twiddles of hi = 2m, 2m+1 side by side: a thread always needs both (the two children of
+// a radix-4 block, two neighbouring blocks of a radix-2 stage), so 32-bit policies fetch them with ONE 128-bit load
+// (tw_pair).  Measured with a throw-away build that simply skipped every second twiddle load: N = 1024 polymul +4 %,
+// N = 4096 +6.5 % -- the loads' issue slots and LSU queue entries, not their bytes, were what cost.  (A pair of 64-bit
+// twiddles is 32 bytes: two loads either way, and side by side each of them would use half of every cache line it
+// touches -- measured -3.5 % at N = 4096 -- so the 64-bit policies keep the first order.)
+// tw_slot() is the host-side map reference index -> device slot; tw_idx() the device-side one.
 inline int ntt_num_passes(int logn, int loge) { return (logn + loge - 1) / loge; }
 inline int ntt_pass_s0(int logn, int loge, int p) {
     const int P = ntt_num_passes(logn, loge), base = logn / P, rem = logn % P;
     if (ntt_front_rem(P)) return p == 0 ? 0 : (logn - (P - 1) * loge) + (p - 1) * loge;
     return p * base + (p < rem ? p : rem);
 }
-inline u64 tw_slot(int logn, int loge, u64 ref_index) {
+inline u64 tw_slot(int logn, int loge, u64 ref_index, bool paired) {
     if (ref_index == 0) return 0;
     int s = 0;
     while ((2ull << s) <= ref_index) s++;  // 2^s <= ref_index < 2^(s+1)
@@ -70,7 +77,8 @@ inline u64 tw_slot(int logn, int loge, u64 ref_index) {
     while (p + 1 < P && ntt_pass_s0(logn, loge, p + 1) <= s) p++;
     const int s0 = ntt_pass_s0(logn, loge, p), ls = s - s0;
     const u64 j = ref_index - (1ull << s), H = j >> ls, hi = j & ((1ull << ls) - 1);
-    return (1ull << s) + (hi << s0) + H;
+    if (!paired || p == 0 || ls == 0) return (1ull << s) + (hi << s0) + H;
+    return (1ull << s) + ((hi >> 1) << (s0 + 1)) + (H << 1) + (hi & 1);   // pairs (2m, 2m+1) of hi side by side (tw_idx)
 }
 // coefficients per thread (log2): 32 for 32-bit words, 16 for 64-bit words (register budget of the
 // polymul kernel, which keeps NTT(a) in registers while transforming b)
@@ -114,6 +122,56 @@ template <class M, int LOGN> FHE_HD typename M::T tw_load(const TwSrc<M> &tw, in
     }
 }
 
+// device slot of the twiddle of local stage LS (global stage s0 + LS), block index hi, butterfly-group row H
+template <class M> FHE_HD constexpr bool tw_paired() { return sizeof(typename M::T) == 8; }
+template <class M, int PASS, int S0, int LS> FHE_HD constexpr int tw_idx(int hi, int H) {
+    return (!tw_paired<M>() || PASS == 0 || LS == 0) ? (1 << (S0 + LS)) + (hi << S0) + H
+                                                     : (1 << (S0 + LS)) + ((hi >> 1) << (S0 + 1)) + (H << 1) + (hi & 1);
+}
+// the twiddles of blocks hi (even) and hi + 1 of local stage LS >= 1: one vector load where they sit side by side
+template <class M, int LOGN, int PASS, int S0, int LS>
+FHE_HD void tw_pair(const TwSrc<M> &tw, int hi, int H, typename M::T &t0, typename M::T &t1) {
+    static_assert(LS >= 1, "a stage with one twiddle per row has no pairs");
+    const int i = tw_idx<M, PASS, S0, LS>(hi, H), j = tw_idx<M, PASS, S0, LS>(hi + 1, H);
+    if constexpr (PASS == 0) {
+        t0 = tw.c0[i];
+        t1 = tw.c0[j];
+    } else {
+#if defined(__CUDA_ARCH__)
+        if constexpr (tw_paired<M>()) {   // j == i + 1, i even
+            bool done = false;
+            if constexpr (M::RADIX4) {
+                if constexpr (M::compact(LOGN)) {
+                    const uint2 w = *reinterpret_cast<const uint2 *>(tw.tabw + i);
+                    t0 = typename M::T{w.x, (w.x << 16) - w.x};
+                    t1 = typename M::T{w.y, (w.y << 16) - w.y};
+                    done = true;
+                }
+            }
+            if (!done) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(tw.tab + i);
+                t0 = typename M::T{q.x, q.y};
+                t1 = typename M::T{q.z, q.w};
+            }
+            return;
+        }
+#endif
+        t0 = tw_load<M, LOGN>(tw, i);
+        t1 = tw_load<M, LOGN>(tw, j);
+    }
+}
+// twiddle of block hi of a stage: fetched as the pair (hi, hi + 1) when hi is even, remembered in tp for hi + 1
+template <class M, int LOGN, int PASS, int S0, int LS>
+FHE_HD typename M::T stage_tw(const TwSrc<M> &tw, int hi, int H, typename M::T (&tp)[2]) {
+    if constexpr (LS == 0) {
+        const int i = tw_idx<M, PASS, S0, 0>(0, H);
+        return (PASS == 0) ? tw.c0[i] : tw_load<M, LOGN>(tw, i);
+    } else {
+        if ((hi & 1) == 0) tw_pair<M, LOGN, PASS, S0, LS>(tw, hi, H, tp[0], tp[1]);
+        return tp[hi & 1];
+    }
+}
+
 // One butterfly stage (local stage LS of pass PASS) over the thread's registers.  All trip counts are
 // compile-time constants so the register array never gets dynamically indexed.
 template <class M, int LOGN, int LOGE, int PASS, int LS>
@@ -124,11 +182,11 @@ FHE_HD void fwd_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
 #pragma unroll
     for (int qi = 0; qi < (S::E >> g); qi++) {
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);  // pass 0: u < 2^nL
+        typename M::T tp[2];
 #pragma unroll
         for (int hi = 0; hi < (1 << LS); hi++) {
             // reference index (1<<s) + (H<<LS) + hi, stored at the lane-contiguous slot (see tw_slot)
-            const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
-            const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw_load<M, LOGN>(tw, twi);
+            const typename M::T t = stage_tw<M, LOGN, PASS, s0, LS>(tw, hi, H, tp);
 #pragma unroll
             for (int lo = 0; lo < half; lo++) {
                 const int ru = (hi << (g - LS)) | lo;
@@ -162,13 +220,12 @@ FHE_HD void fwd_stage4(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LO
 #pragma unroll
     for (int qi = 0; qi < (S::E >> g); qi++) {
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
+        typename M::T tp[2];
 #pragma unroll
         for (int hi = 0; hi < (1 << LS); hi++) {
-            const int i1 = (1 << (s0 + LS)) + (hi << s0) + H;
-            const int i2 = (1 << (s0 + LS + 1)) + ((2 * hi) << s0) + H, i3 = i2 + (1 << s0);
-            const typename M::T t1 = (PASS == 0) ? tw.c0[i1] : tw_load<M, LOGN>(tw, i1);
-            const typename M::T t2 = (PASS == 0) ? tw.c0[i2] : tw_load<M, LOGN>(tw, i2);
-            const typename M::T t3 = (PASS == 0) ? tw.c0[i3] : tw_load<M, LOGN>(tw, i3);
+            const typename M::T t1 = stage_tw<M, LOGN, PASS, s0, LS>(tw, hi, H, tp);
+            typename M::T t2, t3;   // the children 2 hi and 2 hi + 1 (the latter's slot holds parent * child)
+            tw_pair<M, LOGN, PASS, s0, LS + 1>(tw, 2 * hi, H, t2, t3);
 #pragma unroll
             for (int lo = 0; lo < h; lo++) {
                 const int b = qi * G + (hi << (g - LS)) + lo;
@@ -203,10 +260,10 @@ FHE_HD void fwd_stage2(typename M::W (&x)[1 << LOGE], typename M::W (&y)[1 << LO
 #pragma unroll
     for (int qi = 0; qi < (S::E >> g); qi++) {
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
+        typename M::T tp[2];
 #pragma unroll
         for (int hi = 0; hi < (1 << LS); hi++) {
-            const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
-            const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw_load<M, LOGN>(tw, twi);
+            const typename M::T t = stage_tw<M, LOGN, PASS, s0, LS>(tw, hi, H, tp);
 #pragma unroll
             for (int lo = 0; lo < half; lo++) {
                 const int ru = (hi << (g - LS)) | lo;
@@ -243,6 +300,7 @@ FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
 #pragma unroll
     for (int qi = 0; qi < (S::E >> g); qi++) {
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
+        typename M::T tp[2];
 #pragma unroll
         for (int hi = 0; hi < (1 << LS); hi++) {
             if constexpr (PASS == 0 && LS == 0) {
@@ -250,8 +308,7 @@ FHE_HD void inv_stage(typename M::W (&x)[1 << LOGE], int tid, const M &m, const 
                 for (int lo = 0; lo < half; lo++)
                     m.template inv_last_k<K>(x[qi * G + lo], x[qi * G + lo + half], ninv, s_ninv);
             } else {
-                const int twi = (1 << (s0 + LS)) + (hi << s0) + H;
-                const typename M::T t = (PASS == 0) ? tw.c0[twi] : tw_load<M, LOGN>(tw, twi);
+                const typename M::T t = stage_tw<M, LOGN, PASS, s0, LS>(tw, hi, H, tp);
 #pragma unroll
                 for (int lo = 0; lo < half; lo++) {
                     const int ru = (hi << (g - LS)) | lo;
@@ -324,13 +381,12 @@ FHE_HD void inv_stage4(typename M::W (&x)[1 << LOGE], int tid, const M &m, const
 #pragma unroll
     for (int qi = 0; qi < (S::E >> g); qi++) {
         const int H = (PASS == 0) ? 0 : ((tid + qi * S::T) >> nL);
+        typename M::T tp[2];
 #pragma unroll
         for (int hi = 0; hi < (1 << LP); hi++) {
-            const int i1 = (1 << (s0 + LP)) + (hi << s0) + H;
-            const int i2 = (1 << (s0 + LS)) + ((2 * hi) << s0) + H, i3 = i2 + (1 << s0);
-            const typename M::T t1 = (PASS == 0) ? tw.c0[i1] : tw_load<M, LOGN>(tw, i1);
-            const typename M::T t2 = (PASS == 0) ? tw.c0[i2] : tw_load<M, LOGN>(tw, i2);
-            const typename M::T t3 = (PASS == 0) ? tw.c0[i3] : tw_load<M, LOGN>(tw, i3);
+            const typename M::T t1 = stage_tw<M, LOGN, PASS, s0, LP>(tw, hi, H, tp);
+            typename M::T t2, t3;
+            tw_pair<M, LOGN, PASS, s0, LS>(tw, 2 * hi, H, t2, t3);
 #pragma unroll
             for (int lo = 0; lo < h; lo++) {
                 const int b = qi * G + (hi << (g - LP)) + lo;

@@ -212,7 +212,7 @@ template <class M> void expand_tables(const HostTables &t, ExpandedTables<M> &x,
         radix4_patch(ri, t.q, logn, loge, true);
     }
     for (u64 i = 0; i < t.n; i++) {
-        const u64 slot = tw_slot(logn, loge, i);
+        const u64 slot = tw_slot(logn, loge, i, sizeof(T) == 8);
         x.fwd[slot] = make_tw((W)rf[i], (W)t.q, (T *)nullptr);
         x.inv[slot] = make_tw((W)ri[i], (W)t.q, (T *)nullptr);
     }
