@@ -365,7 +365,7 @@ struct Fermat32 : Small32 {
 #endif
     static constexpr bool FIRST_SHIFT = FHE_FERMAT_FIRST_SHIFT != 0;
 #ifndef FHE_FERMAT_COMPACT_MIN   // smallest log2 n whose later passes read 4-byte twiddles (ntt_core.cuh: tw_load)
-#define FHE_FERMAT_COMPACT_MIN 13
+#define FHE_FERMAT_COMPACT_MIN 12
 #endif
     FHE_HD static constexpr bool compact(int logn) { return logn >= FHE_FERMAT_COMPACT_MIN; }
 

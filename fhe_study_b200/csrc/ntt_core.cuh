@@ -138,7 +138,10 @@ FHE_HD void tw_pair(const TwSrc<M> &tw, int hi, int H, typename M::T &t0, typena
         t1 = tw.c0[j];
     } else {
 #if defined(__CUDA_ARCH__)
-        if constexpr (tw_paired<M>()) {   // j == i + 1, i even
+        // j == i + 1, i even.  Below n = 1024 a transform is a few threads of a warp (the digit transforms of the fused
+        // torus kernels): the loads are broadcasts, and unpacking a 128-bit load costs IMAD.MOVs on the pipe that binds
+        // there (n = 64, k = 4 external product: 6.93 -> 6.59 M/s with vector loads) -- two adjacent 64-bit loads instead.
+        if constexpr (tw_paired<M>() && LOGN >= 10) {
             bool done = false;
             if constexpr (M::RADIX4) {
                 if constexpr (M::compact(LOGN)) {
@@ -163,9 +166,10 @@ FHE_HD void tw_pair(const TwSrc<M> &tw, int hi, int H, typename M::T &t0, typena
 // twiddle of block hi of a stage: fetched as the pair (hi, hi + 1) when hi is even, remembered in tp for hi + 1
 template <class M, int LOGN, int PASS, int S0, int LS>
 FHE_HD typename M::T stage_tw(const TwSrc<M> &tw, int hi, int H, typename M::T (&tp)[2]) {
-    if constexpr (LS == 0) {
-        const int i = tw_idx<M, PASS, S0, 0>(0, H);
-        return (PASS == 0) ? tw.c0[i] : tw_load<M, LOGN>(tw, i);
+    if constexpr (PASS == 0) {   // constant bank: the operand is read in place, nothing to pair up
+        return tw.c0[tw_idx<M, 0, S0, LS>(hi, H)];
+    } else if constexpr (LS == 0) {
+        return tw_load<M, LOGN>(tw, tw_idx<M, PASS, S0, 0>(0, H));
     } else {
         if ((hi & 1) == 0) tw_pair<M, LOGN, PASS, S0, LS>(tw, hi, H, tp[0], tp[1]);
         return tp[hi & 1];
