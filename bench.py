@@ -41,8 +41,8 @@ WIRE_BITS = 17  # ceil(log2 q): the bit-packed wire of the end-to-end leg
 # 2 radix-2 stages x 512 = 3328, twice; inverse 4 x 256 x 3 + 512 + the n^-1 stage's 1024 = 4608; pointwise 1024.
 # SURVEY 8d's algorithmic count for the same polymul is 17408.
 MODMUL_EXECUTED = 2 * 3328 + 4608 + 1024
-NCU_TRAFFIC_BYTES = 1073865000 + 503086336
-NCU_TRAFFIC_SOURCE = "profiles/r2_polymul_n1024_q65537_u64_fermat32_ncu_full_c.csv (ncu --set full of tools/prof.py polymul 10 65537 65536)"
+NCU_TRAFFIC_BYTES = 1073800000 + 498943744
+NCU_TRAFFIC_SOURCE = "profiles/r2_polymul_n1024_q65537_u64_fermat32_ncu_full_d.csv (ncu --set full of tools/prof.py polymul 10 65537 65536)"
 
 
 def peaks():
@@ -586,7 +586,7 @@ def main():
             "modmul_executed_per_polymul": MODMUL_EXECUTED if N == 1024 else None,
             "executed_frac": (MODMUL_EXECUTED * batch / (kern_ms * 1e-3)) / modmul_peak if N == 1024 else None,
             "peak_source": "fhe_int_peak(1) microbenchmark, this run",
-            "note": "frac counts SURVEY 8d's algorithmic modmuls (17408 per polymul) against the Shoup-modmul peak; the radix-4 Fermat32 kernel executes 12288 twiddle products (executed_frac).  ncu (profiles/r2_polymul_n1024_q65537_u64_fermat32_ncu_full_c.csv): fmaheavy (IMAD) pipe 71 % active (radix-2 Small32 kernel: 81 %), ALU pipe 56 %, LSU 27 %, issue slots 64 %, long-scoreboard the top stall, DRAM 1.577 GB per launch for 1.611 GB algorithmic: co-limited by HBM, the integer pipe and issue",
+            "note": "frac counts SURVEY 8d's algorithmic modmuls (17408 per polymul) against the Shoup-modmul peak; the radix-4 Fermat32 kernel executes 12288 twiddle products (executed_frac).  ncu (profiles/r2_polymul_n1024_q65537_u64_fermat32_ncu_full_d.csv): fmaheavy (IMAD) pipe 73 % active (radix-2 Small32 kernel: 81 %), ALU pipe 56 %, LSU 24 %, issue slots 64 %, long-scoreboard the top stall, DRAM 1.573 GB per launch for 1.611 GB algorithmic: co-limited by HBM, the integer pipe and issue",
         },
         "u32_device_format": {
             "value": value_u32, "unit": "polymul/s", "algorithmic_bytes_per_polymul": 3 * N * 4,
