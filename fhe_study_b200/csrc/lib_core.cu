@@ -111,6 +111,7 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u64 *a, const u64 *b, 
                 int flags, cudaStream_t st) {
     int rc;
     mode = mul_mode_for(plan, mode, flags);
+    if (mode == MODE_MULS && plan->staged == 2) flags |= STAGE_TMA;
     if (plan->fermat) {  // q = 65537: radix-4 butterflies (kind 3, and kind 0 at n = 2^15)
         rc = ntt_launch_fermat32(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st);
         if (!rc) count_launch(1);
@@ -130,6 +131,7 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const u32 *a, const u32 *b, 
                 int flags, cudaStream_t st) {
     int rc;
     mode = mul_mode_for(plan, mode, flags);
+    if (mode == MODE_MULS && plan->staged == 2) flags |= STAGE_TMA;
     if (plan->fermat) {  // q = 65537: radix-4 butterflies (kind 3, and kind 0 at n = 2^15)
         rc = ntt_launch_fermat32_u32(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st);
         if (!rc) count_launch(1);
@@ -151,6 +153,7 @@ int launch_plan(const fhe_ntt_plan *plan, int mode, const pk32 *a, const pk32 *b
                 int flags, cudaStream_t st) {
     int rc;
     mode = mul_mode_for(plan, mode, flags);
+    if (mode == MODE_MULS && plan->staged == 2) flags |= STAGE_TMA;
     if (plan->fermat) {  // q = 65537: radix-4 butterflies (kind 3, and kind 0 at n = 2^15)
         rc = ntt_launch_fermat32_pk(plan->logn, plan->loge, mode, plan->pfm, a, b, c, c_evals, batch, flags, st);
         if (!rc) count_launch(1);
@@ -370,6 +373,7 @@ int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
     //   dual-operand (MODE_MUL2): N=2048 94.9 -> 99.7; slower elsewhere (N=1024 217 -> 199, N=16384 6.75 -> 5.84)
     //   NTT(a) parked in the output row (MODE_MULG): N=16384 6.75 -> 7.76 (two 64-register CTAs per SM); N=8192 unchanged
     //   persistent + cp.async operand staging (MODE_MULS): N=16384 6.75 -> 6.93, N=8192 18.7 -> 15.5: off
+    //   (FHE_NTT_STAGED=2: the same loop with the operands posted as TMA bulk copies by one thread)
     // FHE_NTT_DUAL / FHE_NTT_GPARK / FHE_NTT_STAGED = 0|1 override (tuning knobs and tests).
     const bool w32 = p->kind == 0 || p->kind == 3;
     p->dual = w32 && p->logn == 11;
@@ -377,7 +381,7 @@ int fhe_ntt_plan_create(uint64_t q, uint64_t n, fhe_ntt_plan **out) {
     p->gpark = (w32 && p->logn >= 13) || (!w32 && p->logn == 13);  // 32-bit N=8192: unchanged for the radix-2 kernels, 19.5 -> 19.9 M/s under Fermat32  // 62-bit q, N=8192: 3.89 -> 4.05 M/s; N=16384: 1.86 -> 1.83 (off)
     if (const char *e = getenv("FHE_NTT_GPARK")) p->gpark = atoi(e) != 0;
     p->staged = 0;
-    if (const char *e = getenv("FHE_NTT_STAGED")) p->staged = atoi(e) != 0;
+    if (const char *e = getenv("FHE_NTT_STAGED")) p->staged = atoi(e) < 0 ? 0 : atoi(e) > 2 ? 2 : atoi(e);  // 1: cp.async (LDGSTS), 2: bulk copies (TMA)
     int rc = p->kind == 0 ? upload_tables(p.get(), p->p32)
              : p->kind == 3 ? upload_tables(p.get(), p->psm)
              : p->kind == 1 ? upload_tables(p.get(), p->p64)

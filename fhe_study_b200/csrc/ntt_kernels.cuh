@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "ntt_core.cuh"
+#include "tc_common.cuh"   // mbarrier / cp.async.bulk wrappers (the TMA-staged polymul below)
 
 namespace fhe {
 
@@ -36,7 +37,7 @@ template <class M> struct NttParams {
 //            is the difference between one 512-thread CTA of ~116 registers and two of 64 per SM
 enum NttMode { MODE_FWD = 0, MODE_INV = 1, MODE_MUL = 2, MODE_MUL2 = 3, MODE_MULS = 4, MODE_MULG = 5 };
 __host__ __device__ constexpr bool is_mul_mode(int mode) { return mode >= MODE_MUL; }
-enum MulFlags { A_IS_EVALS = 1, B_IS_EVALS = 2, B_BROADCAST = 4 };  // B_BROADCAST: b is ONE polynomial, used for every product
+enum MulFlags { A_IS_EVALS = 1, B_IS_EVALS = 2, B_BROADCAST = 4, STAGE_TMA = 64 /* internal: MODE_MULS with bulk copies */ };  // B_BROADCAST: b is ONE polynomial, used for every product
 
 template <int LOGN, int LOGE> struct KernelGeom {
     typedef NttShape<LOGN, LOGE> S;
@@ -546,9 +547,15 @@ template <class M, int LOGN, int LOGE, typename IOW> struct StagedGeom {
     static constexpr size_t exch_bytes = ((size_t)PADW * sizeof(typename M::W) + 15) / 16 * 16;
     static constexpr size_t smem = exch_bytes + (size_t)S::N * sizeof(IOW);
     static constexpr bool fits = S::T >= 128 && S::T <= 1024 && smem <= 227 * 1024;
+    // resident CTAs asked of ptxas: two where two fit shared memory and 64 registers per thread can hold the shape
+    static constexpr int minb = S::T <= 256 ? FHE_STAGED_MINB_256 : (S::T <= 512 && 2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
 };
-template <class M, int LOGN, int LOGE, typename IOW>
-__global__ void __launch_bounds__(NttShape<LOGN, LOGE>::T, NttShape<LOGN, LOGE>::T <= 256 ? FHE_STAGED_MINB_256 : 1)
+// TMA = true (FHE_NTT_STAGED=2): the same loop with the staging done by the TMA unit instead -- ONE thread posts the
+// whole operand row as bulk copies (cp.async.bulk, UBLKCP) that complete on an mbarrier; no thread issues a per-word
+// copy, and the waits are mbarrier.try_wait on the phase bit.  The row is read by every thread, so a CTA barrier
+// separates the read-out of the staging buffer from the next bulk copy into it.
+template <class M, int LOGN, int LOGE, typename IOW, bool TMA>
+__global__ void __launch_bounds__(NttShape<LOGN, LOGE>::T, StagedGeom<M, LOGN, LOGE, IOW>::minb)
 ntt_mul_staged_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restrict__ a, const IOW *__restrict__ b,
                       IOW *__restrict__ c, IOW *__restrict__ c_evals, size_t batch, int flags) {
     typedef NttShape<LOGN, LOGE> S;
@@ -563,26 +570,59 @@ ntt_mul_staged_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restr
     const TwSrc<M> twf = {P.c_fwd, P.fwd, P.fwdw};
     const TwSrc<M> twi = {P.c_inv, P.inv, P.invw};
     constexpr int LAST = S::P - 1;
+    __shared__ __align__(8) unsigned long long stage_bar;  // TMA only
+    const u32 bar = tc_smem_u32(&stage_bar);
+    u32 phase = 0;
+    if constexpr (TMA) {
+        if (tid == 0) {
+            tc_mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     auto stage = [&](const IOW *src) {
+        if constexpr (TMA) {
+            if (tid == 0) {
+                constexpr u32 BYTES = (u32)(S::N * sizeof(IOW)), CH = BYTES < 32768u ? BYTES : 32768u;
+                const u32 dst = tc_smem_u32(smem_raw + SG::exch_bytes);
+                tc_mbar_expect_tx(bar, BYTES);
 #pragma unroll
-        for (int e = 0; e < S::E; e++) cp_async_word<sizeof(IOW)>(stg + S::pos(0, 0, e), src + t0 + S::pos(0, 0, e));
-        cp_async_commit();
+                for (u32 o = 0; o < BYTES; o += CH) tc_bulk_g2s(dst + o, reinterpret_cast<const char *>(src) + o, CH, bar);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < S::E; e++) cp_async_word<sizeof(IOW)>(stg + S::pos(0, 0, e), src + t0 + S::pos(0, 0, e));
+            cp_async_commit();
+        }
+    };
+    auto staged = [&]() {   // the operand posted last has landed
+        if constexpr (TMA) {
+            tc_mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            cp_async_wait_all();
+        }
+    };
+    auto drained = [&]() {  // every thread has read its words out of the staging buffer
+        if constexpr (TMA) __syncthreads();
     };
     size_t poly = blockIdx.x;
     if (poly < batch) stage(a + poly * S::N);
     for (; poly < batch; poly += gridDim.x) {
         const size_t off = poly * S::N;
         W x[S::E], A[S::E];
-        cp_async_wait_all();
+        staged();
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = (W)stg[S::pos(0, 0, e)];
+        drained();
         stage((flags & B_BROADCAST) ? b : b + off);
         fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
 #pragma unroll
         for (int e = 0; e < S::E; e++) A[e] = m.fwd_out(x[e]);
-        cp_async_wait_all();
+        staged();
 #pragma unroll
         for (int e = 0; e < S::E; e++) x[e] = (W)stg[S::pos(0, 0, e)];
+        drained();
         if (poly + gridDim.x < batch) stage(a + (poly + gridDim.x) * S::N);
         fwd_chain<M, LOGN, LOGE>(x, sm, tid, m, twf);
 #pragma unroll
@@ -600,11 +640,11 @@ ntt_mul_staged_kernel(const __grid_constant__ NttParams<M> P, const IOW *__restr
         store_poly<M, LOGN, LOGE, 0, true, true, IOW>(x, c + off, true, sm, tid);
     }
 }
-template <class M, int LOGN, int LOGE, typename IOW>
+template <class M, int LOGN, int LOGE, typename IOW, bool TMA>
 int launch_staged(const NttParams<M> &P, const IOW *a, const IOW *b, IOW *c, IOW *c_evals, size_t batch, int flags,
                   cudaStream_t st) {
     typedef StagedGeom<M, LOGN, LOGE, IOW> SG;
-    auto kern = ntt_mul_staged_kernel<M, LOGN, LOGE, IOW>;
+    auto kern = ntt_mul_staged_kernel<M, LOGN, LOGE, IOW, TMA>;
     static std::atomic<int> resident[64];
     int dev = 0;
     FHE_CUDA_OK(cudaGetDevice(&dev));
@@ -669,8 +709,12 @@ int launch_modes(int mode, const NttParams<M> &P, const IOW *a, const IOW *b, IO
             return launch_one<M, LOGN, LE, MODE_MUL, IOW>(P, a, b, c, c_evals, batch, flags, st);
         case MODE_MULS:
             if constexpr (staged_instantiated(LOGN) && !IoTraits<IOW>::packed && StagedGeom<M, LOGN, LE, IOW>::fits) {
-                if ((flags & (A_IS_EVALS | B_IS_EVALS)) == 0)
-                    return launch_staged<M, LOGN, LE, IOW>(P, a, b, c, c_evals, batch, flags, st);
+                if ((flags & (A_IS_EVALS | B_IS_EVALS)) == 0) {
+                    // bulk copies need 16-byte aligned rows (a row is a multiple of 32 KB: only the bases matter)
+                    const bool tma = (flags & STAGE_TMA) && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+                    return tma ? launch_staged<M, LOGN, LE, IOW, true>(P, a, b, c, c_evals, batch, flags, st)
+                               : launch_staged<M, LOGN, LE, IOW, false>(P, a, b, c, c_evals, batch, flags, st);
+                }
             }
             return launch_one<M, LOGN, LE, MODE_MUL, IOW>(P, a, b, c, c_evals, batch, flags, st);
         case MODE_MUL2:
