@@ -1,11 +1,17 @@
 """Seeded random shapes through the C ABI against the oracle: the shapes nobody listed by hand (odd batch sizes,
 unusual k / l / beta, degrees outside the fused kernels' lists, non-power-of-two BFV degrees)."""
+import os
+
 import numpy as np
 import pytest
 
 from primes import Q17, Q22, Q30, Q62, Q63
 
 pytestmark = pytest.mark.gpu
+
+# FHE_FUZZ_SEEDS=<count> widens every seed range below for a soak run (tools/run_fuzz_soak.sh; the log of the last one is
+# profiles/r2_fuzz_soak.log); the default ranges keep the suite under a minute
+SOAK = int(os.environ.get("FHE_FUZZ_SEEDS", "0"))
 
 
 @pytest.fixture(scope="module")
@@ -16,7 +22,7 @@ def fhe():
     return f
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(max(12, SOAK)))
 def test_random_ntt_and_polymul(fhe, orc, seed):
     rng = np.random.default_rng(seed)
     q = [Q17, Q22, Q30, Q62, Q63, 12289, 7681][rng.integers(0, 7)]
@@ -35,7 +41,7 @@ def test_random_ntt_and_polymul(fhe, orc, seed):
     assert np.array_equal(plan.mul(fa, b, flags=fhe.A_IS_EVALS), c)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(max(10, SOAK)))
 def test_random_torus_shapes(fhe, orc, seed):
     rng = np.random.default_rng(100 + seed)
     n = 1 << int(rng.integers(1, 12))
@@ -62,7 +68,7 @@ def test_random_torus_shapes(fhe, orc, seed):
             assert np.array_equal(got[i], want)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(max(10, SOAK)))
 def test_random_key_switch_and_bootstrap_shapes(fhe, orc, seed):
     rng = np.random.default_rng(200 + seed)
     kn_in, kn_out = int(rng.integers(1, 200)), int(rng.integers(1, 200))
@@ -86,7 +92,7 @@ def test_random_key_switch_and_bootstrap_shapes(fhe, orc, seed):
                           orc.bootstrapping(n, k, ksk2, table, cts.reshape(-1), c_kn, threads=4))
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(max(8, SOAK)))
 def test_random_bfv_and_gfhe_shapes(fhe, orc, seed):
     rng = np.random.default_rng(300 + seed)
     q = [Q17, 12289, Q30, 257][rng.integers(0, 4)]
