@@ -369,8 +369,8 @@ template <class M, int LOGN, int LOGE, int MODE> struct ASmem {
 #ifndef FHE_MULG_MINB_512
 #define FHE_MULG_MINB_512 2
 #endif
-#ifndef FHE_MULG_MINB_256
-#define FHE_MULG_MINB_256 4
+#ifndef FHE_MULG_MINB_256   // N = 8192: three CTAs of 80 registers (no spills) against four of 64 (16 spilled words):
+#define FHE_MULG_MINB_256 3  // q = 65537 polymul 21.4 -> 21.8 M/s (A/B/A in one session, tools/run_mulg_ab.sh)
 #endif
 #ifndef FHE_MULG_MINB_128
 #define FHE_MULG_MINB_128 8
